@@ -1,0 +1,420 @@
+// k_chain.cuh -- K5..K7: anchors -> chains -> per-read decision, for a batch of read chunks.
+//
+// Input: the step's anchors as (64-bit key, d2) pairs already sorted by key =
+// entry | bucket(contig*2+strand) | target | query, which is the reference's per-bucket
+// std::sort order (spatial_index.cc:411-417, key spatial_index.h:22-25; (target, query) pairs
+// are unique so the d2 tie-break never fires) with buckets in the reference's DP order
+// (contig-major, '+' before '-', spatial_index.cc:420-422).
+//
+//   k_inject_carry   anchors of the previous chunk's surviving chains re-enter the buckets
+//                    (spatial_index.cc:303-322), before the search appends its hits
+//   k_mark_segments  heads of (entry, bucket) runs in the sorted array
+//   k_chain_dp       the banded chaining DP (spatial_index.cc:434-540), one thread per
+//                    (entry, bucket) segment -- buckets are independent until the running
+//                    global max is applied
+//   k_chain_select   one thread per entry: running max across buckets in order, top-3 end
+//                    candidates, traceback with used-flags, primary chains, MAPQ
+//                    (spatial_index.cc:542-576, :165-274), then StreamingMap's stop / output
+//                    decision and tag sums (sigmap.cc:667-745); survivors' anchors go to the
+//                    carry pool for the next chunk.
+// All float arithmetic mirrors the reference expression by expression (no FMA).
+#ifndef SB_K_CHAIN_CUH
+#define SB_K_CHAIN_CUH
+
+#include "sb_device.cuh"
+
+namespace sb {
+
+struct ChainArgs {
+  const uint64_t *key;   // sorted
+  const float *dist;     // sorted alongside
+  unsigned long long n;  // anchors this step
+  KeyLayout kl;
+  float radius;
+  float *score;
+  uint32_t *pred;        // bit31 = anchor_is_used
+  uint32_t *seg_start;
+  uint32_t seg_cap;
+  Counters *ctr;
+};
+
+__global__ void k_inject_carry(const uint32_t *__restrict__ entry_slot, const uint32_t *__restrict__ n_queries,
+                               const SlotState *__restrict__ slots, const CarryAnchor *__restrict__ pool0,
+                               const CarryAnchor *__restrict__ pool1, uint32_t B, KeyLayout kl,
+                               uint64_t *__restrict__ out_key, float *__restrict__ out_dist,
+                               unsigned long long cap, Counters *__restrict__ ctr) {
+  const uint32_t b = (blockIdx.x * blockDim.x + threadIdx.x) / 32, lane = threadIdx.x & 31;
+  if (b >= B) return;
+  if (n_queries[b] == 0) return;  // GenerateChains is not called for this entry
+  const SlotState st = slots[entry_slot[b]];
+  if (st.carry_n == 0) return;
+  const CarryAnchor *src = (st.pool ? pool1 : pool0) + st.carry_off;
+  unsigned long long base = 0;
+  if (lane == 0) base = atomicAdd(&ctr->n_anchors, (unsigned long long)st.carry_n);
+  base = __shfl_sync(0xffffffffu, base, 0);
+  for (uint32_t i = lane; i < st.carry_n; i += 32) {
+    const CarryAnchor c = src[i];
+    if (base + i < cap) {
+      out_key[base + i] = kl.pack(b, c.bucket, c.target, c.query);
+      out_dist[base + i] = c.dist;
+    }
+  }
+}
+
+__global__ void k_mark_segments(ChainArgs a) {
+  const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.n) return;
+  const uint64_t s = a.kl.seg(a.key[i]);
+  if (i == 0 || a.kl.seg(a.key[i - 1]) != s) {
+    const uint32_t at = atomicAdd(&a.ctr->n_segments, 1u);
+    if (at < a.seg_cap) a.seg_start[at] = (uint32_t)i;
+  }
+}
+
+constexpr int kBand = 5000;        // chaining_band_length, spatial_index.cc:286
+constexpr int kMaxTargetGap = 5000;
+constexpr int kMaxGap = 2000;
+constexpr int kMaxSkips = 25;
+
+__global__ void __launch_bounds__(128) k_chain_dp(ChainArgs a) {
+  const uint32_t sidx = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t nseg = min(a.ctr->n_segments, a.seg_cap);
+  if (sidx >= nseg) return;
+  const long long s = a.seg_start[sidx];
+  const uint64_t segkey = a.kl.seg(a.key[s]);
+  const double radius = (double)a.radius;
+  for (long long i = s; i < (long long)a.n; ++i) {
+    const uint64_t k = a.key[i];
+    if (a.kl.seg(k) != segkey) break;
+    const int32_t ct = (int32_t)a.kl.target(k), cq = (int32_t)a.kl.query(k);
+    // spatial_index.cc:438-444: 1 - 0.2 * distance / search_radius in double, then float
+    const float coef = (float)__dsub_rn(1.0, __ddiv_rn(__dmul_rn(0.2, (double)a.dist[i]), radius));
+    float sc = __fmul_rn(coef, (float)kDim);
+    long long pr = i;
+    const long long lo = (i - s > kBand) ? i - kBand : s;
+    int skips = 0;
+    for (long long j = i - 1; j >= lo; --j) {
+      const uint64_t kj = a.key[j];
+      const int32_t pt = (int32_t)a.kl.target(kj), pq = (int32_t)a.kl.query(kj);
+      if (pq == cq) continue;
+      if (pt == ct) continue;
+      if (pt + kMaxTargetGap < ct) break;
+      const int32_t dt = ct - pt, dq = cq - pq;
+      if (dq < 0) continue;
+      float cur = 0.0f;
+      const int32_t m = min(min(dt, dq), kDim);
+      const float matching = __fmul_rn((float)m, coef);
+      const int32_t gap = abs(dt - dq);
+      const float gs = __fdiv_rn((float)dq, (float)dt);
+      if (gap < kMaxGap && gs < 5.0f && gs > 0.75f) cur = __fadd_rn(a.score[j], matching);
+      if (cur > sc) {
+        sc = cur;
+        pr = j;
+        --skips;
+      } else {
+        ++skips;
+        if (skips > kMaxSkips) break;
+      }
+    }
+    a.score[i] = sc;
+    a.pred[i] = (uint32_t)pr;
+  }
+}
+
+struct ChainTmp {
+  float score;
+  uint32_t contig, start, end, n, dir, end_idx;
+  uint32_t state;  // 0 candidate, 1 primary (order in `rank`), 2 rejected
+  uint32_t rank;
+};
+
+struct SelectArgs {
+  ChainArgs c;
+  const uint32_t *entry_slot;
+  const uint32_t *n_queries;   // 0 => GenerateChains not called (copy state forward)
+  const uint32_t *n_features;
+  const uint8_t *absent;       // 1 => the slot has no chunk this round (pure copy-forward)
+  SlotState *slots;
+  uint32_t B;
+  ChainTmp *scratch;           // [B][max_chains]
+  uint32_t max_chains;
+  uint32_t out_pool;
+  ChainRec *pool_chain[2];
+  CarryAnchor *pool_anchor[2];
+  unsigned long long pool_chain_cap, pool_anchor_cap;
+  smb_params prm;
+};
+
+__device__ __forceinline__ unsigned long long lower_bound_key(const uint64_t *key, unsigned long long n,
+                                                              uint64_t v) {
+  unsigned long long lo = 0, hi = n;
+  while (lo < hi) {
+    unsigned long long mid = (lo + hi) >> 1;
+    if (key[mid] < v) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// spatial_index.h:38-44 operator> on (score, n, dir, contig, start, end)
+__device__ __forceinline__ bool chain_greater(const ChainTmp &x, const ChainTmp &y) {
+  if (x.score != y.score) return x.score > y.score;
+  if (x.n != y.n) return x.n > y.n;
+  if (x.dir != y.dir) return x.dir > y.dir;
+  if (x.contig != y.contig) return x.contig > y.contig;
+  if (x.start != y.start) return x.start > y.start;
+  return x.end > y.end;
+}
+
+__global__ void __launch_bounds__(64) k_chain_select(SelectArgs a) {
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= a.B) return;
+  const uint32_t slot = a.entry_slot[b];
+  SlotState st = a.slots[slot];
+  const uint32_t op = a.out_pool;
+  Counters *ctr = a.c.ctr;
+
+  if (a.n_queries[b] == 0) {
+    // chains unchanged (chunk skipped: <= 50 features, or no chunk this round); move the
+    // slot's records to the pool that survives the next round
+    if (st.n_chains > 0) {
+      unsigned long long co = atomicAdd(&ctr->carry_chain_used[op], (unsigned long long)st.n_chains);
+      unsigned long long ao = atomicAdd(&ctr->carry_anchor_used[op], (unsigned long long)st.carry_n);
+      if (co + st.n_chains > a.pool_chain_cap || ao + st.carry_n > a.pool_anchor_cap) {
+        atomicOr(&ctr->error, 2u);
+      } else {
+        const ChainRec *sc = a.pool_chain[st.pool] + st.chain_off;
+        const CarryAnchor *sa = a.pool_anchor[st.pool] + st.carry_off;
+        for (uint32_t i = 0; i < st.n_chains; ++i) a.pool_chain[op][co + i] = sc[i];
+        for (uint32_t i = 0; i < st.carry_n; ++i) a.pool_anchor[op][ao + i] = sa[i];
+      }
+      st.chain_off = co;
+      st.carry_off = ao;
+    }
+    st.pool = op;
+    st.stop = 0;
+    a.slots[slot] = st;
+    return;
+  }
+
+  const KeyLayout kl = a.c.kl;
+  const uint64_t *key = a.c.key;
+  const float *score = a.c.score;
+  uint32_t *pred = a.c.pred;
+  const unsigned long long lo = lower_bound_key(key, a.c.n, (uint64_t)b << kl.sh_e());
+  const unsigned long long hi = lower_bound_key(key, a.c.n, ((uint64_t)b + 1) << kl.sh_e());
+  ChainTmp *ch = a.scratch + (size_t)b * a.max_chains;
+  uint32_t nch = 0;
+  float gmax = 0.0f;  // max_chaining_score, spatial_index.cc:419
+  const float min_score = 10.0f;
+
+  unsigned long long i = lo;
+  while (i < hi) {
+    const uint64_t segkey = kl.seg(key[i]);
+    const uint32_t bucket = kl.bucket(key[i]);
+    // end candidates of this bucket: only the best three are ever traced (:555-557)
+    float top_s[3];
+    unsigned long long top_i[3];
+    int ntop = 0;
+    unsigned long long j = i;
+    for (; j < hi && kl.seg(key[j]) == segkey; ++j) {
+      const float sc = score[j];
+      if (sc > gmax) gmax = sc;
+      if (sc >= min_score && sc > __fdiv_rn(gmax, 2.0f)) {
+        // order: score desc, index desc (compare(), spatial_index.cc:11-20); j only grows,
+        // so on equal score the newcomer goes first
+        int p = ntop < 3 ? ntop : 3;
+        while (p > 0 && sc >= top_s[p - 1]) --p;
+        if (p < 3) {
+          for (int t = (ntop < 3 ? ntop : 2); t > p; --t) {
+            top_s[t] = top_s[t - 1];
+            top_i[t] = top_i[t - 1];
+          }
+          top_s[p] = sc;
+          top_i[p] = j;
+          if (ntop < 3) ++ntop;
+        }
+      }
+    }
+    const float half = __fdiv_rn(gmax, 2.0f);
+    for (int r = 0; r < ntop; ++r) {
+      const unsigned long long e = top_i[r];
+      // ---- TracebackChains (spatial_index.cc:165-220)
+      if (!(pred[e] & 0x80000000u)) {
+        unsigned long long s = e;
+        uint32_t n = 1;
+        bool hit_used = false;
+        uint32_t p = pred[s] & 0x7FFFFFFFu;
+        if (p != s && (pred[p] & 0x80000000u)) hit_used = true;
+        pred[s] |= 0x80000000u;
+        while (p != s && !(pred[p] & 0x80000000u)) {
+          s = p;
+          ++n;
+          p = pred[s] & 0x7FFFFFFFu;
+          if (p != s && (pred[p] & 0x80000000u)) hit_used = true;
+          pred[s] |= 0x80000000u;
+        }
+        if (n >= 2) {
+          float sc = score[e];
+          if (hit_used) sc = __fsub_rn(sc, score[pred[s] & 0x7FFFFFFFu]);
+          if (nch < a.max_chains) {
+            ChainTmp c;
+            c.score = sc;
+            c.contig = bucket >> 1;
+            c.start = kl.target(key[s]);
+            c.end = kl.target(key[e]);
+            c.n = n;
+            c.dir = (bucket & 1u) ? 0u : 1u;  // strand bit 0 = Positive (enum value 1)
+            c.end_idx = (uint32_t)e;
+            c.state = 0;
+            c.rank = 0;
+            ch[nch++] = c;
+          } else {
+            st.flags |= 2u;
+            atomicOr(&ctr->error, 4u);
+          }
+        }
+      }
+      if (score[e] < half) break;  // :564-567
+    }
+    i = j;
+  }
+
+  // ---- GeneratePrimaryChains (spatial_index.cc:222-253) by repeated extraction of the max
+  uint32_t n_prim = 0;
+  uint32_t prim_first = 0, prim_second = 0;
+  float last_primary_score = 0.0f;
+  for (;;) {
+    int best = -1;
+    for (uint32_t c = 0; c < nch; ++c)
+      if (ch[c].state == 0 && (best < 0 || chain_greater(ch[c], ch[best]))) best = (int)c;
+    if (best < 0) break;
+    if (n_prim > 0 && ch[best].score < __fdiv_rn(last_primary_score, 3.0f)) break;
+    bool ok = true;
+    for (uint32_t c = 0; c < nch && ok; ++c) {
+      if (ch[c].state != 1 || ch[c].contig != ch[best].contig) continue;
+      const uint32_t mx = max(ch[best].start, ch[c].start), mn = min(ch[best].end, ch[c].end);
+      if (!(mx > mn)) ok = false;
+    }
+    if (ok) {
+      ch[best].state = 1;
+      ch[best].rank = n_prim;
+      if (n_prim == 0) prim_first = (uint32_t)best;
+      if (n_prim == 1) prim_second = (uint32_t)best;
+      last_primary_score = ch[best].score;
+      ++n_prim;
+    } else {
+      ch[best].state = 2;
+    }
+  }
+
+  // ---- write survivors to the carry pool, primary order, anchors end -> start
+  unsigned long long co = 0, ao = 0;
+  uint32_t total_anchors = 0;
+  for (uint32_t c = 0; c < nch; ++c)
+    if (ch[c].state == 1) total_anchors += ch[c].n;
+  bool pool_ok = true;
+  if (n_prim > 0) {
+    co = atomicAdd(&ctr->carry_chain_used[op], (unsigned long long)n_prim);
+    ao = atomicAdd(&ctr->carry_anchor_used[op], (unsigned long long)total_anchors);
+    if (co + n_prim > a.pool_chain_cap || ao + total_anchors > a.pool_anchor_cap) {
+      atomicOr(&ctr->error, 2u);
+      pool_ok = false;
+    }
+  }
+  float mean = 0.0f;
+  uint32_t mapq0 = 0;
+  if (n_prim == 1) {
+    mapq0 = 60;  // spatial_index.cc:255-258
+  } else if (n_prim >= 2) {
+    const float ratio = __fdiv_rn(ch[prim_second].score, ch[prim_first].score);
+    int mq = (int)__fmul_rn(40.0f, __fsub_rn(1.0f, ratio));
+    mq = mq > 60 ? 60 : (mq < 0 ? 0 : mq);
+    mapq0 = (uint32_t)(uint8_t)mq;
+  }
+  if (pool_ok && n_prim > 0) {
+    // ranks are 0..n_prim-1; emit in rank order
+    uint32_t aoff = 0;
+    for (uint32_t r = 0; r < n_prim; ++r) {
+      uint32_t c = 0;
+      while (!(ch[c].state == 1 && ch[c].rank == r)) ++c;
+      mean = __fadd_rn(mean, ch[c].score);
+      ChainRec rec;
+      rec.score = ch[c].score;
+      rec.contig = ch[c].contig;
+      rec.start = ch[c].start;
+      rec.end = ch[c].end;
+      rec.n_anchors = ch[c].n;
+      rec.mapq = r == 0 ? mapq0 : 0;
+      rec.dir = ch[c].dir;
+      rec.anchor_off = aoff;
+      a.pool_chain[op][co + r] = rec;
+      const uint32_t bucket = (ch[c].contig << 1) | (ch[c].dir ? 0u : 1u);
+      uint32_t idx = ch[c].end_idx;
+      CarryAnchor *dst = a.pool_anchor[op] + ao + aoff;
+      for (uint32_t k = 0; k < ch[c].n; ++k) {
+        CarryAnchor ca;
+        ca.target = kl.target(key[idx]);
+        ca.query = kl.query(key[idx]);
+        ca.dist = a.c.dist[idx];
+        ca.bucket = bucket;
+        dst[k] = ca;
+        idx = pred[idx] & 0x7FFFFFFFu;
+      }
+      aoff += ch[c].n;
+    }
+    mean = __fdiv_rn(mean, (float)n_prim);
+  }
+
+  // ---- StreamingMap decision + tag sums on chains[0] (sigmap.cc:667-687, :701-745)
+  st.n_chains = n_prim;
+  st.chain_off = co;
+  st.carry_off = ao;
+  st.carry_n = total_anchors;
+  st.pool = op;
+  st.num_events += a.n_features[b];  // sigmap.cc:666
+  st.stop = 0;
+  st.mapped = 0;
+  st.cm = 0;
+  st.s1 = st.s2 = st.sm = st.ad = st.at = st.aq = 0.0f;
+  if (n_prim > 0 && pool_ok) {
+    const ChainTmp &c0 = ch[prim_first];
+    const float s0 = c0.score;
+    const float s1 = n_prim > 1 ? ch[prim_second].score : 0.0f;
+    float ad = 0.0f, at = 0.0f, aq = 0.0f;
+    const CarryAnchor *an = a.pool_anchor[op] + ao;  // chain 0 is first
+    for (uint32_t k = 0; k < c0.n; ++k) {
+      ad = __fadd_rn(ad, an[k].dist);
+      if (k + 1 < c0.n) {
+        at = __fadd_rn(at, (float)(uint32_t)(an[k].target - an[k + 1].target));
+        aq = __fadd_rn(aq, (float)(uint32_t)(an[k].query - an[k + 1].query));
+      }
+    }
+    st.ad = __fdiv_rn(ad, (float)c0.n);
+    st.at = __fdiv_rn(at, (float)c0.n);
+    st.aq = __fdiv_rn(aq, (float)c0.n);
+    st.s1 = s0;
+    st.s2 = s1;
+    st.sm = mean;
+    st.cm = c0.n;
+    st.c0_contig = c0.contig;
+    st.c0_start = c0.start;
+    st.c0_end = c0.end;
+    st.c0_dir = c0.dir;
+    st.c0_mapq = mapq0;
+    st.q_first = an[0].query;
+    st.q_last = an[c0.n - 1].query;
+    if (n_prim >= 2) {
+      const float ratio = __fdiv_rn(s0, s1);
+      if (ratio >= a.prm.stop_mapping || s0 >= __fmul_rn(a.prm.stop_mapping_mean, mean)) st.stop = 1;
+      if (ratio >= a.prm.stop_mapping_output || s0 >= __fmul_rn(a.prm.stop_mapping_mean_output, mean))
+        st.mapped = 1;
+    } else {
+      if (c0.n >= (uint32_t)a.prm.min_num_anchors) st.stop = 1;
+      if (c0.n >= (uint32_t)a.prm.min_num_anchors_output) st.mapped = 1;
+    }
+  }
+  a.slots[slot] = st;
+}
+
+}  // namespace sb
+#endif

@@ -1,0 +1,129 @@
+// sb_device.cuh -- shared device-side definitions of the B200 mapping engine.
+//
+// Everything here is compiled for sm_100a only, with -fmad=false: the event features must
+// reproduce the reference's strict IEEE fp32/fp64 arithmetic bit for bit, so
+// no multiply-add contraction is allowed anywhere in this library.
+#ifndef SB_DEVICE_CUH
+#define SB_DEVICE_CUH
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/sigmap_b200.h"
+
+namespace sb {
+
+constexpr int kChunk = SMB_CHUNK;       // 4000 samples
+constexpr int kDim = SMB_DIM;           // 6
+constexpr int kFeatCap = SMB_CHUNK;     // per-chunk event/feature capacity (peaks < samples)
+constexpr int kMinFeatures = 50;        // sigmap.cc:660: GenerateChains only if size() > 50
+constexpr uint32_t kMaxHits = SMB_MAX_HITS;
+constexpr int kLeaf = 32;               // points per leaf block = one warp
+constexpr int kFan = 32;                // children per inner node = one warp
+constexpr int kMaxLevels = 8;
+
+// growable device buffer (contents are NOT preserved across growth)
+template <class T>
+struct DevBuf {
+  T *p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = n + n / 4 + 64;
+    cudaError_t e = cudaMalloc((void **)&p, want * sizeof(T));
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+// ---- flat device index over the Morton-sorted window points (replaces nanoflann) ----
+// Level 0 = AABBs of the 32-point leaf blocks; level l+1 = AABBs of 32 consecutive level-l
+// boxes.  Boxes of one parent are stored together as [group][12][32] floats (lo0..lo5,
+// hi0..hi5, lane-minor) so one warp tests 32 children with 12 coalesced 128-byte loads.
+struct IndexView {
+  uint64_t n_points;    // N (point cloud size); windows W = N - 5
+  uint64_t n_windows;
+  uint32_t n_blocks;    // leaf blocks = ceil(W / 32)
+  int n_levels;         // number of box levels; the top level has <= 32 boxes (1 group)
+  uint32_t level_count[kMaxLevels];  // boxes per level
+  const float *level_box[kMaxLevels];
+  const float *leaf_vals;     // [n_blocks][6][32]
+  const uint32_t *leaf_tpos;  // [n_blocks*32] target position (pos >> 1, low 32 bits)
+  const uint32_t *leaf_bucket;// [n_blocks*32] contig*2 + strand (0 = '+'), ~0u = padding
+  const uint32_t *leaf_widx;  // [n_blocks*32] window index in the original cloud
+};
+
+// per-step packing of the 64-bit sort key: entry | bucket | target | query
+struct KeyLayout {
+  int qbits, tbits, bbits, ebits;
+  __host__ __device__ int sh_t() const { return qbits; }
+  __host__ __device__ int sh_b() const { return qbits + tbits; }
+  __host__ __device__ int sh_e() const { return qbits + tbits + bbits; }
+  __host__ __device__ int total() const { return qbits + tbits + bbits + ebits; }
+  __host__ __device__ uint64_t pack(uint32_t e, uint32_t b, uint32_t t, uint32_t q) const {
+    return ((uint64_t)e << sh_e()) | ((uint64_t)b << sh_b()) | ((uint64_t)t << sh_t()) | q;
+  }
+  __host__ __device__ uint32_t query(uint64_t k) const { return (uint32_t)(k & ((1ull << qbits) - 1)); }
+  __host__ __device__ uint32_t target(uint64_t k) const { return (uint32_t)((k >> sh_t()) & ((1ull << tbits) - 1)); }
+  __host__ __device__ uint32_t bucket(uint64_t k) const { return (uint32_t)((k >> sh_b()) & ((1ull << bbits) - 1)); }
+  __host__ __device__ uint32_t entry(uint64_t k) const { return (uint32_t)(k >> sh_e()); }
+  __host__ __device__ uint64_t seg(uint64_t k) const { return k >> sh_b(); }  // (entry, bucket)
+};
+
+// carried anchor (anchor of a surviving chain, re-injected next chunk: spatial_index.cc:303-322)
+struct CarryAnchor {
+  uint32_t target, query;
+  float dist;
+  uint32_t bucket;
+};
+
+// chain record kept per read slot between chunks (SignalAnchorChain minus the anchors)
+struct ChainRec {
+  float score;
+  uint32_t contig, start, end, n_anchors, mapq, dir;
+  uint32_t anchor_off;  // first anchor of this chain inside the slot's carry range
+};
+
+// per read-slot state carried between chunks + the last decision
+struct SlotState {
+  uint32_t num_events;   // query offset of the next chunk (sigmap.cc:666)
+  uint32_t n_chains;
+  uint32_t pool;         // which carry pool holds this slot's chains/anchors
+  uint32_t pad0;
+  uint64_t chain_off;    // ChainRec index into pool_chain[pool]
+  uint64_t carry_off;    // CarryAnchor index into pool_anchor[pool]
+  uint32_t carry_n;
+  uint32_t flags;        // bit0 query capped at 5000 hits; bit1 chain scratch overflow
+  // decision inputs/outputs of the last GenerateChains (sigmap.cc:667-745)
+  float s1, s2, sm, ad, at, aq;
+  uint32_t cm, c0_contig, c0_start, c0_end, c0_dir, c0_mapq, q_first, q_last;
+  uint32_t stop, mapped;
+};
+
+struct Counters {
+  unsigned long long n_anchors;     // anchors written this step (hits + carried)
+  unsigned long long n_hits;        // hits only
+  unsigned long long n_queries;
+  unsigned long long n_capped;
+  unsigned long long n_events_raw;
+  unsigned long long n_events_kept;
+  unsigned long long carry_anchor_used[2];
+  unsigned long long carry_chain_used[2];
+  unsigned int n_segments;
+  unsigned int work;                // dynamic work counter for the search kernel
+  unsigned int error;               // bit0 anchor overflow, bit1 carry overflow, bit2 chain scratch
+  unsigned int pad;
+};
+
+}  // namespace sb
+#endif

@@ -1,0 +1,1317 @@
+// sb_engine.cu -- context, device index build, the batched pipeline step, the read scheduler
+// and the C ABI of include/sigmap_b200.h.
+//
+// Execution model (replaces the OpenMP taskloop of sigmap.cc:618-632): instead of one host
+// thread walking one read chunk by chunk, all still-active reads advance together in ROUNDS;
+// round k maps chunk k of every active read as one batch (split into steps that fit the
+// anchor buffers):
+//   events (3 kernels) -> query table -> carry re-injection + radius search -> device radix
+//   sort by (entry, bucket, target, query) -> chaining DP -> per-read selection/decision.
+// The only host<->device traffic per step is a counter readback (anchor count) and, per
+// round, 12 bytes per active read (stop flag, kept events, chain count).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <cub/device/device_radix_sort.cuh>
+#include <string>
+#include <vector>
+
+#include "k_chain.cuh"
+#include "k_events.cuh"
+#include "k_index.cuh"
+#include "sb_device.cuh"
+
+using namespace sb;
+
+namespace {
+thread_local std::string g_create_error;
+
+inline int bits_for(uint64_t max_value) {  // bits needed to represent values 0..max_value
+  int b = 1;
+  while (b < 64 && (max_value >> b)) ++b;
+  return b;
+}
+}  // namespace
+
+// ------------------------------------------------------------------ small kernels
+namespace sb {
+
+__global__ void k_reset_step(Counters *c) {
+  c->n_anchors = 0;
+  c->n_hits = 0;
+  c->n_queries = 0;
+  c->n_capped = 0;
+  c->n_events_raw = 0;
+  c->n_events_kept = 0;
+  c->n_segments = 0;
+  c->work = 0;
+}
+
+// queries per entry (spatial_index.cc:349-409 with Q3: seeds at step, 2*step, ... while
+// count < (F-5)/step  =>  floor((F-6)/step) of them) and their exclusive scan; one block.
+__global__ void k_query_table(const uint32_t *__restrict__ n_features, uint32_t B, uint32_t B_present,
+                              int step, uint32_t *__restrict__ n_queries, uint32_t *__restrict__ q_off,
+                              Counters *ctr) {
+  __shared__ uint32_t warp_excl[32];
+  __shared__ uint32_t tile_total;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+  uint32_t carry = 0;  // identical in every thread
+  for (uint32_t base = 0; base < B; base += blockDim.x) {
+    const uint32_t b = base + threadIdx.x;
+    uint32_t nq = 0;
+    if (b < B_present) {
+      const uint32_t F = n_features[b];
+      if (F > (uint32_t)kMinFeatures) nq = (F - kDim) / (uint32_t)step;
+    }
+    uint32_t incl = nq;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += t;
+    }
+    if (lane == 31) warp_excl[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+      const uint32_t v = lane < n_warps ? warp_excl[lane] : 0;
+      uint32_t in = v;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, in, d);
+        if (lane >= d) in += t;
+      }
+      warp_excl[lane] = in - v;
+      if (lane == 31) tile_total = in;
+    }
+    __syncthreads();
+    if (b < B) {
+      n_queries[b] = nq;
+      q_off[b] = carry + warp_excl[wid] + (incl - nq);
+    }
+    carry += tile_total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    q_off[B] = carry;
+    ctr->n_queries = carry;
+  }
+}
+
+struct RoundInfo {
+  uint32_t stop, num_events, n_chains;
+};
+__global__ void k_gather_round(const SlotState *__restrict__ slots, const uint32_t *__restrict__ ids,
+                               uint32_t n, RoundInfo *__restrict__ out) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const SlotState &s = slots[ids[i]];
+  out[i] = RoundInfo{s.stop, s.num_events, s.n_chains};
+}
+
+// stage hook: scatter user features (concatenated) into the [B][kFeatCap] layout
+__global__ void k_scatter_features(const float *__restrict__ src, const uint32_t *__restrict__ feat_off,
+                                   uint32_t B, float *__restrict__ dst, uint32_t *__restrict__ n_features) {
+  const uint32_t b = blockIdx.x;
+  if (b >= B) return;
+  const uint32_t o = feat_off[b], n = min(feat_off[b + 1] - o, (uint32_t)kFeatCap);
+  if (threadIdx.x == 0) n_features[b] = n;
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
+    dst[(size_t)b * kFeatCap + i] = src[o + i];
+}
+
+// stage hook: per-query hit counts from sorted (qid << 32 | widx) keys
+__global__ void k_count_by_query(const uint64_t *__restrict__ key, unsigned long long n,
+                                 unsigned long long *__restrict__ counts) {
+  unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) atomicAdd(&counts[key[i] >> 32], 1ull);
+}
+
+}  // namespace sb
+
+// ------------------------------------------------------------------ context
+struct SlotSpace {
+  uint32_t n_slots = 0;
+  DevBuf<SlotState> slots;
+  DevBuf<ChainRec> pool_chain[2];
+  DevBuf<CarryAnchor> pool_anchor[2];
+  std::vector<uint32_t> h_events, h_nchains;  // host mirror, refreshed every round
+  uint32_t round = 0;
+};
+
+struct Workspace {
+  // per-entry
+  DevBuf<uint32_t> entry_slot, n_features, n_raw_events, n_queries, q_off;
+  DevBuf<uint8_t> absent;
+  DevBuf<uint64_t> chunk_start;
+  DevBuf<float> chunk_offset, chunk_scale;
+  // events (transposed)
+  DevBuf<float> ps, pss, t1, t2, means, features;
+  // anchors
+  DevBuf<uint64_t> key_a, key_b;
+  DevBuf<float> dist_a, dist_b, score;
+  DevBuf<uint32_t> pred, seg_start;
+  DevBuf<unsigned char> cub_temp;
+  DevBuf<ChainTmp> chain_tmp;
+  // round readback
+  DevBuf<uint32_t> ids;
+  DevBuf<RoundInfo> round_info;
+};
+
+struct smb_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  // index
+  bool has_index = false;
+  IndexView ix{};
+  DevBuf<float> leaf_vals, level[kMaxLevels];
+  DevBuf<uint32_t> leaf_tpos, leaf_bucket, leaf_widx;
+  uint32_t max_tpos = 0, max_bucket = 0;
+  std::vector<uint32_t> contig_len;
+  // uploaded reads
+  size_t n_reads = 0;
+  DevBuf<int16_t> raw, kept;
+  DevBuf<uint64_t> d_read_off, d_kept_off;
+  DevBuf<float> d_dig, d_range, d_offset;
+  DevBuf<uint32_t> d_kept_len;
+  std::vector<uint64_t> h_kept_off;
+  std::vector<uint32_t> h_kept_len;
+  std::vector<float> h_offset, h_scale;
+  // work
+  Workspace ws;
+  SlotSpace map_slots;
+  Counters *d_ctr = nullptr;
+  Counters *h_ctr = nullptr;  // pinned
+  cudaEvent_t ev[6] = {};
+  smb_stats stats{};
+  uint32_t max_batch_chunks = 16384;
+  uint64_t max_batch_anchors = 192ull << 20;
+  double est_anchors_per_chunk = 20000.0;
+  // streaming
+  SlotSpace *stream_slots = nullptr;
+  smb_params stream_params{};
+  std::vector<std::vector<int16_t>> stream_pending;  // kept samples not yet forming a chunk
+  std::vector<float> stream_offset, stream_scale;
+  std::vector<uint32_t> stream_chunks, stream_kept;
+};
+
+struct smb_batch {
+  smb_ctx *ctx;
+  SlotSpace sp;
+};
+
+#define CK(call)                                                                      \
+  do {                                                                                \
+    cudaError_t e_ = (call);                                                          \
+    if (e_ != cudaSuccess) {                                                          \
+      ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                  \
+      return SMB_ERR_CUDA;                                                            \
+    }                                                                                 \
+  } while (0)
+
+#define LAUNCH_CHECK()                                                                \
+  do {                                                                                \
+    ctx->stats.launches++;                                                            \
+    cudaError_t e_ = cudaGetLastError();                                              \
+    if (e_ != cudaSuccess) {                                                          \
+      ctx->err = std::string("kernel launch: ") + cudaGetErrorString(e_);             \
+      return SMB_ERR_CUDA;                                                            \
+    }                                                                                 \
+  } while (0)
+
+static int fail(smb_ctx *ctx, int code, const std::string &msg) {
+  ctx->err = msg;
+  return code;
+}
+
+// ------------------------------------------------------------------ index build
+static int build_index(smb_ctx *ctx, const uint64_t *pos, const float *val, size_t n) {
+  if (n < (size_t)kDim) return fail(ctx, SMB_ERR_ARG, "point cloud smaller than the index dimension");
+  if (n - (kDim - 1) > 0xFFFFFFF0ull)
+    return fail(ctx, SMB_ERR_CAPACITY, "more than 2^32 window points: shard the index by contig");
+  const uint64_t W = n - (kDim - 1);
+  const uint32_t n_blocks = (uint32_t)((W + kLeaf - 1) / kLeaf);
+  float vmin = val[0], vmax = val[0];
+  uint32_t max_tpos = 0, max_bucket = 0;
+  for (size_t i = 0; i < n; ++i) {
+    vmin = std::min(vmin, val[i]);
+    vmax = std::max(vmax, val[i]);
+    max_tpos = std::max(max_tpos, (uint32_t)(pos[i] >> 1));
+    max_bucket = std::max(max_bucket, (uint32_t)(((pos[i] >> 33) << 1) | (pos[i] & 1)));
+  }
+  const float span = std::max(vmax - vmin, 1e-6f);
+  cudaStream_t s = ctx->stream;
+  DevBuf<float> d_val;
+  DevBuf<uint64_t> d_pos, code_a, code_b;
+  DevBuf<uint32_t> w_a, w_b;
+  DevBuf<unsigned char> tmp;
+  CK(d_val.ensure(n));
+  CK(d_pos.ensure(n));
+  CK(code_a.ensure(W));
+  CK(code_b.ensure(W));
+  CK(w_a.ensure(W));
+  CK(w_b.ensure(W));
+  CK(cudaMemcpyAsync(d_val.p, val, n * sizeof(float), cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(d_pos.p, pos, n * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+  k_morton<<<(unsigned)((W + 255) / 256), 256, 0, s>>>(d_val.p, W, vmin, 1.0f / span, code_a.p, w_a.p);
+  LAUNCH_CHECK();
+  size_t tb = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tb, code_a.p, code_b.p, w_a.p, w_b.p, (uint64_t)W, 0, 60, s);
+  CK(tmp.ensure(tb));
+  CK(cub::DeviceRadixSort::SortPairs(tmp.p, tb, code_a.p, code_b.p, w_a.p, w_b.p, (uint64_t)W, 0, 60, s));
+  ctx->stats.launches += 8;
+  CK(ctx->leaf_vals.ensure((size_t)n_blocks * kDim * kLeaf));
+  CK(ctx->leaf_tpos.ensure((size_t)n_blocks * kLeaf));
+  CK(ctx->leaf_bucket.ensure((size_t)n_blocks * kLeaf));
+  CK(ctx->leaf_widx.ensure((size_t)n_blocks * kLeaf));
+  k_build_leaves<<<(unsigned)(((uint64_t)n_blocks * kLeaf + 255) / 256), 256, 0, s>>>(
+      d_val.p, d_pos.p, w_b.p, W, n_blocks, ctx->leaf_vals.p, ctx->leaf_tpos.p, ctx->leaf_bucket.p,
+      ctx->leaf_widx.p);
+  LAUNCH_CHECK();
+  IndexView ix{};
+  ix.n_points = n;
+  ix.n_windows = W;
+  ix.n_blocks = n_blocks;
+  uint32_t count = n_blocks;
+  int L = 0;
+  for (;;) {
+    if (L >= kMaxLevels) return fail(ctx, SMB_ERR_CAPACITY, "index hierarchy deeper than kMaxLevels");
+    const uint32_t groups = (count + kFan - 1) / kFan, padded = groups * kFan;
+    CK(ctx->level[L].ensure((size_t)groups * 12 * kFan));
+    if (L == 0) {
+      k_boxes_level0<<<(padded * 32 + 255) / 256, 256, 0, s>>>(ctx->leaf_vals.p, ctx->leaf_bucket.p,
+                                                              n_blocks, padded, ctx->level[0].p);
+    } else {
+      // parents of level L-1 are the boxes of level L; count == number of groups of L-1
+      k_boxes_up<<<(padded * 32 + 255) / 256, 256, 0, s>>>(ctx->level[L - 1].p, ix.level_count[L - 1],
+                                                          padded, ctx->level[L].p);
+    }
+    LAUNCH_CHECK();
+    ix.level_count[L] = count;
+    ix.level_box[L] = ctx->level[L].p;
+    ++L;
+    if (count <= (uint32_t)kFan) break;
+    count = groups;
+  }
+  ix.n_levels = L;
+  ix.leaf_vals = ctx->leaf_vals.p;
+  ix.leaf_tpos = ctx->leaf_tpos.p;
+  ix.leaf_bucket = ctx->leaf_bucket.p;
+  ix.leaf_widx = ctx->leaf_widx.p;
+  CK(cudaStreamSynchronize(s));
+  d_val.release();
+  d_pos.release();
+  code_a.release();
+  code_b.release();
+  w_a.release();
+  w_b.release();
+  tmp.release();
+  ctx->ix = ix;
+  ctx->max_tpos = max_tpos;
+  ctx->max_bucket = max_bucket;
+  ctx->has_index = true;
+  return SMB_OK;
+}
+
+// ------------------------------------------------------------------ the pipeline step
+enum StepSource { SRC_RAW_KEPT, SRC_PA_FLOAT, SRC_FEATURES };
+
+struct StepEntries {
+  uint32_t B = 0, B_present = 0;           // present entries first, absent ones after
+  std::vector<uint32_t> slot;
+  std::vector<uint64_t> chunk_start;       // SRC_RAW_KEPT / SRC_PA_FLOAT: sample index of the chunk
+  std::vector<float> offset, scale;        // SRC_RAW_KEPT
+  const void *samples = nullptr;           // device pointer (kept int16 or pA float)
+  const float *d_features = nullptr;       // SRC_FEATURES: concatenated features (device)
+  const uint32_t *d_feat_off = nullptr;    // SRC_FEATURES: B_present+1 offsets (device)
+};
+
+static int ensure_event_ws(smb_ctx *ctx, uint32_t B) {
+  Workspace &w = ctx->ws;
+  const uint32_t Bp = (B + 31) & ~31u;
+  const size_t tr = (size_t)(kChunk + 1) * Bp;
+  CK(w.ps.ensure(tr));
+  CK(w.pss.ensure(tr));
+  CK(w.t1.ensure(tr));
+  CK(w.t2.ensure(tr));
+  CK(w.means.ensure((size_t)B * kFeatCap));
+  return SMB_OK;
+}
+
+static int run_events(smb_ctx *ctx, StepSource src, const void *samples, uint32_t B,
+                      uint32_t *d_peaks_out) {
+  Workspace &w = ctx->ws;
+  cudaStream_t s = ctx->stream;
+  const uint32_t Bp = (B + 31) & ~31u;
+  int rc = ensure_event_ws(ctx, B);
+  if (rc) return rc;
+  if (src == SRC_RAW_KEPT)
+    k_ev_prefix<true><<<(B + 127) / 128, 128, 0, s>>>(samples, w.chunk_start.p, w.chunk_offset.p,
+                                                      w.chunk_scale.p, w.ps.p, w.pss.p, B, Bp);
+  else
+    k_ev_prefix<false><<<(B + 127) / 128, 128, 0, s>>>(samples, w.chunk_start.p, nullptr, nullptr,
+                                                       w.ps.p, w.pss.p, B, Bp);
+  LAUNCH_CHECK();
+  dim3 g((B + 127) / 128, (kChunk + 1 + kStrip - 1) / kStrip);
+  k_ev_tstat<<<g, 128, 0, s>>>(w.ps.p, w.pss.p, w.t1.p, w.t2.p, B, Bp);
+  LAUNCH_CHECK();
+  k_ev_features<<<(B + 127) / 128, 128, 0, s>>>(w.t1.p, w.t2.p, w.ps.p, w.means.p, w.features.p,
+                                                w.n_features.p, w.n_raw_events.p, d_peaks_out, B, Bp,
+                                                ctx->d_ctr);
+  LAUNCH_CHECK();
+  return SMB_OK;
+}
+
+// Returns SMB_OK, an error, or +1 when the anchor buffer overflowed (caller splits the batch).
+static int run_step(smb_ctx *ctx, SlotSpace &sp, const StepEntries &en, StepSource src,
+                    const smb_params &prm, uint32_t out_pool) {
+  Workspace &w = ctx->ws;
+  cudaStream_t s = ctx->stream;
+  const uint32_t B = en.B, Bpres = en.B_present;
+  if (B == 0) return SMB_OK;
+  if (!ctx->has_index) return fail(ctx, SMB_ERR_STATE, "no index loaded");
+  // ---- key layout for this step
+  uint32_t max_ev = 0;
+  for (uint32_t b = 0; b < Bpres; ++b) max_ev = std::max(max_ev, sp.h_events[en.slot[b]]);
+  KeyLayout kl;
+  kl.qbits = bits_for((uint64_t)max_ev + kFeatCap);
+  kl.tbits = bits_for(ctx->max_tpos);
+  kl.bbits = bits_for(ctx->max_bucket);
+  kl.ebits = bits_for(B - 1);
+  if (kl.total() > 64) return fail(ctx, SMB_ERR_CAPACITY, "sort key exceeds 64 bits: lower max_batch_chunks");
+  const uint64_t cap = ctx->max_batch_anchors;
+  if (cap >= (1ull << 31)) return fail(ctx, SMB_ERR_ARG, "max_batch_anchors must stay below 2^31");
+
+  // ---- per-entry arrays
+  CK(w.entry_slot.ensure(B));
+  CK(w.absent.ensure(B));
+  CK(w.n_features.ensure(B));
+  CK(w.n_raw_events.ensure(B));
+  CK(w.n_queries.ensure(B));
+  CK(w.q_off.ensure(B + 1));
+  CK(w.features.ensure((size_t)std::max(Bpres, 1u) * kFeatCap));
+  CK(cudaMemcpyAsync(w.entry_slot.p, en.slot.data(), B * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+  ctx->stats.h2d_bytes += B * sizeof(uint32_t);
+  CK(cudaEventRecord(ctx->ev[0], s));
+  k_reset_step<<<1, 1, 0, s>>>(ctx->d_ctr);
+  LAUNCH_CHECK();
+  CK(cudaMemsetAsync(w.n_features.p, 0, B * sizeof(uint32_t), s));
+  if (Bpres > 0) {
+    if (src == SRC_FEATURES) {
+      k_scatter_features<<<Bpres, 256, 0, s>>>(en.d_features, en.d_feat_off, Bpres, w.features.p, w.n_features.p);
+      LAUNCH_CHECK();
+    } else {
+      CK(w.chunk_start.ensure(Bpres));
+      CK(cudaMemcpyAsync(w.chunk_start.p, en.chunk_start.data(), Bpres * sizeof(uint64_t),
+                         cudaMemcpyHostToDevice, s));
+      ctx->stats.h2d_bytes += Bpres * sizeof(uint64_t);
+      if (src == SRC_RAW_KEPT) {
+        CK(w.chunk_offset.ensure(Bpres));
+        CK(w.chunk_scale.ensure(Bpres));
+        CK(cudaMemcpyAsync(w.chunk_offset.p, en.offset.data(), Bpres * sizeof(float), cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(w.chunk_scale.p, en.scale.data(), Bpres * sizeof(float), cudaMemcpyHostToDevice, s));
+        ctx->stats.h2d_bytes += 2 * Bpres * sizeof(float);
+      }
+      int rc = run_events(ctx, src, en.samples, Bpres, nullptr);
+      if (rc) return rc;
+    }
+  }
+  CK(cudaEventRecord(ctx->ev[1], s));
+  k_query_table<<<1, 1024, 0, s>>>(w.n_features.p, B, Bpres, prm.step_size, w.n_queries.p, w.q_off.p, ctx->d_ctr);
+  LAUNCH_CHECK();
+
+  // ---- anchors: carried ones first, then the radius search appends its hits
+  CK(w.key_a.ensure(cap));
+  CK(w.key_b.ensure(cap));
+  CK(w.dist_a.ensure(cap));
+  CK(w.dist_b.ensure(cap));
+  CK(w.score.ensure(cap));
+  CK(w.pred.ensure(cap));
+  k_inject_carry<<<(B * 32 + 255) / 256, 256, 0, s>>>(w.entry_slot.p, w.n_queries.p, sp.slots.p,
+                                                     sp.pool_anchor[0].p, sp.pool_anchor[1].p, B, kl,
+                                                     w.key_a.p, w.dist_a.p, cap, ctx->d_ctr);
+  LAUNCH_CHECK();
+  SearchArgs sa{};
+  sa.features = w.features.p;
+  sa.q_off = w.q_off.p;
+  sa.entry_slot = w.entry_slot.p;
+  sa.slots = sp.slots.p;
+  sa.slots_mut = sp.slots.p;
+  sa.B = B;
+  sa.step = prm.step_size;
+  sa.radius = prm.search_radius;
+  sa.key = kl;
+  sa.out_key = w.key_a.p;
+  sa.out_dist = w.dist_a.p;
+  sa.cap = cap;
+  sa.ctr = ctx->d_ctr;
+  int n_sm = 148;
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device);
+  CK(cudaEventRecord(ctx->ev[2], s));
+  k_radius_search<false><<<n_sm * 8, kSearchWarps * 32, 0, s>>>(ctx->ix, sa);
+  LAUNCH_CHECK();
+  ctx->stats.search_launches++;
+  CK(cudaEventRecord(ctx->ev[3], s));
+  CK(cudaMemcpyAsync(ctx->h_ctr, ctx->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  ctx->stats.d2h_bytes += sizeof(Counters);
+  const unsigned long long n = ctx->h_ctr->n_anchors;
+  float ms = 0;
+  cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+  ctx->stats.ms_events += ms;
+  cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]);
+  ctx->stats.ms_search += ms;
+  if (n > cap) return 1;  // overflow: nothing has been committed to the slots yet
+  ctx->stats.queries += ctx->h_ctr->n_queries;
+  ctx->stats.hits += ctx->h_ctr->n_hits;
+  ctx->stats.anchors += n;
+  ctx->stats.capped_queries += ctx->h_ctr->n_capped;
+  ctx->stats.raw_events += ctx->h_ctr->n_events_raw;
+  ctx->stats.events += ctx->h_ctr->n_events_kept;
+  ctx->stats.chunks += Bpres;
+  ctx->stats.steps++;
+
+  // ---- sort by (entry, bucket, target, query)
+  CK(cudaEventRecord(ctx->ev[0], s));
+  const uint64_t *keys = w.key_a.p;
+  const float *dists = w.dist_a.p;
+  if (n > 1) {
+    size_t tb = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tb, w.key_a.p, w.key_b.p, w.dist_a.p, w.dist_b.p,
+                                    (uint64_t)n, 0, kl.total(), s);
+    CK(w.cub_temp.ensure(tb));
+    CK(cub::DeviceRadixSort::SortPairs(w.cub_temp.p, tb, w.key_a.p, w.key_b.p, w.dist_a.p, w.dist_b.p,
+                                       (uint64_t)n, 0, kl.total(), s));
+    ctx->stats.launches += 2 + (kl.total() + 7) / 8;
+    keys = w.key_b.p;
+    dists = w.dist_b.p;
+  }
+  CK(cudaEventRecord(ctx->ev[1], s));
+
+  // ---- chaining
+  ChainArgs ca{};
+  ca.key = keys;
+  ca.dist = dists;
+  ca.n = n;
+  ca.kl = kl;
+  ca.radius = prm.search_radius;
+  ca.score = w.score.p;
+  ca.pred = w.pred.p;
+  const uint64_t seg_cap64 = std::min<uint64_t>(std::max<uint64_t>(n, 1), (uint64_t)B * (ctx->max_bucket + 1ull));
+  ca.seg_cap = (uint32_t)seg_cap64;
+  CK(w.seg_start.ensure(ca.seg_cap));
+  ca.seg_start = w.seg_start.p;
+  ca.ctr = ctx->d_ctr;
+  if (n > 0) {
+    k_mark_segments<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ca);
+    LAUNCH_CHECK();
+    k_chain_dp<<<(ca.seg_cap + 127) / 128, 128, 0, s>>>(ca);
+    LAUNCH_CHECK();
+  }
+  SelectArgs se{};
+  se.c = ca;
+  se.entry_slot = w.entry_slot.p;
+  se.n_queries = w.n_queries.p;
+  se.n_features = w.n_features.p;
+  se.absent = nullptr;
+  se.slots = sp.slots.p;
+  se.B = B;
+  se.max_chains = std::min<uint32_t>(3u * (ctx->max_bucket + 1u), 4096u);
+  CK(w.chain_tmp.ensure((size_t)B * se.max_chains));
+  se.scratch = w.chain_tmp.p;
+  se.out_pool = out_pool;
+  for (int p = 0; p < 2; ++p) {
+    se.pool_chain[p] = sp.pool_chain[p].p;
+    se.pool_anchor[p] = sp.pool_anchor[p].p;
+  }
+  se.pool_chain_cap = sp.pool_chain[out_pool].cap;
+  se.pool_anchor_cap = sp.pool_anchor[out_pool].cap;
+  se.prm = prm;
+  k_chain_select<<<(B + 63) / 64, 64, 0, s>>>(se);
+  LAUNCH_CHECK();
+  CK(cudaEventRecord(ctx->ev[2], s));
+  CK(cudaMemcpyAsync(ctx->h_ctr, ctx->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  ctx->stats.d2h_bytes += sizeof(Counters);
+  cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+  ctx->stats.ms_sort += ms;
+  cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]);
+  ctx->stats.ms_chain += ms;
+  if (ctx->h_ctr->error & 2u) return fail(ctx, SMB_ERR_CAPACITY, "carry pool overflow");
+  if (ctx->h_ctr->error & 4u) return fail(ctx, SMB_ERR_CAPACITY, "per-read chain scratch overflow");
+  if (Bpres) ctx->est_anchors_per_chunk = 0.5 * ctx->est_anchors_per_chunk + 0.5 * ((double)n / Bpres);
+  return SMB_OK;
+}
+
+// ------------------------------------------------------------------ slot space helpers
+static int slots_init(smb_ctx *ctx, SlotSpace &sp, uint32_t n_slots) {
+  sp.n_slots = n_slots;
+  CK(sp.slots.ensure(std::max(n_slots, 1u)));
+  CK(cudaMemsetAsync(sp.slots.p, 0, (size_t)std::max(n_slots, 1u) * sizeof(SlotState), ctx->stream));
+  sp.h_events.assign(n_slots, 0);
+  sp.h_nchains.assign(n_slots, 0);
+  sp.round = 0;
+  return SMB_OK;
+}
+
+static void slots_release(SlotSpace &sp) {
+  sp.slots.release();
+  for (int p = 0; p < 2; ++p) {
+    sp.pool_chain[p].release();
+    sp.pool_anchor[p].release();
+  }
+}
+
+// prepare the out pool of a round: capacity for every participating slot, counters zeroed
+static int round_begin(smb_ctx *ctx, SlotSpace &sp, const std::vector<uint32_t> &slots, int step,
+                       uint32_t out_pool) {
+  uint64_t need_anchor = 0, need_chain = 0;
+  const uint32_t max_chains = std::min<uint32_t>(3u * (ctx->max_bucket + 1u), 4096u);
+  for (uint32_t sl : slots) {
+    // a chain has strictly increasing query positions: <= one anchor per seed position
+    need_anchor += (uint64_t)(sp.h_events[sl] + kFeatCap) / (uint32_t)std::max(step, 1) + 4ull * max_chains;
+    need_chain += max_chains;
+  }
+  // growing a pool would lose nothing: the out pool holds no live data at round start
+  CK(sp.pool_anchor[out_pool].ensure(need_anchor + 64));
+  CK(sp.pool_chain[out_pool].ensure(need_chain + 64));
+  if (!sp.pool_anchor[1 - out_pool].p) CK(sp.pool_anchor[1 - out_pool].ensure(64));
+  if (!sp.pool_chain[1 - out_pool].p) CK(sp.pool_chain[1 - out_pool].ensure(64));
+  CK(cudaMemsetAsync(&ctx->d_ctr->carry_anchor_used[out_pool], 0, sizeof(unsigned long long), ctx->stream));
+  CK(cudaMemsetAsync(&ctx->d_ctr->carry_chain_used[out_pool], 0, sizeof(unsigned long long), ctx->stream));
+  CK(cudaMemsetAsync(&ctx->d_ctr->error, 0, sizeof(unsigned int), ctx->stream));
+  return SMB_OK;
+}
+
+// refresh the host mirror (stop flag, kept events, chain count) of the given slots
+static int round_readback(smb_ctx *ctx, SlotSpace &sp, const std::vector<uint32_t> &slots,
+                          std::vector<RoundInfo> &out) {
+  const uint32_t n = (uint32_t)slots.size();
+  out.resize(n);
+  if (!n) return SMB_OK;
+  Workspace &w = ctx->ws;
+  CK(w.ids.ensure(n));
+  CK(w.round_info.ensure(n));
+  CK(cudaMemcpyAsync(w.ids.p, slots.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+  k_gather_round<<<(n + 255) / 256, 256, 0, ctx->stream>>>(sp.slots.p, w.ids.p, n, w.round_info.p);
+  LAUNCH_CHECK();
+  CK(cudaMemcpyAsync(out.data(), w.round_info.p, n * sizeof(RoundInfo), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->stats.h2d_bytes += n * sizeof(uint32_t);
+  ctx->stats.d2h_bytes += n * sizeof(RoundInfo);
+  for (uint32_t i = 0; i < n; ++i) {
+    sp.h_events[slots[i]] = out[i].num_events;
+    sp.h_nchains[slots[i]] = out[i].n_chains;
+  }
+  return SMB_OK;
+}
+
+// run one round over `present` (entries with a chunk) + `absent` slots, splitting into steps
+template <class FillFn>
+static int run_round(smb_ctx *ctx, SlotSpace &sp, const std::vector<uint32_t> &present,
+                     const std::vector<uint32_t> &absent, StepSource src, const smb_params &prm,
+                     FillFn fill /* (StepEntries&, first, count) for present entries */) {
+  const uint32_t out_pool = sp.round & 1u;
+  std::vector<uint32_t> all(present);
+  all.insert(all.end(), absent.begin(), absent.end());
+  int rc = round_begin(ctx, sp, all, prm.step_size, out_pool);
+  if (rc) return rc;
+  // absent slots ride along with the first step (pure copy-forward)
+  size_t at = 0;
+  bool absent_done = absent.empty();
+  const int kbits = bits_for(ctx->max_tpos) + bits_for(ctx->max_bucket);
+  while (at < present.size() || !absent_done) {
+    uint32_t max_ev = 0;
+    for (size_t i = at; i < present.size(); ++i) max_ev = std::max(max_ev, sp.h_events[present[i]]);
+    const int ebits_max = 64 - kbits - bits_for((uint64_t)max_ev + kFeatCap);
+    if (ebits_max < 1) return fail(ctx, SMB_ERR_CAPACITY, "sort key does not fit 64 bits");
+    uint64_t Bmax = std::min<uint64_t>(ctx->max_batch_chunks, ebits_max >= 31 ? (1ull << 31) : (1ull << ebits_max));
+    uint64_t by_anchors = (uint64_t)(0.6 * (double)ctx->max_batch_anchors / std::max(ctx->est_anchors_per_chunk, 1.0));
+    uint32_t count = (uint32_t)std::min<uint64_t>(present.size() - at, std::max<uint64_t>(1, std::min(Bmax, by_anchors)));
+    for (;;) {
+      StepEntries en;
+      en.B_present = count;
+      en.slot.assign(present.begin() + at, present.begin() + at + count);
+      fill(en, at, count);
+      if (!absent_done) en.slot.insert(en.slot.end(), absent.begin(), absent.end());
+      en.B = (uint32_t)en.slot.size();
+      rc = run_step(ctx, sp, en, src, prm, out_pool);
+      if (rc == 1) {  // anchor buffer overflow: halve and retry
+        if (count <= 1) return fail(ctx, SMB_ERR_CAPACITY, "one chunk overflows max_batch_anchors");
+        ctx->est_anchors_per_chunk *= 2.0;
+        count = (count + 1) / 2;
+        continue;
+      }
+      if (rc) return rc;
+      break;
+    }
+    absent_done = true;
+    at += count;
+  }
+  sp.round++;
+  return SMB_OK;
+}
+
+// ------------------------------------------------------------------ final rows (A.4)
+static void make_row(const smb_ctx *ctx, const SlotState &st, uint32_t read_len, uint32_t chunks_used,
+                     smb_mapping *m) {
+  memset(m, 0, sizeof *m);
+  const uint32_t bp_per_sec = 450, sample_rate = 4000, chunk_size = 4000;
+  m->read_len = read_len;
+  m->chunks = chunks_used;
+  m->n_chains = st.n_chains;
+  m->num_events = st.num_events;
+  m->mapq = 61;  // sigmap.cc:864
+  m->flags = st.flags & 1u;
+  if (st.n_chains >= 1) {
+    m->cm = st.cm;
+    m->s1 = st.s1;
+    m->s2 = st.s2;
+    m->sm = st.sm;
+    m->ad = st.ad;
+    m->at = st.at;
+    m->aq = st.aq;
+    if (st.mapped) {
+      // sigmap.cc:694-696, :746-766
+      volatile float scale_num = (float)chunks_used * chunk_size / st.num_events;
+      volatile float scale_den = (float)sample_rate / bp_per_sec;
+      const float scale = scale_num / scale_den;
+      m->mapped = 1;
+      m->q_start = (uint32_t)(scale * st.q_last);
+      m->q_end = (uint32_t)(scale * st.q_first);
+      m->strand_plus = st.c0_dir;
+      m->contig = st.c0_contig;
+      const uint32_t clen = st.c0_contig < ctx->contig_len.size() ? ctx->contig_len[st.c0_contig] : 0;
+      m->t_start = st.c0_dir ? st.c0_start : (uint32_t)(clen + 1 - st.c0_end);
+      m->frag_len = st.c0_end - st.c0_start + 1;
+      m->mapq = st.c0_mapq & 63u;
+    }
+  }
+}
+
+// ================================================================== C ABI
+extern "C" {
+
+void smb_default_params(smb_params *p) {
+  p->search_radius = 0.08f;
+  p->step_size = 2;
+  p->max_num_chunks = 30;
+  p->min_num_anchors = 10;
+  p->min_num_anchors_output = 10;
+  p->stop_mapping = 1.4f;
+  p->stop_mapping_output = 1.2f;
+  p->stop_mapping_mean = 5.0f;
+  p->stop_mapping_mean_output = 5.0f;
+}
+
+int smb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+const char *smb_last_error(const smb_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int smb_create(smb_ctx **out, int device) {
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    g_create_error = "no CUDA device available; sigmap_b200 has no CPU fallback";
+    return SMB_ERR_NO_DEVICE;
+  }
+  if (device < 0 || device >= n) {
+    g_create_error = "device index out of range";
+    return SMB_ERR_ARG;
+  }
+  smb_ctx *ctx = new smb_ctx();
+  ctx->device = device;
+  auto bail = [&](const char *what, cudaError_t err) {
+    g_create_error = std::string(what) + ": " + cudaGetErrorString(err);
+    delete ctx;
+    return SMB_ERR_CUDA;
+  };
+  if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
+  if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess)
+    return bail("cudaStreamCreate", e);
+  if ((e = cudaMalloc((void **)&ctx->d_ctr, sizeof(Counters))) != cudaSuccess) return bail("cudaMalloc", e);
+  if ((e = cudaMemset(ctx->d_ctr, 0, sizeof(Counters))) != cudaSuccess) return bail("cudaMemset", e);
+  if ((e = cudaMallocHost((void **)&ctx->h_ctr, sizeof(Counters))) != cudaSuccess) return bail("cudaMallocHost", e);
+  for (auto &ev : ctx->ev)
+    if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail("cudaEventCreate", e);
+  *out = ctx;
+  return SMB_OK;
+}
+
+void smb_destroy(smb_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->stream_slots) {
+    slots_release(*ctx->stream_slots);
+    delete ctx->stream_slots;
+  }
+  slots_release(ctx->map_slots);
+  Workspace &w = ctx->ws;
+  w.entry_slot.release(); w.n_features.release(); w.n_raw_events.release(); w.n_queries.release();
+  w.q_off.release(); w.absent.release(); w.chunk_start.release(); w.chunk_offset.release();
+  w.chunk_scale.release(); w.ps.release(); w.pss.release(); w.t1.release(); w.t2.release();
+  w.means.release(); w.features.release(); w.key_a.release(); w.key_b.release(); w.dist_a.release();
+  w.dist_b.release(); w.score.release(); w.pred.release(); w.seg_start.release(); w.cub_temp.release();
+  w.chain_tmp.release(); w.ids.release(); w.round_info.release();
+  ctx->leaf_vals.release(); ctx->leaf_tpos.release(); ctx->leaf_bucket.release(); ctx->leaf_widx.release();
+  for (auto &l : ctx->level) l.release();
+  ctx->raw.release(); ctx->kept.release(); ctx->d_read_off.release(); ctx->d_kept_off.release();
+  ctx->d_dig.release(); ctx->d_range.release(); ctx->d_offset.release(); ctx->d_kept_len.release();
+  for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+  if (ctx->d_ctr) cudaFree(ctx->d_ctr);
+  if (ctx->h_ctr) cudaFreeHost(ctx->h_ctr);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+void smb_stats_reset(smb_ctx *ctx) { memset(&ctx->stats, 0, sizeof ctx->stats); }
+
+int smb_stats_get(smb_ctx *ctx, smb_stats *out) {
+  ctx->stats.ms_total = ctx->stats.ms_events + ctx->stats.ms_search + ctx->stats.ms_sort +
+                        ctx->stats.ms_chain + ctx->stats.ms_filter;
+  *out = ctx->stats;
+  return SMB_OK;
+}
+
+int smb_set_limits(smb_ctx *ctx, uint32_t max_batch_chunks, uint64_t max_batch_anchors) {
+  if (max_batch_chunks) ctx->max_batch_chunks = max_batch_chunks;
+  if (max_batch_anchors) {
+    if (max_batch_anchors >= (1ull << 31)) return fail(ctx, SMB_ERR_ARG, "max_batch_anchors must be < 2^31");
+    ctx->max_batch_anchors = max_batch_anchors;
+  }
+  return SMB_OK;
+}
+
+// -------------------------------------------------------------------- index
+int smb_index_set_points(smb_ctx *ctx, const uint64_t *pos, const float *val, size_t n) {
+  CK(cudaSetDevice(ctx->device));
+  return build_index(ctx, pos, val, n);
+}
+
+int smb_index_load(smb_ctx *ctx, const char *prefix) {
+  uint64_t *pos = nullptr;
+  float *val = nullptr;
+  size_t n = 0;
+  int dim = 0, ml = 0;
+  int rc = smbh_pt_read(prefix, &pos, &val, &n, &dim, &ml);
+  if (rc) return fail(ctx, rc, std::string("cannot read ") + prefix + ".pt");
+  if (dim != kDim) {
+    smbh_free(pos);
+    smbh_free(val);
+    return fail(ctx, SMB_ERR_ARG, "index dimension is not 6");
+  }
+  rc = smb_index_set_points(ctx, pos, val, n);
+  smbh_free(pos);
+  smbh_free(val);
+  return rc;
+}
+
+int smb_index_set_contigs(smb_ctx *ctx, const uint32_t *lengths, uint32_t n_contigs) {
+  ctx->contig_len.assign(lengths, lengths + n_contigs);
+  return SMB_OK;
+}
+
+uint64_t smb_index_num_points(const smb_ctx *ctx) { return ctx->has_index ? ctx->ix.n_points : 0; }
+uint32_t smb_index_num_contigs(const smb_ctx *ctx) { return (uint32_t)ctx->contig_len.size(); }
+
+// ------------------------------------------------------------ whole hot path
+int smb_reads_upload(smb_ctx *ctx, const int16_t *raw, const uint64_t *read_off, const float *dig,
+                     const float *range, const float *offset, size_t n_reads) {
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  ctx->n_reads = n_reads;
+  if (n_reads == 0) return SMB_OK;
+  if (n_reads > 0xFFFFFFF0ull) return fail(ctx, SMB_ERR_ARG, "too many reads");
+  const uint64_t total = read_off[n_reads];
+  ctx->h_kept_off.resize(n_reads);
+  ctx->h_offset.assign(offset, offset + n_reads);
+  ctx->h_scale.resize(n_reads);
+  for (size_t r = 0; r < n_reads; ++r) {
+    // 64-sample (128-byte) aligned, non-overlapping regions: the events kernel loads int4
+    ctx->h_kept_off[r] = ((read_off[r] + 63) & ~63ull) + 64ull * r;
+    ctx->h_scale[r] = range[r] / dig[r];  // float / float as signal_batch.cc:195
+  }
+  const uint64_t kept_total = ((total + 63) & ~63ull) + 64ull * n_reads + 64;
+  CK(ctx->raw.ensure(total + 8));
+  CK(ctx->kept.ensure(kept_total));
+  CK(ctx->d_read_off.ensure(n_reads + 1));
+  CK(ctx->d_kept_off.ensure(n_reads));
+  CK(ctx->d_dig.ensure(n_reads));
+  CK(ctx->d_range.ensure(n_reads));
+  CK(ctx->d_offset.ensure(n_reads));
+  CK(ctx->d_kept_len.ensure(n_reads));
+  CK(cudaMemcpyAsync(ctx->raw.p, raw, total * sizeof(int16_t), cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(ctx->d_read_off.p, read_off, (n_reads + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(ctx->d_kept_off.p, ctx->h_kept_off.data(), n_reads * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(ctx->d_dig.p, dig, n_reads * sizeof(float), cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(ctx->d_range.p, range, n_reads * sizeof(float), cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(ctx->d_offset.p, offset, n_reads * sizeof(float), cudaMemcpyHostToDevice, s));
+  ctx->stats.h2d_bytes += total * 2 + n_reads * 28 + 8;
+  CK(cudaEventRecord(ctx->ev[5], s));
+  k_filter_compact<<<(unsigned)n_reads, kFilterThreads, 0, s>>>(ctx->raw.p, ctx->d_read_off.p, ctx->d_dig.p,
+                                                              ctx->d_range.p, ctx->d_offset.p, ctx->d_kept_off.p,
+                                                              ctx->kept.p, ctx->d_kept_len.p, (uint32_t)n_reads);
+  LAUNCH_CHECK();
+  CK(cudaEventRecord(ctx->ev[4], s));
+  ctx->h_kept_len.resize(n_reads);
+  CK(cudaMemcpyAsync(ctx->h_kept_len.data(), ctx->d_kept_len.p, n_reads * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  ctx->stats.d2h_bytes += n_reads * 4;
+  float ms = 0;
+  cudaEventElapsedTime(&ms, ctx->ev[5], ctx->ev[4]);
+  ctx->stats.ms_filter += ms;
+  return SMB_OK;
+}
+
+int smb_map_uploaded(smb_ctx *ctx, const smb_params *prm_in, smb_mapping *out) {
+  CK(cudaSetDevice(ctx->device));
+  if (!ctx->has_index) return fail(ctx, SMB_ERR_STATE, "no index loaded");
+  smb_params prm = *prm_in;
+  if (prm.step_size < 1) return fail(ctx, SMB_ERR_ARG, "step_size must be >= 1");
+  const size_t R = ctx->n_reads;
+  SlotSpace &sp = ctx->map_slots;
+  int rc = slots_init(ctx, sp, (uint32_t)R);
+  if (rc) return rc;
+  std::vector<uint32_t> n_chunks(R), chunks_used(R, 1);
+  std::vector<uint32_t> active;
+  for (size_t r = 0; r < R; ++r) {
+    n_chunks[r] = ctx->h_kept_len[r] / kChunk;  // tail dropped, sigmap.cc:643
+    if (n_chunks[r] > 0 && prm.max_num_chunks > 0) active.push_back((uint32_t)r);
+  }
+  std::vector<RoundInfo> info;
+  const std::vector<uint32_t> none;
+  uint32_t round = 0;
+  while (!active.empty()) {
+    auto fill = [&](StepEntries &en, size_t first, uint32_t count) {
+      en.samples = ctx->kept.p;
+      en.chunk_start.resize(count);
+      en.offset.resize(count);
+      en.scale.resize(count);
+      for (uint32_t i = 0; i < count; ++i) {
+        const uint32_t r = active[first + i];
+        en.chunk_start[i] = ctx->h_kept_off[r] + (uint64_t)kChunk * round;
+        en.offset[i] = ctx->h_offset[r];
+        en.scale[i] = ctx->h_scale[r];
+      }
+    };
+    rc = run_round(ctx, sp, active, none, SRC_RAW_KEPT, prm, fill);
+    if (rc) return rc;
+    rc = round_readback(ctx, sp, active, info);
+    if (rc) return rc;
+    ctx->stats.samples += (uint64_t)active.size() * kChunk;
+    std::vector<uint32_t> next;
+    next.reserve(active.size());
+    for (size_t i = 0; i < active.size(); ++i) {
+      const uint32_t r = active[i];
+      chunks_used[r] = round + 1;
+      const bool more = round + 1 < n_chunks[r] && round + 1 < (uint32_t)prm.max_num_chunks;
+      if (!info[i].stop && more) next.push_back(r);
+    }
+    active.swap(next);
+    ++round;
+  }
+  // final rows
+  std::vector<SlotState> st(std::max<size_t>(R, 1));
+  if (R) {
+    CK(cudaMemcpyAsync(st.data(), sp.slots.p, R * sizeof(SlotState), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->stats.d2h_bytes += R * sizeof(SlotState);
+  }
+  for (size_t r = 0; r < R; ++r) make_row(ctx, st[r], ctx->h_kept_len[r], chunks_used[r], &out[r]);
+  return SMB_OK;
+}
+
+int smb_map_reads(smb_ctx *ctx, const int16_t *raw, const uint64_t *read_off, const float *dig,
+                  const float *range, const float *offset, size_t n_reads, const smb_params *params,
+                  smb_mapping *out) {
+  int rc = smb_reads_upload(ctx, raw, read_off, dig, range, offset, n_reads);
+  if (rc) return rc;
+  return smb_map_uploaded(ctx, params, out);
+}
+
+// ------------------------------------------------------------- stage hooks
+int smb_stage_raw_to_pa(smb_ctx *ctx, const int16_t *raw, size_t n, float dig, float offset, float range,
+                        float *out, size_t *n_out) {
+  CK(cudaSetDevice(ctx->device));
+  uint64_t off[2] = {0, n};
+  int rc = smb_reads_upload(ctx, raw, off, &dig, &range, &offset, 1);
+  if (rc) return rc;
+  const uint32_t kept = ctx->h_kept_len[0];
+  *n_out = kept;
+  if (!kept) return SMB_OK;
+  DevBuf<float> d;
+  CK(d.ensure(kept));
+  k_raw_to_pa<<<(kept + 255) / 256, 256, 0, ctx->stream>>>(ctx->kept.p + ctx->h_kept_off[0], kept, offset,
+                                                          ctx->h_scale[0], d.p);
+  LAUNCH_CHECK();
+  CK(cudaMemcpyAsync(out, d.p, kept * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  d.release();
+  return SMB_OK;
+}
+
+static int stage_events_common(smb_ctx *ctx, const float *pa, size_t n_chunks, uint32_t *d_peaks) {
+  Workspace &w = ctx->ws;
+  cudaStream_t s = ctx->stream;
+  const uint32_t B = (uint32_t)n_chunks;
+  DevBuf<float> d_pa;
+  CK(d_pa.ensure((size_t)B * kChunk));
+  CK(cudaMemcpyAsync(d_pa.p, pa, (size_t)B * kChunk * sizeof(float), cudaMemcpyHostToDevice, s));
+  std::vector<uint64_t> start(B);
+  for (uint32_t b = 0; b < B; ++b) start[b] = (uint64_t)b * kChunk;
+  CK(w.chunk_start.ensure(B));
+  CK(w.n_features.ensure(B));
+  CK(w.n_raw_events.ensure(B));
+  CK(w.features.ensure((size_t)B * kFeatCap));
+  CK(cudaMemcpyAsync(w.chunk_start.p, start.data(), B * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+  int rc = run_events(ctx, SRC_PA_FLOAT, d_pa.p, B, d_peaks);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(s));
+  d_pa.release();
+  return SMB_OK;
+}
+
+int smb_stage_events(smb_ctx *ctx, const float *pa, size_t n_chunks, float *features, uint32_t *n_features) {
+  CK(cudaSetDevice(ctx->device));
+  if (n_chunks == 0) return SMB_OK;
+  int rc = stage_events_common(ctx, pa, n_chunks, nullptr);
+  if (rc) return rc;
+  CK(cudaMemcpy(features, ctx->ws.features.p, n_chunks * kFeatCap * sizeof(float), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(n_features, ctx->ws.n_features.p, n_chunks * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  return SMB_OK;
+}
+
+int smb_stage_detect(smb_ctx *ctx, const float *pa, float *tstat1, float *tstat2, uint32_t *peaks,
+                     uint32_t *n_peaks, float *means, uint32_t *n_events) {
+  CK(cudaSetDevice(ctx->device));
+  DevBuf<uint32_t> d_peaks;
+  CK(d_peaks.ensure(kFeatCap));
+  int rc = stage_events_common(ctx, pa, 1, d_peaks.p);
+  if (rc) return rc;
+  const uint32_t Bp = 32;
+  uint32_t ne = 0;
+  CK(cudaMemcpy(&ne, ctx->ws.n_raw_events.p, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  if (n_events) *n_events = ne;
+  if (n_peaks) *n_peaks = ne;  // #events == #peaks (the last peak only closes the count)
+  if (tstat1) CK(cudaMemcpy2D(tstat1, sizeof(float), ctx->ws.t1.p, Bp * sizeof(float), sizeof(float), kChunk + 1, cudaMemcpyDeviceToHost));
+  if (tstat2) CK(cudaMemcpy2D(tstat2, sizeof(float), ctx->ws.t2.p, Bp * sizeof(float), sizeof(float), kChunk + 1, cudaMemcpyDeviceToHost));
+  if (peaks && ne) CK(cudaMemcpy(peaks, d_peaks.p, ne * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  if (means && ne) CK(cudaMemcpy(means, ctx->ws.means.p, ne * sizeof(float), cudaMemcpyDeviceToHost));
+  d_peaks.release();
+  return SMB_OK;
+}
+
+int smb_stage_radius(smb_ctx *ctx, const float *queries, size_t nq, float radius, uint64_t *hit_off,
+                     uint64_t *hit_idx, float *hit_d2, uint64_t cap) {
+  CK(cudaSetDevice(ctx->device));
+  if (!ctx->has_index) return fail(ctx, SMB_ERR_STATE, "no index loaded");
+  if (nq > 0xFFFFFFF0ull) return fail(ctx, SMB_ERR_ARG, "too many queries");
+  cudaStream_t s = ctx->stream;
+  hit_off[0] = 0;
+  if (nq == 0) return SMB_OK;
+  DevBuf<float> d_q, d_a, d_b;
+  DevBuf<uint64_t> k_a, k_b;
+  DevBuf<unsigned long long> cnt;
+  DevBuf<unsigned char> tmp;
+  const uint64_t dcap = std::max<uint64_t>(cap, 1);
+  CK(d_q.ensure(nq * kDim));
+  CK(k_a.ensure(dcap));
+  CK(k_b.ensure(dcap));
+  CK(d_a.ensure(dcap));
+  CK(d_b.ensure(dcap));
+  CK(cnt.ensure(nq));
+  CK(cudaMemcpyAsync(d_q.p, queries, nq * kDim * sizeof(float), cudaMemcpyHostToDevice, s));
+  k_reset_step<<<1, 1, 0, s>>>(ctx->d_ctr);
+  LAUNCH_CHECK();
+  SearchArgs sa{};
+  sa.features = d_q.p;
+  sa.n_queries = (uint32_t)nq;
+  sa.radius = radius;
+  sa.out_key = k_a.p;
+  sa.out_dist = d_a.p;
+  sa.cap = dcap;
+  sa.ctr = ctx->d_ctr;
+  int n_sm = 148;
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device);
+  k_radius_search<true><<<n_sm * 8, kSearchWarps * 32, 0, s>>>(ctx->ix, sa);
+  LAUNCH_CHECK();
+  CK(cudaMemcpyAsync(ctx->h_ctr, ctx->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  const unsigned long long n = ctx->h_ctr->n_anchors;
+  if (n > cap) return fail(ctx, SMB_ERR_CAPACITY, "smb_stage_radius: more hits than cap");
+  CK(cudaMemsetAsync(cnt.p, 0, nq * sizeof(unsigned long long), s));
+  const uint64_t *keys = k_a.p;
+  const float *dd = d_a.p;
+  if (n > 1) {
+    size_t tb = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tb, k_a.p, k_b.p, d_a.p, d_b.p, (uint64_t)n, 0, 64, s);
+    CK(tmp.ensure(tb));
+    CK(cub::DeviceRadixSort::SortPairs(tmp.p, tb, k_a.p, k_b.p, d_a.p, d_b.p, (uint64_t)n, 0, 64, s));
+    keys = k_b.p;
+    dd = d_b.p;
+  }
+  if (n > 0) {
+    k_count_by_query<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(keys, n, cnt.p);
+    LAUNCH_CHECK();
+  }
+  std::vector<unsigned long long> h_cnt(nq);
+  std::vector<uint64_t> h_keys(n);
+  CK(cudaMemcpyAsync(h_cnt.data(), cnt.p, nq * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+  if (n) {
+    CK(cudaMemcpyAsync(h_keys.data(), keys, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(hit_d2, dd, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+  }
+  CK(cudaStreamSynchronize(s));
+  for (size_t q = 0; q < nq; ++q) hit_off[q + 1] = hit_off[q] + h_cnt[q];
+  for (unsigned long long i = 0; i < n; ++i) hit_idx[i] = h_keys[i] & 0xFFFFFFFFull;
+  d_q.release(); d_a.release(); d_b.release(); k_a.release(); k_b.release(); cnt.release(); tmp.release();
+  return SMB_OK;
+}
+
+// ------------------------------------------------------------- batch of read slots
+int smb_batch_create(smb_ctx *ctx, uint32_t n_slots, smb_batch **batch) {
+  CK(cudaSetDevice(ctx->device));
+  smb_batch *b = new smb_batch{ctx, {}};
+  int rc = slots_init(ctx, b->sp, n_slots);
+  if (rc) {
+    delete b;
+    return rc;
+  }
+  *batch = b;
+  return SMB_OK;
+}
+
+void smb_batch_destroy(smb_batch *b) {
+  if (!b) return;
+  cudaSetDevice(b->ctx->device);
+  cudaStreamSynchronize(b->ctx->stream);
+  slots_release(b->sp);
+  delete b;
+}
+
+int smb_batch_reset(smb_batch *b) { return slots_init(b->ctx, b->sp, b->sp.n_slots); }
+
+int smb_batch_generate_chains(smb_batch *b, const uint32_t *slots, uint32_t n, const float *features,
+                              const uint32_t *feat_off, const smb_params *prm) {
+  smb_ctx *ctx = b->ctx;
+  CK(cudaSetDevice(ctx->device));
+  if (prm->step_size < 1) return fail(ctx, SMB_ERR_ARG, "step_size must be >= 1");
+  std::vector<uint32_t> present(slots, slots + n), absent;
+  std::vector<uint8_t> seen(b->sp.n_slots, 0);
+  for (uint32_t i = 0; i < n; ++i) {
+    if (slots[i] >= b->sp.n_slots || seen[slots[i]]) return fail(ctx, SMB_ERR_ARG, "bad or repeated slot");
+    seen[slots[i]] = 1;
+  }
+  for (uint32_t sl = 0; sl < b->sp.n_slots; ++sl)
+    if (!seen[sl] && b->sp.h_nchains[sl] > 0) absent.push_back(sl);
+  DevBuf<float> d_feat;
+  DevBuf<uint32_t> d_off;
+  const uint32_t total = feat_off[n];
+  CK(d_feat.ensure(std::max(total, 1u)));
+  CK(d_off.ensure(n + 1));
+  CK(cudaMemcpyAsync(d_feat.p, features, total * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  std::vector<uint32_t> rel(n + 1);
+  auto fill = [&](StepEntries &en, size_t first, uint32_t count) {
+    // offsets of this step's slice, rebased so the device sees [first, first+count]
+    for (uint32_t i = 0; i <= count; ++i) rel[i] = feat_off[first + i];
+    cudaMemcpyAsync(d_off.p, rel.data(), (count + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream);
+    en.d_features = d_feat.p;
+    en.d_feat_off = d_off.p;
+  };
+  int rc = run_round(ctx, b->sp, present, absent, SRC_FEATURES, *prm, fill);
+  if (rc == SMB_OK) {
+    std::vector<RoundInfo> info;
+    std::vector<uint32_t> all(present);
+    all.insert(all.end(), absent.begin(), absent.end());
+    rc = round_readback(ctx, b->sp, all, info);
+  }
+  cudaStreamSynchronize(ctx->stream);
+  d_feat.release();
+  d_off.release();
+  return rc;
+}
+
+static int slot_state(smb_batch *b, uint32_t slot, SlotState *st) {
+  smb_ctx *ctx = b->ctx;
+  if (slot >= b->sp.n_slots) return fail(ctx, SMB_ERR_ARG, "slot out of range");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMemcpy(st, b->sp.slots.p + slot, sizeof(SlotState), cudaMemcpyDeviceToHost));
+  return SMB_OK;
+}
+
+int smb_batch_chain_count(smb_batch *b, uint32_t slot, uint32_t *n_chains) {
+  SlotState st;
+  int rc = slot_state(b, slot, &st);
+  if (rc) return rc;
+  *n_chains = st.n_chains;
+  return SMB_OK;
+}
+
+int smb_batch_get_chains(smb_batch *b, uint32_t slot, smb_chain *out, uint32_t cap) {
+  smb_ctx *ctx = b->ctx;
+  SlotState st;
+  int rc = slot_state(b, slot, &st);
+  if (rc) return rc;
+  const uint32_t n = std::min(cap, st.n_chains);
+  std::vector<ChainRec> recs(std::max(n, 1u));
+  if (n) CK(cudaMemcpy(recs.data(), b->sp.pool_chain[st.pool].p + st.chain_off, n * sizeof(ChainRec), cudaMemcpyDeviceToHost));
+  for (uint32_t i = 0; i < n; ++i)
+    out[i] = smb_chain{recs[i].score, recs[i].contig, recs[i].start, recs[i].end, recs[i].n_anchors,
+                       recs[i].mapq, recs[i].dir};
+  return SMB_OK;
+}
+
+int smb_batch_get_anchors(smb_batch *b, uint32_t slot, uint32_t chain, smb_anchor *out, uint32_t cap) {
+  smb_ctx *ctx = b->ctx;
+  SlotState st;
+  int rc = slot_state(b, slot, &st);
+  if (rc) return rc;
+  if (chain >= st.n_chains) return fail(ctx, SMB_ERR_ARG, "chain out of range");
+  ChainRec rec;
+  CK(cudaMemcpy(&rec, b->sp.pool_chain[st.pool].p + st.chain_off + chain, sizeof(ChainRec), cudaMemcpyDeviceToHost));
+  const uint32_t n = std::min(cap, rec.n_anchors);
+  std::vector<CarryAnchor> an(std::max(n, 1u));
+  if (n) CK(cudaMemcpy(an.data(), b->sp.pool_anchor[st.pool].p + st.carry_off + rec.anchor_off, n * sizeof(CarryAnchor), cudaMemcpyDeviceToHost));
+  for (uint32_t i = 0; i < n; ++i) out[i] = smb_anchor{an[i].target, an[i].query, an[i].dist};
+  return SMB_OK;
+}
+
+// ---------------------------------------------------------------- streaming
+// Channels keep, on the host, the filtered remainder that does not yet fill a chunk (H9:
+// chunk boundaries are defined on the filtered stream); completed chunks of all channels are
+// mapped as one round.
+int smb_stream_open(smb_ctx *ctx, uint32_t n_channels, const smb_params *params) {
+  CK(cudaSetDevice(ctx->device));
+  if (!ctx->has_index) return fail(ctx, SMB_ERR_STATE, "no index loaded");
+  if (ctx->stream_slots) smb_stream_close(ctx);
+  ctx->stream_slots = new SlotSpace();
+  int rc = slots_init(ctx, *ctx->stream_slots, n_channels);
+  if (rc) return rc;
+  ctx->stream_params = *params;
+  ctx->stream_pending.assign(n_channels, {});
+  ctx->stream_offset.assign(n_channels, 0.f);
+  ctx->stream_scale.assign(n_channels, 1.f);
+  ctx->stream_chunks.assign(n_channels, 0);
+  ctx->stream_kept.assign(n_channels, 0);
+  return SMB_OK;
+}
+
+int smb_stream_close(smb_ctx *ctx) {
+  if (ctx->stream_slots) {
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    slots_release(*ctx->stream_slots);
+    delete ctx->stream_slots;
+    ctx->stream_slots = nullptr;
+  }
+  return SMB_OK;
+}
+
+int smb_stream_begin_read(smb_ctx *ctx, uint32_t ch, float dig, float range, float offset) {
+  if (!ctx->stream_slots || ch >= ctx->stream_slots->n_slots) return fail(ctx, SMB_ERR_ARG, "bad channel");
+  CK(cudaSetDevice(ctx->device));
+  SlotSpace &sp = *ctx->stream_slots;
+  CK(cudaMemsetAsync(sp.slots.p + ch, 0, sizeof(SlotState), ctx->stream));
+  sp.h_events[ch] = 0;
+  sp.h_nchains[ch] = 0;
+  ctx->stream_pending[ch].clear();
+  ctx->stream_offset[ch] = offset;
+  ctx->stream_scale[ch] = range / dig;
+  ctx->stream_chunks[ch] = 0;
+  ctx->stream_kept[ch] = 0;
+  return SMB_OK;
+}
+
+int smb_stream_round(smb_ctx *ctx, const uint32_t *channels, uint32_t n, const int16_t *samples,
+                     const uint32_t *sample_off, uint8_t *decisions, smb_mapping *maps) {
+  if (!ctx->stream_slots) return fail(ctx, SMB_ERR_STATE, "stream not open");
+  CK(cudaSetDevice(ctx->device));
+  SlotSpace &sp = *ctx->stream_slots;
+  const smb_params &prm = ctx->stream_params;
+  // host-side range filter of the incoming samples (same expression as K1) and chunk cutting
+  std::vector<uint32_t> present;
+  std::vector<int16_t> chunk_samples;
+  for (uint32_t i = 0; i < n; ++i) {
+    const uint32_t ch = channels[i];
+    if (ch >= sp.n_slots) return fail(ctx, SMB_ERR_ARG, "bad channel");
+    std::vector<int16_t> &pend = ctx->stream_pending[ch];
+    const float off = ctx->stream_offset[ch], scale = ctx->stream_scale[ch];
+    for (uint32_t k = sample_off[i]; k < sample_off[i + 1]; ++k) {
+      volatile float sum = (float)samples[k] + off;
+      volatile float pa = sum * scale;
+      if (pa > 30.0f && pa < 200.0f) pend.push_back(samples[k]);
+    }
+    ctx->stream_kept[ch] += 0;
+    if (pend.size() >= (size_t)kChunk && ctx->stream_chunks[ch] < (uint32_t)prm.max_num_chunks) {
+      present.push_back(ch);
+      chunk_samples.insert(chunk_samples.end(), pend.begin(), pend.begin() + kChunk);
+      pend.erase(pend.begin(), pend.begin() + kChunk);
+    }
+  }
+  // all other channels with live chains are carried forward
+  std::vector<uint8_t> seen(sp.n_slots, 0);
+  for (uint32_t ch : present) seen[ch] = 1;
+  std::vector<uint32_t> absent;
+  for (uint32_t ch = 0; ch < sp.n_slots; ++ch)
+    if (!seen[ch] && sp.h_nchains[ch] > 0) absent.push_back(ch);
+  if (!present.empty() || !absent.empty()) {
+    DevBuf<int16_t> d_s;
+    CK(d_s.ensure(std::max<size_t>(chunk_samples.size(), 8)));
+    CK(cudaMemcpyAsync(d_s.p, chunk_samples.data(), chunk_samples.size() * sizeof(int16_t), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->stats.h2d_bytes += chunk_samples.size() * 2;
+    auto fill = [&](StepEntries &en, size_t first, uint32_t count) {
+      en.samples = d_s.p;
+      en.chunk_start.resize(count);
+      en.offset.resize(count);
+      en.scale.resize(count);
+      for (uint32_t i = 0; i < count; ++i) {
+        const uint32_t ch = present[first + i];
+        en.chunk_start[i] = (uint64_t)(first + i) * kChunk;
+        en.offset[i] = ctx->stream_offset[ch];
+        en.scale[i] = ctx->stream_scale[ch];
+      }
+    };
+    int rc = run_round(ctx, sp, present, absent, SRC_RAW_KEPT, prm, fill);
+    if (rc) return rc;
+    ctx->stats.samples += (uint64_t)present.size() * kChunk;
+    for (uint32_t ch : present) {
+      ctx->stream_chunks[ch]++;
+      ctx->stream_kept[ch] += kChunk;
+    }
+    cudaStreamSynchronize(ctx->stream);
+    d_s.release();
+  }
+  // decisions + provisional rows for the channels named in this call
+  std::vector<uint32_t> ids(channels, channels + n);
+  std::vector<RoundInfo> info;
+  std::vector<uint32_t> everyone(present);
+  everyone.insert(everyone.end(), absent.begin(), absent.end());
+  int rc = round_readback(ctx, sp, everyone, info);
+  if (rc) return rc;
+  std::vector<SlotState> st(sp.n_slots ? sp.n_slots : 1);
+  CK(cudaMemcpy(st.data(), sp.slots.p, sp.n_slots * sizeof(SlotState), cudaMemcpyDeviceToHost));
+  ctx->stats.d2h_bytes += sp.n_slots * sizeof(SlotState);
+  for (uint32_t i = 0; i < n; ++i) {
+    const uint32_t ch = channels[i];
+    const bool mapped_chunk = seen[ch] != 0;
+    if (decisions) decisions[i] = (mapped_chunk && st[ch].stop) ? 1 : 0;
+    if (maps) {
+      const uint32_t used = std::max(ctx->stream_chunks[ch], 1u);
+      make_row(ctx, st[ch], ctx->stream_kept[ch] + (uint32_t)ctx->stream_pending[ch].size(), used, &maps[i]);
+    }
+  }
+  return SMB_OK;
+}
+
+}  // extern "C"
