@@ -1,0 +1,383 @@
+#!/usr/bin/env python
+"""bench.py -- raw samples/s mapped by the B200 hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU path
+
+Workload at N=1 = BASELINE.json configs[1]: E. coli-sized 4.6 Mbp synthetic reference,
+20 000 simulated reads (R9.4 6-mer model, noise 1.0), full-read mapping (every chunk of every
+read is consumed).  One "step" = one pass of the whole hot path over that read batch.
+N>1 (torchrun, one rank per GPU): reads are sharded, every rank maps its own 20 000 reads
+against a replicated index, no data-path collective ("weak" scaling).
+
+value  = samples mapped / time with the raw int16 reads already resident in HBM
+e2e    = the same through smb_map_reads() with pinned HOST buffers (H2D + D2H inside)
+Times are CUDA-event times on the library's stream, max over ranks.
+"""
+import argparse
+import json
+import os
+import re
+import shutil
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FULL_READ_CLI = ["--max-num-chunks", "100000", "--stop-mapping", "1e30", "--stop-mapping-mean",
+                 "1e30", "--min-num-anchors", "2000000000"]
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--ref-bp", type=int, default=4_600_000)
+    ap.add_argument("--contigs", type=int, default=1)
+    ap.add_argument("--reads", type=int, default=20000, help="reads per GPU")
+    ap.add_argument("--noise", type=float, default=1.0)
+    ap.add_argument("--mode", default="full", choices=["full", "default"],
+                    help="full = full-read mapping (configs[1]); default = reference stop rules")
+    ap.add_argument("--cpu-sample-reads", type=int, default=300)
+    ap.add_argument("--ref-step-reads", type=int, default=100)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--seed", type=int, default=20251017)
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        if not shutil.which("nvidia-smi"):
+            return
+        self.proc = subprocess.Popen(
+            ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+             "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        self.t = threading.Thread(target=self._read, daemon=True)
+        self.t.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        # "under load": samples at or above the median (the sampler also sees idle gaps)
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def dist_setup(n_gpus):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
+    return rank, world, local, dist
+
+
+def build_workload(args, rank):
+    from sigmap_b200 import host as H
+    model = H.load_pore_model()
+    per = args.ref_bp // args.contigs
+    ref = H.sim_reference(args.seed, [per] * args.contigs)
+    pos, val = H.build_point_cloud(ref, model[0])
+    reads = H.sim_reads(args.seed + 1, ref, args.reads, first_read=rank * args.reads,
+                        noise=args.noise, model=model)
+    return H, model, ref, pos, val, reads
+
+
+def workload_name(args):
+    return (f"{args.ref_bp / 1e6:.1f} Mbp synthetic reference x{args.contigs} contig(s), "
+            f"{args.reads} simulated reads/GPU (R9.4 6-mer model, noise {args.noise}), "
+            f"{'full-read' if args.mode == 'full' else 'default stop rules'} mapping")
+
+
+# ------------------------------------------------------------------ reference arm helpers
+def ref_prepare(args, H, ref, reads, n_sample, workdir):
+    """FASTA + reference-built index (.pt/.si) + a BLOW5 holding the first n_sample reads."""
+    from oracle.oracle import REF_BIN
+    fasta = os.path.join(workdir, "ref.fa")
+    ref.write_fasta(fasta)
+    prefix = os.path.join(workdir, "idx")
+    t0 = time.time()
+    r = subprocess.run([REF_BIN, "-i", "-r", fasta, "-p", H.MODEL_PATH, "-o", prefix],
+                       capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("reference index build failed: " + r.stderr[-400:])
+    sig = os.path.join(workdir, "sig")
+    os.makedirs(sig, exist_ok=True)
+    n = min(n_sample, reads.n)
+    sub = H.ReadSet(reads.names[:n], reads.raw[:int(reads.read_off[n])], reads.read_off[:n + 1],
+                    H.DIGITISATION, H.RANGE, H.OFFSET)
+    sub.write_blow5(os.path.join(sig, "sample.blow5"))
+    return fasta, prefix, sig, n, time.time() - t0
+
+
+def ref_map_once(args, H, fasta, prefix, sig, workdir, threads):
+    from oracle.oracle import REF_BIN
+    out = os.path.join(workdir, "ref.paf")
+    cmd = [REF_BIN, "-m", "-r", fasta, "-p", H.MODEL_PATH, "-x", prefix, "-s", sig, "-o", out,
+           "-t", str(threads)]
+    if args.mode == "full":
+        cmd += FULL_READ_CLI
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("reference mapping failed: " + r.stderr[-400:])
+    m = re.search(r"Finished mapping in ([0-9.eE+-]+)", r.stderr)
+    secs = float(m.group(1))
+    samples = 0
+    for line in open(out):
+        ci = re.search(r"ci:i:(\d+)", line)
+        sl = re.search(r"sl:i:(\d+)", line)
+        if ci and sl and int(sl.group(1)) >= 4000:
+            samples += int(ci.group(1)) * 4000
+    return samples, secs
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle.oracle import Ref
+    if not Ref.available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref was not built"}))
+        return
+    H, model, ref, pos, val, reads = build_workload(
+        argparse.Namespace(**{**vars(args), "reads": max(args.ref_step_reads, 1)}), 0)
+    threads = os.cpu_count() or 1
+    workdir = tempfile.mkdtemp(prefix="sigmap_ref_")
+    try:
+        fasta, prefix, sig, n, t_idx = ref_prepare(args, H, ref, reads, args.ref_step_reads, workdir)
+        for _ in range(args.warmup):
+            ref_map_once(args, H, fasta, prefix, sig, workdir, threads)
+        tot_s, tot_t = 0, 0.0
+        for _ in range(args.steps):
+            s, t = ref_map_once(args, H, fasta, prefix, sig, workdir, threads)
+            tot_s += s
+            tot_t += t
+    finally:
+        shutil.rmtree(workdir, ignore_errors=True)
+    value = tot_s / tot_t
+    sample = (f"{n} reads of the workload per step, sigmap_ref -m -t {threads} "
+              f"(map phase only, 'Finished mapping in')")
+    print(json.dumps({
+        "impl": "reference", "metric": "raw samples/sec mapped", "value": value, "unit": "samples/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1000.0 * tot_t / max(args.steps, 1), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args), "sample_reads_per_step": n},
+        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": threads, "kind": "reference",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ------------------------------------------------------------------ our arm
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    rank, world, local, dist = dist_setup(args.gpus)
+    import torch
+    from sigmap_b200.mapper import Mapper, default_params, full_read_params
+
+    t_setup = time.time()
+    H, model, ref, pos, val, reads = build_workload(args, rank)
+    mapper = Mapper(local)  # raises if there is no CUDA device: no fallback
+    mapper.set_index(pos, val)
+    mapper.set_contigs(ref.lengths)
+    params = full_read_params() if args.mode == "full" else default_params()
+    # pinned host staging of the raw reads (e2e leg copies from here every step)
+    pinned = torch.empty(len(reads.raw), dtype=torch.int16, pin_memory=True)
+    pinned.numpy()[:] = reads.raw
+    reads.raw = pinned.numpy()
+    t_setup = time.time() - t_setup
+
+    def barrier():
+        torch.cuda.synchronize(local)
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(local)
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local}")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ---- device-resident leg
+    mapper.upload_reads(reads)
+    for _ in range(args.warmup):
+        rows = mapper.map_uploaded(params)
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    mapper.stats_reset()
+    mapper.timer_start()
+    t_wall = time.time()
+    for _ in range(args.steps):
+        rows = mapper.map_uploaded(params)
+    ms = mapper.timer_stop()
+    t_wall = time.time() - t_wall
+    barrier()
+    st = mapper.stats()
+    clocks = sampler.stop()
+    ms = max_over_ranks(ms)
+    samples_total = sum_over_ranks(float(st["samples"]))
+    value = samples_total / (ms / 1000.0)
+    n_mapped = sum(1 for m in rows if m.mapped)
+    # concordance with the simulation truth (sanity, not a parity claim)
+    ok = 0
+    for r, m in enumerate(rows):
+        c, s, e, plus = (int(v) for v in reads.truth[r])
+        if m.mapped and m.contig == c and m.strand_plus == plus and m.t_start < e + 50 and \
+                m.t_start + m.frag_len > s - 50:
+            ok += 1
+
+    # ---- end-to-end leg: host buffers in, rows out, copies inside the timed region
+    mapper.map_reads(reads, params)  # one warm-up
+    barrier()
+    mapper.stats_reset()
+    mapper.timer_start()
+    e2e_steps = max(1, min(args.steps, 2))
+    for _ in range(e2e_steps):
+        mapper.map_reads(reads, params)
+    ms_e2e = mapper.timer_stop()
+    barrier()
+    st2 = mapper.stats()
+    ms_e2e = max_over_ranks(ms_e2e)
+    e2e_samples = sum_over_ranks(float(st2["samples"]))
+    e2e_value = e2e_samples / (ms_e2e / 1000.0)
+
+    # ---- roofline of the dominant kernel (radius search), live CUDA-event timing
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    L = max(st["search_launches"], 1)
+    alg_bytes = (24.0 * st["queries"] + 44.0 * st["hits"]) / L   # SURVEY.md 8(d) per-unit figures
+    dur_s = st["ms_search"] / 1000.0 / L
+    achieved = alg_bytes / dur_s / 1e9 if dur_s > 0 else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "search_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+    pipeline_bytes = (2.0 * st["samples"] + 8.0 * st["events"] + 24.0 * st["queries"] +
+                      44.0 * st["hits"] + 44.0 * st["anchors"])
+
+    out = {
+        "metric": "raw samples/sec mapped", "value": value, "unit": "samples/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args), "l2": "inputs larger than L2 (raw reads + index)",
+                   "index_points": int(len(pos)), "reads_per_gpu": args.reads,
+                   "parallelism": f"read-sharded x{world}, index replicated"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "samples/s",
+                "h2d_bytes_per_step": int(st2["h2d_bytes"] // e2e_steps),
+                "d2h_bytes_per_step": int(st2["d2h_bytes"] // e2e_steps)},
+        "gpu_launches": int(st["launches"]),
+        "roofline": {"bound": "hbm", "kernel": "k_radius_search", "achieved": achieved, "peak": peak,
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                     "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
+                     "avg_launch_ms": dur_s * 1000.0, "launches": int(st["search_launches"])},
+        "pipeline": {"algorithmic_GBps": pipeline_bytes / (ms / 1000.0) / 1e9 / max(world, 1),
+                     "frac_of_hbm": pipeline_bytes / (ms / 1000.0) / 1e9 / max(world, 1) / peak,
+                     "kernel_ms_per_step": {k: st[k] / max(args.steps, 1) for k in
+                                            ("ms_filter", "ms_events", "ms_search", "ms_sort", "ms_chain")},
+                     "wall_ms_per_step": 1000.0 * t_wall / max(args.steps, 1),
+                     "counters_per_step": {k: int(st[k] // max(args.steps, 1)) for k in
+                                           ("samples", "events", "queries", "hits", "anchors",
+                                            "capped_queries", "chunks", "steps")}},
+        "mapped_reads": n_mapped, "truth_concordant_reads": ok, "setup_s": t_setup,
+    }
+
+    # ---- CPU baseline: the reference's own binary on this box's host cores (rank 0, N=1)
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            from oracle.oracle import Ref
+            if Ref.available():
+                threads = os.cpu_count() or 1
+                workdir = tempfile.mkdtemp(prefix="sigmap_cpu_")
+                try:
+                    fasta, prefix, sig, n, _ = ref_prepare(args, H, ref, reads, args.cpu_sample_reads, workdir)
+                    s, t = ref_map_once(args, H, fasta, prefix, sig, workdir, threads)
+                finally:
+                    shutil.rmtree(workdir, ignore_errors=True)
+                out["cpu_baseline"] = {
+                    "value": s / t, "unit": "samples/s", "cores": threads, "kind": "reference",
+                    "sample": f"first {n} reads of the workload, oracle/_ref/sigmap_ref -m -t {threads}, "
+                              f"map phase only ({t:.1f} s)"}
+            else:
+                out["cpu_baseline"] = {"value": None, "unit": "samples/s", "cores": 0, "kind": "reference",
+                                       "sample": "oracle/_ref not built on this box"}
+        except Exception as e:  # the baseline is reported, never fatal
+            out["cpu_baseline"] = {"value": None, "unit": "samples/s", "cores": 0, "kind": "reference",
+                                   "sample": f"failed: {e}"}
+    if rank == 0:
+        print(json.dumps(out))
+    mapper.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

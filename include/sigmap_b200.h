@@ -109,6 +109,10 @@ void smb_destroy(smb_ctx *ctx);
 const char *smb_last_error(const smb_ctx *ctx); /* ctx may be NULL: last create() error */
 void smb_stats_reset(smb_ctx *ctx);
 int smb_stats_get(smb_ctx *ctx, smb_stats *out);
+/* Device-side stopwatch on the library's own stream (CUDA events): start records an event,
+ * stop records a second one, synchronises and returns the elapsed milliseconds. */
+int smb_timer_start(smb_ctx *ctx);
+int smb_timer_stop(smb_ctx *ctx, double *ms);
 /* tuning: max chunks per pipeline step and anchor capacity per step (0 = keep default) */
 int smb_set_limits(smb_ctx *ctx, uint32_t max_batch_chunks, uint64_t max_batch_anchors);
 

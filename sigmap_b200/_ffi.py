@@ -137,6 +137,8 @@ PROTOTYPES = {
     "smb_last_error": (C.c_char_p, [C.c_void_p]),
     "smb_stats_reset": (None, [C.c_void_p]),
     "smb_stats_get": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
+    "smb_timer_start": (C.c_int, [C.c_void_p]),
+    "smb_timer_stop": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "smb_set_limits": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint64]),
     "smb_index_load": (C.c_int, [C.c_void_p, C.c_char_p]),
     "smb_index_set_points": (C.c_int, [C.c_void_p, u64p, f32p, C.c_size_t]),

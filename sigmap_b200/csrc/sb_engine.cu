@@ -184,6 +184,7 @@ struct smb_ctx {
   Counters *d_ctr = nullptr;
   Counters *h_ctr = nullptr;  // pinned
   cudaEvent_t ev[6] = {};
+  cudaEvent_t timer[2] = {};
   smb_stats stats{};
   uint32_t max_batch_chunks = 16384;
   uint64_t max_batch_anchors = 192ull << 20;
@@ -744,6 +745,8 @@ int smb_create(smb_ctx **out, int device) {
   if ((e = cudaMallocHost((void **)&ctx->h_ctr, sizeof(Counters))) != cudaSuccess) return bail("cudaMallocHost", e);
   for (auto &ev : ctx->ev)
     if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail("cudaEventCreate", e);
+  for (auto &ev : ctx->timer)
+    if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail("cudaEventCreate", e);
   *out = ctx;
   return SMB_OK;
 }
@@ -769,6 +772,7 @@ void smb_destroy(smb_ctx *ctx) {
   ctx->raw.release(); ctx->kept.release(); ctx->d_read_off.release(); ctx->d_kept_off.release();
   ctx->d_dig.release(); ctx->d_range.release(); ctx->d_offset.release(); ctx->d_kept_len.release();
   for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+  for (auto &ev : ctx->timer) if (ev) cudaEventDestroy(ev);
   if (ctx->d_ctr) cudaFree(ctx->d_ctr);
   if (ctx->h_ctr) cudaFreeHost(ctx->h_ctr);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -781,6 +785,22 @@ int smb_stats_get(smb_ctx *ctx, smb_stats *out) {
   ctx->stats.ms_total = ctx->stats.ms_events + ctx->stats.ms_search + ctx->stats.ms_sort +
                         ctx->stats.ms_chain + ctx->stats.ms_filter;
   *out = ctx->stats;
+  return SMB_OK;
+}
+
+int smb_timer_start(smb_ctx *ctx) {
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaEventRecord(ctx->timer[0], ctx->stream));
+  return SMB_OK;
+}
+
+int smb_timer_stop(smb_ctx *ctx, double *ms) {
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaEventRecord(ctx->timer[1], ctx->stream));
+  CK(cudaEventSynchronize(ctx->timer[1]));
+  float f = 0;
+  CK(cudaEventElapsedTime(&f, ctx->timer[0], ctx->timer[1]));
+  *ms = f;
   return SMB_OK;
 }
 
@@ -858,13 +878,24 @@ int smb_reads_upload(smb_ctx *ctx, const int16_t *raw, const uint64_t *read_off,
   CK(cudaMemcpyAsync(ctx->d_range.p, range, n_reads * sizeof(float), cudaMemcpyHostToDevice, s));
   CK(cudaMemcpyAsync(ctx->d_offset.p, offset, n_reads * sizeof(float), cudaMemcpyHostToDevice, s));
   ctx->stats.h2d_bytes += total * 2 + n_reads * 28 + 8;
+  CK(cudaStreamSynchronize(s));
+  return SMB_OK;
+}
+
+}  // extern "C"
+
+// K1 over all uploaded reads: (30,200) pA filter + compaction, then kept lengths to the host
+static int filter_reads(smb_ctx *ctx) {
+  const size_t n_reads = ctx->n_reads;
+  ctx->h_kept_len.resize(n_reads);
+  if (!n_reads) return SMB_OK;
+  cudaStream_t s = ctx->stream;
   CK(cudaEventRecord(ctx->ev[5], s));
   k_filter_compact<<<(unsigned)n_reads, kFilterThreads, 0, s>>>(ctx->raw.p, ctx->d_read_off.p, ctx->d_dig.p,
                                                               ctx->d_range.p, ctx->d_offset.p, ctx->d_kept_off.p,
                                                               ctx->kept.p, ctx->d_kept_len.p, (uint32_t)n_reads);
   LAUNCH_CHECK();
   CK(cudaEventRecord(ctx->ev[4], s));
-  ctx->h_kept_len.resize(n_reads);
   CK(cudaMemcpyAsync(ctx->h_kept_len.data(), ctx->d_kept_len.p, n_reads * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
   ctx->stats.d2h_bytes += n_reads * 4;
@@ -874,6 +905,8 @@ int smb_reads_upload(smb_ctx *ctx, const int16_t *raw, const uint64_t *read_off,
   return SMB_OK;
 }
 
+extern "C" {
+
 int smb_map_uploaded(smb_ctx *ctx, const smb_params *prm_in, smb_mapping *out) {
   CK(cudaSetDevice(ctx->device));
   if (!ctx->has_index) return fail(ctx, SMB_ERR_STATE, "no index loaded");
@@ -882,6 +915,8 @@ int smb_map_uploaded(smb_ctx *ctx, const smb_params *prm_in, smb_mapping *out) {
   const size_t R = ctx->n_reads;
   SlotSpace &sp = ctx->map_slots;
   int rc = slots_init(ctx, sp, (uint32_t)R);
+  if (rc) return rc;
+  rc = filter_reads(ctx);  // K1: part of the mapped path, redone on every call
   if (rc) return rc;
   std::vector<uint32_t> n_chunks(R), chunks_used(R, 1);
   std::vector<uint32_t> active;
@@ -946,6 +981,8 @@ int smb_stage_raw_to_pa(smb_ctx *ctx, const int16_t *raw, size_t n, float dig, f
   CK(cudaSetDevice(ctx->device));
   uint64_t off[2] = {0, n};
   int rc = smb_reads_upload(ctx, raw, off, &dig, &range, &offset, 1);
+  if (rc) return rc;
+  rc = filter_reads(ctx);
   if (rc) return rc;
   const uint32_t kept = ctx->h_kept_len[0];
   *n_out = kept;

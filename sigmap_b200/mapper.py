@@ -94,6 +94,14 @@ class Mapper:
         self._check(F.lib.smb_set_limits(self._ctx, max_batch_chunks, max_batch_anchors),
                     "smb_set_limits")
 
+    def timer_start(self):
+        self._check(F.lib.smb_timer_start(self._ctx), "smb_timer_start")
+
+    def timer_stop(self):
+        ms = C.c_double()
+        self._check(F.lib.smb_timer_stop(self._ctx, C.byref(ms)), "smb_timer_stop")
+        return ms.value
+
     # ------------------------------------------------------------------ stats
     def stats_reset(self):
         F.lib.smb_stats_reset(self._ctx)
