@@ -100,3 +100,70 @@ def same_chains(a, b):
 def paf_cols(line):
     """PAF row without the wall-clock tag mt (compare everything else)."""
     return [c for c in line.rstrip("\n").split("\t") if not c.startswith("mt:f:")]
+
+
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+
+class Golden:
+    """tests/golden/: outputs of the unmodified reference on committed inputs
+    (tests/make_golden.py)."""
+
+    def __init__(self):
+        import json
+        self.z = np.load(os.path.join(GOLDEN_DIR, "stages.npz"))
+        self.paf = json.load(open(os.path.join(GOLDEN_DIR, "paf.json")))
+
+    def __getitem__(self, k):
+        return self.z[k]
+
+    def genome(self, host):
+        lens = self.z["contig_len"]
+        seq = self.z["contig_seq"].tobytes()
+        o, seqs = 0, []
+        for l in lens:
+            seqs.append(seq[o:o + int(l)])
+            o += int(l)
+        return host.Reference([f"contig_{i}" for i in range(len(lens))], seqs)
+
+    def reads(self, host):
+        return host.ReadSet([str(n) for n in self.z["read_names"]], self.z["raw"], self.z["read_off"],
+                            host.DIGITISATION, host.RANGE, host.OFFSET, self.z["truth"])
+
+    def real_read(self, r):
+        o = self.z["real_off"]
+        return (self.z["real_raw"][int(o[r]):int(o[r + 1])], float(self.z["real_dig"][r]),
+                float(self.z["real_offset"][r]), float(self.z["real_range"][r]))
+
+    def chunk_features(self, ci):
+        o = self.z["feat_off"]
+        return self.z["feat"][int(o[ci]):int(o[ci + 1])]
+
+    def hits(self, name, k):
+        o = self.z[f"hits_{name}_off"]
+        s = slice(int(o[k]), int(o[k + 1]))
+        return self.z[f"hits_{name}_idx"][s], self.z[f"hits_{name}_d2"][s]
+
+    def chain_states(self):
+        """yield (read, chunk, [chain dicts]) in generation order"""
+        ro = ao = 0
+        for r, c, n_rec, n_anc in self.z["chain_key"]:
+            rec = self.z["chain_rec"][ro:ro + n_rec]
+            anc = self.z["chain_anc"][ao:ao + n_anc]
+            ro += int(n_rec)
+            ao += int(n_anc)
+            chains, a0 = [], 0
+            for row in rec:
+                na = int(row[7])
+                chains.append(dict(score=row[0:1].view(np.float32)[0], contig=int(row[1]),
+                                   start=int(row[2]), end=int(row[3]), n_anchors=int(row[4]),
+                                   mapq=int(row[5]), dir=int(row[6]),
+                                   anchors=[(int(t), int(q), np.array([d], np.uint32).view(np.float32)[0])
+                                            for t, q, d in anc[a0:a0 + na]]))
+                a0 += na
+            yield int(r), int(c), chains
+
+
+@pytest.fixture(scope="session")
+def golden():
+    return Golden()

@@ -1,0 +1,127 @@
+"""CPU tests (no GPU): the C-ABI library loads and exports every symbol include/sigmap_b200.h
+declares, refuses to run without a CUDA device (no CPU fallback), and the host-only helpers
+(file formats, PAF text, simulator) behave like the reference's I/O layer."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, bits
+
+HEADER = os.path.join(ROOT, "include", "sigmap_b200.h")
+
+
+def _declared():
+    txt = open(HEADER).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(smbh?_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_every_declared_symbol_is_exported_and_bound():
+    from sigmap_b200 import _ffi
+    names = _declared()
+    assert len(names) >= 45
+    assert _ffi.MISSING == []
+    for n in names:
+        assert hasattr(_ffi.lib, n), f"{n} declared in the header but not exported"
+        assert n in _ffi.PROTOTYPES, f"{n} has no ctypes prototype"
+    nm = subprocess.run(["nm", "-D", "--defined-only", _ffi.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (smbh?_[a-z0-9_]+)", nm))
+    assert set(names) <= exported
+    # nothing of the test oracle is linked into the product
+    assert "orc_" not in nm and "liboracle" not in subprocess.run(
+        ["ldd", _ffi.LIB_PATH], capture_output=True, text=True).stdout
+
+
+def test_struct_sizes_match_header():
+    from sigmap_b200 import _ffi
+    src = '#include "sigmap_b200.h"\n#include <stdio.h>\nint main(){printf("%zu %zu %zu %zu %zu\\n",' \
+          'sizeof(smb_params),sizeof(smb_mapping),sizeof(smb_chain),sizeof(smb_anchor),sizeof(smb_stats));}'
+    exe = "/tmp/smb_sizes"
+    subprocess.run(["gcc", "-x", "c", "-", "-I", os.path.join(ROOT, "include"), "-o", exe],
+                   input=src, text=True, check=True)
+    got = [int(x) for x in subprocess.run([exe], capture_output=True, text=True).stdout.split()]
+    assert got == [C.sizeof(_ffi.Params), C.sizeof(_ffi.Mapping), C.sizeof(_ffi.Chain),
+                   C.sizeof(_ffi.Anchor), C.sizeof(_ffi.Stats)]
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from sigmap_b200 import _ffi
+    from sigmap_b200.mapper import Mapper, SigmapError
+    assert _ffi.lib.smb_device_count() == 0
+    with pytest.raises(SigmapError, match="no CUDA device"):
+        Mapper(0)
+    ctx = C.c_void_p()
+    assert _ffi.lib.smb_create(C.byref(ctx), 0) == -4 and not ctx.value
+
+
+def test_product_never_imports_the_oracle():
+    for base, _, files in os.walk(os.path.join(ROOT, "sigmap_b200")):
+        for f in files:
+            if f.endswith((".py", ".cc", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(base, f), errors="ignore").read()
+                assert "oracle" not in txt.lower() or f in ("NOTICE.md",), f"{f} mentions the oracle"
+
+
+def test_default_params_are_the_cli_defaults():
+    from sigmap_b200.mapper import default_params
+    p = default_params()
+    assert (p.step_size, p.max_num_chunks, p.min_num_anchors, p.min_num_anchors_output) == (2, 30, 10, 10)
+    assert np.float32(p.search_radius) == np.float32(0.08)
+    assert (p.stop_mapping, p.stop_mapping_mean) == (np.float32(1.4), 5.0)
+    assert p.stop_mapping_output == np.float32(1.2) and p.stop_mapping_mean_output == 5.0
+
+
+def test_pore_model_and_fasta_round_trip(host, model, tmp_path):
+    mean, stdv = model
+    assert mean.shape == (4096,) and 50 < mean.min() < mean.max() < 130
+    # first row of the bundled R9.4 model: AAAAAA 86.486336
+    assert abs(mean[0] - 86.486336) < 1e-4 and stdv.min() > 0
+    g = host.sim_reference(3, [1234, 77, 5000])
+    p = str(tmp_path / "x.fa")
+    g.write_fasta(p)
+    back = host.Reference.read_fasta(p)
+    assert back.names == g.names and back.seqs == g.seqs
+    assert set(b"".join(g.seqs)) <= set(b"ACGT")
+    assert max(len(l) for l in open(p).read().split("\n")) <= 60  # 60-column FASTA
+
+
+def test_blow5_round_trip_and_reference_reader(host, model, ref, tmp_path):
+    g = host.sim_reference(4, [30000])
+    reads = host.sim_reads(9, g, 5, min_bases=300, max_bases=900, model=model)
+    assert reads.n == 5 and reads.read_off[-1] == len(reads.raw)
+    d = tmp_path / "sig"
+    d.mkdir()
+    p = str(d / "r.blow5")
+    reads.write_blow5(p)
+    back = host.ReadSet.read_blow5(p)
+    assert back.names == reads.names
+    assert np.array_equal(back.raw, reads.raw) and np.array_equal(back.read_off, reads.read_off)
+    assert np.array_equal(back.digitisation, reads.digitisation)
+    assert np.array_equal(bits(back.range), bits(reads.range))
+    # determinism: any slice of the read stream can be generated independently (rank sharding)
+    part = host.sim_reads(9, g, 2, first_read=3, min_bases=300, max_bases=900, model=model)
+    assert np.array_equal(part.read(0), reads.read(3)) and np.array_equal(part.read(1), reads.read(4))
+    assert np.array_equal(part.truth, reads.truth[3:])
+
+
+def test_format_paf_rows(host):
+    from sigmap_b200 import _ffi
+    m = _ffi.Mapping(mapped=1, read_len=22979, q_start=58, q_end=432, strand_plus=1, contig=0,
+                     t_start=49622, frag_len=369, mapq=60, chunks=1, n_chains=1, cm=20,
+                     s1=77.451462, s2=0.0, sm=77.451462, ad=0.055596, at=18.4, aq=16.5)
+    cols = host.format_paf(m, "read_00000", "contig_0", 60000, 1.5).rstrip("\n").split("\t")
+    assert cols[:12] == ["read_00000", "22979", "58", "432", "+", "contig_0", "60000", "49622",
+                         "49991", "22979", "369", "60"]
+    assert cols[12].startswith("mt:f:") and cols[13:16] == ["ci:i:1", "sl:i:22979", "cm:i:20"]
+    assert cols[16] == "nc:i:1" and cols[17] == "s1:f:77.451462"
+    u = _ffi.Mapping(mapped=0, read_len=3999, mapq=61, chunks=1)
+    cols = host.format_paf(u, "short", "", 0, 0.0).rstrip("\n").split("\t")
+    assert cols[:12] == ["short", "3999"] + ["*"] * 9 + ["61"]
+    assert [c[:5] for c in cols[12:]] == ["mt:f:", "ci:i:", "sl:i:"]
