@@ -25,6 +25,20 @@
 
 namespace sb {
 
+// per (entry, bucket) segment: where it lies in the sorted anchor array and what the DP
+// found there.  Slot index = KeyLayout::seg(key) = entry << bbits | bucket, so the table is
+// ordered like the reference's bucket loop by construction (no atomics, no scan).
+struct SegRec {
+  uint32_t start;     // first anchor of the segment; kSegEmpty = no anchors
+  uint32_t end;       // one past the last anchor
+  uint32_t ntop;      // local end candidates kept (<= 3)
+  float max;          // max chaining score over the segment's linked anchors (see k_chain_dp)
+  float top_s[3];     // best three local end candidates: score desc, index desc
+  uint32_t top_i[3];
+};
+constexpr uint32_t kSegEmpty = 0xFFFFFFFFu;
+constexpr int kPrepTile = 256;  // anchors per k_chain_prep block = per compacted work list tile
+
 struct ChainArgs {
   const uint64_t *key;   // sorted
   const float *dist;     // sorted alongside
@@ -33,8 +47,10 @@ struct ChainArgs {
   float radius;
   float *score;
   uint32_t *pred;        // bit31 = anchor_is_used
-  uint32_t *seg_start;
-  uint32_t seg_cap;
+  SegRec *seg;           // [n_slots], memset to 0xFF before k_chain_prep
+  uint32_t n_slots;      // B << bbits
+  uint32_t *link_list;   // [n_tiles * kPrepTile] indices of linked anchors, ascending per tile
+  uint32_t *link_count;  // [n_tiles]
   Counters *ctr;
 };
 
@@ -61,64 +77,188 @@ __global__ void k_inject_carry(const uint32_t *__restrict__ entry_slot, const ui
   }
 }
 
-__global__ void k_mark_segments(ChainArgs a) {
-  const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= a.n) return;
-  const uint64_t s = a.kl.seg(a.key[i]);
-  if (i == 0 || a.kl.seg(a.key[i - 1]) != s) {
-    const uint32_t at = atomicAdd(&a.ctr->n_segments, 1u);
-    if (at < a.seg_cap) a.seg_start[at] = (uint32_t)i;
-  }
-}
-
 constexpr int kBand = 5000;        // chaining_band_length, spatial_index.cc:286
 constexpr int kMaxTargetGap = 5000;
 constexpr int kMaxGap = 2000;
 constexpr int kMaxSkips = 25;
 
-__global__ void __launch_bounds__(128) k_chain_dp(ChainArgs a) {
-  const uint32_t sidx = blockIdx.x * blockDim.x + threadIdx.x;
-  const uint32_t nseg = min(a.ctr->n_segments, a.seg_cap);
-  if (sidx >= nseg) return;
-  const long long s = a.seg_start[sidx];
-  const uint64_t segkey = a.kl.seg(a.key[s]);
-  const double radius = (double)a.radius;
-  for (long long i = s; i < (long long)a.n; ++i) {
+// The chaining DP (spatial_index.cc:434-540) in two kernels.
+//
+// Anchors of one (entry, bucket) segment look strictly sequential: anchor i reads the scores
+// of its predecessors.  But a predecessor j only ever changes anchor i's score if the pair
+// passes the gap test (|dt - dq| < 2000 and 0.75 < dq/dt < 5, :499-520) inside the lookback
+// range (same segment, i - j <= 5000, t_i - t_j <= 5000) -- and that test needs positions
+// only, no scores.  At the reference's anchor density 80-88 % of the anchors (random
+// background hits) have NO such predecessor: their score is the initial 6 * coef and their
+// predecessor is themselves whatever the lookback does.  So:
+//
+//   k_chain_prep  one thread per anchor, fully parallel: initial score, pred = self, segment
+//                 bounds, and the position-only test "is there any gap-compatible predecessor
+//                 in the maximal lookback range" (a superset of the range the reference's
+//                 skip counter actually visits).  Linked anchors are compacted, in order,
+//                 into a per-tile work list.
+//   k_chain_dp    one thread per segment walks only the linked anchors (5-8x fewer sequential
+//                 steps) and runs the reference's lookback on them exactly: continue / break
+//                 rules, running best, +-1 skip counter with its > 25 break.
+//
+// gap_scale tests as integers: 0.75 < fl(dq/dt) < 5  <=>  3*dt < 4*dq and dq < 5*dt, exact
+// because dq/dt differs from either bound by >= 1/(4*dt) >= 5e-5 while fp32 rounding moves
+// it by < 3e-7 (dt <= 5000 here, |dq| < 2^24).
+__device__ __forceinline__ bool gap_compatible(int32_t dt, int32_t dq) {
+  return abs(dt - dq) < kMaxGap && dq < 5 * dt && 4 * dq > 3 * dt;
+}
+
+// spatial_index.cc:438-444: 1 - 0.2 * distance / search_radius in double, then float
+__device__ __forceinline__ float distance_coefficient(float dist, double radius) {
+  return (float)__dsub_rn(1.0, __ddiv_rn(__dmul_rn(0.2, (double)dist), radius));
+}
+
+__global__ void __launch_bounds__(kPrepTile) k_chain_prep(ChainArgs a) {
+  __shared__ uint32_t warp_base[kPrepTile / 32];
+  const long long n = (long long)a.n;
+  const long long i = (long long)blockIdx.x * kPrepTile + threadIdx.x;
+  const KeyLayout kl = a.kl;
+  bool linked = false;
+  if (i < n) {
     const uint64_t k = a.key[i];
-    if (a.kl.seg(k) != segkey) break;
-    const int32_t ct = (int32_t)a.kl.target(k), cq = (int32_t)a.kl.query(k);
-    // spatial_index.cc:438-444: 1 - 0.2 * distance / search_radius in double, then float
-    const float coef = (float)__dsub_rn(1.0, __ddiv_rn(__dmul_rn(0.2, (double)a.dist[i]), radius));
-    float sc = __fmul_rn(coef, (float)kDim);
-    long long pr = i;
-    const long long lo = (i - s > kBand) ? i - kBand : s;
-    int skips = 0;
+    const uint64_t sg = kl.seg(k);
+    const uint64_t kp = i > 0 ? a.key[i - 1] : 0ull;
+    if (sg < a.n_slots) {
+      if (i == 0 || kl.seg(kp) != sg) {
+        a.seg[sg].start = (uint32_t)i;
+        if (i > 0 && kl.seg(kp) < a.n_slots) a.seg[kl.seg(kp)].end = (uint32_t)i;
+      }
+      if (i == n - 1) a.seg[sg].end = (uint32_t)n;
+    }
+    a.score[i] = __fmul_rn(distance_coefficient(a.dist[i], (double)a.radius), (float)kDim);
+    a.pred[i] = (uint32_t)i;
+    const int32_t ti = (int32_t)kl.target(k), qi = (int32_t)kl.query(k);
+    const long long lo = i > kBand ? i - kBand : 0;
     for (long long j = i - 1; j >= lo; --j) {
       const uint64_t kj = a.key[j];
-      const int32_t pt = (int32_t)a.kl.target(kj), pq = (int32_t)a.kl.query(kj);
-      if (pq == cq) continue;
-      if (pt == ct) continue;
-      if (pt + kMaxTargetGap < ct) break;
-      const int32_t dt = ct - pt, dq = cq - pq;
-      if (dq < 0) continue;
-      float cur = 0.0f;
-      const int32_t m = min(min(dt, dq), kDim);
-      const float matching = __fmul_rn((float)m, coef);
-      const int32_t gap = abs(dt - dq);
-      const float gs = __fdiv_rn((float)dq, (float)dt);
-      if (gap < kMaxGap && gs < 5.0f && gs > 0.75f) cur = __fadd_rn(a.score[j], matching);
-      if (cur > sc) {
-        sc = cur;
-        pr = j;
-        --skips;
-      } else {
-        ++skips;
-        if (skips > kMaxSkips) break;
+      if (kl.seg(kj) != sg) break;
+      const int32_t pt = (int32_t)kl.target(kj);
+      if (pt + kMaxTargetGap < ti) break;
+      if (gap_compatible(ti - pt, qi - (int32_t)kl.query(kj))) {
+        linked = true;
+        break;
       }
     }
-    a.score[i] = sc;
-    a.pred[i] = (uint32_t)pr;
   }
+  // ordered compaction of the tile's linked anchors
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const unsigned m = __ballot_sync(0xffffffffu, linked);
+  if (lane == 0) warp_base[wid] = __popc(m);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t acc = 0;
+    for (int w = 0; w < kPrepTile / 32; ++w) {
+      const uint32_t t = warp_base[w];
+      warp_base[w] = acc;
+      acc += t;
+    }
+    a.link_count[blockIdx.x] = acc;
+  }
+  __syncthreads();
+  if (linked)
+    a.link_list[(size_t)blockIdx.x * kPrepTile + warp_base[wid] + __popc(m & ((1u << lane) - 1u))] = (uint32_t)i;
+}
+
+constexpr int kDpThreads = 128;
+
+__global__ void __launch_bounds__(kDpThreads) k_chain_dp(ChainArgs a) {
+  const uint32_t slot = blockIdx.x * kDpThreads + threadIdx.x;
+  if (slot >= a.n_slots) return;
+  SegRec r = a.seg[slot];
+  if (r.start == kSegEmpty) return;
+  const long long s = r.start, e = r.end;
+  const KeyLayout kl = a.kl;
+  const double radius = (double)a.radius;
+  const uint64_t *key = a.key;
+  float *score = a.score;
+
+  // max over the linked anchors only: the others score <= 6, and every comparison this max
+  // feeds has a candidate score >= min_chaining_score = 10 on the other side (:545-567)
+  float runmax = 0.0f;
+  float ts0 = 0.f, ts1 = 0.f, ts2 = 0.f;  // best three local end candidates
+  uint32_t ti0 = 0, ti1 = 0, ti2 = 0;
+  int ntop = 0;
+
+  for (long long tile = s / kPrepTile; tile * kPrepTile < e; ++tile) {
+    const uint32_t cnt = a.link_count[tile];
+    const uint32_t *list = a.link_list + tile * kPrepTile;
+    for (uint32_t c = 0; c < cnt; ++c) {
+      const long long i = list[c];
+      if (i < s) continue;
+      if (i >= e) break;
+      const uint64_t k = key[i];
+      const int32_t ti = (int32_t)kl.target(k), qi = (int32_t)kl.query(k);
+      const float ci = distance_coefficient(a.dist[i], radius);
+      float M = __fmul_rn(ci, (float)kDim);  // chaining_scores[anchor_index]
+      long long best = i;
+      int S = 0;  // num_skips
+      const long long lo = (i - s > kBand) ? i - kBand : s;
+      bool stopped = false;
+      for (long long j0 = i - 1; j0 >= lo && !stopped; j0 -= 4) {
+        uint64_t kj[4];
+        float sj[4];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {  // four predecessors at a time, loads issued together
+          const long long j = j0 - v >= lo ? j0 - v : lo;
+          kj[v] = key[j];
+          sj[v] = score[j];
+        }
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          if (stopped) continue;
+          if (j0 - v < lo) {
+            stopped = true;
+            continue;
+          }
+          const int32_t pt = (int32_t)kl.target(kj[v]), pq = (int32_t)kl.query(kj[v]);
+          if (pq == qi || pt == ti) continue;
+          if (pt + kMaxTargetGap < ti) {
+            stopped = true;
+            continue;
+          }
+          const int32_t dt = ti - pt, dq = qi - pq;
+          if (dq < 0) continue;
+          float cur = 0.0f;
+          if (gap_compatible(dt, dq)) cur = __fadd_rn(sj[v], __fmul_rn((float)min(min(dt, dq), kDim), ci));
+          if (cur > M) {
+            M = cur;
+            best = j0 - v;
+            --S;
+          } else if (++S > kMaxSkips) {
+            stopped = true;
+          }
+        }
+      }
+      score[i] = M;
+      a.pred[i] = (uint32_t)best;
+      // ---- running max and local end candidates (spatial_index.cc:542-549); the caller
+      // applies the max of the earlier buckets, which only shortens this list.  Order: score
+      // desc, index desc (compare(), :11-20); i only grows, so a tie puts the newcomer first.
+      if (M > runmax) runmax = M;
+      if (M >= 10.0f && M > __fdiv_rn(runmax, 2.0f)) {
+        if (ntop < 1 || M >= ts0) {
+          ts2 = ts1; ti2 = ti1; ts1 = ts0; ti1 = ti0; ts0 = M; ti0 = (uint32_t)i;
+          if (ntop < 3) ++ntop;
+        } else if (ntop < 2 || M >= ts1) {
+          ts2 = ts1; ti2 = ti1; ts1 = M; ti1 = (uint32_t)i;
+          if (ntop < 3) ++ntop;
+        } else if (ntop < 3 || M >= ts2) {
+          ts2 = M; ti2 = (uint32_t)i;
+          if (ntop < 3) ++ntop;
+        }
+      }
+    }
+  }
+  r.ntop = (uint32_t)ntop;
+  r.max = runmax;
+  r.top_s[0] = ts0; r.top_s[1] = ts1; r.top_s[2] = ts2;
+  r.top_i[0] = ti0; r.top_i[1] = ti1; r.top_i[2] = ti2;
+  a.seg[slot] = r;
 }
 
 struct ChainTmp {
@@ -144,16 +284,6 @@ struct SelectArgs {
   unsigned long long pool_chain_cap, pool_anchor_cap;
   smb_params prm;
 };
-
-__device__ __forceinline__ unsigned long long lower_bound_key(const uint64_t *key, unsigned long long n,
-                                                              uint64_t v) {
-  unsigned long long lo = 0, hi = n;
-  while (lo < hi) {
-    unsigned long long mid = (lo + hi) >> 1;
-    if (key[mid] < v) lo = mid + 1; else hi = mid;
-  }
-  return lo;
-}
 
 // spatial_index.h:38-44 operator> on (score, n, dir, contig, start, end)
 __device__ __forceinline__ bool chain_greater(const ChainTmp &x, const ChainTmp &y) {
@@ -200,44 +330,24 @@ __global__ void __launch_bounds__(64) k_chain_select(SelectArgs a) {
   const uint64_t *key = a.c.key;
   const float *score = a.c.score;
   uint32_t *pred = a.c.pred;
-  const unsigned long long lo = lower_bound_key(key, a.c.n, (uint64_t)b << kl.sh_e());
-  const unsigned long long hi = lower_bound_key(key, a.c.n, ((uint64_t)b + 1) << kl.sh_e());
   ChainTmp *ch = a.scratch + (size_t)b * a.max_chains;
   uint32_t nch = 0;
   float gmax = 0.0f;  // max_chaining_score, spatial_index.cc:419
-  const float min_score = 10.0f;
 
-  unsigned long long i = lo;
-  while (i < hi) {
-    const uint64_t segkey = kl.seg(key[i]);
-    const uint32_t bucket = kl.bucket(key[i]);
-    // end candidates of this bucket: only the best three are ever traced (:555-557)
-    float top_s[3];
-    unsigned long long top_i[3];
-    int ntop = 0;
-    unsigned long long j = i;
-    for (; j < hi && kl.seg(key[j]) == segkey; ++j) {
-      const float sc = score[j];
-      if (sc > gmax) gmax = sc;
-      if (sc >= min_score && sc > __fdiv_rn(gmax, 2.0f)) {
-        // order: score desc, index desc (compare(), spatial_index.cc:11-20); j only grows,
-        // so on equal score the newcomer goes first
-        int p = ntop < 3 ? ntop : 3;
-        while (p > 0 && sc >= top_s[p - 1]) --p;
-        if (p < 3) {
-          for (int t = (ntop < 3 ? ntop : 2); t > p; --t) {
-            top_s[t] = top_s[t - 1];
-            top_i[t] = top_i[t - 1];
-          }
-          top_s[p] = sc;
-          top_i[p] = j;
-          if (ntop < 3) ++ntop;
-        }
-      }
-    }
+  // buckets in the reference's order (contig-major, '+' first): slot = entry << bbits | bucket
+  const uint32_t n_buckets = 1u << kl.bbits;
+  for (uint32_t bucket = 0; bucket < n_buckets; ++bucket) {
+    const SegRec rec = a.c.seg[((size_t)b << kl.bbits) | bucket];
+    if (rec.start == kSegEmpty) continue;
+    // The DP kept the segment's best three end candidates under its own running max; the
+    // reference's test also includes the max of the earlier buckets (gprev), which removes
+    // exactly the candidates with score <= gprev/2 -- a suffix of the list (:545-549).
+    const float half_prev = __fdiv_rn(gmax, 2.0f);
+    if (rec.max > gmax) gmax = rec.max;
     const float half = __fdiv_rn(gmax, 2.0f);
-    for (int r = 0; r < ntop; ++r) {
-      const unsigned long long e = top_i[r];
+    for (uint32_t r = 0; r < rec.ntop; ++r) {
+      if (!(rec.top_s[r] > half_prev)) break;
+      const unsigned long long e = rec.top_i[r];
       // ---- TracebackChains (spatial_index.cc:165-220)
       if (!(pred[e] & 0x80000000u)) {
         unsigned long long s = e;
@@ -276,7 +386,6 @@ __global__ void __launch_bounds__(64) k_chain_select(SelectArgs a) {
       }
       if (score[e] < half) break;  // :564-567
     }
-    i = j;
   }
 
   // ---- GeneratePrimaryChains (spatial_index.cc:222-253) by repeated extraction of the max

@@ -13,6 +13,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <cub/device/device_radix_sort.cuh>
 #include <string>
@@ -150,7 +151,8 @@ struct Workspace {
   // anchors
   DevBuf<uint64_t> key_a, key_b;
   DevBuf<float> dist_a, dist_b, score;
-  DevBuf<uint32_t> pred, seg_start;
+  DevBuf<uint32_t> pred, link_list, link_count;
+  DevBuf<SegRec> seg;
   DevBuf<unsigned char> cub_temp;
   DevBuf<ChainTmp> chain_tmp;
   // round readback
@@ -186,8 +188,9 @@ struct smb_ctx {
   cudaEvent_t ev[6] = {};
   cudaEvent_t timer[2] = {};
   smb_stats stats{};
-  uint32_t max_batch_chunks = 16384;
-  uint64_t max_batch_anchors = 192ull << 20;
+  uint32_t max_batch_chunks = 32768;
+  uint64_t max_batch_anchors = 640ull << 20;  // x 32 B of sort/DP buffers = 20 GB of the 180 GB HBM
+  uint64_t last_cap = 0;
   double est_anchors_per_chunk = 20000.0;
   // streaming
   SlotSpace *stream_slots = nullptr;
@@ -381,8 +384,12 @@ static int run_step(smb_ctx *ctx, SlotSpace &sp, const StepEntries &en, StepSour
   kl.bbits = bits_for(ctx->max_bucket);
   kl.ebits = bits_for(B - 1);
   if (kl.total() > 64) return fail(ctx, SMB_ERR_CAPACITY, "sort key exceeds 64 bits: lower max_batch_chunks");
-  const uint64_t cap = ctx->max_batch_anchors;
-  if (cap >= (1ull << 31)) return fail(ctx, SMB_ERR_ARG, "max_batch_anchors must stay below 2^31");
+  if (ctx->max_batch_anchors >= (1ull << 31)) return fail(ctx, SMB_ERR_ARG, "max_batch_anchors must stay below 2^31");
+  // anchor buffers sized from the running estimate (they grow on overflow, up to the limit)
+  const uint64_t cap = std::min<uint64_t>(
+      ctx->max_batch_anchors,
+      std::max<uint64_t>((uint64_t)(1.5 * ctx->est_anchors_per_chunk * std::max(Bpres, 1u)) + (1u << 20), w.key_a.cap));
+  ctx->last_cap = cap;
 
   // ---- per-entry arrays
   CK(w.entry_slot.ensure(B));
@@ -499,15 +506,22 @@ static int run_step(smb_ctx *ctx, SlotSpace &sp, const StepEntries &en, StepSour
   ca.radius = prm.search_radius;
   ca.score = w.score.p;
   ca.pred = w.pred.p;
-  const uint64_t seg_cap64 = std::min<uint64_t>(std::max<uint64_t>(n, 1), (uint64_t)B * (ctx->max_bucket + 1ull));
-  ca.seg_cap = (uint32_t)seg_cap64;
-  CK(w.seg_start.ensure(ca.seg_cap));
-  ca.seg_start = w.seg_start.p;
+  const uint64_t n_slots64 = (uint64_t)B << kl.bbits;
+  if (n_slots64 >= (1ull << 31)) return fail(ctx, SMB_ERR_CAPACITY, "segment table too large: lower max_batch_chunks");
+  ca.n_slots = (uint32_t)n_slots64;
+  CK(w.seg.ensure(ca.n_slots));
+  ca.seg = w.seg.p;
   ca.ctr = ctx->d_ctr;
+  CK(cudaMemsetAsync(w.seg.p, 0xFF, (size_t)ca.n_slots * sizeof(SegRec), s));
   if (n > 0) {
-    k_mark_segments<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ca);
+    const unsigned n_tiles = (unsigned)((n + kPrepTile - 1) / kPrepTile);
+    CK(w.link_list.ensure((size_t)n_tiles * kPrepTile));
+    CK(w.link_count.ensure(n_tiles));
+    ca.link_list = w.link_list.p;
+    ca.link_count = w.link_count.p;
+    k_chain_prep<<<n_tiles, kPrepTile, 0, s>>>(ca);
     LAUNCH_CHECK();
-    k_chain_dp<<<(ca.seg_cap + 127) / 128, 128, 0, s>>>(ca);
+    k_chain_dp<<<(ca.n_slots + kDpThreads - 1) / kDpThreads, kDpThreads, 0, s>>>(ca);
     LAUNCH_CHECK();
   }
   SelectArgs se{};
@@ -638,10 +652,12 @@ static int run_round(smb_ctx *ctx, SlotSpace &sp, const std::vector<uint32_t> &p
       if (!absent_done) en.slot.insert(en.slot.end(), absent.begin(), absent.end());
       en.B = (uint32_t)en.slot.size();
       rc = run_step(ctx, sp, en, src, prm, out_pool);
-      if (rc == 1) {  // anchor buffer overflow: halve and retry
-        if (count <= 1) return fail(ctx, SMB_ERR_CAPACITY, "one chunk overflows max_batch_anchors");
+      if (rc == 1) {  // anchor buffer overflow: grow the buffers, or halve the step at the limit
         ctx->est_anchors_per_chunk *= 2.0;
-        count = (count + 1) / 2;
+        if (ctx->last_cap >= ctx->max_batch_anchors) {
+          if (count <= 1) return fail(ctx, SMB_ERR_CAPACITY, "one chunk overflows max_batch_anchors");
+          count = (count + 1) / 2;
+        }
         continue;
       }
       if (rc) return rc;
@@ -765,7 +781,7 @@ void smb_destroy(smb_ctx *ctx) {
   w.q_off.release(); w.absent.release(); w.chunk_start.release(); w.chunk_offset.release();
   w.chunk_scale.release(); w.ps.release(); w.pss.release(); w.t1.release(); w.t2.release();
   w.means.release(); w.features.release(); w.key_a.release(); w.key_b.release(); w.dist_a.release();
-  w.dist_b.release(); w.score.release(); w.pred.release(); w.seg_start.release(); w.cub_temp.release();
+  w.dist_b.release(); w.score.release(); w.pred.release(); w.seg.release(); w.link_list.release(); w.link_count.release(); w.cub_temp.release();
   w.chain_tmp.release(); w.ids.release(); w.round_info.release();
   ctx->leaf_vals.release(); ctx->leaf_tpos.release(); ctx->leaf_bucket.release(); ctx->leaf_widx.release();
   for (auto &l : ctx->level) l.release();

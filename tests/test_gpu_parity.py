@@ -228,7 +228,7 @@ def test_small_batches_give_identical_rows(mapper, small):
     try:
         again = mapper.map_reads(small.reads)
     finally:
-        mapper.set_limits(max_batch_chunks=16384)
+        mapper.set_limits(max_batch_chunks=32768)
     a = mapper.paf_lines(small.reads, base, small.ref.names)
     b = mapper.paf_lines(small.reads, again, small.ref.names)
     assert a == b
