@@ -46,6 +46,7 @@ struct ChainArgs {
   KeyLayout kl;
   float radius;
   float *score;
+  float *coef;           // distance coefficient per anchor (k_chain_prep)
   uint32_t *pred;        // bit31 = anchor_is_used
   SegRec *seg;           // [n_slots], memset to 0xFF before k_chain_prep
   uint32_t n_slots;      // B << bbits
@@ -130,7 +131,9 @@ __global__ void __launch_bounds__(kPrepTile) k_chain_prep(ChainArgs a) {
       }
       if (i == n - 1) a.seg[sg].end = (uint32_t)n;
     }
-    a.score[i] = __fmul_rn(distance_coefficient(a.dist[i], (double)a.radius), (float)kDim);
+    const float ci = distance_coefficient(a.dist[i], (double)a.radius);
+    a.coef[i] = ci;
+    a.score[i] = __fmul_rn(ci, (float)kDim);
     a.pred[i] = (uint32_t)i;
     const int32_t ti = (int32_t)kl.target(k), qi = (int32_t)kl.query(k);
     const long long lo = i > kBand ? i - kBand : 0;
@@ -166,14 +169,24 @@ __global__ void __launch_bounds__(kPrepTile) k_chain_prep(ChainArgs a) {
 
 constexpr int kDpThreads = 128;
 
+// A group of W lanes owns a segment.  For each linked anchor the lanes load W consecutive
+// predecessors in one coalesced access, every lane scores one of them, and the reference's
+// sequential lookback is resolved with one prefix-max scan and three ballots; deeper lookbacks
+// take further blocks of W.
+template <int W>
 __global__ void __launch_bounds__(kDpThreads) k_chain_dp(ChainArgs a) {
-  const uint32_t slot = blockIdx.x * kDpThreads + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int gl = lane & (W - 1);
+  const int gshift = lane & ~(W - 1);
+  const unsigned wmask = (W == 32) ? 0xffffffffu : ((1u << W) - 1u);
+  const unsigned gmask = wmask << gshift;
+  const unsigned le = (2u << gl) - 1u;  // lanes 0..gl of the group
+  const uint32_t slot = (blockIdx.x * kDpThreads + threadIdx.x) / W;
   if (slot >= a.n_slots) return;
   SegRec r = a.seg[slot];
   if (r.start == kSegEmpty) return;
   const long long s = r.start, e = r.end;
   const KeyLayout kl = a.kl;
-  const double radius = (double)a.radius;
   const uint64_t *key = a.key;
   float *score = a.score;
 
@@ -193,49 +206,58 @@ __global__ void __launch_bounds__(kDpThreads) k_chain_dp(ChainArgs a) {
       if (i >= e) break;
       const uint64_t k = key[i];
       const int32_t ti = (int32_t)kl.target(k), qi = (int32_t)kl.query(k);
-      const float ci = distance_coefficient(a.dist[i], radius);
-      float M = __fmul_rn(ci, (float)kDim);  // chaining_scores[anchor_index]
+      float M = score[i];  // 6 * coef from k_chain_prep = chaining_scores[anchor_index]
+      const float ci = a.coef[i];
       long long best = i;
       int S = 0;  // num_skips
       const long long lo = (i - s > kBand) ? i - kBand : s;
-      bool stopped = false;
-      for (long long j0 = i - 1; j0 >= lo && !stopped; j0 -= 4) {
-        uint64_t kj[4];
-        float sj[4];
-#pragma unroll
-        for (int v = 0; v < 4; ++v) {  // four predecessors at a time, loads issued together
-          const long long j = j0 - v >= lo ? j0 - v : lo;
-          kj[v] = key[j];
-          sj[v] = score[j];
-        }
-#pragma unroll
-        for (int v = 0; v < 4; ++v) {
-          if (stopped) continue;
-          if (j0 - v < lo) {
-            stopped = true;
-            continue;
-          }
-          const int32_t pt = (int32_t)kl.target(kj[v]), pq = (int32_t)kl.query(kj[v]);
-          if (pq == qi || pt == ti) continue;
-          if (pt + kMaxTargetGap < ti) {
-            stopped = true;
-            continue;
-          }
+      for (long long jb = i - 1;; jb -= W) {
+        const long long j = jb - gl;
+        // ---- my predecessor: >= 0 candidate score (counted), -1 continue, -2 lookback ends
+        float cd = -2.0f;
+        if (j >= lo) {
+          const uint64_t kj = key[j];
+          const int32_t pt = (int32_t)kl.target(kj), pq = (int32_t)kl.query(kj);
           const int32_t dt = ti - pt, dq = qi - pq;
-          if (dq < 0) continue;
-          float cur = 0.0f;
-          if (gap_compatible(dt, dq)) cur = __fadd_rn(sj[v], __fmul_rn((float)min(min(dt, dq), kDim), ci));
-          if (cur > M) {
-            M = cur;
-            best = j0 - v;
-            --S;
-          } else if (++S > kMaxSkips) {
-            stopped = true;
-          }
+          if (pq == qi || pt == ti) cd = -1.0f;
+          else if (pt + kMaxTargetGap < ti) cd = -2.0f;
+          else if (dq < 0) cd = -1.0f;
+          else if (gap_compatible(dt, dq)) cd = __fadd_rn(score[j], __fmul_rn((float)min(min(dt, dq), kDim), ci));
+          else cd = 0.0f;
         }
+        // ---- resolve the W predecessors in order (lane 0 = most recent)
+        const bool counted = cd >= 0.0f;
+        const unsigned cntm = (__ballot_sync(gmask, counted) >> gshift) & wmask;
+        unsigned impm = 0u;
+        if (__ballot_sync(gmask, cd > M) & gmask) {
+          float pm = counted ? cd : 0.0f;  // inclusive prefix max of the candidate scores
+#pragma unroll
+          for (int d = 1; d < W; d <<= 1) {
+            const float t = __shfl_up_sync(gmask, pm, d, W);
+            if (gl >= d) pm = fmaxf(pm, t);
+          }
+          float ex = __shfl_up_sync(gmask, pm, 1, W);
+          ex = fmaxf(gl == 0 ? 0.0f : ex, M);
+          impm = (__ballot_sync(gmask, counted && cd > ex) >> gshift) & wmask;
+        }
+        const int Sl = S + __popc(cntm & ~impm & le) - __popc(impm & le);
+        const bool stop_here = (counted && !((impm >> gl) & 1u) && Sl > kMaxSkips) || cd == -2.0f;
+        const unsigned stopm = (__ballot_sync(gmask, stop_here) >> gshift) & wmask;
+        const unsigned below = stopm ? ((stopm & (0u - stopm)) - 1u) : wmask;
+        const unsigned imp_b = impm & below;
+        if (imp_b) {
+          const int L = 31 - __clz(imp_b);
+          M = __shfl_sync(gmask, cd, L, W);
+          best = jb - L;
+        }
+        if (stopm) break;
+        S += __popc(cntm & ~impm) - __popc(impm);
       }
-      score[i] = M;
-      a.pred[i] = (uint32_t)best;
+      if (gl == 0) {
+        score[i] = M;
+        a.pred[i] = (uint32_t)best;
+      }
+      __syncwarp(gmask);  // the score is visible to the group's later lookbacks
       // ---- running max and local end candidates (spatial_index.cc:542-549); the caller
       // applies the max of the earlier buckets, which only shortens this list.  Order: score
       // desc, index desc (compare(), :11-20); i only grows, so a tie puts the newcomer first.
@@ -254,11 +276,13 @@ __global__ void __launch_bounds__(kDpThreads) k_chain_dp(ChainArgs a) {
       }
     }
   }
-  r.ntop = (uint32_t)ntop;
-  r.max = runmax;
-  r.top_s[0] = ts0; r.top_s[1] = ts1; r.top_s[2] = ts2;
-  r.top_i[0] = ti0; r.top_i[1] = ti1; r.top_i[2] = ti2;
-  a.seg[slot] = r;
+  if (gl == 0) {
+    r.ntop = (uint32_t)ntop;
+    r.max = runmax;
+    r.top_s[0] = ts0; r.top_s[1] = ts1; r.top_s[2] = ts2;
+    r.top_i[0] = ti0; r.top_i[1] = ti1; r.top_i[2] = ti2;
+    a.seg[slot] = r;
+  }
 }
 
 struct ChainTmp {

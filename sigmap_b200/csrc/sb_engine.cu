@@ -150,7 +150,7 @@ struct Workspace {
   DevBuf<float> ps, pss, t1, t2, means, features;
   // anchors
   DevBuf<uint64_t> key_a, key_b;
-  DevBuf<float> dist_a, dist_b, score;
+  DevBuf<float> dist_a, dist_b, score, coef;
   DevBuf<uint32_t> pred, link_list, link_count;
   DevBuf<SegRec> seg;
   DevBuf<unsigned char> cub_temp;
@@ -192,6 +192,7 @@ struct smb_ctx {
   uint64_t max_batch_anchors = 640ull << 20;  // x 32 B of sort/DP buffers = 20 GB of the 180 GB HBM
   uint64_t last_cap = 0;
   double est_anchors_per_chunk = 20000.0;
+  unsigned dp_width = 32;  // k_chain_dp lanes per segment (8/16/32); SMB_DP_WIDTH overrides (tuning)
   // streaming
   SlotSpace *stream_slots = nullptr;
   smb_params stream_params{};
@@ -435,6 +436,7 @@ static int run_step(smb_ctx *ctx, SlotSpace &sp, const StepEntries &en, StepSour
   CK(w.dist_a.ensure(cap));
   CK(w.dist_b.ensure(cap));
   CK(w.score.ensure(cap));
+  CK(w.coef.ensure(cap));
   CK(w.pred.ensure(cap));
   k_inject_carry<<<(B * 32 + 255) / 256, 256, 0, s>>>(w.entry_slot.p, w.n_queries.p, sp.slots.p,
                                                      sp.pool_anchor[0].p, sp.pool_anchor[1].p, B, kl,
@@ -505,6 +507,7 @@ static int run_step(smb_ctx *ctx, SlotSpace &sp, const StepEntries &en, StepSour
   ca.kl = kl;
   ca.radius = prm.search_radius;
   ca.score = w.score.p;
+  ca.coef = w.coef.p;
   ca.pred = w.pred.p;
   const uint64_t n_slots64 = (uint64_t)B << kl.bbits;
   if (n_slots64 >= (1ull << 31)) return fail(ctx, SMB_ERR_CAPACITY, "segment table too large: lower max_batch_chunks");
@@ -521,7 +524,11 @@ static int run_step(smb_ctx *ctx, SlotSpace &sp, const StepEntries &en, StepSour
     ca.link_count = w.link_count.p;
     k_chain_prep<<<n_tiles, kPrepTile, 0, s>>>(ca);
     LAUNCH_CHECK();
-    k_chain_dp<<<(ca.n_slots + kDpThreads - 1) / kDpThreads, kDpThreads, 0, s>>>(ca);
+    const unsigned dp_w = ctx->dp_width;  // lanes per segment
+    const unsigned dp_grid = (unsigned)(((uint64_t)ca.n_slots * dp_w + kDpThreads - 1) / kDpThreads);
+    if (dp_w == 8) k_chain_dp<8><<<dp_grid, kDpThreads, 0, s>>>(ca);
+    else if (dp_w == 16) k_chain_dp<16><<<dp_grid, kDpThreads, 0, s>>>(ca);
+    else k_chain_dp<32><<<dp_grid, kDpThreads, 0, s>>>(ca);
     LAUNCH_CHECK();
   }
   SelectArgs se{};
@@ -748,6 +755,10 @@ int smb_create(smb_ctx **out, int device) {
   }
   smb_ctx *ctx = new smb_ctx();
   ctx->device = device;
+  if (const char *e = getenv("SMB_DP_WIDTH")) {
+    const int wv = atoi(e);
+    if (wv == 8 || wv == 16 || wv == 32) ctx->dp_width = (unsigned)wv;
+  }
   auto bail = [&](const char *what, cudaError_t err) {
     g_create_error = std::string(what) + ": " + cudaGetErrorString(err);
     delete ctx;
@@ -781,7 +792,7 @@ void smb_destroy(smb_ctx *ctx) {
   w.q_off.release(); w.absent.release(); w.chunk_start.release(); w.chunk_offset.release();
   w.chunk_scale.release(); w.ps.release(); w.pss.release(); w.t1.release(); w.t2.release();
   w.means.release(); w.features.release(); w.key_a.release(); w.key_b.release(); w.dist_a.release();
-  w.dist_b.release(); w.score.release(); w.pred.release(); w.seg.release(); w.link_list.release(); w.link_count.release(); w.cub_temp.release();
+  w.dist_b.release(); w.score.release(); w.coef.release(); w.pred.release(); w.seg.release(); w.link_list.release(); w.link_count.release(); w.cub_temp.release();
   w.chain_tmp.release(); w.ids.release(); w.round_info.release();
   ctx->leaf_vals.release(); ctx->leaf_tpos.release(); ctx->leaf_bucket.release(); ctx->leaf_widx.release();
   for (auto &l : ctx->level) l.release();
