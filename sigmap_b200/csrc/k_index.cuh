@@ -134,7 +134,8 @@ constexpr int kStageCap = 128;           // staged hits per warp before one glob
 
 struct SearchArgs {
   // queries: either pipeline mode (features of batch entries) or stage mode (explicit)
-  const float *features;       // pipeline: [B][kFeatCap]; stage: [nq][6]
+  const float *features;       // pipeline: rows of kFeatCap floats; stage: [nq][6]
+  const uint32_t *feat_row;    // pipeline: feature row of each batch entry
   const uint32_t *q_off;       // pipeline: exclusive scan of queries per entry, B+1 entries
   const uint32_t *entry_slot;  // pipeline: batch entry -> slot
   const SlotState *slots;      // pipeline: num_events (query offset) per slot
@@ -223,7 +224,7 @@ k_radius_search(const IndexView ix, const SearchArgs a) {
         const uint32_t p = (uint32_t)a.step * (k + 1);   // seeds at step, 2*step, ... (Q3)
         slot = __ldg(a.entry_slot + entry);
         qpos = p + a.slots[slot].num_events;              // position + query_start_offset
-        const float *f = a.features + (size_t)entry * kFeatCap + p;
+        const float *f = a.features + (size_t)__ldg(a.feat_row + entry) * kFeatCap + p;
 #pragma unroll
         for (int d = 0; d < kDim; ++d) q[d] = __ldg(f + d);
       }

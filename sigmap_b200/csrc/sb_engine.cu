@@ -121,6 +121,30 @@ __global__ void k_scatter_features(const float *__restrict__ src, const uint32_t
     dst[(size_t)b * kFeatCap + i] = src[o + i];
 }
 
+// cached features: n_features of this step's entries from the lookahead block's rows (+ the
+// event counters the events kernel would have bumped had it run inside this step)
+__global__ void k_gather_nfeat(const uint32_t *__restrict__ nf_cache, const uint32_t *__restrict__ nraw_cache,
+                               const uint32_t *__restrict__ feat_row, uint32_t B,
+                               uint32_t *__restrict__ n_features, Counters *ctr) {
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t nf = 0, nr = 0;
+  if (b < B) {
+    const uint32_t row = feat_row[b];
+    nf = nf_cache[row];
+    nr = nraw_cache[row];
+    n_features[b] = nf;
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    nf += __shfl_xor_sync(0xffffffffu, nf, d);
+    nr += __shfl_xor_sync(0xffffffffu, nr, d);
+  }
+  if ((threadIdx.x & 31) == 0 && (nf | nr)) {
+    atomicAdd(&ctr->n_events_kept, (unsigned long long)nf);
+    atomicAdd(&ctr->n_events_raw, (unsigned long long)nr);
+  }
+}
+
 // stage hook: per-query hit counts from sorted (qid << 32 | widx) keys
 __global__ void k_count_by_query(const uint64_t *__restrict__ key, unsigned long long n,
                                  unsigned long long *__restrict__ counts) {
@@ -142,7 +166,10 @@ struct SlotSpace {
 
 struct Workspace {
   // per-entry
-  DevBuf<uint32_t> entry_slot, n_features, n_raw_events, n_queries, q_off;
+  DevBuf<uint32_t> entry_slot, n_features, n_raw_events, n_queries, q_off, feat_row;
+  // event lookahead block of the offline path: features of chunks [r0, r1) of the active reads
+  DevBuf<float> feat_cache;
+  DevBuf<uint32_t> nf_cache, nraw_cache;
   DevBuf<uint8_t> absent;
   DevBuf<uint64_t> chunk_start;
   DevBuf<float> chunk_offset, chunk_scale;
@@ -180,6 +207,7 @@ struct smb_ctx {
   std::vector<uint64_t> h_kept_off;
   std::vector<uint32_t> h_kept_len;
   std::vector<float> h_offset, h_scale;
+  std::vector<uint32_t> h_feat_row;
   // work
   Workspace ws;
   SlotSpace map_slots;
@@ -320,7 +348,7 @@ static int build_index(smb_ctx *ctx, const uint64_t *pos, const float *val, size
 }
 
 // ------------------------------------------------------------------ the pipeline step
-enum StepSource { SRC_RAW_KEPT, SRC_PA_FLOAT, SRC_FEATURES };
+enum StepSource { SRC_RAW_KEPT, SRC_PA_FLOAT, SRC_FEATURES, SRC_CACHED };
 
 struct StepEntries {
   uint32_t B = 0, B_present = 0;           // present entries first, absent ones after
@@ -330,6 +358,7 @@ struct StepEntries {
   const void *samples = nullptr;           // device pointer (kept int16 or pA float)
   const float *d_features = nullptr;       // SRC_FEATURES: concatenated features (device)
   const uint32_t *d_feat_off = nullptr;    // SRC_FEATURES: B_present+1 offsets (device)
+  std::vector<uint32_t> feat_row;          // SRC_CACHED: row of each present entry in ws.feat_cache
 };
 
 static int ensure_event_ws(smb_ctx *ctx, uint32_t B) {
@@ -345,7 +374,8 @@ static int ensure_event_ws(smb_ctx *ctx, uint32_t B) {
 }
 
 static int run_events(smb_ctx *ctx, StepSource src, const void *samples, uint32_t B,
-                      uint32_t *d_peaks_out) {
+                      uint32_t *d_peaks_out, float *d_features = nullptr, uint32_t *d_n_features = nullptr,
+                      uint32_t *d_n_raw = nullptr) {
   Workspace &w = ctx->ws;
   cudaStream_t s = ctx->stream;
   const uint32_t Bp = (B + 31) & ~31u;
@@ -361,9 +391,12 @@ static int run_events(smb_ctx *ctx, StepSource src, const void *samples, uint32_
   dim3 g((B + 127) / 128, (kChunk + 1 + kStrip - 1) / kStrip);
   k_ev_tstat<<<g, 128, 0, s>>>(w.ps.p, w.pss.p, w.t1.p, w.t2.p, B, Bp);
   LAUNCH_CHECK();
-  k_ev_features<<<(B + 127) / 128, 128, 0, s>>>(w.t1.p, w.t2.p, w.ps.p, w.means.p, w.features.p,
-                                                w.n_features.p, w.n_raw_events.p, d_peaks_out, B, Bp,
-                                                ctx->d_ctr);
+  CK(w.n_raw_events.ensure(B));
+  k_ev_features<<<(B + 127) / 128, 128, 0, s>>>(w.t1.p, w.t2.p, w.ps.p, w.means.p,
+                                                d_features ? d_features : w.features.p,
+                                                d_n_features ? d_n_features : w.n_features.p,
+                                                d_n_raw ? d_n_raw : w.n_raw_events.p, d_peaks_out, B, Bp,
+                                                d_n_raw ? nullptr : ctx->d_ctr);
   LAUNCH_CHECK();
   return SMB_OK;
 }
@@ -399,9 +432,18 @@ static int run_step(smb_ctx *ctx, SlotSpace &sp, const StepEntries &en, StepSour
   CK(w.n_raw_events.ensure(B));
   CK(w.n_queries.ensure(B));
   CK(w.q_off.ensure(B + 1));
-  CK(w.features.ensure((size_t)std::max(Bpres, 1u) * kFeatCap));
+  if (src != SRC_CACHED) CK(w.features.ensure((size_t)std::max(Bpres, 1u) * kFeatCap));
+  CK(w.feat_row.ensure(B));
   CK(cudaMemcpyAsync(w.entry_slot.p, en.slot.data(), B * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
   ctx->stats.h2d_bytes += B * sizeof(uint32_t);
+  {
+    // feature row of every entry: identity into ws.features, or rows of the lookahead block
+    std::vector<uint32_t> &rows = ctx->h_feat_row;
+    rows.resize(B);
+    for (uint32_t b = 0; b < B; ++b) rows[b] = (src == SRC_CACHED && b < Bpres) ? en.feat_row[b] : (b < Bpres ? b : 0);
+    CK(cudaMemcpyAsync(w.feat_row.p, rows.data(), B * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    ctx->stats.h2d_bytes += B * sizeof(uint32_t);
+  }
   CK(cudaEventRecord(ctx->ev[0], s));
   k_reset_step<<<1, 1, 0, s>>>(ctx->d_ctr);
   LAUNCH_CHECK();
@@ -409,6 +451,10 @@ static int run_step(smb_ctx *ctx, SlotSpace &sp, const StepEntries &en, StepSour
   if (Bpres > 0) {
     if (src == SRC_FEATURES) {
       k_scatter_features<<<Bpres, 256, 0, s>>>(en.d_features, en.d_feat_off, Bpres, w.features.p, w.n_features.p);
+      LAUNCH_CHECK();
+    } else if (src == SRC_CACHED) {
+      k_gather_nfeat<<<(Bpres + 255) / 256, 256, 0, s>>>(w.nf_cache.p, w.nraw_cache.p, w.feat_row.p, Bpres,
+                                                         w.n_features.p, ctx->d_ctr);
       LAUNCH_CHECK();
     } else {
       CK(w.chunk_start.ensure(Bpres));
@@ -443,7 +489,8 @@ static int run_step(smb_ctx *ctx, SlotSpace &sp, const StepEntries &en, StepSour
                                                      w.key_a.p, w.dist_a.p, cap, ctx->d_ctr);
   LAUNCH_CHECK();
   SearchArgs sa{};
-  sa.features = w.features.p;
+  sa.features = src == SRC_CACHED ? w.feat_cache.p : w.features.p;
+  sa.feat_row = w.feat_row.p;
   sa.q_off = w.q_off.p;
   sa.entry_slot = w.entry_slot.p;
   sa.slots = sp.slots.p;
@@ -789,7 +836,7 @@ void smb_destroy(smb_ctx *ctx) {
   slots_release(ctx->map_slots);
   Workspace &w = ctx->ws;
   w.entry_slot.release(); w.n_features.release(); w.n_raw_events.release(); w.n_queries.release();
-  w.q_off.release(); w.absent.release(); w.chunk_start.release(); w.chunk_offset.release();
+  w.q_off.release(); w.feat_row.release(); w.feat_cache.release(); w.nf_cache.release(); w.nraw_cache.release(); w.absent.release(); w.chunk_start.release(); w.chunk_offset.release();
   w.chunk_scale.release(); w.ps.release(); w.pss.release(); w.t1.release(); w.t2.release();
   w.means.release(); w.features.release(); w.key_a.release(); w.key_b.release(); w.dist_a.release();
   w.dist_b.release(); w.score.release(); w.coef.release(); w.pred.release(); w.seg.release(); w.link_list.release(); w.link_count.release(); w.cub_temp.release();
@@ -954,20 +1001,63 @@ int smb_map_uploaded(smb_ctx *ctx, const smb_params *prm_in, smb_mapping *out) {
   std::vector<RoundInfo> info;
   const std::vector<uint32_t> none;
   uint32_t round = 0;
+  // Event detection does not depend on the mapping state, only on the raw signal, and its
+  // kernels are one-thread-per-chunk sequential scans that want as many chunks per launch as
+  // possible.  So events run in LOOKAHEAD BLOCKS: chunks [ev_r0, ev_r1) of every read active
+  // at ev_r0 in one launch, cached as feature rows; the block is several rounds deep only
+  // while most reads survive from round to round (full-read mapping), one round deep when
+  // the stop rules retire most reads after their first chunk.
+  const uint32_t kEvRowCap = 96u << 10;
+  uint32_t ev_r0 = 0, ev_r1 = 0;
+  std::vector<uint32_t> row_base(R, 0);
+  size_t prev_active = 0;
+  auto chunk_limit = [&](uint32_t r) { return std::min<uint32_t>(n_chunks[r], (uint32_t)prm.max_num_chunks); };
   while (!active.empty()) {
-    auto fill = [&](StepEntries &en, size_t first, uint32_t count) {
-      en.samples = ctx->kept.p;
-      en.chunk_start.resize(count);
-      en.offset.resize(count);
-      en.scale.resize(count);
-      for (uint32_t i = 0; i < count; ++i) {
-        const uint32_t r = active[first + i];
-        en.chunk_start[i] = ctx->h_kept_off[r] + (uint64_t)kChunk * round;
-        en.offset[i] = ctx->h_offset[r];
-        en.scale[i] = ctx->h_scale[r];
+    if (round >= ev_r1) {
+      uint32_t depth = 1;
+      if (round > 0 && active.size() * 2 > prev_active)
+        depth = (uint32_t)std::min<size_t>(8, std::max<size_t>(1, kEvRowCap / active.size()));
+      ev_r0 = round;
+      ev_r1 = round + depth;
+      std::vector<uint64_t> cs;
+      std::vector<float> co, csc;
+      for (uint32_t r : active) {
+        row_base[r] = (uint32_t)cs.size();
+        const uint32_t lim = std::min(chunk_limit(r), ev_r1);
+        for (uint32_t c = round; c < lim; ++c) {
+          cs.push_back(ctx->h_kept_off[r] + (uint64_t)kChunk * c);
+          co.push_back(ctx->h_offset[r]);
+          csc.push_back(ctx->h_scale[r]);
+        }
       }
+      const uint32_t rows = (uint32_t)cs.size();
+      Workspace &w = ctx->ws;
+      cudaStream_t s = ctx->stream;
+      CK(w.chunk_start.ensure(rows));
+      CK(w.chunk_offset.ensure(rows));
+      CK(w.chunk_scale.ensure(rows));
+      CK(w.feat_cache.ensure((size_t)rows * kFeatCap));
+      CK(w.nf_cache.ensure(rows));
+      CK(w.nraw_cache.ensure(rows));
+      CK(cudaMemcpyAsync(w.chunk_start.p, cs.data(), rows * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+      CK(cudaMemcpyAsync(w.chunk_offset.p, co.data(), rows * sizeof(float), cudaMemcpyHostToDevice, s));
+      CK(cudaMemcpyAsync(w.chunk_scale.p, csc.data(), rows * sizeof(float), cudaMemcpyHostToDevice, s));
+      ctx->stats.h2d_bytes += rows * 16ull;
+      CK(cudaEventRecord(ctx->ev[5], s));
+      rc = run_events(ctx, SRC_RAW_KEPT, ctx->kept.p, rows, nullptr, w.feat_cache.p, w.nf_cache.p, w.nraw_cache.p);
+      if (rc) return rc;
+      CK(cudaEventRecord(ctx->ev[4], s));
+      CK(cudaStreamSynchronize(s));  // cs/co/csc go out of scope; also gives the event time
+      float ms = 0;
+      cudaEventElapsedTime(&ms, ctx->ev[5], ctx->ev[4]);
+      ctx->stats.ms_events += ms;
+    }
+    prev_active = active.size();
+    auto fill = [&](StepEntries &en, size_t first, uint32_t count) {
+      en.feat_row.resize(count);
+      for (uint32_t i = 0; i < count; ++i) en.feat_row[i] = row_base[active[first + i]] + (round - ev_r0);
     };
-    rc = run_round(ctx, sp, active, none, SRC_RAW_KEPT, prm, fill);
+    rc = run_round(ctx, sp, active, none, SRC_CACHED, prm, fill);
     if (rc) return rc;
     rc = round_readback(ctx, sp, active, info);
     if (rc) return rc;
