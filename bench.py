@@ -346,7 +346,7 @@ def main():
                      "wall_ms_per_step": 1000.0 * t_wall / max(args.steps, 1),
                      "counters_per_step": {k: int(st[k] // max(args.steps, 1)) for k in
                                            ("samples", "events", "queries", "hits", "anchors",
-                                            "capped_queries", "chunks", "steps")}},
+                                            "capped_queries", "chunks", "steps", "linked")}},
         "mapped_reads": n_mapped, "truth_concordant_reads": ok, "setup_s": t_setup,
     }
 

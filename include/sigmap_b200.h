@@ -99,6 +99,8 @@ typedef struct smb_stats {
   double ms_events, ms_search, ms_sort, ms_chain, ms_filter, ms_total; /* CUDA-event ms */
   uint64_t search_launches; /* launches of the radius-search kernel (ms_search / this) */
   uint64_t h2d_bytes, d2h_bytes;
+  uint64_t linked;         /* anchors the chaining DP had to walk sequentially (have a
+                              gap-compatible predecessor); the rest are settled in parallel */
 } smb_stats;
 
 /* ------------------------------------------------------------------ context */

@@ -109,6 +109,7 @@ class Stats(C.Structure):
         ("search_launches", C.c_uint64),
         ("h2d_bytes", C.c_uint64),
         ("d2h_bytes", C.c_uint64),
+        ("linked", C.c_uint64),
     ]
 
 

@@ -78,6 +78,32 @@ __global__ void k_inject_carry(const uint32_t *__restrict__ entry_slot, const ui
   }
 }
 
+// The radix sort skips the query bits (two passes fewer): it orders by (entry, bucket, target)
+// and, being stable, leaves the rare anchors that share all three in arrival order.  This
+// kernel finishes the reference's (target, query) order (spatial_index.h:22-25) by sorting
+// each such run in place; (target, query) pairs are unique inside a segment, so the result
+// is fully determined.  One thread per run head.
+__global__ void k_fix_ties(uint64_t *__restrict__ key, float *__restrict__ dist, uint32_t n, int lo_bits) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t hi = key[i] >> lo_bits;
+  if (i > 0 && (key[i - 1] >> lo_bits) == hi) return;  // inside a run: its head handles it
+  uint32_t e = i + 1;
+  while (e < n && (key[e] >> lo_bits) == hi) ++e;
+  for (uint32_t x = i + 1; x < e; ++x) {  // insertion sort of [i, e) by the full key
+    const uint64_t kk = key[x];
+    const float dd = dist[x];
+    uint32_t y = x;
+    while (y > i && key[y - 1] > kk) {
+      key[y] = key[y - 1];
+      dist[y] = dist[y - 1];
+      --y;
+    }
+    key[y] = kk;
+    dist[y] = dd;
+  }
+}
+
 constexpr int kBand = 5000;        // chaining_band_length, spatial_index.cc:286
 constexpr int kMaxTargetGap = 5000;
 constexpr int kMaxGap = 2000;
@@ -114,39 +140,79 @@ __device__ __forceinline__ float distance_coefficient(float dist, double radius)
   return (float)__dsub_rn(1.0, __ddiv_rn(__dmul_rn(0.2, (double)dist), radius));
 }
 
+constexpr int kPrepHalo = 128;  // predecessors staged in shared memory ahead of the tile
+
 __global__ void __launch_bounds__(kPrepTile) k_chain_prep(ChainArgs a) {
+  // the tile's anchors and the kPrepHalo before it, unpacked: segment id, target, query
+  __shared__ uint32_t s_seg[kPrepHalo + kPrepTile];
+  __shared__ int32_t s_t[kPrepHalo + kPrepTile];
+  __shared__ int32_t s_q[kPrepHalo + kPrepTile];
   __shared__ uint32_t warp_base[kPrepTile / 32];
-  const long long n = (long long)a.n;
-  const long long i = (long long)blockIdx.x * kPrepTile + threadIdx.x;
+  const uint32_t n = (uint32_t)a.n;  // < 2^31
+  const uint32_t tile0 = blockIdx.x * kPrepTile;
+  const uint32_t i = tile0 + threadIdx.x;
   const KeyLayout kl = a.kl;
+  for (int x = threadIdx.x; x < kPrepHalo + kPrepTile; x += kPrepTile) {
+    const long long g = (long long)tile0 - kPrepHalo + x;
+    uint32_t sg = 0xFFFFFFFFu;
+    int32_t t = 0, q = 0;
+    if (g >= 0 && g < (long long)n) {
+      const uint64_t k = a.key[g];
+      sg = (uint32_t)kl.seg(k);
+      t = (int32_t)kl.target(k);
+      q = (int32_t)kl.query(k);
+    }
+    s_seg[x] = sg;
+    s_t[x] = t;
+    s_q[x] = q;
+  }
+  __syncthreads();
   bool linked = false;
   if (i < n) {
-    const uint64_t k = a.key[i];
-    const uint64_t sg = kl.seg(k);
-    const uint64_t kp = i > 0 ? a.key[i - 1] : 0ull;
+    const int me = kPrepHalo + threadIdx.x;
+    const uint32_t sg = s_seg[me];
+    const int32_t ti = s_t[me], qi = s_q[me];
     if (sg < a.n_slots) {
-      if (i == 0 || kl.seg(kp) != sg) {
-        a.seg[sg].start = (uint32_t)i;
-        if (i > 0 && kl.seg(kp) < a.n_slots) a.seg[kl.seg(kp)].end = (uint32_t)i;
+      const uint32_t sp = s_seg[me - 1];  // 0xFFFFFFFF before the first anchor
+      if (i == 0 || sp != sg) {
+        a.seg[sg].start = i;
+        if (i > 0 && sp < a.n_slots) a.seg[sp].end = i;
       }
-      if (i == n - 1) a.seg[sg].end = (uint32_t)n;
+      if (i == n - 1) a.seg[sg].end = n;
+    }
+    // position-only link test over the maximal lookback range
+    const int depth = (int)min(i, (uint32_t)kBand);
+    const int in_smem = min(depth, kPrepHalo);
+    int d = 1;
+    bool open = true;  // the range continues past what has been looked at
+    for (; d <= in_smem; ++d) {
+      const int x = me - d;
+      const int32_t pt = s_t[x];
+      if (s_seg[x] != sg || pt + kMaxTargetGap < ti) {
+        open = false;
+        break;
+      }
+      if (gap_compatible(ti - pt, qi - s_q[x])) {
+        linked = true;
+        open = false;
+        break;
+      }
+    }
+    if (open) {  // rare: deeper than the staged halo
+      for (; d <= depth; ++d) {
+        const uint64_t kj = a.key[i - d];
+        const int32_t pt = (int32_t)kl.target(kj);
+        if ((uint32_t)kl.seg(kj) != sg || pt + kMaxTargetGap < ti) break;
+        if (gap_compatible(ti - pt, qi - (int32_t)kl.query(kj))) {
+          linked = true;
+          break;
+        }
+      }
     }
     const float ci = distance_coefficient(a.dist[i], (double)a.radius);
     a.coef[i] = ci;
     a.score[i] = __fmul_rn(ci, (float)kDim);
-    a.pred[i] = (uint32_t)i;
-    const int32_t ti = (int32_t)kl.target(k), qi = (int32_t)kl.query(k);
-    const long long lo = i > kBand ? i - kBand : 0;
-    for (long long j = i - 1; j >= lo; --j) {
-      const uint64_t kj = a.key[j];
-      if (kl.seg(kj) != sg) break;
-      const int32_t pt = (int32_t)kl.target(kj);
-      if (pt + kMaxTargetGap < ti) break;
-      if (gap_compatible(ti - pt, qi - (int32_t)kl.query(kj))) {
-        linked = true;
-        break;
-      }
-    }
+    a.pred[i] = i;
   }
   // ordered compaction of the tile's linked anchors
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -161,10 +227,11 @@ __global__ void __launch_bounds__(kPrepTile) k_chain_prep(ChainArgs a) {
       acc += t;
     }
     a.link_count[blockIdx.x] = acc;
+    if (acc) atomicAdd(&a.ctr->n_linked, (unsigned long long)acc);
   }
   __syncthreads();
   if (linked)
-    a.link_list[(size_t)blockIdx.x * kPrepTile + warp_base[wid] + __popc(m & ((1u << lane) - 1u))] = (uint32_t)i;
+    a.link_list[(size_t)blockIdx.x * kPrepTile + warp_base[wid] + __popc(m & ((1u << lane) - 1u))] = i;
 }
 
 constexpr int kDpThreads = 128;

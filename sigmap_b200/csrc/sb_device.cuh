@@ -117,6 +117,7 @@ struct Counters {
   unsigned long long n_capped;
   unsigned long long n_events_raw;
   unsigned long long n_events_kept;
+  unsigned long long n_linked;      // anchors with a gap-compatible predecessor (k_chain_prep)
   unsigned long long carry_anchor_used[2];
   unsigned long long carry_chain_used[2];
   unsigned int n_segments;

@@ -46,6 +46,7 @@ __global__ void k_reset_step(Counters *c) {
   c->n_capped = 0;
   c->n_events_raw = 0;
   c->n_events_kept = 0;
+  c->n_linked = 0;
   c->n_segments = 0;
   c->work = 0;
 }
@@ -534,13 +535,16 @@ static int run_step(smb_ctx *ctx, SlotSpace &sp, const StepEntries &en, StepSour
   const uint64_t *keys = w.key_a.p;
   const float *dists = w.dist_a.p;
   if (n > 1) {
+    // radix sort on (entry, bucket, target) only; k_fix_ties orders equal-target runs by query
     size_t tb = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, tb, w.key_a.p, w.key_b.p, w.dist_a.p, w.dist_b.p,
-                                    (uint64_t)n, 0, kl.total(), s);
+                                    (uint64_t)n, kl.qbits, kl.total(), s);
     CK(w.cub_temp.ensure(tb));
     CK(cub::DeviceRadixSort::SortPairs(w.cub_temp.p, tb, w.key_a.p, w.key_b.p, w.dist_a.p, w.dist_b.p,
-                                       (uint64_t)n, 0, kl.total(), s));
-    ctx->stats.launches += 2 + (kl.total() + 7) / 8;
+                                       (uint64_t)n, kl.qbits, kl.total(), s));
+    ctx->stats.launches += 2 + (kl.total() - kl.qbits + 7) / 8;
+    k_fix_ties<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(w.key_b.p, w.dist_b.p, (uint32_t)n, kl.qbits);
+    LAUNCH_CHECK();
     keys = w.key_b.p;
     dists = w.dist_b.p;
   }
@@ -607,6 +611,7 @@ static int run_step(smb_ctx *ctx, SlotSpace &sp, const StepEntries &en, StepSour
   ctx->stats.ms_sort += ms;
   cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]);
   ctx->stats.ms_chain += ms;
+  ctx->stats.linked += ctx->h_ctr->n_linked;
   if (ctx->h_ctr->error & 2u) return fail(ctx, SMB_ERR_CAPACITY, "carry pool overflow");
   if (ctx->h_ctr->error & 4u) return fail(ctx, SMB_ERR_CAPACITY, "per-read chain scratch overflow");
   if (Bpres) ctx->est_anchors_per_chunk = 0.5 * ctx->est_anchors_per_chunk + 0.5 * ((double)n / Bpres);
