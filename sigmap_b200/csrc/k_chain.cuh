@@ -37,7 +37,7 @@ struct SegRec {
   uint32_t top_i[3];
 };
 constexpr uint32_t kSegEmpty = 0xFFFFFFFFu;
-constexpr int kPrepTile = 256;  // anchors per k_chain_prep block = per compacted work list tile
+constexpr int kPrepTile = 1024;  // anchors per k_chain_prep block = per compacted work list tile
 
 struct ChainArgs {
   const uint64_t *key;   // sorted
@@ -140,19 +140,21 @@ __device__ __forceinline__ float distance_coefficient(float dist, double radius)
   return (float)__dsub_rn(1.0, __ddiv_rn(__dmul_rn(0.2, (double)dist), radius));
 }
 
-constexpr int kPrepHalo = 128;  // predecessors staged in shared memory ahead of the tile
+constexpr int kPrepHalo = 128;     // predecessors staged in shared memory ahead of the tile
+constexpr int kPrepThreads = 256;  // kPrepTile / kPrepThreads anchors per thread
+constexpr uint32_t kPending = 0x40000000u;  // pred[] bit: linked anchor not yet settled by the DP
 
-__global__ void __launch_bounds__(kPrepTile) k_chain_prep(ChainArgs a) {
+__global__ void __launch_bounds__(kPrepThreads) k_chain_prep(ChainArgs a) {
   // the tile's anchors and the kPrepHalo before it, unpacked: segment id, target, query
   __shared__ uint32_t s_seg[kPrepHalo + kPrepTile];
   __shared__ int32_t s_t[kPrepHalo + kPrepTile];
   __shared__ int32_t s_q[kPrepHalo + kPrepTile];
-  __shared__ uint32_t warp_base[kPrepTile / 32];
-  const uint32_t n = (uint32_t)a.n;  // < 2^31
+  __shared__ uint32_t warp_base[kPrepThreads / 32];
+  __shared__ uint32_t tile_count;
+  const uint32_t n = (uint32_t)a.n;  // < 2^30
   const uint32_t tile0 = blockIdx.x * kPrepTile;
-  const uint32_t i = tile0 + threadIdx.x;
   const KeyLayout kl = a.kl;
-  for (int x = threadIdx.x; x < kPrepHalo + kPrepTile; x += kPrepTile) {
+  for (int x = threadIdx.x; x < kPrepHalo + kPrepTile; x += kPrepThreads) {
     const long long g = (long long)tile0 - kPrepHalo + x;
     uint32_t sg = 0xFFFFFFFFu;
     int32_t t = 0, q = 0;
@@ -166,96 +168,108 @@ __global__ void __launch_bounds__(kPrepTile) k_chain_prep(ChainArgs a) {
     s_t[x] = t;
     s_q[x] = q;
   }
+  if (threadIdx.x == 0) tile_count = 0;
   __syncthreads();
-  bool linked = false;
-  if (i < n) {
-    const int me = kPrepHalo + threadIdx.x;
-    const uint32_t sg = s_seg[me];
-    const int32_t ti = s_t[me], qi = s_q[me];
-    if (sg < a.n_slots) {
-      const uint32_t sp = s_seg[me - 1];  // 0xFFFFFFFF before the first anchor
-      if (i == 0 || sp != sg) {
-        a.seg[sg].start = i;
-        if (i > 0 && sp < a.n_slots) a.seg[sp].end = i;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int sub = 0; sub < kPrepTile / kPrepThreads; ++sub) {
+    const int local = sub * kPrepThreads + threadIdx.x;
+    const uint32_t i = tile0 + local;
+    bool linked = false;
+    if (i < n) {
+      const int me = kPrepHalo + local;
+      const uint32_t sg = s_seg[me];
+      const int32_t ti = s_t[me], qi = s_q[me];
+      if (sg < a.n_slots) {
+        const uint32_t sp = s_seg[me - 1];  // 0xFFFFFFFF before the first anchor
+        if (i == 0 || sp != sg) {
+          a.seg[sg].start = i;
+          if (i > 0 && sp < a.n_slots) a.seg[sp].end = i;
+        }
+        if (i == n - 1) a.seg[sg].end = n;
       }
-      if (i == n - 1) a.seg[sg].end = n;
-    }
-    // position-only link test over the maximal lookback range
-    const int depth = (int)min(i, (uint32_t)kBand);
-    const int in_smem = min(depth, kPrepHalo);
-    int d = 1;
-    bool open = true;  // the range continues past what has been looked at
-    for (; d <= in_smem; ++d) {
-      const int x = me - d;
-      const int32_t pt = s_t[x];
-      if (s_seg[x] != sg || pt + kMaxTargetGap < ti) {
-        open = false;
-        break;
-      }
-      if (gap_compatible(ti - pt, qi - s_q[x])) {
-        linked = true;
-        open = false;
-        break;
-      }
-    }
-    if (open) {  // rare: deeper than the staged halo
-      for (; d <= depth; ++d) {
-        const uint64_t kj = a.key[i - d];
-        const int32_t pt = (int32_t)kl.target(kj);
-        if ((uint32_t)kl.seg(kj) != sg || pt + kMaxTargetGap < ti) break;
-        if (gap_compatible(ti - pt, qi - (int32_t)kl.query(kj))) {
+      // position-only link test over the maximal lookback range
+      const int depth = (int)min(i, (uint32_t)kBand);
+      const int in_smem = min(depth, me);
+      int d = 1;
+      bool open = true;  // the range continues past what has been looked at
+      for (; d <= in_smem; ++d) {
+        const int x = me - d;
+        const int32_t pt = s_t[x];
+        if (s_seg[x] != sg || pt + kMaxTargetGap < ti) {
+          open = false;
+          break;
+        }
+        if (gap_compatible(ti - pt, qi - s_q[x])) {
           linked = true;
+          open = false;
           break;
         }
       }
+      if (open) {  // rare: deeper than what is staged
+        for (; d <= depth; ++d) {
+          const uint64_t kj = a.key[i - d];
+          const int32_t pt = (int32_t)kl.target(kj);
+          if ((uint32_t)kl.seg(kj) != sg || pt + kMaxTargetGap < ti) break;
+          if (gap_compatible(ti - pt, qi - (int32_t)kl.query(kj))) {
+            linked = true;
+            break;
+          }
+        }
+      }
+      const float ci = distance_coefficient(a.dist[i], (double)a.radius);
+      a.coef[i] = ci;
+      a.score[i] = __fmul_rn(ci, (float)kDim);
+      a.pred[i] = linked ? (i | kPending) : i;
     }
-    const float ci = distance_coefficient(a.dist[i], (double)a.radius);
-    a.coef[i] = ci;
-    a.score[i] = __fmul_rn(ci, (float)kDim);
-    a.pred[i] = i;
+    // ordered compaction of the linked anchors (sub-tiles are consecutive index ranges)
+    const unsigned m = __ballot_sync(0xffffffffu, linked);
+    if (lane == 0) warp_base[wid] = __popc(m);
+    __syncthreads();
+    const uint32_t base = tile_count;
+    uint32_t before = 0, total = 0;
+    for (int w = 0; w < kPrepThreads / 32; ++w) {
+      const uint32_t t = warp_base[w];
+      if (w < wid) before += t;
+      total += t;
+    }
+    if (linked)
+      a.link_list[(size_t)blockIdx.x * kPrepTile + base + before + __popc(m & ((1u << lane) - 1u))] = i;
+    __syncthreads();
+    if (threadIdx.x == 0) tile_count = base + total;
   }
-  // ordered compaction of the tile's linked anchors
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const unsigned m = __ballot_sync(0xffffffffu, linked);
-  if (lane == 0) warp_base[wid] = __popc(m);
   __syncthreads();
   if (threadIdx.x == 0) {
-    uint32_t acc = 0;
-    for (int w = 0; w < kPrepTile / 32; ++w) {
-      const uint32_t t = warp_base[w];
-      warp_base[w] = acc;
-      acc += t;
-    }
-    a.link_count[blockIdx.x] = acc;
-    if (acc) atomicAdd(&a.ctr->n_linked, (unsigned long long)acc);
+    a.link_count[blockIdx.x] = tile_count;
+    if (tile_count) atomicAdd(&a.ctr->n_linked, (unsigned long long)tile_count);
   }
-  __syncthreads();
-  if (linked)
-    a.link_list[(size_t)blockIdx.x * kPrepTile + warp_base[wid] + __popc(m & ((1u << lane) - 1u))] = i;
 }
 
 constexpr int kDpThreads = 128;
+constexpr int kDpFreePasses = 2;  // thread-parallel passes before the in-order cooperative path
 
-// A group of W lanes owns a segment.  For each linked anchor the lanes load W consecutive
-// predecessors in one coalesced access, every lane scores one of them, and the reference's
-// sequential lookback is resolved with one prefix-max scan and three ballots; deeper lookbacks
-// take further blocks of W.
-template <int W>
+// A warp owns a segment and takes its linked anchors 32 at a time, one per lane.
+//  * Thread-parallel passes: every lane runs the reference's lookback for its own anchor.  An
+//    anchor's score only depends on the scores of its gap-compatible predecessors; if one of
+//    them is still pending (a linked anchor earlier in the same 32) the lane defers, otherwise
+//    its result is final.  Background hits form chains of 2-3 anchors, so two passes settle
+//    almost everything.
+//  * What is still pending after that (true-locus clusters, where every anchor links to the
+//    previous one) is settled in order by the whole warp: lanes load 32 consecutive predecessors
+//    coalesced, score one each, and the sequential rules (continue/break, running best, +-1 skip
+//    counter with its > 25 break) are resolved with a prefix-max scan and ballots.
 __global__ void __launch_bounds__(kDpThreads) k_chain_dp(ChainArgs a) {
   const int lane = threadIdx.x & 31;
-  const int gl = lane & (W - 1);
-  const int gshift = lane & ~(W - 1);
-  const unsigned wmask = (W == 32) ? 0xffffffffu : ((1u << W) - 1u);
-  const unsigned gmask = wmask << gshift;
-  const unsigned le = (2u << gl) - 1u;  // lanes 0..gl of the group
-  const uint32_t slot = (blockIdx.x * kDpThreads + threadIdx.x) / W;
+  const unsigned full = 0xffffffffu;
+  const unsigned le = (2u << lane) - 1u;  // lanes 0..lane
+  const uint32_t slot = (blockIdx.x * kDpThreads + threadIdx.x) / 32;
   if (slot >= a.n_slots) return;
   SegRec r = a.seg[slot];
   if (r.start == kSegEmpty) return;
-  const long long s = r.start, e = r.end;
+  const uint32_t s = r.start, e = r.end;
   const KeyLayout kl = a.kl;
   const uint64_t *key = a.key;
   float *score = a.score;
+  uint32_t *pred = a.pred;
 
   // max over the linked anchors only: the others score <= 6, and every comparison this max
   // feeds has a candidate score >= min_chaining_score = 10 on the other side (:545-567)
@@ -264,86 +278,157 @@ __global__ void __launch_bounds__(kDpThreads) k_chain_dp(ChainArgs a) {
   uint32_t ti0 = 0, ti1 = 0, ti2 = 0;
   int ntop = 0;
 
-  for (long long tile = s / kPrepTile; tile * kPrepTile < e; ++tile) {
+  for (uint32_t tile = s / kPrepTile; tile * kPrepTile < e; ++tile) {
     const uint32_t cnt = a.link_count[tile];
-    const uint32_t *list = a.link_list + tile * kPrepTile;
-    for (uint32_t c = 0; c < cnt; ++c) {
-      const long long i = list[c];
-      if (i < s) continue;
-      if (i >= e) break;
-      const uint64_t k = key[i];
-      const int32_t ti = (int32_t)kl.target(k), qi = (int32_t)kl.query(k);
-      float M = score[i];  // 6 * coef from k_chain_prep = chaining_scores[anchor_index]
-      const float ci = a.coef[i];
-      long long best = i;
-      int S = 0;  // num_skips
-      const long long lo = (i - s > kBand) ? i - kBand : s;
-      for (long long jb = i - 1;; jb -= W) {
-        const long long j = jb - gl;
-        // ---- my predecessor: >= 0 candidate score (counted), -1 continue, -2 lookback ends
-        float cd = -2.0f;
-        if (j >= lo) {
-          const uint64_t kj = key[j];
-          const int32_t pt = (int32_t)kl.target(kj), pq = (int32_t)kl.query(kj);
-          const int32_t dt = ti - pt, dq = qi - pq;
-          if (pq == qi || pt == ti) cd = -1.0f;
-          else if (pt + kMaxTargetGap < ti) cd = -2.0f;
-          else if (dq < 0) cd = -1.0f;
-          else if (gap_compatible(dt, dq)) cd = __fadd_rn(score[j], __fmul_rn((float)min(min(dt, dq), kDim), ci));
-          else cd = 0.0f;
-        }
-        // ---- resolve the W predecessors in order (lane 0 = most recent)
-        const bool counted = cd >= 0.0f;
-        const unsigned cntm = (__ballot_sync(gmask, counted) >> gshift) & wmask;
-        unsigned impm = 0u;
-        if (__ballot_sync(gmask, cd > M) & gmask) {
-          float pm = counted ? cd : 0.0f;  // inclusive prefix max of the candidate scores
-#pragma unroll
-          for (int d = 1; d < W; d <<= 1) {
-            const float t = __shfl_up_sync(gmask, pm, d, W);
-            if (gl >= d) pm = fmaxf(pm, t);
+    const uint32_t *list = a.link_list + (size_t)tile * kPrepTile;
+    for (uint32_t c0 = 0; c0 < cnt; c0 += 32) {
+      const uint32_t c = c0 + lane;
+      uint32_t i = c < cnt ? list[c] : 0xFFFFFFFFu;
+      const bool valid = c < cnt && i >= s && i < e;
+      if (!__ballot_sync(full, valid)) continue;
+      int32_t ti = 0, qi = 0;
+      float ci = 0.0f, init = 0.0f, M = 0.0f;
+      uint32_t lo = 0;
+      if (valid) {
+        const uint64_t k = key[i];
+        ti = (int32_t)kl.target(k);
+        qi = (int32_t)kl.query(k);
+        ci = a.coef[i];
+        init = score[i];  // 6 * coef from k_chain_prep = chaining_scores[anchor_index]
+        lo = (i - s > (uint32_t)kBand) ? i - kBand : s;
+      }
+      bool todo = valid;
+      // ---- thread-parallel passes
+      for (int pass = 0; pass < kDpFreePasses; ++pass) {
+        if (todo) {
+          M = init;
+          uint32_t best = i;
+          int S = 0;  // num_skips
+          bool defer = false;
+          for (uint32_t j = i; j-- > lo;) {
+            const uint64_t kj = key[j];
+            const int32_t pt = (int32_t)kl.target(kj), pq = (int32_t)kl.query(kj);
+            if (pq == qi || pt == ti) continue;
+            if (pt + kMaxTargetGap < ti) break;
+            const int32_t dt = ti - pt, dq = qi - pq;
+            if (dq < 0) continue;
+            float cur = 0.0f;
+            if (gap_compatible(dt, dq)) {
+              if (pred[j] & kPending) {
+                defer = true;
+                break;
+              }
+              cur = __fadd_rn(score[j], __fmul_rn((float)min(min(dt, dq), kDim), ci));
+            }
+            if (cur > M) {
+              M = cur;
+              best = j;
+              --S;
+            } else if (++S > kMaxSkips) {
+              break;
+            }
           }
-          float ex = __shfl_up_sync(gmask, pm, 1, W);
-          ex = fmaxf(gl == 0 ? 0.0f : ex, M);
-          impm = (__ballot_sync(gmask, counted && cd > ex) >> gshift) & wmask;
+          if (!defer) {
+            score[i] = M;
+            pred[i] = best;  // clears kPending
+            todo = false;
+          }
         }
-        const int Sl = S + __popc(cntm & ~impm & le) - __popc(impm & le);
-        const bool stop_here = (counted && !((impm >> gl) & 1u) && Sl > kMaxSkips) || cd == -2.0f;
-        const unsigned stopm = (__ballot_sync(gmask, stop_here) >> gshift) & wmask;
-        const unsigned below = stopm ? ((stopm & (0u - stopm)) - 1u) : wmask;
-        const unsigned imp_b = impm & below;
-        if (imp_b) {
-          const int L = 31 - __clz(imp_b);
-          M = __shfl_sync(gmask, cd, L, W);
-          best = jb - L;
+        __syncwarp(full);  // settled scores are visible to the lanes that deferred
+        if (!__ballot_sync(full, todo)) break;
+      }
+      // ---- what is left, in order, by the whole warp
+      unsigned left = __ballot_sync(full, todo);
+      while (left) {
+        const int src = __ffs(left) - 1;
+        left &= left - 1;
+        const uint32_t ii = __shfl_sync(full, i, src);
+        const int32_t tii = __shfl_sync(full, ti, src), qii = __shfl_sync(full, qi, src);
+        const float cii = __shfl_sync(full, ci, src);
+        const uint32_t loi = __shfl_sync(full, lo, src);
+        float Mi = __shfl_sync(full, init, src);
+        uint32_t best = ii;
+        int S = 0;
+        for (uint32_t jb = ii;; jb -= 32) {  // block of predecessors jb-1 .. jb-32
+          // ---- my predecessor: >= 0 candidate score (counted), -1 continue, -2 lookback ends
+          float cd = -2.0f;
+          if (jb >= loi + 1u + (uint32_t)lane) {
+            const uint32_t j = jb - 1u - (uint32_t)lane;
+            const uint64_t kj = key[j];
+            const int32_t pt = (int32_t)kl.target(kj), pq = (int32_t)kl.query(kj);
+            const int32_t dt = tii - pt, dq = qii - pq;
+            if (pq == qii || pt == tii) cd = -1.0f;
+            else if (pt + kMaxTargetGap < tii) cd = -2.0f;
+            else if (dq < 0) cd = -1.0f;
+            else if (gap_compatible(dt, dq)) cd = __fadd_rn(score[j], __fmul_rn((float)min(min(dt, dq), kDim), cii));
+            else cd = 0.0f;
+          }
+          // ---- resolve the 32 predecessors in order (lane 0 = most recent)
+          const bool counted = cd >= 0.0f;
+          const unsigned cntm = __ballot_sync(full, counted);
+          unsigned impm = 0u;
+          if (__ballot_sync(full, cd > Mi)) {
+            float pm = counted ? cd : 0.0f;  // inclusive prefix max of the candidate scores
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+              const float t = __shfl_up_sync(full, pm, d);
+              if (lane >= d) pm = fmaxf(pm, t);
+            }
+            float ex = __shfl_up_sync(full, pm, 1);
+            ex = fmaxf(lane == 0 ? 0.0f : ex, Mi);
+            impm = __ballot_sync(full, counted && cd > ex);
+          }
+          const int Sl = S + __popc(cntm & ~impm & le) - __popc(impm & le);
+          const bool stop_here = (counted && !((impm >> lane) & 1u) && Sl > kMaxSkips) || cd == -2.0f;
+          const unsigned stopm = __ballot_sync(full, stop_here);
+          const unsigned below = stopm ? ((stopm & (0u - stopm)) - 1u) : full;
+          const unsigned imp_b = impm & below;
+          if (imp_b) {
+            const int L = 31 - __clz(imp_b);
+            Mi = __shfl_sync(full, cd, L);
+            best = jb - 1u - (uint32_t)L;
+          }
+          if (stopm) break;
+          S += __popc(cntm & ~impm) - __popc(impm);
         }
-        if (stopm) break;
-        S += __popc(cntm & ~impm) - __popc(impm);
+        if (lane == src) {
+          M = Mi;
+          score[ii] = Mi;
+          pred[ii] = best;
+        }
+        __syncwarp(full);  // visible to the later anchors of this batch
       }
-      if (gl == 0) {
-        score[i] = M;
-        a.pred[i] = (uint32_t)best;
+      // ---- running max and local end candidates (spatial_index.cc:542-549), lanes in order;
+      // the caller applies the max of the earlier buckets, which only shortens this list.
+      // Order: score desc, index desc (compare(), :11-20); a tie puts the later anchor first.
+      float pm = valid ? M : 0.0f;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const float t = __shfl_up_sync(full, pm, d);
+        if (lane >= d) pm = fmaxf(pm, t);
       }
-      __syncwarp(gmask);  // the score is visible to the group's later lookbacks
-      // ---- running max and local end candidates (spatial_index.cc:542-549); the caller
-      // applies the max of the earlier buckets, which only shortens this list.  Order: score
-      // desc, index desc (compare(), :11-20); i only grows, so a tie puts the newcomer first.
-      if (M > runmax) runmax = M;
-      if (M >= 10.0f && M > __fdiv_rn(runmax, 2.0f)) {
-        if (ntop < 1 || M >= ts0) {
-          ts2 = ts1; ti2 = ti1; ts1 = ts0; ti1 = ti0; ts0 = M; ti0 = (uint32_t)i;
+      pm = fmaxf(pm, runmax);
+      unsigned candm = __ballot_sync(full, valid && M >= 10.0f && M > __fdiv_rn(pm, 2.0f));
+      runmax = __shfl_sync(full, pm, 31);
+      while (candm) {
+        const int l = __ffs(candm) - 1;
+        candm &= candm - 1;
+        const float Ml = __shfl_sync(full, M, l);
+        const uint32_t il = __shfl_sync(full, i, l);
+        if (ntop < 1 || Ml >= ts0) {
+          ts2 = ts1; ti2 = ti1; ts1 = ts0; ti1 = ti0; ts0 = Ml; ti0 = il;
           if (ntop < 3) ++ntop;
-        } else if (ntop < 2 || M >= ts1) {
-          ts2 = ts1; ti2 = ti1; ts1 = M; ti1 = (uint32_t)i;
+        } else if (ntop < 2 || Ml >= ts1) {
+          ts2 = ts1; ti2 = ti1; ts1 = Ml; ti1 = il;
           if (ntop < 3) ++ntop;
-        } else if (ntop < 3 || M >= ts2) {
-          ts2 = M; ti2 = (uint32_t)i;
+        } else if (ntop < 3 || Ml >= ts2) {
+          ts2 = Ml; ti2 = il;
           if (ntop < 3) ++ntop;
         }
       }
     }
   }
-  if (gl == 0) {
+  if (lane == 0) {
     r.ntop = (uint32_t)ntop;
     r.max = runmax;
     r.top_s[0] = ts0; r.top_s[1] = ts1; r.top_s[2] = ts2;

@@ -221,7 +221,6 @@ struct smb_ctx {
   uint64_t max_batch_anchors = 640ull << 20;  // x 32 B of sort/DP buffers = 20 GB of the 180 GB HBM
   uint64_t last_cap = 0;
   double est_anchors_per_chunk = 20000.0;
-  unsigned dp_width = 32;  // k_chain_dp lanes per segment (8/16/32); SMB_DP_WIDTH overrides (tuning)
   // streaming
   SlotSpace *stream_slots = nullptr;
   smb_params stream_params{};
@@ -419,7 +418,7 @@ static int run_step(smb_ctx *ctx, SlotSpace &sp, const StepEntries &en, StepSour
   kl.bbits = bits_for(ctx->max_bucket);
   kl.ebits = bits_for(B - 1);
   if (kl.total() > 64) return fail(ctx, SMB_ERR_CAPACITY, "sort key exceeds 64 bits: lower max_batch_chunks");
-  if (ctx->max_batch_anchors >= (1ull << 31)) return fail(ctx, SMB_ERR_ARG, "max_batch_anchors must stay below 2^31");
+  if (ctx->max_batch_anchors >= (1ull << 30)) return fail(ctx, SMB_ERR_ARG, "max_batch_anchors must stay below 2^30");
   // anchor buffers sized from the running estimate (they grow on overflow, up to the limit)
   const uint64_t cap = std::min<uint64_t>(
       ctx->max_batch_anchors,
@@ -573,13 +572,9 @@ static int run_step(smb_ctx *ctx, SlotSpace &sp, const StepEntries &en, StepSour
     CK(w.link_count.ensure(n_tiles));
     ca.link_list = w.link_list.p;
     ca.link_count = w.link_count.p;
-    k_chain_prep<<<n_tiles, kPrepTile, 0, s>>>(ca);
+    k_chain_prep<<<n_tiles, kPrepThreads, 0, s>>>(ca);
     LAUNCH_CHECK();
-    const unsigned dp_w = ctx->dp_width;  // lanes per segment
-    const unsigned dp_grid = (unsigned)(((uint64_t)ca.n_slots * dp_w + kDpThreads - 1) / kDpThreads);
-    if (dp_w == 8) k_chain_dp<8><<<dp_grid, kDpThreads, 0, s>>>(ca);
-    else if (dp_w == 16) k_chain_dp<16><<<dp_grid, kDpThreads, 0, s>>>(ca);
-    else k_chain_dp<32><<<dp_grid, kDpThreads, 0, s>>>(ca);
+    k_chain_dp<<<(unsigned)(((uint64_t)ca.n_slots * 32 + kDpThreads - 1) / kDpThreads), kDpThreads, 0, s>>>(ca);
     LAUNCH_CHECK();
   }
   SelectArgs se{};
@@ -807,10 +802,6 @@ int smb_create(smb_ctx **out, int device) {
   }
   smb_ctx *ctx = new smb_ctx();
   ctx->device = device;
-  if (const char *e = getenv("SMB_DP_WIDTH")) {
-    const int wv = atoi(e);
-    if (wv == 8 || wv == 16 || wv == 32) ctx->dp_width = (unsigned)wv;
-  }
   auto bail = [&](const char *what, cudaError_t err) {
     g_create_error = std::string(what) + ": " + cudaGetErrorString(err);
     delete ctx;
@@ -886,7 +877,7 @@ int smb_timer_stop(smb_ctx *ctx, double *ms) {
 int smb_set_limits(smb_ctx *ctx, uint32_t max_batch_chunks, uint64_t max_batch_anchors) {
   if (max_batch_chunks) ctx->max_batch_chunks = max_batch_chunks;
   if (max_batch_anchors) {
-    if (max_batch_anchors >= (1ull << 31)) return fail(ctx, SMB_ERR_ARG, "max_batch_anchors must be < 2^31");
+    if (max_batch_anchors >= (1ull << 30)) return fail(ctx, SMB_ERR_ARG, "max_batch_anchors must be < 2^30");
     ctx->max_batch_anchors = max_batch_anchors;
   }
   return SMB_OK;
