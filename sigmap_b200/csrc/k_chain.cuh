@@ -145,10 +145,8 @@ constexpr int kPrepThreads = 256;  // kPrepTile / kPrepThreads anchors per threa
 constexpr uint32_t kPending = 0x40000000u;  // pred[] bit: linked anchor not yet settled by the DP
 
 __global__ void __launch_bounds__(kPrepThreads) k_chain_prep(ChainArgs a) {
-  // the tile's anchors and the kPrepHalo before it, unpacked: segment id, target, query
-  __shared__ uint32_t s_seg[kPrepHalo + kPrepTile];
-  __shared__ int32_t s_t[kPrepHalo + kPrepTile];
-  __shared__ int32_t s_q[kPrepHalo + kPrepTile];
+  // the tile's anchors and the kPrepHalo before it, unpacked: {segment id, target, query, -}
+  __shared__ int4 s_a[kPrepHalo + kPrepTile];
   __shared__ uint32_t warp_base[kPrepThreads / 32];
   __shared__ uint32_t tile_count;
   const uint32_t n = (uint32_t)a.n;  // < 2^30
@@ -156,17 +154,14 @@ __global__ void __launch_bounds__(kPrepThreads) k_chain_prep(ChainArgs a) {
   const KeyLayout kl = a.kl;
   for (int x = threadIdx.x; x < kPrepHalo + kPrepTile; x += kPrepThreads) {
     const long long g = (long long)tile0 - kPrepHalo + x;
-    uint32_t sg = 0xFFFFFFFFu;
-    int32_t t = 0, q = 0;
+    int4 v = make_int4(-1, 0, 0, 0);
     if (g >= 0 && g < (long long)n) {
       const uint64_t k = a.key[g];
-      sg = (uint32_t)kl.seg(k);
-      t = (int32_t)kl.target(k);
-      q = (int32_t)kl.query(k);
+      v.x = (int)(uint32_t)kl.seg(k);
+      v.y = (int32_t)kl.target(k);
+      v.z = (int32_t)kl.query(k);
     }
-    s_seg[x] = sg;
-    s_t[x] = t;
-    s_q[x] = q;
+    s_a[x] = v;
   }
   if (threadIdx.x == 0) tile_count = 0;
   __syncthreads();
@@ -177,10 +172,11 @@ __global__ void __launch_bounds__(kPrepThreads) k_chain_prep(ChainArgs a) {
     bool linked = false;
     if (i < n) {
       const int me = kPrepHalo + local;
-      const uint32_t sg = s_seg[me];
-      const int32_t ti = s_t[me], qi = s_q[me];
+      const int4 mine = s_a[me];
+      const uint32_t sg = (uint32_t)mine.x;
+      const int32_t ti = mine.y, qi = mine.z;
       if (sg < a.n_slots) {
-        const uint32_t sp = s_seg[me - 1];  // 0xFFFFFFFF before the first anchor
+        const uint32_t sp = (uint32_t)s_a[me - 1].x;  // 0xFFFFFFFF before the first anchor
         if (i == 0 || sp != sg) {
           a.seg[sg].start = i;
           if (i > 0 && sp < a.n_slots) a.seg[sp].end = i;
@@ -193,13 +189,12 @@ __global__ void __launch_bounds__(kPrepThreads) k_chain_prep(ChainArgs a) {
       int d = 1;
       bool open = true;  // the range continues past what has been looked at
       for (; d <= in_smem; ++d) {
-        const int x = me - d;
-        const int32_t pt = s_t[x];
-        if (s_seg[x] != sg || pt + kMaxTargetGap < ti) {
+        const int4 p = s_a[me - d];
+        if (p.x != mine.x || p.y + kMaxTargetGap < ti) {
           open = false;
           break;
         }
-        if (gap_compatible(ti - pt, qi - s_q[x])) {
+        if (gap_compatible(ti - p.y, qi - p.z)) {
           linked = true;
           open = false;
           break;

@@ -242,12 +242,14 @@ k_radius_search(const IndexView ix, const SearchArgs a) {
         const uint32_t group = top & 0x07FFFFFFu;
         // ---- every lane tests one child box of (level, group)
         const float *g = ix.level_box[level] + (size_t)group * 12 * kFan + lane;
+        // boxes only prune (with slack), so this distance may use FMA; the accept test below
+        // may not
         float s = 0.0f;
 #pragma unroll
         for (int d = 0; d < kDim; ++d) {
           const float lo = __ldg(g + d * kFan), hi = __ldg(g + (kDim + d) * kFan);
           const float dd = fmaxf(fmaxf(lo - q[d], q[d] - hi), 0.0f);
-          s += dd * dd;
+          s = __fmaf_rn(dd, dd, s);
         }
         uint32_t mask = __ballot_sync(0xffffffffu, s <= r2_prune);
         if (level > 0) {
