@@ -101,6 +101,8 @@ typedef struct smb_stats {
   uint64_t h2d_bytes, d2h_bytes;
   uint64_t linked;         /* anchors the chaining DP had to walk sequentially (have a
                               gap-compatible predecessor); the rest are settled in parallel */
+  uint64_t seg_sort_steps; /* steps whose anchors were sorted per entry in shared memory
+                              (the others fell back to the global radix sort) */
 } smb_stats;
 
 /* ------------------------------------------------------------------ context */

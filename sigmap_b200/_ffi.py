@@ -110,6 +110,7 @@ class Stats(C.Structure):
         ("h2d_bytes", C.c_uint64),
         ("d2h_bytes", C.c_uint64),
         ("linked", C.c_uint64),
+        ("seg_sort_steps", C.c_uint64),
     ]
 
 

@@ -59,7 +59,9 @@ __global__ void k_inject_carry(const uint32_t *__restrict__ entry_slot, const ui
                                const SlotState *__restrict__ slots, const CarryAnchor *__restrict__ pool0,
                                const CarryAnchor *__restrict__ pool1, uint32_t B, KeyLayout kl,
                                uint64_t *__restrict__ out_key, float *__restrict__ out_dist,
-                               unsigned long long cap, Counters *__restrict__ ctr) {
+                               unsigned long long cap, Counters *__restrict__ ctr, RunRec *__restrict__ runs,
+                               uint32_t *__restrict__ run_count, uint32_t *__restrict__ entry_total,
+                               uint32_t runs_cap) {
   const uint32_t b = (blockIdx.x * blockDim.x + threadIdx.x) / 32, lane = threadIdx.x & 31;
   if (b >= B) return;
   if (n_queries[b] == 0) return;  // GenerateChains is not called for this entry
@@ -67,7 +69,16 @@ __global__ void k_inject_carry(const uint32_t *__restrict__ entry_slot, const ui
   if (st.carry_n == 0) return;
   const CarryAnchor *src = (st.pool ? pool1 : pool0) + st.carry_off;
   unsigned long long base = 0;
-  if (lane == 0) base = atomicAdd(&ctr->n_anchors, (unsigned long long)st.carry_n);
+  if (lane == 0) {
+    base = atomicAdd(&ctr->n_anchors, (unsigned long long)st.carry_n);
+    if (runs) {  // the carried anchors are one run of this entry (k_sort.cuh)
+      const uint32_t r = atomicAdd(&run_count[b], 1u);
+      if (r < runs_cap) runs[(size_t)b * runs_cap + r] = RunRec{(uint32_t)base, st.carry_n};
+      else atomicOr(&ctr->error, 8u);
+      const uint32_t t = atomicAdd(&entry_total[b], st.carry_n) + st.carry_n;
+      atomicMax(&ctr->max_entry_anchors, t);
+    }
+  }
   base = __shfl_sync(0xffffffffu, base, 0);
   for (uint32_t i = lane; i < st.carry_n; i += 32) {
     const CarryAnchor c = src[i];

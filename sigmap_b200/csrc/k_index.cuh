@@ -3,17 +3,19 @@
 //
 // Layout (see IndexView in sb_device.cuh): the N-5 window points value[w..w+5]
 // (sigmap_adaptor.h:89-97) are sorted by a 60-bit Morton code (6 dims x 10 bits) and cut into
-// 32-point leaf blocks stored SoA ([block][dim][lane]) so a warp evaluates one block with six
-// coalesced 128-byte loads; axis-aligned boxes of 32 consecutive blocks / boxes form a
-// pointer-free fan-out-32 hierarchy.  A query is handled by ONE WARP: it pops (level, group)
-// entries from a small shared-memory stack, every lane tests one child box against the query
-// ball, and the ballot decides what to push / which leaf blocks to evaluate.
+// 8-point leaves; 8 consecutive leaves / nodes form the next level's node, pointer-free.  A
+// query is handled by ONE WARP that advances FOUR tree nodes (or four leaves) per step, one per
+// 8-lane group: every lane tests one child box (three 16-byte loads) or evaluates one point
+// (three 8-byte loads), so each step keeps four independent 128/64-byte-coalesced request
+// groups in flight and the whole warp stays busy at fan-out 8 -- where a 6-D hierarchy prunes
+// far better than at fan-out 32 (the ball of radius 0.28 meets ~30 8-point leaves but ~28
+// 32-point blocks: 4x fewer points to evaluate, 2.5x fewer boxes to test).
 //
 // Exactness: the accept test is the reference's own fp32 expression
 //   d2 = ((e0+e1)+e2)+e3, then +e4, +e5, e_k = (q_k - v_k)^2, accept iff d2 < radius
 // (nanoflann.hpp:383-408, :249-251, :1362; the "radius" is already squared, Q4) without FMA.
-// Boxes only prune, with a relative slack of 1e-4 on the squared radius, so no point the
-// exact test would accept is ever lost.
+// Boxes only prune: half extents are rounded outwards when built and the test keeps a relative
+// slack of 1e-4 on the squared radius, so no point the exact test would accept is ever lost.
 #ifndef SB_K_INDEX_CUH
 #define SB_K_INDEX_CUH
 
@@ -21,7 +23,8 @@
 
 namespace sb {
 
-constexpr float kPadValue = 1.0e18f;  // padding points / boxes: never inside any ball
+constexpr float kPadValue = 1.0e18f;  // padding points: never inside any ball
+constexpr float kPadExtent = -1.0e18f;  // padding boxes: negative half extent, never met
 
 // ------------------------------------------------------------------ build
 __device__ __forceinline__ uint64_t spread10(uint32_t v) {
@@ -51,86 +54,120 @@ __global__ void k_morton(const float *__restrict__ val, uint64_t n_windows, floa
 // sorted rank i -> leaf arrays; one thread per slot of the padded leaf array
 __global__ void k_build_leaves(const float *__restrict__ val, const uint64_t *__restrict__ pos,
                                const uint32_t *__restrict__ order, uint64_t n_windows,
-                               uint32_t n_blocks, float *__restrict__ leaf_vals,
-                               uint32_t *__restrict__ leaf_tpos, uint32_t *__restrict__ leaf_bucket,
-                               uint32_t *__restrict__ leaf_widx) {
+                               uint32_t n_leaves, float2 *__restrict__ leaf_vals,
+                               uint2 *__restrict__ leaf_tb, uint32_t *__restrict__ leaf_widx) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (uint64_t)n_blocks * kLeaf) return;
-  const uint32_t blk = (uint32_t)(i / kLeaf), lane = (uint32_t)(i % kLeaf);
-  float *v = leaf_vals + (size_t)blk * kDim * kLeaf + lane;
+  if (i >= (uint64_t)n_leaves * kLeaf) return;
+  const uint32_t leaf = (uint32_t)(i / kLeaf), sub = (uint32_t)(i % kLeaf);
+  float2 *v = leaf_vals + (size_t)leaf * 3 * kLeaf + sub;
   if (i < n_windows) {
     const uint32_t w = order[i];
 #pragma unroll
-    for (int d = 0; d < kDim; ++d) v[d * kLeaf] = val[(uint64_t)w + d];
+    for (int k = 0; k < 3; ++k) v[k * kLeaf] = make_float2(val[(uint64_t)w + 2 * k], val[(uint64_t)w + 2 * k + 1]);
     const uint64_t P = pos[w];
-    leaf_tpos[i] = (uint32_t)(P >> 1);                              // spatial_index.cc:380-381
-    leaf_bucket[i] = (uint32_t)((P >> 33) << 1) | (uint32_t)(P & 1); // contig*2 + strand
+    // target = pos >> 1 (spatial_index.cc:380-381); bucket = contig*2 + strand
+    leaf_tb[i] = make_uint2((uint32_t)(P >> 1), (uint32_t)((P >> 33) << 1) | (uint32_t)(P & 1));
     leaf_widx[i] = w;
   } else {
 #pragma unroll
-    for (int d = 0; d < kDim; ++d) v[d * kLeaf] = kPadValue;
-    leaf_tpos[i] = 0;
-    leaf_bucket[i] = 0xFFFFFFFFu;
+    for (int k = 0; k < 3; ++k) v[k * kLeaf] = make_float2(kPadValue, kPadValue);
+    leaf_tb[i] = make_uint2(0u, 0xFFFFFFFFu);
     leaf_widx[i] = 0xFFFFFFFFu;
   }
 }
 
-// boxes of level 0: one warp per leaf block; box j of a level is stored in group j/32, lane j%32
-__device__ __forceinline__ void store_box(float *level, uint32_t j, const float *lo, const float *hi) {
-  float *g = level + (size_t)(j / kFan) * 12 * kFan + (j % kFan);
+// box [lo, hi] -> centre + outward-rounded half extent, stored as child `j` of node record `rec`
+__device__ __forceinline__ void store_child_box(float4 *rec, int j, const float *lo, const float *hi, bool real) {
+  float c[kDim], h[kDim];
 #pragma unroll
   for (int d = 0; d < kDim; ++d) {
-    g[d * kFan] = lo[d];
-    g[(kDim + d) * kFan] = hi[d];
-  }
-}
-
-__global__ void k_boxes_level0(const float *__restrict__ leaf_vals, const uint32_t *__restrict__ leaf_bucket,
-                               uint32_t n_blocks, uint32_t n_boxes_padded, float *__restrict__ level) {
-  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) / 32, lane = threadIdx.x & 31;
-  if (warp >= n_boxes_padded) return;
-  float lo[kDim], hi[kDim];
-  const bool real = warp < n_blocks && leaf_bucket[(size_t)warp * kLeaf + lane] != 0xFFFFFFFFu;
-#pragma unroll
-  for (int d = 0; d < kDim; ++d) {
-    float v = real ? leaf_vals[((size_t)warp * kDim + d) * kLeaf + lane] : 0.0f;
-    lo[d] = real ? v : kPadValue;
-    hi[d] = real ? v : -kPadValue;
-#pragma unroll
-    for (int s = 16; s > 0; s >>= 1) {
-      lo[d] = fminf(lo[d], __shfl_xor_sync(0xffffffffu, lo[d], s));
-      hi[d] = fmaxf(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], s));
+    if (real) {
+      c[d] = 0.5f * (lo[d] + hi[d]);
+      const float e = fmaxf(hi[d] - c[d], c[d] - lo[d]);
+      h[d] = e + 1.0e-6f * e + 1.0e-6f;  // covers the fp32 rounding of c, e and of the test itself
+    } else {
+      c[d] = 0.0f;
+      h[d] = kPadExtent;
     }
   }
-  if (lane == 0) store_box(level, warp, lo, hi);
+  rec[j] = make_float4(c[0], c[1], c[2], c[3]);
+  rec[kFan + j] = make_float4(c[4], c[5], h[0], h[1]);
+  rec[2 * kFan + j] = make_float4(h[2], h[3], h[4], h[5]);
 }
 
-// boxes of level l+1 from level l: one warp per parent (= one group of level l)
-__global__ void k_boxes_up(const float *__restrict__ child, uint32_t n_child, uint32_t n_parent_padded,
-                           float *__restrict__ parent) {
-  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) / 32, lane = threadIdx.x & 31;
-  if (warp >= n_parent_padded) return;
+// level-0 nodes: thread (n, j) boxes leaf 8n + j
+__global__ void k_nodes_level0(const float2 *__restrict__ leaf_vals, const uint2 *__restrict__ leaf_tb,
+                               uint32_t n_leaves, uint32_t n_nodes, float4 *__restrict__ nodes) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_nodes * kFan) return;
+  const uint32_t n = t / kFan, j = t % kFan, leaf = t;
   float lo[kDim], hi[kDim];
-  const uint32_t j = warp * kFan + lane;
-  const bool real = j < n_child;
-  const float *g = child + (size_t)warp * 12 * kFan + lane;
 #pragma unroll
   for (int d = 0; d < kDim; ++d) {
-    lo[d] = real ? g[d * kFan] : kPadValue;
-    hi[d] = real ? g[(kDim + d) * kFan] : -kPadValue;
+    lo[d] = 3.0e38f;
+    hi[d] = -3.0e38f;
+  }
+  bool real = false;
+  if (leaf < n_leaves) {
+    for (int p = 0; p < kLeaf; ++p) {
+      if (leaf_tb[(size_t)leaf * kLeaf + p].y == 0xFFFFFFFFu) continue;
+      real = true;
 #pragma unroll
-    for (int s = 16; s > 0; s >>= 1) {
-      lo[d] = fminf(lo[d], __shfl_xor_sync(0xffffffffu, lo[d], s));
-      hi[d] = fmaxf(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], s));
+      for (int k = 0; k < 3; ++k) {
+        const float2 v = leaf_vals[((size_t)leaf * 3 + k) * kLeaf + p];
+        lo[2 * k] = fminf(lo[2 * k], v.x);
+        hi[2 * k] = fmaxf(hi[2 * k], v.x);
+        lo[2 * k + 1] = fminf(lo[2 * k + 1], v.y);
+        hi[2 * k + 1] = fmaxf(hi[2 * k + 1], v.y);
+      }
     }
   }
-  if (lane == 0) store_box(parent, warp, lo, hi);
+  store_child_box(nodes + (size_t)n * 3 * kFan, (int)j, lo, hi, real);
+}
+
+// level l+1 from level l: thread (n, j) boxes child node 8n + j of the level below
+__global__ void k_nodes_up(const float4 *__restrict__ child, uint32_t n_child, uint32_t n_nodes,
+                           float4 *__restrict__ nodes) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_nodes * kFan) return;
+  const uint32_t n = t / kFan, j = t % kFan, m = t;
+  float lo[kDim], hi[kDim];
+#pragma unroll
+  for (int d = 0; d < kDim; ++d) {
+    lo[d] = 3.0e38f;
+    hi[d] = -3.0e38f;
+  }
+  bool real = false;
+  if (m < n_child) {
+    const float4 *rec = child + (size_t)m * 3 * kFan;
+    for (int p = 0; p < kFan; ++p) {
+      const float4 a = rec[p], b = rec[kFan + p], c = rec[2 * kFan + p];
+      if (b.z < 0.0f) continue;  // padding child
+      real = true;
+      const float cc[kDim] = {a.x, a.y, a.z, a.w, b.x, b.y};
+      const float hh[kDim] = {b.z, b.w, c.x, c.y, c.z, c.w};
+#pragma unroll
+      for (int d = 0; d < kDim; ++d) {
+        lo[d] = fminf(lo[d], cc[d] - hh[d]);
+        hi[d] = fmaxf(hi[d], cc[d] + hh[d]);
+      }
+    }
+  }
+  store_child_box(nodes + (size_t)n * 3 * kFan, (int)j, lo, hi, real);
 }
 
 // ------------------------------------------------------------------ search
 constexpr int kSearchWarps = 8;          // warps per CTA
-constexpr int kStackCap = 32 * kMaxLevels;
+constexpr int kLevelCap = 64;            // entries per level stack: the children of one 8-node step
+constexpr int kLeafQueueCap = 128;       // < 8 left over + 64 pushed per step
 constexpr int kStageCap = 128;           // staged hits per warp before one global reservation
+constexpr int kSearchGrab = 4;           // queries per grab of the dynamic work counter
+
+// dynamic shared memory per warp: staging (key part, point id, d2), leaf queue, level counts,
+// and one 64-entry stack per node level
+__host__ __device__ inline size_t search_smem_per_warp(int n_levels) {
+  return (size_t)kStageCap * 16 + (size_t)kLeafQueueCap * 4 + 16 * 4 + (size_t)n_levels * kLevelCap * 4;
+}
 
 struct SearchArgs {
   // queries: either pipeline mode (features of batch entries) or stage mode (explicit)
@@ -149,6 +186,11 @@ struct SearchArgs {
   unsigned long long cap;      // capacity of out_key/out_dist
   Counters *ctr;
   SlotState *slots_mut;        // to flag capped queries
+  // pipeline mode: where each entry's hits went (k_sort.cuh); runs == nullptr disables it
+  RunRec *runs;                // [B][runs_cap]
+  uint32_t *run_count;         // [B]
+  uint32_t *entry_total;       // [B] anchors per entry so far
+  uint32_t runs_cap;
 };
 
 __device__ __forceinline__ float exact_d2(const float q[kDim], const float v[kDim]) {
@@ -164,34 +206,91 @@ __device__ __forceinline__ float exact_d2(const float q[kDim], const float v[kDi
   return r;
 }
 
+// largest entry e in [0, B) with q_off[e] <= qi (q_off is non-decreasing, q_off[0] = 0 <= qi
+// < q_off[B]); 32-ary search by the whole warp: three rounds for 32 K entries
+__device__ __forceinline__ uint32_t find_entry(const uint32_t *__restrict__ q_off, uint32_t B, uint32_t qi,
+                                               int lane) {
+  uint32_t lo = 0, hi = B;
+  while (hi - lo > 1) {
+    const uint32_t stride = (hi - lo + 31u) / 32u;
+    const uint32_t idx = lo + stride * (uint32_t)lane;
+    const bool le = idx < hi && __ldg(q_off + idx) <= qi;
+    const int k = __popc(__ballot_sync(0xffffffffu, le)) - 1;  // lane 0 (idx = lo) is always true
+    lo += stride * (uint32_t)k;
+    hi = min(lo + stride, hi);
+  }
+  return lo;
+}
+
 // STAGE=false: hits become sort keys (entry|bucket|target|query) + d2, capped at 5000/query.
 // STAGE=true : key = query_id << 32 | window index, no cap (parity hook, compared as sets).
+//
+// Traversal: depth-first over LEVELS, eight nodes wide.  Every level has its own small stack;
+// the warp always works on the lowest non-empty level, pops up to eight of its nodes (two per
+// 8-lane group), tests their 64 child boxes with six independent 16-byte loads per lane in
+// flight, and pushes the survivors onto the (empty) stack of the level below -- so a level
+// never holds more than the 64 children of one step.  Surviving leaves queue up and are
+// evaluated eight at a time the same way.
 template <bool STAGE>
-__global__ void __launch_bounds__(kSearchWarps * 32)
+__global__ void __launch_bounds__(kSearchWarps * 32, 4)
 k_radius_search(const IndexView ix, const SearchArgs a) {
-  __shared__ uint32_t s_stack[kSearchWarps][kStackCap];
-  __shared__ uint64_t s_key[kSearchWarps][kStageCap];
-  __shared__ float s_dist[kSearchWarps][kStageCap];
+  extern __shared__ __align__(16) unsigned char s_dyn[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  uint32_t *stack = s_stack[wid];
-  uint64_t *st_key = s_key[wid];
-  float *st_dist = s_dist[wid];
+  const int grp = lane >> 3, sub = lane & 7;
+  const unsigned full = 0xffffffffu;
+  const unsigned lt = (1u << lane) - 1u;
+  const int n_levels = ix.n_levels;
+  unsigned char *mine = s_dyn + (size_t)wid * search_smem_per_warp(n_levels);
+  uint64_t *st_qk = reinterpret_cast<uint64_t *>(mine);
+  uint32_t *st_pid = reinterpret_cast<uint32_t *>(mine + kStageCap * 8);
+  float *st_dist = reinterpret_cast<float *>(mine + kStageCap * 12);
+  uint32_t *leafq = reinterpret_cast<uint32_t *>(mine + kStageCap * 16);
+  uint32_t *lcnt = leafq + kLeafQueueCap;          // [16] nodes waiting per level
+  uint32_t *lstk = lcnt + 16;                      // [n_levels][kLevelCap]
   const uint32_t nq = STAGE ? a.n_queries : a.q_off[a.B];
   const float r2 = a.radius;
   const float r2_prune = r2 * 1.0001f + 1e-12f;
+  const int top_level = n_levels - 1;
+  const uint32_t n_top = ix.level_count[top_level];  // <= 8
   int staged = 0;
   unsigned long long my_hits = 0, my_capped = 0;
+  // entry of the previous query and its query range (consecutive queries mostly share it)
+  uint32_t entry = 0, e_q0 = 1, e_q1 = 0, slot = 0, ev_off = 0, frow = 0;
+  uint32_t staged_entry = 0;  // the entry every staged hit belongs to (a run never mixes entries)
 
+  // staged hits -> global: one reservation, then target/bucket of every hit fetched with all
+  // loads of a pass in flight (they are off the traversal's critical path here)
   auto flush = [&]() {
     if (staged == 0) return;
     unsigned long long base = 0;
-    if (lane == 0) base = atomicAdd(&a.ctr->n_anchors, (unsigned long long)staged);
-    base = __shfl_sync(0xffffffffu, base, 0);
-    for (int i = lane; i < staged; i += 32) {
-      unsigned long long o = base + i;
-      if (o < a.cap) {
-        a.out_key[o] = st_key[i];
-        a.out_dist[o] = st_dist[i];
+    if (lane == 0) {
+      base = atomicAdd(&a.ctr->n_anchors, (unsigned long long)staged);
+      if (!STAGE && a.runs) {  // all staged hits belong to staged_entry
+        const uint32_t r = atomicAdd(&a.run_count[staged_entry], 1u);
+        if (r < a.runs_cap) a.runs[(size_t)staged_entry * a.runs_cap + r] = RunRec{(uint32_t)base, (uint32_t)staged};
+        else atomicOr(&a.ctr->error, 8u);
+        const uint32_t t = atomicAdd(&a.entry_total[staged_entry], (uint32_t)staged) + (uint32_t)staged;
+        atomicMax(&a.ctr->max_entry_anchors, t);
+      }
+    }
+    base = __shfl_sync(full, base, 0);
+#pragma unroll
+    for (int i0 = 0; i0 < kStageCap; i0 += 32) {
+      const int i = i0 + lane;
+      if (i < staged) {
+        const unsigned long long o = base + i;
+        const uint32_t pid = st_pid[i];
+        uint64_t key;
+        if (STAGE) {
+          key = st_qk[i] | __ldg(ix.leaf_widx + pid);
+        } else {
+          const uint2 tb = __ldg(ix.leaf_tb + pid);
+          key = st_qk[i] | ((uint64_t)tb.y << a.key.sh_b()) | ((uint64_t)tb.x << a.key.sh_t());
+        }
+        if (o < a.cap) {
+          a.out_key[o] = key;
+          a.out_dist[o] = st_dist[i];
+        }
       }
     }
     __syncwarp();
@@ -199,117 +298,145 @@ k_radius_search(const IndexView ix, const SearchArgs a) {
   };
 
   for (;;) {
-    // dynamic work distribution: 4 queries per grab
     uint32_t q0 = 0;
-    if (lane == 0) q0 = atomicAdd(&a.ctr->work, 4u);
-    q0 = __shfl_sync(0xffffffffu, q0, 0);
+    if (lane == 0) q0 = atomicAdd(&a.ctr->work, (unsigned)kSearchGrab);
+    q0 = __shfl_sync(full, q0, 0);
     if (q0 >= nq) break;
-    const uint32_t q1 = min(q0 + 4u, nq);
+    const uint32_t q1 = min(q0 + (uint32_t)kSearchGrab, nq);
     for (uint32_t qi = q0; qi < q1; ++qi) {
       // ---- locate the query
       float q[kDim];
-      uint32_t entry = 0, qpos = 0, slot = 0;
+      uint64_t qk;
       if (STAGE) {
 #pragma unroll
         for (int d = 0; d < kDim; ++d) q[d] = __ldg(a.features + (size_t)qi * kDim + d);
+        qk = (uint64_t)qi << 32;
       } else {
-        // binary search: largest entry with q_off[entry] <= qi
-        uint32_t lo = 0, hi = a.B;
-        while (hi - lo > 1) {
-          uint32_t mid = (lo + hi) >> 1;
-          if (__ldg(a.q_off + mid) <= qi) lo = mid; else hi = mid;
+        if (qi < e_q0 || qi >= e_q1) {
+          flush();
+          entry = find_entry(a.q_off, a.B, qi, lane);
+          staged_entry = entry;
+          e_q0 = __ldg(a.q_off + entry);
+          e_q1 = __ldg(a.q_off + entry + 1);
+          slot = __ldg(a.entry_slot + entry);
+          ev_off = a.slots[slot].num_events;  // query_start_offset
+          frow = __ldg(a.feat_row + entry);
         }
-        entry = lo;
-        const uint32_t k = qi - __ldg(a.q_off + entry);
-        const uint32_t p = (uint32_t)a.step * (k + 1);   // seeds at step, 2*step, ... (Q3)
-        slot = __ldg(a.entry_slot + entry);
-        qpos = p + a.slots[slot].num_events;              // position + query_start_offset
-        const float *f = a.features + (size_t)__ldg(a.feat_row + entry) * kFeatCap + p;
+        const uint32_t p = (uint32_t)a.step * (qi - e_q0 + 1u);  // seeds at step, 2*step, ... (Q3)
+        const float *f = a.features + (size_t)frow * kFeatCap + p;
 #pragma unroll
         for (int d = 0; d < kDim; ++d) q[d] = __ldg(f + d);
+        qk = a.key.pack(entry, 0u, 0u, p + ev_off);
       }
       uint32_t qhits = 0;
       bool capped = false;
-      int sp = 0;
-      if (lane == 0) stack[0] = ((uint32_t)(ix.n_levels - 1) << 27);  // (top level, group 0)
-      sp = 1;
+      // L = lowest level with nodes waiting (n_levels when none), c = how many wait there
+      int L = top_level, c = (int)n_top, nleaf = 0;
+      if (lane < 16) lcnt[lane] = 0u;
+      if (lane < (int)n_top) lstk[top_level * kLevelCap + lane] = (uint32_t)lane;
       __syncwarp();
-      while (sp > 0) {
-        const uint32_t top = stack[sp - 1];
-        --sp;
-        __syncwarp();
-        const int level = (int)(top >> 27);
-        const uint32_t group = top & 0x07FFFFFFu;
-        // ---- every lane tests one child box of (level, group)
-        const float *g = ix.level_box[level] + (size_t)group * 12 * kFan + lane;
-        // boxes only prune (with slack), so this distance may use FMA; the accept test below
-        // may not
-        float s = 0.0f;
+      for (;;) {
+        if (nleaf >= 8 || (L >= n_levels && nleaf > 0)) {
+          // ---- leaf step: up to eight leaves, two per 8-lane group, one point each per lane
+          const int take = min(nleaf, 8);
+          const bool hasA = grp < take, hasB = grp + 4 < take;
+          const uint32_t leafA = hasA ? leafq[nleaf - 1 - grp] : 0u;
+          const uint32_t leafB = hasB ? leafq[nleaf - 5 - grp] : 0u;
+          nleaf -= take;
+          const float2 *la = ix.leaf_vals + (size_t)leafA * (3 * kLeaf) + sub;
+          const float2 *lb = ix.leaf_vals + (size_t)leafB * (3 * kLeaf) + sub;
+          const float2 a01 = __ldg(la), a23 = __ldg(la + kLeaf), a45 = __ldg(la + 2 * kLeaf);
+          const float2 b01 = __ldg(lb), b23 = __ldg(lb + kLeaf), b45 = __ldg(lb + 2 * kLeaf);
+          const float va[kDim] = {a01.x, a01.y, a23.x, a23.y, a45.x, a45.y};
+          const float vb[kDim] = {b01.x, b01.y, b23.x, b23.y, b45.x, b45.y};
+          const float d2a = exact_d2(q, va), d2b = exact_d2(q, vb);
+          const uint32_t hitA = __ballot_sync(full, hasA && d2a < r2);
+          const uint32_t hitB = __ballot_sync(full, hasB && d2b < r2);
+          __syncwarp();  // leafq reads are done before a later node step pushes
+          bool stop = false;
 #pragma unroll
-        for (int d = 0; d < kDim; ++d) {
-          const float lo = __ldg(g + d * kFan), hi = __ldg(g + (kDim + d) * kFan);
-          const float dd = fmaxf(fmaxf(lo - q[d], q[d] - hi), 0.0f);
-          s = __fmaf_rn(dd, dd, s);
-        }
-        uint32_t mask = __ballot_sync(0xffffffffu, s <= r2_prune);
-        if (level > 0) {
-          // push child groups (level-1, group*32 + bit)
-          const int n = __popc(mask);
-          if (mask & (1u << lane)) {
-            const int at = sp + __popc(mask & ((1u << lane) - 1u));
-            stack[at] = ((uint32_t)(level - 1) << 27) | (group * kFan + lane);
-          }
-          sp += n;
-          __syncwarp();
-          continue;
-        }
-        // ---- level 0: surviving children are leaf blocks; evaluate them one by one
-        while (mask) {
-          const int bit = __ffs(mask) - 1;
-          mask &= mask - 1;
-          const uint32_t blk = group * kFan + bit;
-          const float *lv = ix.leaf_vals + (size_t)blk * kDim * kLeaf + lane;
-          float v[kDim];
-#pragma unroll
-          for (int d = 0; d < kDim; ++d) v[d] = __ldg(lv + d * kLeaf);
-          const float d2 = exact_d2(q, v);
-          uint32_t hit = __ballot_sync(0xffffffffu, d2 < r2);
-          if (!hit) continue;
-          if (!STAGE) {
-            const uint32_t room = kMaxHits - qhits;
-            if ((uint32_t)__popc(hit) > room) {
-              // keep the first `room` hits in lane order (deterministic)
-              uint32_t keep = 0, m = hit;
-              for (uint32_t c = 0; c < room; ++c) {
-                keep |= m & (0u - m);
-                m &= m - 1;
+          for (int half = 0; half < 2; ++half) {
+            uint32_t hit = half ? hitB : hitA;
+            if (!hit || stop) continue;
+            if (!STAGE) {
+              const uint32_t room = kMaxHits - qhits;
+              if ((uint32_t)__popc(hit) > room) {
+                // keep the first `room` hits in lane order (deterministic)
+                uint32_t keep = 0, m = hit;
+                for (uint32_t k = 0; k < room; ++k) {
+                  keep |= m & (0u - m);
+                  m &= m - 1;
+                }
+                hit = keep;
+                capped = true;
               }
-              hit = keep;
-              capped = true;
+            }
+            const int nh = __popc(hit);
+            if (staged + nh > kStageCap) flush();
+            if (hit & (1u << lane)) {
+              const int at = staged + __popc(hit & lt);
+              st_pid[at] = (half ? leafB : leafA) * kLeaf + sub;
+              st_dist[at] = half ? d2b : d2a;
+              st_qk[at] = qk;
+            }
+            __syncwarp();
+            staged += nh;
+            qhits += nh;
+            if (!STAGE && qhits >= kMaxHits) {
+              capped = true;  // conservatively: there may have been more than 5000
+              stop = true;    // the reference stops taking hits after 5000 (spatial_index.cc:371-372)
             }
           }
-          const int nh = __popc(hit);
-          if (staged + nh > kStageCap) flush();
-          if (hit & (1u << lane)) {
-            const int at = staged + __popc(hit & ((1u << lane) - 1u));
-            const size_t pi = (size_t)blk * kLeaf + lane;
-            uint64_t key;
-            if (STAGE) {
-              key = ((uint64_t)qi << 32) | __ldg(ix.leaf_widx + pi);
-            } else {
-              key = a.key.pack(entry, __ldg(ix.leaf_bucket + pi), __ldg(ix.leaf_tpos + pi), qpos);
+          if (stop) break;
+        } else if (L < n_levels) {
+          // ---- node step: up to eight nodes of level L, two per 8-lane group
+          const int take = min(c, 8);
+          const bool hasA = grp < take, hasB = grp + 4 < take;
+          const uint32_t *stk = lstk + L * kLevelCap;
+          const uint32_t nodeA = hasA ? stk[c - 1 - grp] : 0u;
+          const uint32_t nodeB = hasB ? stk[c - 5 - grp] : 0u;
+          c -= take;
+          const float4 *base = ix.level_node[L] + sub;
+          const float4 *ra = base + (size_t)nodeA * (3 * kFan);
+          const float4 *rb = base + (size_t)nodeB * (3 * kFan);
+          const float4 a0 = __ldg(ra), a1 = __ldg(ra + kFan), a2 = __ldg(ra + 2 * kFan);
+          const float4 b0 = __ldg(rb), b1 = __ldg(rb + kFan), b2 = __ldg(rb + 2 * kFan);
+          // boxes only prune (with slack), so this distance may use FMA; the accept test may not
+          float sa, sb, t;
+          t = fmaxf(fabsf(q[0] - a0.x) - a1.z, 0.0f); sa = t * t;
+          t = fmaxf(fabsf(q[1] - a0.y) - a1.w, 0.0f); sa = __fmaf_rn(t, t, sa);
+          t = fmaxf(fabsf(q[2] - a0.z) - a2.x, 0.0f); sa = __fmaf_rn(t, t, sa);
+          t = fmaxf(fabsf(q[3] - a0.w) - a2.y, 0.0f); sa = __fmaf_rn(t, t, sa);
+          t = fmaxf(fabsf(q[4] - a1.x) - a2.z, 0.0f); sa = __fmaf_rn(t, t, sa);
+          t = fmaxf(fabsf(q[5] - a1.y) - a2.w, 0.0f); sa = __fmaf_rn(t, t, sa);
+          t = fmaxf(fabsf(q[0] - b0.x) - b1.z, 0.0f); sb = t * t;
+          t = fmaxf(fabsf(q[1] - b0.y) - b1.w, 0.0f); sb = __fmaf_rn(t, t, sb);
+          t = fmaxf(fabsf(q[2] - b0.z) - b2.x, 0.0f); sb = __fmaf_rn(t, t, sb);
+          t = fmaxf(fabsf(q[3] - b0.w) - b2.y, 0.0f); sb = __fmaf_rn(t, t, sb);
+          t = fmaxf(fabsf(q[4] - b1.x) - b2.z, 0.0f); sb = __fmaf_rn(t, t, sb);
+          t = fmaxf(fabsf(q[5] - b1.y) - b2.w, 0.0f); sb = __fmaf_rn(t, t, sb);
+          const uint32_t mA = __ballot_sync(full, hasA && sa <= r2_prune);
+          const uint32_t mB = __ballot_sync(full, hasB && sb <= r2_prune);
+          const int nA = __popc(mA), nB = __popc(mB);
+          if (L > 0) {
+            if (nA + nB) {
+              // descend: the level below is empty (it is always drained before this one)
+              uint32_t *dst = lstk + (L - 1) * kLevelCap;
+              if (mA & (1u << lane)) dst[__popc(mA & lt)] = nodeA * kFan + sub;
+              if (mB & (1u << lane)) dst[nA + __popc(mB & lt)] = nodeB * kFan + sub;
+              lcnt[L] = (uint32_t)c;
+              --L;
+              c = nA + nB;
             }
-            st_key[at] = key;
-            st_dist[at] = d2;
+          } else {
+            if (mA & (1u << lane)) leafq[nleaf + __popc(mA & lt)] = nodeA * kFan + sub;
+            if (mB & (1u << lane)) leafq[nleaf + nA + __popc(mB & lt)] = nodeB * kFan + sub;
+            nleaf += nA + nB;
           }
           __syncwarp();
-          staged += nh;
-          qhits += nh;
-          if (!STAGE && qhits >= kMaxHits) {
-            capped = true;  // conservatively: there may have been more than 5000
-            sp = 0;  // the reference stops taking hits after 5000 (spatial_index.cc:371-372)
-            break;
-          }
+          while (c == 0 && ++L < n_levels) c = (int)lcnt[L];  // climb to the next waiting level
+        } else {
+          break;
         }
       }
       my_hits += qhits;

@@ -20,9 +20,9 @@ constexpr int kDim = SMB_DIM;           // 6
 constexpr int kFeatCap = SMB_CHUNK;     // per-chunk event/feature capacity (peaks < samples)
 constexpr int kMinFeatures = 50;        // sigmap.cc:660: GenerateChains only if size() > 50
 constexpr uint32_t kMaxHits = SMB_MAX_HITS;
-constexpr int kLeaf = 32;               // points per leaf block = one warp
-constexpr int kFan = 32;                // children per inner node = one warp
-constexpr int kMaxLevels = 8;
+constexpr int kLeaf = 8;                // points per leaf = one 8-lane group (32-byte sectors)
+constexpr int kFan = 8;                 // children per node; a warp tests 4 nodes per step
+constexpr int kMaxLevels = 12;          // 8^12 leaves: never reached below 2^32 points
 
 // growable device buffer (contents are NOT preserved across growth)
 template <class T>
@@ -47,20 +47,24 @@ struct DevBuf {
 };
 
 // ---- flat device index over the Morton-sorted window points (replaces nanoflann) ----
-// Level 0 = AABBs of the 32-point leaf blocks; level l+1 = AABBs of 32 consecutive level-l
-// boxes.  Boxes of one parent are stored together as [group][12][32] floats (lo0..lo5,
-// hi0..hi5, lane-minor) so one warp tests 32 children with 12 coalesced 128-byte loads.
+// Leaves hold 8 consecutive points of the Morton order; a node holds the boxes of its 8
+// children (level 0: leaves 8n..8n+7, level l: nodes 8n..8n+7 of level l-1), pointer-free.
+// A warp works on FOUR nodes (or leaves) per step, one 8-lane group each, so records are laid
+// out for 8 lanes:
+//   node  = [3][8 children] float4: (c0 c1 c2 c3) (c4 c5 h0 h1) (h2 h3 h4 h5), box = centre +-
+//           half extent, 384 bytes, three fully coalesced 128-byte loads per lane group;
+//   leaf  = [3][8 points] float2: (v0 v1) (v2 v3) (v4 v5), 192 bytes.
 struct IndexView {
   uint64_t n_points;    // N (point cloud size); windows W = N - 5
   uint64_t n_windows;
-  uint32_t n_blocks;    // leaf blocks = ceil(W / 32)
-  int n_levels;         // number of box levels; the top level has <= 32 boxes (1 group)
-  uint32_t level_count[kMaxLevels];  // boxes per level
-  const float *level_box[kMaxLevels];
-  const float *leaf_vals;     // [n_blocks][6][32]
-  const uint32_t *leaf_tpos;  // [n_blocks*32] target position (pos >> 1, low 32 bits)
-  const uint32_t *leaf_bucket;// [n_blocks*32] contig*2 + strand (0 = '+'), ~0u = padding
-  const uint32_t *leaf_widx;  // [n_blocks*32] window index in the original cloud
+  uint32_t n_leaves;    // ceil(W / 8)
+  int n_levels;         // node levels; the top level has <= 8 nodes
+  uint32_t level_count[kMaxLevels];  // nodes per level
+  const float4 *level_node[kMaxLevels];
+  const float2 *leaf_vals;    // [n_leaves][3][8]
+  const uint2 *leaf_tb;       // [n_leaves*8] {target position (pos >> 1, low 32 bits),
+                              //               contig*2 + strand (0 = '+'), ~0u = padding}
+  const uint32_t *leaf_widx;  // [n_leaves*8] window index in the original cloud
 };
 
 // per-step packing of the 64-bit sort key: entry | bucket | target | query
@@ -120,10 +124,17 @@ struct Counters {
   unsigned long long n_linked;      // anchors with a gap-compatible predecessor (k_chain_prep)
   unsigned long long carry_anchor_used[2];
   unsigned long long carry_chain_used[2];
+  unsigned long long sort_cursor;   // output position of the per-entry sort (k_seg_sort)
   unsigned int n_segments;
   unsigned int work;                // dynamic work counter for the search kernel
-  unsigned int error;               // bit0 anchor overflow, bit1 carry overflow, bit2 chain scratch
-  unsigned int pad;
+  unsigned int error;               // bit0 anchor overflow, bit1 carry overflow, bit2 chain scratch,
+                                    // bit3 run table overflow, bit4 entry too dense for k_seg_sort
+  unsigned int max_entry_anchors;   // most anchors any one entry received this step
+};
+
+// where one flush of the search kernel (or the carry injection) wrote hits of one entry
+struct RunRec {
+  uint32_t start, count;
 };
 
 }  // namespace sb

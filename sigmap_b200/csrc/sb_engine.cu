@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "k_chain.cuh"
+#include "k_sort.cuh"
 #include "k_events.cuh"
 #include "k_index.cuh"
 #include "sb_device.cuh"
@@ -49,6 +50,9 @@ __global__ void k_reset_step(Counters *c) {
   c->n_linked = 0;
   c->n_segments = 0;
   c->work = 0;
+  c->sort_cursor = 0;
+  c->max_entry_anchors = 0;
+  c->error &= ~24u;  // per-step bits (run table overflow, dense entry); the others are per round
 }
 
 // queries per entry (spatial_index.cc:349-409 with Q3: seeds at step, 2*step, ... while
@@ -181,6 +185,8 @@ struct Workspace {
   DevBuf<float> dist_a, dist_b, score, coef;
   DevBuf<uint32_t> pred, link_list, link_count;
   DevBuf<SegRec> seg;
+  DevBuf<RunRec> runs;
+  DevBuf<uint32_t> run_count, entry_total;
   DevBuf<unsigned char> cub_temp;
   DevBuf<ChainTmp> chain_tmp;
   // round readback
@@ -195,9 +201,16 @@ struct smb_ctx {
   // index
   bool has_index = false;
   IndexView ix{};
-  DevBuf<float> leaf_vals, level[kMaxLevels];
-  DevBuf<uint32_t> leaf_tpos, leaf_bucket, leaf_widx;
+  DevBuf<float2> leaf_vals;
+  DevBuf<float4> level[kMaxLevels];
+  DevBuf<uint2> leaf_tb;
+  DevBuf<uint32_t> leaf_widx;
   uint32_t max_tpos = 0, max_bucket = 0;
+  unsigned search_grid_main = 148 * 4;
+  DevBuf<uint64_t> bucket_base;   // linear coordinate of every bucket's target 0 (k_sort.cuh)
+  int gshift = 0;
+  uint32_t n_coarse = 1;
+  bool seg_sort = true;           // per-entry shared-memory sort; SMB_SORT=global forces the radix sort
   std::vector<uint32_t> contig_len;
   // uploaded reads
   size_t n_reads = 0;
@@ -258,20 +271,38 @@ static int fail(smb_ctx *ctx, int code, const std::string &msg) {
   return code;
 }
 
+// persistent grid of the search kernel: every CTA that fits on the device, no more
+static size_t search_smem(const smb_ctx *ctx) { return kSearchWarps * search_smem_per_warp(ctx->ix.n_levels); }
+
+template <bool STAGE>
+static unsigned search_grid(smb_ctx *ctx) {
+  int n = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_radius_search<STAGE>, kSearchWarps * 32,
+                                                    search_smem(ctx)) != cudaSuccess || n < 1)
+    n = 4;
+  int n_sm = 148;
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device);
+  return (unsigned)(n_sm * n);
+}
+
 // ------------------------------------------------------------------ index build
 static int build_index(smb_ctx *ctx, const uint64_t *pos, const float *val, size_t n) {
   if (n < (size_t)kDim) return fail(ctx, SMB_ERR_ARG, "point cloud smaller than the index dimension");
   if (n - (kDim - 1) > 0xFFFFFFF0ull)
     return fail(ctx, SMB_ERR_CAPACITY, "more than 2^32 window points: shard the index by contig");
   const uint64_t W = n - (kDim - 1);
-  const uint32_t n_blocks = (uint32_t)((W + kLeaf - 1) / kLeaf);
+  const uint32_t n_leaves = (uint32_t)((W + kLeaf - 1) / kLeaf);
   float vmin = val[0], vmax = val[0];
   uint32_t max_tpos = 0, max_bucket = 0;
+  std::vector<uint64_t> bucket_span;  // 1 + largest target seen per bucket
   for (size_t i = 0; i < n; ++i) {
     vmin = std::min(vmin, val[i]);
     vmax = std::max(vmax, val[i]);
-    max_tpos = std::max(max_tpos, (uint32_t)(pos[i] >> 1));
-    max_bucket = std::max(max_bucket, (uint32_t)(((pos[i] >> 33) << 1) | (pos[i] & 1)));
+    const uint32_t t = (uint32_t)(pos[i] >> 1), b = (uint32_t)(((pos[i] >> 33) << 1) | (pos[i] & 1));
+    max_tpos = std::max(max_tpos, t);
+    max_bucket = std::max(max_bucket, b);
+    if (b >= bucket_span.size()) bucket_span.resize((size_t)b + 1, 0);
+    bucket_span[b] = std::max<uint64_t>(bucket_span[b], (uint64_t)t + 1);
   }
   const float span = std::max(vmax - vmin, 1e-6f);
   cudaStream_t s = ctx->stream;
@@ -294,43 +325,38 @@ static int build_index(smb_ctx *ctx, const uint64_t *pos, const float *val, size
   CK(tmp.ensure(tb));
   CK(cub::DeviceRadixSort::SortPairs(tmp.p, tb, code_a.p, code_b.p, w_a.p, w_b.p, (uint64_t)W, 0, 60, s));
   ctx->stats.launches += 8;
-  CK(ctx->leaf_vals.ensure((size_t)n_blocks * kDim * kLeaf));
-  CK(ctx->leaf_tpos.ensure((size_t)n_blocks * kLeaf));
-  CK(ctx->leaf_bucket.ensure((size_t)n_blocks * kLeaf));
-  CK(ctx->leaf_widx.ensure((size_t)n_blocks * kLeaf));
-  k_build_leaves<<<(unsigned)(((uint64_t)n_blocks * kLeaf + 255) / 256), 256, 0, s>>>(
-      d_val.p, d_pos.p, w_b.p, W, n_blocks, ctx->leaf_vals.p, ctx->leaf_tpos.p, ctx->leaf_bucket.p,
-      ctx->leaf_widx.p);
+  CK(ctx->leaf_vals.ensure((size_t)n_leaves * 3 * kLeaf));
+  CK(ctx->leaf_tb.ensure((size_t)n_leaves * kLeaf));
+  CK(ctx->leaf_widx.ensure((size_t)n_leaves * kLeaf));
+  k_build_leaves<<<(unsigned)(((uint64_t)n_leaves * kLeaf + 255) / 256), 256, 0, s>>>(
+      d_val.p, d_pos.p, w_b.p, W, n_leaves, ctx->leaf_vals.p, ctx->leaf_tb.p, ctx->leaf_widx.p);
   LAUNCH_CHECK();
   IndexView ix{};
   ix.n_points = n;
   ix.n_windows = W;
-  ix.n_blocks = n_blocks;
-  uint32_t count = n_blocks;
+  ix.n_leaves = n_leaves;
+  uint32_t n_child = n_leaves;
   int L = 0;
   for (;;) {
     if (L >= kMaxLevels) return fail(ctx, SMB_ERR_CAPACITY, "index hierarchy deeper than kMaxLevels");
-    const uint32_t groups = (count + kFan - 1) / kFan, padded = groups * kFan;
-    CK(ctx->level[L].ensure((size_t)groups * 12 * kFan));
-    if (L == 0) {
-      k_boxes_level0<<<(padded * 32 + 255) / 256, 256, 0, s>>>(ctx->leaf_vals.p, ctx->leaf_bucket.p,
-                                                              n_blocks, padded, ctx->level[0].p);
-    } else {
-      // parents of level L-1 are the boxes of level L; count == number of groups of L-1
-      k_boxes_up<<<(padded * 32 + 255) / 256, 256, 0, s>>>(ctx->level[L - 1].p, ix.level_count[L - 1],
-                                                          padded, ctx->level[L].p);
-    }
+    const uint32_t n_nodes = (n_child + kFan - 1) / kFan;
+    if (n_nodes >= (1u << 28)) return fail(ctx, SMB_ERR_CAPACITY, "index level exceeds 2^28 nodes");
+    CK(ctx->level[L].ensure((size_t)n_nodes * 3 * kFan));
+    const unsigned blocks = (unsigned)(((uint64_t)n_nodes * kFan + 255) / 256);
+    if (L == 0)
+      k_nodes_level0<<<blocks, 256, 0, s>>>(ctx->leaf_vals.p, ctx->leaf_tb.p, n_leaves, n_nodes, ctx->level[0].p);
+    else
+      k_nodes_up<<<blocks, 256, 0, s>>>(ctx->level[L - 1].p, n_child, n_nodes, ctx->level[L].p);
     LAUNCH_CHECK();
-    ix.level_count[L] = count;
-    ix.level_box[L] = ctx->level[L].p;
+    ix.level_count[L] = n_nodes;
+    ix.level_node[L] = ctx->level[L].p;
     ++L;
-    if (count <= (uint32_t)kFan) break;
-    count = groups;
+    if (n_nodes <= (uint32_t)kFan) break;  // the search starts from all nodes of the top level
+    n_child = n_nodes;
   }
   ix.n_levels = L;
   ix.leaf_vals = ctx->leaf_vals.p;
-  ix.leaf_tpos = ctx->leaf_tpos.p;
-  ix.leaf_bucket = ctx->leaf_bucket.p;
+  ix.leaf_tb = ctx->leaf_tb.p;
   ix.leaf_widx = ctx->leaf_widx.p;
   CK(cudaStreamSynchronize(s));
   d_val.release();
@@ -340,7 +366,19 @@ static int build_index(smb_ctx *ctx, const uint64_t *pos, const float *val, size
   w_a.release();
   w_b.release();
   tmp.release();
+  {
+    // linear coordinate g = bucket_base[bucket] + target: monotone in the sort order, dense
+    // enough to be cut into equal-width bins by the per-entry sort
+    std::vector<uint64_t> base(bucket_span.size() + 1, 0);
+    for (size_t b = 0; b < bucket_span.size(); ++b) base[b + 1] = base[b] + bucket_span[b];
+    CK(ctx->bucket_base.ensure(base.size()));
+    CK(cudaMemcpy(ctx->bucket_base.p, base.data(), base.size() * sizeof(uint64_t), cudaMemcpyHostToDevice));
+    ctx->gshift = 0;
+    while ((base.back() >> ctx->gshift) >= (uint64_t)kCoarseBins) ++ctx->gshift;
+    ctx->n_coarse = (uint32_t)(base.back() >> ctx->gshift) + 1;
+  }
   ctx->ix = ix;
+  ctx->search_grid_main = search_grid<false>(ctx);
   ctx->max_tpos = max_tpos;
   ctx->max_bucket = max_bucket;
   ctx->has_index = true;
@@ -484,9 +522,19 @@ static int run_step(smb_ctx *ctx, SlotSpace &sp, const StepEntries &en, StepSour
   CK(w.score.ensure(cap));
   CK(w.coef.ensure(cap));
   CK(w.pred.ensure(cap));
+  const bool want_seg = ctx->seg_sort;
+  if (want_seg) {
+    CK(w.runs.ensure((size_t)B * kRunsCap));
+    CK(w.run_count.ensure(B));
+    CK(w.entry_total.ensure(B));
+    CK(cudaMemsetAsync(w.run_count.p, 0, B * sizeof(uint32_t), s));
+    CK(cudaMemsetAsync(w.entry_total.p, 0, B * sizeof(uint32_t), s));
+  }
   k_inject_carry<<<(B * 32 + 255) / 256, 256, 0, s>>>(w.entry_slot.p, w.n_queries.p, sp.slots.p,
                                                      sp.pool_anchor[0].p, sp.pool_anchor[1].p, B, kl,
-                                                     w.key_a.p, w.dist_a.p, cap, ctx->d_ctr);
+                                                     w.key_a.p, w.dist_a.p, cap, ctx->d_ctr,
+                                                     want_seg ? w.runs.p : nullptr, w.run_count.p,
+                                                     w.entry_total.p, (uint32_t)kRunsCap);
   LAUNCH_CHECK();
   SearchArgs sa{};
   sa.features = src == SRC_CACHED ? w.feat_cache.p : w.features.p;
@@ -503,10 +551,12 @@ static int run_step(smb_ctx *ctx, SlotSpace &sp, const StepEntries &en, StepSour
   sa.out_dist = w.dist_a.p;
   sa.cap = cap;
   sa.ctr = ctx->d_ctr;
-  int n_sm = 148;
-  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device);
+  sa.runs = want_seg ? w.runs.p : nullptr;
+  sa.run_count = w.run_count.p;
+  sa.entry_total = w.entry_total.p;
+  sa.runs_cap = kRunsCap;
   CK(cudaEventRecord(ctx->ev[2], s));
-  k_radius_search<false><<<n_sm * 8, kSearchWarps * 32, 0, s>>>(ctx->ix, sa);
+  k_radius_search<false><<<ctx->search_grid_main, kSearchWarps * 32, search_smem(ctx), s>>>(ctx->ix, sa);
   LAUNCH_CHECK();
   ctx->stats.search_launches++;
   CK(cudaEventRecord(ctx->ev[3], s));
@@ -533,7 +583,37 @@ static int run_step(smb_ctx *ctx, SlotSpace &sp, const StepEntries &en, StepSour
   CK(cudaEventRecord(ctx->ev[0], s));
   const uint64_t *keys = w.key_a.p;
   const float *dists = w.dist_a.p;
-  if (n > 1) {
+  bool sorted = n <= 1;
+  // per-entry sort in shared memory (k_sort.cuh) when every entry is small enough for a few
+  // passes over its runs and the run table did not overflow
+  if (!sorted && want_seg && !(ctx->h_ctr->error & 8u) &&
+      ctx->h_ctr->max_entry_anchors <= 8u * (unsigned)kSortCap) {
+    SegSortArgs ss{};
+    ss.key_in = w.key_a.p;
+    ss.dist_in = w.dist_a.p;
+    ss.key_out = w.key_b.p;
+    ss.dist_out = w.dist_b.p;
+    ss.runs = w.runs.p;
+    ss.run_count = w.run_count.p;
+    ss.B = B;
+    ss.kl = kl;
+    ss.bucket_base = ctx->bucket_base.p;
+    ss.gshift = ctx->gshift;
+    ss.n_coarse = ctx->n_coarse;
+    ss.ctr = ctx->d_ctr;
+    k_seg_sort<<<B, kSortThreads, kSortSmemBytes, s>>>(ss);
+    LAUNCH_CHECK();
+    CK(cudaMemcpyAsync(ctx->h_ctr, ctx->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    ctx->stats.d2h_bytes += sizeof(Counters);
+    if (!(ctx->h_ctr->error & 16u)) {
+      sorted = true;
+      ctx->stats.seg_sort_steps++;
+      keys = w.key_b.p;
+      dists = w.dist_b.p;
+    }
+  }
+  if (!sorted) {
     // radix sort on (entry, bucket, target) only; k_fix_ties orders equal-target runs by query
     size_t tb = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, tb, w.key_a.p, w.key_b.p, w.dist_a.p, w.dist_b.p,
@@ -817,6 +897,11 @@ int smb_create(smb_ctx **out, int device) {
     if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail("cudaEventCreate", e);
   for (auto &ev : ctx->timer)
     if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail("cudaEventCreate", e);
+  // the per-entry sort keeps a whole part of an entry in shared memory (200 KB of the 227 KB)
+  if ((e = cudaFuncSetAttribute(k_seg_sort, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)kSortSmemBytes)) != cudaSuccess)
+    return bail("cudaFuncSetAttribute(k_seg_sort)", e);
+  if (const char *env = getenv("SMB_SORT")) ctx->seg_sort = strcmp(env, "global") != 0;
   *out = ctx;
   return SMB_OK;
 }
@@ -835,9 +920,9 @@ void smb_destroy(smb_ctx *ctx) {
   w.q_off.release(); w.feat_row.release(); w.feat_cache.release(); w.nf_cache.release(); w.nraw_cache.release(); w.absent.release(); w.chunk_start.release(); w.chunk_offset.release();
   w.chunk_scale.release(); w.ps.release(); w.pss.release(); w.t1.release(); w.t2.release();
   w.means.release(); w.features.release(); w.key_a.release(); w.key_b.release(); w.dist_a.release();
-  w.dist_b.release(); w.score.release(); w.coef.release(); w.pred.release(); w.seg.release(); w.link_list.release(); w.link_count.release(); w.cub_temp.release();
+  w.dist_b.release(); w.score.release(); w.coef.release(); w.pred.release(); w.seg.release(); w.runs.release(); w.run_count.release(); w.entry_total.release(); w.link_list.release(); w.link_count.release(); w.cub_temp.release();
   w.chain_tmp.release(); w.ids.release(); w.round_info.release();
-  ctx->leaf_vals.release(); ctx->leaf_tpos.release(); ctx->leaf_bucket.release(); ctx->leaf_widx.release();
+  ctx->leaf_vals.release(); ctx->leaf_tb.release(); ctx->leaf_widx.release(); ctx->bucket_base.release();
   for (auto &l : ctx->level) l.release();
   ctx->raw.release(); ctx->kept.release(); ctx->d_read_off.release(); ctx->d_kept_off.release();
   ctx->d_dig.release(); ctx->d_range.release(); ctx->d_offset.release(); ctx->d_kept_len.release();
@@ -1192,9 +1277,7 @@ int smb_stage_radius(smb_ctx *ctx, const float *queries, size_t nq, float radius
   sa.out_dist = d_a.p;
   sa.cap = dcap;
   sa.ctr = ctx->d_ctr;
-  int n_sm = 148;
-  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device);
-  k_radius_search<true><<<n_sm * 8, kSearchWarps * 32, 0, s>>>(ctx->ix, sa);
+  k_radius_search<true><<<search_grid<true>(ctx), kSearchWarps * 32, search_smem(ctx), s>>>(ctx->ix, sa);
   LAUNCH_CHECK();
   CK(cudaMemcpyAsync(ctx->h_ctr, ctx->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
