@@ -47,9 +47,11 @@ def parse_args():
     ap.add_argument("--noise", type=float, default=1.0)
     ap.add_argument("--mode", default="full", choices=["full", "default"],
                     help="full = full-read mapping (configs[1]); default = reference stop rules")
-    ap.add_argument("--cpu-sample-reads", type=int, default=300)
+    ap.add_argument("--cpu-sample-reads", type=int, default=1500)
     ap.add_argument("--ref-step-reads", type=int, default=100)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--channels", type=int, default=512, help="read-until leg: concurrent channels")
+    ap.add_argument("--stream-rounds", type=int, default=24, help="read-until leg: timed rounds (0 = skip)")
     ap.add_argument("--seed", type=int, default=20251017)
     return ap.parse_args()
 
@@ -219,6 +221,62 @@ def run_reference(args):
     }))
 
 
+# ------------------------------------------------------------------ read-until latency leg
+def stream_latency(mapper, reads, n_channels, rounds, warm=3):
+    """BASELINE.json's second metric (configs[3]): 512 concurrent channels, one 4 000-sample chunk
+    per channel per round, default stop rules, finished channels refilled with the next read.
+    Latency of a chunk = duration of the smb_stream_round call that carries it (host samples in,
+    stop decision out, copies included), host clock; p50 over all chunks of the timed rounds."""
+    import numpy as np
+    from sigmap_b200.mapper import default_params
+    if rounds <= 0 or reads.n == 0:
+        return None
+    chunk = 4000
+    mapper.stream_open(n_channels, default_params())
+    cur, at, nxt = [0] * n_channels, [0] * n_channels, 0
+
+    def assign(ch):
+        nonlocal nxt
+        for _ in range(reads.n):  # next read holding at least one chunk
+            r = nxt % reads.n
+            nxt += 1
+            if int(reads.read_off[r + 1] - reads.read_off[r]) >= chunk:
+                break
+        cur[ch], at[ch] = r, 0
+        mapper.stream_begin_read(ch, float(reads.digitisation[r]), float(reads.range[r]),
+                                 float(reads.offset[r]))
+
+    for ch in range(n_channels):
+        assign(ch)
+    channels = np.arange(n_channels, dtype=np.uint32)
+    off = (np.arange(n_channels + 1, dtype=np.uint64) * chunk).astype(np.uint32)
+    samples = np.zeros(n_channels * chunk, np.int16)
+    lat, stops = [], 0
+    for rd in range(warm + rounds):
+        for ch in range(n_channels):
+            o = int(reads.read_off[cur[ch]]) + at[ch]
+            samples[ch * chunk:(ch + 1) * chunk] = reads.raw[o:o + chunk]
+        t0 = time.perf_counter()
+        dec, _ = mapper.stream_round_arrays(channels, samples, off)
+        dt = time.perf_counter() - t0
+        if rd >= warm:
+            lat.append(dt * 1000.0)
+            stops += int(dec.sum())
+        for ch in range(n_channels):
+            at[ch] += chunk
+            r = cur[ch]
+            if dec[ch] or at[ch] + chunk > int(reads.read_off[r + 1] - reads.read_off[r]):
+                assign(ch)
+    mapper.stream_close()
+    lat.sort()
+    q = lambda f: lat[min(len(lat) - 1, int(f * len(lat)))]
+    return {"metric": "per-chunk latency, read-until mode", "unit": "ms", "p50": q(0.5), "p90": q(0.9),
+            "max": lat[-1], "channels": n_channels, "rounds": rounds, "chunks": rounds * n_channels,
+            "stop_decisions": stops, "chunk_samples": chunk,
+            "samples_per_s": rounds * n_channels * chunk / (sum(lat) / 1000.0),
+            "timed": "smb_stream_round call, host buffers in -> decisions out (host clock)"}
+
+
 # ------------------------------------------------------------------ our arm
 def main():
     args = parse_args()
@@ -305,6 +363,12 @@ def main():
     e2e_samples = sum_over_ranks(float(st2["samples"]))
     e2e_value = e2e_samples / (ms_e2e / 1000.0)
 
+    # ---- read-until leg (per-chunk latency, 512 channels), rank 0 only
+    latency = None
+    if rank == 0 and args.stream_rounds > 0:
+        latency = stream_latency(mapper, reads, args.channels, args.stream_rounds)
+    barrier()
+
     # ---- roofline of the dominant kernel (radius search), live CUDA-event timing
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
@@ -347,6 +411,7 @@ def main():
                      "counters_per_step": {k: int(st[k] // max(args.steps, 1)) for k in
                                            ("samples", "events", "queries", "hits", "anchors",
                                             "capped_queries", "chunks", "steps", "linked")}},
+        "latency": latency,
         "mapped_reads": n_mapped, "truth_concordant_reads": ok, "setup_s": t_setup,
     }
 

@@ -209,12 +209,19 @@ class Mapper:
         off[1:] = np.cumsum([len(s) for s in sample_lists])
         samples = (np.concatenate(sample_lists).astype(np.int16) if len(sample_lists)
                    else np.zeros(0, np.int16))
-        dec = np.zeros(max(len(channels), 1), np.uint8)
-        maps = (F.Mapping * max(len(channels), 1))()
-        self._check(F.lib.smb_stream_round(self._ctx, F.ptr(channels, F.u32p), len(channels),
+        return self.stream_round_arrays(channels, samples, off)
+
+    def stream_round_arrays(self, channels, samples, off):
+        """One round from pre-packed host arrays: channels u32[n], samples i16[off[n]], off u32[n+1]
+        -> (stop decisions u8[n], provisional rows).  This is the call whose duration is the
+        per-chunk latency of read-until mode (submit -> decision)."""
+        n = len(channels)
+        dec = np.zeros(max(n, 1), np.uint8)
+        maps = (F.Mapping * max(n, 1))()
+        self._check(F.lib.smb_stream_round(self._ctx, F.ptr(channels, F.u32p), n,
                                            F.ptr(samples, F.i16p), F.ptr(off, F.u32p),
                                            F.ptr(dec, F.u8p), maps), "smb_stream_round")
-        return dec[:len(channels)].copy(), [maps[i] for i in range(len(channels))]
+        return dec[:n].copy(), [maps[i] for i in range(n)]
 
     def stream_close(self):
         self._check(F.lib.smb_stream_close(self._ctx), "smb_stream_close")

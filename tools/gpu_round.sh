@@ -16,13 +16,11 @@ tail -c 1500 $OUT/bench_ref.json
 fi
 if [ "${SKIP_NCU:-0}" != "1" ]; then
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv \
-    --log-file $OUT/launches.csv python bench.py --reads 4000 --steps 1 --warmup 1 --no-cpu-baseline \
+    --log-file $OUT/launches.csv python bench.py --reads 4000 --steps 1 --warmup 1 --no-cpu-baseline --stream-rounds 0 \
     > $OUT/launches_bench.log 2>&1
 python profiles/summarize_launches.py $OUT/launches.csv > $OUT/launches_summary.txt 2>&1
 head -30 $OUT/launches_summary.txt
-timeout 900 ncu --set full --clock-control none --import-source on \
-    -k regex:'k_radius_search|k_chain_dp|k_chain_prep|k_ev_features|k_ev_prefix|k_ev_tstat|k_fix_ties|DeviceRadixSortOnesweep' \
-    -s 40 -c 24 -o $OUT/prof python bench.py --reads 4000 --steps 1 --warmup 1 --no-cpu-baseline \
-    > $OUT/prof_bench.log 2>&1
-ls -la $OUT
+bash tools/gpu_prof.sh $TAG 'k_radius_search|k_chain_dp|k_chain_prep|k_chain_select|k_seg_sort|k_ev_features' 60 12 \
+    k_radius_search k_chain_dp k_seg_sort k_chain_select k_chain_prep k_ev_features > $OUT/prof.log 2>&1
+tail -20 $OUT/summary.md
 fi
