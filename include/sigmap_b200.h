@@ -103,6 +103,7 @@ typedef struct smb_stats {
                               gap-compatible predecessor); the rest are settled in parallel */
   uint64_t seg_sort_steps; /* steps whose anchors were sorted per entry in shared memory
                               (the others fell back to the global radix sort) */
+  uint64_t exchanges;      /* collectives issued by a contig-sharded run (0 otherwise) */
 } smb_stats;
 
 /* ------------------------------------------------------------------ context */
@@ -132,6 +133,33 @@ int smb_index_set_points(smb_ctx *ctx, const uint64_t *pos, const float *val, si
  * strand coordinate flip (sigmap.cc:754-757) and to size the per-contig buckets. */
 int smb_index_set_contigs(smb_ctx *ctx, const uint32_t *lengths, uint32_t n_contigs);
 uint64_t smb_index_num_points(const smb_ctx *ctx);
+
+/* ------------------------------------------- contig-sharded index (multi-GPU) */
+/* For references whose index exceeds one GPU (SURVEY.md 8e mode 2; the reference itself has no
+ * such mode -- its SpatialIndex::Load, spatial_index.cc:132-163, needs the whole KD-tree in one
+ * address space).  Contigs are partitioned over `world` ranks; every rank is handed every read
+ * (smb_map_reads etc. unchanged), searches and chains against its own contigs, and three small
+ * collectives per pipeline step (running max per bucket, chain candidates) make every rank
+ * return the rows the unsharded run returns, bit for bit.
+ *
+ * Group setup, one of:
+ *   smb_shard_nccl_init    one process per GPU (torchrun): rank 0 calls smb_shard_nccl_unique_id
+ *                          and broadcasts the 128 bytes out of band (torch.distributed, MPI, a
+ *                          file); the collectives are NCCL over NVLink on the context's stream.
+ *   smb_shard_local_group  n contexts inside one process, each then driven by its own host
+ *                          thread; rendezvous on a host barrier + peer copies.
+ * Then every rank calls smb_index_set_points_sharded with the SAME full point cloud and owner
+ * table (smbh_assign_contigs gives a balanced one) and smb_index_set_contigs as usual; all
+ * mapping calls must then be made by every rank with identical arguments. */
+int smbh_assign_contigs(const uint32_t *lengths, uint32_t n_contigs, uint32_t world,
+                        uint32_t *owner /* n_contigs */);
+int smb_shard_local_group(smb_ctx *const *ctxs, uint32_t n);
+int smb_shard_nccl_unique_id(char *id128);
+int smb_shard_nccl_init(smb_ctx *ctx, int rank, int world, const char *id128);
+int smb_shard_rank(const smb_ctx *ctx);
+int smb_shard_world(const smb_ctx *ctx);
+int smb_index_set_points_sharded(smb_ctx *ctx, const uint64_t *pos, const float *val, size_t n,
+                                 const uint32_t *contig_owner, uint32_t n_contigs);
 uint32_t smb_index_num_contigs(const smb_ctx *ctx);
 
 /* ------------------------------------------------------------ whole hot path */

@@ -111,6 +111,7 @@ class Stats(C.Structure):
         ("d2h_bytes", C.c_uint64),
         ("linked", C.c_uint64),
         ("seg_sort_steps", C.c_uint64),
+        ("exchanges", C.c_uint64),
     ]
 
 
@@ -146,6 +147,14 @@ PROTOTYPES = {
     "smb_index_set_points": (C.c_int, [C.c_void_p, u64p, f32p, C.c_size_t]),
     "smb_index_set_contigs": (C.c_int, [C.c_void_p, u32p, C.c_uint32]),
     "smb_index_num_points": (C.c_uint64, [C.c_void_p]),
+    "smbh_assign_contigs": (C.c_int, [u32p, C.c_uint32, C.c_uint32, u32p]),
+    "smb_shard_local_group": (C.c_int, [C.POINTER(C.c_void_p), C.c_uint32]),
+    "smb_shard_nccl_unique_id": (C.c_int, [C.c_char_p]),
+    "smb_shard_nccl_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_char_p]),
+    "smb_shard_rank": (C.c_int, [C.c_void_p]),
+    "smb_shard_world": (C.c_int, [C.c_void_p]),
+    "smb_index_set_points_sharded": (C.c_int, [C.c_void_p, u64p, f32p, C.c_size_t, u32p,
+                                               C.c_uint32]),
     "smb_index_num_contigs": (C.c_uint32, [C.c_void_p]),
     "smb_map_reads": (C.c_int, [C.c_void_p, i16p, u64p, f32p, f32p, f32p, C.c_size_t,
                                 C.POINTER(Params), C.POINTER(Mapping)]),

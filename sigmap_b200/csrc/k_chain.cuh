@@ -49,6 +49,7 @@ struct ChainArgs {
   float *coef;           // distance coefficient per anchor (k_chain_prep)
   uint32_t *pred;        // bit31 = anchor_is_used
   SegRec *seg;           // [n_slots], memset to 0xFF before k_chain_prep
+  float *seg_max;        // [n_slots], zeroed: SegRec::max of every segment (0 when empty)
   uint32_t n_slots;      // B << bbits
   uint32_t *link_list;   // [n_tiles * kPrepTile] indices of linked anchors, ascending per tile
   uint32_t *link_count;  // [n_tiles]
@@ -440,12 +441,39 @@ __global__ void __launch_bounds__(kDpThreads) k_chain_dp(ChainArgs a) {
     r.top_s[0] = ts0; r.top_s[1] = ts1; r.top_s[2] = ts2;
     r.top_i[0] = ti0; r.top_i[1] = ti1; r.top_i[2] = ti2;
     a.seg[slot] = r;
+    a.seg_max[slot] = runmax;
   }
 }
 
-struct ChainTmp {
+// ---------------------------------------------------------------------------------------
+// K7: chains and the per-read decision, in two kernels with an optional exchange in between
+// (contig-sharded index, SURVEY.md 8e mode 2: the buckets of one read live on several GPUs).
+//
+//   k_sel_trace   warp per (entry, bucket) segment: the running max of the EARLIER buckets
+//                 (spatial_index.cc:419, a prefix max over seg_max[], which a sharded run
+//                 all-reduces first), then TracebackChains (spatial_index.cc:165-220) for the
+//                 segment's <= 3 end candidates.  The walk keeps a 32-anchor window of pred[]
+//                 in registers (one lane each) and follows the chain with shuffles: chain
+//                 members are near neighbours in the sorted order, so a window serves 20-30
+//                 steps and the walk issues ~25x fewer dependent global loads than a
+//                 thread-per-read pointer chase.  Visited anchors are written, end -> start,
+//                 to path[], so later copies are parallel gathers.
+//   k_sel_scatter (sharded only) candidates gathered from the other ranks join the per-entry
+//                 lists.
+//   k_sel_final   warp per entry: GeneratePrimaryChains + ComputeMAPQ (spatial_index.cc:222-274)
+//                 on lane 0, then all lanes copy the surviving chains' anchors to the carry
+//                 pool (only chains whose bucket this rank owns), the StreamingMap stop / output
+//                 decision and the tag sums (sigmap.cc:667-745).
+struct CandRec {  // an end candidate whose traceback produced a chain of >= 2 anchors
   float score;
-  uint32_t contig, start, end, n, dir, end_idx;
+  uint32_t entry, bucket, start, end, n;
+  uint32_t end_idx;   // anchor index of the chain end (owner rank's arrays)
+  uint32_t path_off;  // first of n path[] entries (owner rank's arrays)
+  uint32_t owner;     // rank whose index shard holds the bucket
+};
+
+struct ChainTmp {
+  CandRec c;
   uint32_t state;  // 0 candidate, 1 primary (order in `rank`), 2 rejected
   uint32_t rank;
 };
@@ -455,11 +483,15 @@ struct SelectArgs {
   const uint32_t *entry_slot;
   const uint32_t *n_queries;   // 0 => GenerateChains not called (copy state forward)
   const uint32_t *n_features;
-  const uint8_t *absent;       // 1 => the slot has no chunk this round (pure copy-forward)
   SlotState *slots;
   uint32_t B;
   ChainTmp *scratch;           // [B][max_chains]
+  uint32_t *n_scratch;         // [B] candidates per entry (zeroed before k_sel_trace)
   uint32_t max_chains;
+  uint32_t *path;              // [n] traceback paths, a segment's chains packed from seg.start
+  CandRec *cand_list;          // sharded: compact list of this rank's candidates (else nullptr)
+  uint32_t cand_cap;
+  uint32_t rank;               // this rank (0 when not sharded)
   uint32_t out_pool;
   ChainRec *pool_chain[2];
   CarryAnchor *pool_anchor[2];
@@ -467,18 +499,135 @@ struct SelectArgs {
   smb_params prm;
 };
 
+constexpr int kTraceThreads = 128;
+constexpr uint32_t kUsed = 0x80000000u;  // pred[] bit: anchor_is_used (spatial_index.cc:170)
+
+__device__ __forceinline__ void add_candidate(const SelectArgs &a, const CandRec &c) {
+  const uint32_t at = atomicAdd(&a.n_scratch[c.entry], 1u);
+  if (at < a.max_chains) {
+    ChainTmp t;
+    t.c = c;
+    t.state = 0;
+    t.rank = 0;
+    a.scratch[(size_t)c.entry * a.max_chains + at] = t;
+  } else {
+    atomicOr(&a.c.ctr->error, 4u);
+  }
+}
+
+__global__ void __launch_bounds__(kTraceThreads) k_sel_trace(SelectArgs a) {
+  const int lane = threadIdx.x & 31;
+  const unsigned full = 0xffffffffu;
+  const uint32_t slot = (blockIdx.x * kTraceThreads + threadIdx.x) / 32;
+  if (slot >= a.c.n_slots) return;
+  const SegRec rec = a.c.seg[slot];
+  if (rec.start == kSegEmpty || rec.ntop == 0u || rec.ntop > 3u) return;
+  const KeyLayout kl = a.c.kl;
+  const uint32_t bucket = slot & ((1u << kl.bbits) - 1u), entry = slot >> kl.bbits;
+  const uint32_t n = (uint32_t)a.c.n;
+  uint32_t *pred = a.c.pred;
+  const float *score = a.c.score;
+
+  // max_chaining_score before this bucket (buckets in the reference's order, :420-422)
+  float gprev = 0.0f;
+  for (uint32_t k = lane; k < bucket; k += 32) gprev = fmaxf(gprev, a.c.seg_max[slot - bucket + k]);
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) gprev = fmaxf(gprev, __shfl_xor_sync(full, gprev, d));
+  // The DP kept the segment's best three end candidates under its own running max; the
+  // reference's test also includes the earlier buckets' max, which removes exactly the
+  // candidates with score <= gprev/2 -- a suffix of the list (:545-549).
+  const float half_prev = __fdiv_rn(gprev, 2.0f);
+  const float half = __fdiv_rn(fmaxf(gprev, rec.max), 2.0f);
+
+  uint32_t path_at = rec.start;
+  for (uint32_t r = 0; r < rec.ntop; ++r) {
+    if (!(rec.top_s[r] > half_prev)) break;
+    const uint32_t e = rec.top_i[r];
+    // ---- TracebackChains (spatial_index.cc:165-220) over a register window of pred[]
+    uint32_t wlo = e >= 31u ? e - 31u : 0u;
+    uint32_t v = (wlo + lane < n) ? pred[wlo + lane] : 0u;
+    bool dirty = false;
+    if (!(__shfl_sync(full, v, (int)(e - wlo)) & kUsed)) {
+      uint32_t s = e, cnt = 0, stop_pred = e;
+      bool hit_used = false;
+      for (;;) {
+        const uint32_t p = __shfl_sync(full, v, (int)(s - wlo)) & 0x3FFFFFFFu;
+        if ((uint32_t)lane == s - wlo) {
+          v |= kUsed;
+          dirty = true;
+        }
+        if (lane == 0) a.path[path_at + cnt] = s;
+        ++cnt;
+        if (p == s) break;  // chain start: its own predecessor
+        if (p < wlo) {      // slide the window so that p is its last element
+          if (dirty) pred[wlo + lane] = v;
+          dirty = false;
+          __syncwarp(full);
+          wlo = p >= 31u ? p - 31u : 0u;
+          v = (wlo + lane < n) ? pred[wlo + lane] : 0u;
+        }
+        if (__shfl_sync(full, v, (int)(p - wlo)) & kUsed) {
+          hit_used = true;
+          stop_pred = p;
+          break;
+        }
+        s = p;
+      }
+      if (dirty) pred[wlo + lane] = v;
+      __syncwarp(full);
+      if (cnt >= 2u && lane == 0) {
+        CandRec c;
+        c.score = score[e];
+        if (hit_used) c.score = __fsub_rn(c.score, score[stop_pred]);
+        c.entry = entry;
+        c.bucket = bucket;
+        c.start = kl.target(a.c.key[s]);
+        c.end = kl.target(a.c.key[e]);
+        c.n = cnt;
+        c.end_idx = e;
+        c.path_off = path_at;
+        c.owner = a.rank;
+        add_candidate(a, c);
+        if (a.cand_list) {
+          const unsigned long long at = atomicAdd(&a.c.ctr->n_cand, 1ull);
+          if (at < a.cand_cap) a.cand_list[at] = c;
+          else atomicOr(&a.c.ctr->error, 32u);
+        }
+      }
+      if (cnt >= 2u) path_at += cnt;
+    }
+    if (score[e] < half) break;  // :564-567
+  }
+}
+
+// sharded: candidates of the other ranks (gathered lists, `per_rank` records each) join the
+// per-entry scratch lists; the order inside a list is irrelevant (the selection below is a
+// total order on (score, n, dir, contig, start, end)).
+__global__ void k_sel_scatter(SelectArgs a, const CandRec *__restrict__ all, const unsigned long long *__restrict__ counts,
+                              uint32_t world, uint32_t per_rank) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t r = i / per_rank, k = i % per_rank;
+  if (r >= world || r == a.rank || k >= counts[r]) return;
+  add_candidate(a, all[(size_t)r * per_rank + k]);
+}
+
 // spatial_index.h:38-44 operator> on (score, n, dir, contig, start, end)
-__device__ __forceinline__ bool chain_greater(const ChainTmp &x, const ChainTmp &y) {
+__device__ __forceinline__ bool chain_greater(const CandRec &x, const CandRec &y) {
   if (x.score != y.score) return x.score > y.score;
   if (x.n != y.n) return x.n > y.n;
-  if (x.dir != y.dir) return x.dir > y.dir;
-  if (x.contig != y.contig) return x.contig > y.contig;
+  const uint32_t xd = (x.bucket & 1u) ^ 1u, yd = (y.bucket & 1u) ^ 1u;  // strand bit 0 = Positive (enum 1)
+  if (xd != yd) return xd > yd;
+  if ((x.bucket >> 1) != (y.bucket >> 1)) return (x.bucket >> 1) > (y.bucket >> 1);
   if (x.start != y.start) return x.start > y.start;
   return x.end > y.end;
 }
 
-__global__ void __launch_bounds__(64) k_chain_select(SelectArgs a) {
-  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+constexpr int kFinalThreads = 128;
+
+__global__ void __launch_bounds__(kFinalThreads) k_sel_final(SelectArgs a) {
+  const int lane = threadIdx.x & 31;
+  const unsigned full = 0xffffffffu;
+  const uint32_t b = (blockIdx.x * kFinalThreads + threadIdx.x) / 32;
   if (b >= a.B) return;
   const uint32_t slot = a.entry_slot[b];
   SlotState st = a.slots[slot];
@@ -489,126 +638,83 @@ __global__ void __launch_bounds__(64) k_chain_select(SelectArgs a) {
     // chains unchanged (chunk skipped: <= 50 features, or no chunk this round); move the
     // slot's records to the pool that survives the next round
     if (st.n_chains > 0) {
-      unsigned long long co = atomicAdd(&ctr->carry_chain_used[op], (unsigned long long)st.n_chains);
-      unsigned long long ao = atomicAdd(&ctr->carry_anchor_used[op], (unsigned long long)st.carry_n);
+      unsigned long long co = 0, ao = 0;
+      if (lane == 0) {
+        co = atomicAdd(&ctr->carry_chain_used[op], (unsigned long long)st.n_chains);
+        ao = atomicAdd(&ctr->carry_anchor_used[op], (unsigned long long)st.carry_n);
+      }
+      co = __shfl_sync(full, co, 0);
+      ao = __shfl_sync(full, ao, 0);
       if (co + st.n_chains > a.pool_chain_cap || ao + st.carry_n > a.pool_anchor_cap) {
-        atomicOr(&ctr->error, 2u);
+        if (lane == 0) atomicOr(&ctr->error, 2u);
       } else {
         const ChainRec *sc = a.pool_chain[st.pool] + st.chain_off;
         const CarryAnchor *sa = a.pool_anchor[st.pool] + st.carry_off;
-        for (uint32_t i = 0; i < st.n_chains; ++i) a.pool_chain[op][co + i] = sc[i];
-        for (uint32_t i = 0; i < st.carry_n; ++i) a.pool_anchor[op][ao + i] = sa[i];
+        for (uint32_t i = lane; i < st.n_chains; i += 32) a.pool_chain[op][co + i] = sc[i];
+        for (uint32_t i = lane; i < st.carry_n; i += 32) a.pool_anchor[op][ao + i] = sa[i];
       }
       st.chain_off = co;
       st.carry_off = ao;
     }
     st.pool = op;
     st.stop = 0;
-    a.slots[slot] = st;
+    if (lane == 0) a.slots[slot] = st;
     return;
   }
 
   const KeyLayout kl = a.c.kl;
-  const uint64_t *key = a.c.key;
-  const float *score = a.c.score;
-  uint32_t *pred = a.c.pred;
   ChainTmp *ch = a.scratch + (size_t)b * a.max_chains;
-  uint32_t nch = 0;
-  float gmax = 0.0f;  // max_chaining_score, spatial_index.cc:419
-
-  // buckets in the reference's order (contig-major, '+' first): slot = entry << bbits | bucket
-  const uint32_t n_buckets = 1u << kl.bbits;
-  for (uint32_t bucket = 0; bucket < n_buckets; ++bucket) {
-    const SegRec rec = a.c.seg[((size_t)b << kl.bbits) | bucket];
-    if (rec.start == kSegEmpty) continue;
-    // The DP kept the segment's best three end candidates under its own running max; the
-    // reference's test also includes the max of the earlier buckets (gprev), which removes
-    // exactly the candidates with score <= gprev/2 -- a suffix of the list (:545-549).
-    const float half_prev = __fdiv_rn(gmax, 2.0f);
-    if (rec.max > gmax) gmax = rec.max;
-    const float half = __fdiv_rn(gmax, 2.0f);
-    for (uint32_t r = 0; r < rec.ntop; ++r) {
-      if (!(rec.top_s[r] > half_prev)) break;
-      const unsigned long long e = rec.top_i[r];
-      // ---- TracebackChains (spatial_index.cc:165-220)
-      if (!(pred[e] & 0x80000000u)) {
-        unsigned long long s = e;
-        uint32_t n = 1;
-        bool hit_used = false;
-        uint32_t p = pred[s] & 0x7FFFFFFFu;
-        if (p != s && (pred[p] & 0x80000000u)) hit_used = true;
-        pred[s] |= 0x80000000u;
-        while (p != s && !(pred[p] & 0x80000000u)) {
-          s = p;
-          ++n;
-          p = pred[s] & 0x7FFFFFFFu;
-          if (p != s && (pred[p] & 0x80000000u)) hit_used = true;
-          pred[s] |= 0x80000000u;
-        }
-        if (n >= 2) {
-          float sc = score[e];
-          if (hit_used) sc = __fsub_rn(sc, score[pred[s] & 0x7FFFFFFFu]);
-          if (nch < a.max_chains) {
-            ChainTmp c;
-            c.score = sc;
-            c.contig = bucket >> 1;
-            c.start = kl.target(key[s]);
-            c.end = kl.target(key[e]);
-            c.n = n;
-            c.dir = (bucket & 1u) ? 0u : 1u;  // strand bit 0 = Positive (enum value 1)
-            c.end_idx = (uint32_t)e;
-            c.state = 0;
-            c.rank = 0;
-            ch[nch++] = c;
-          } else {
-            st.flags |= 2u;
-            atomicOr(&ctr->error, 4u);
-          }
-        }
-      }
-      if (score[e] < half) break;  // :564-567
-    }
-  }
+  const uint32_t nch = min(a.n_scratch[b], a.max_chains);
+  if (a.n_scratch[b] > a.max_chains) st.flags |= 2u;
 
   // ---- GeneratePrimaryChains (spatial_index.cc:222-253) by repeated extraction of the max
-  uint32_t n_prim = 0;
-  uint32_t prim_first = 0, prim_second = 0;
-  float last_primary_score = 0.0f;
-  for (;;) {
-    int best = -1;
-    for (uint32_t c = 0; c < nch; ++c)
-      if (ch[c].state == 0 && (best < 0 || chain_greater(ch[c], ch[best]))) best = (int)c;
-    if (best < 0) break;
-    if (n_prim > 0 && ch[best].score < __fdiv_rn(last_primary_score, 3.0f)) break;
-    bool ok = true;
-    for (uint32_t c = 0; c < nch && ok; ++c) {
-      if (ch[c].state != 1 || ch[c].contig != ch[best].contig) continue;
-      const uint32_t mx = max(ch[best].start, ch[c].start), mn = min(ch[best].end, ch[c].end);
-      if (!(mx > mn)) ok = false;
-    }
-    if (ok) {
-      ch[best].state = 1;
-      ch[best].rank = n_prim;
-      if (n_prim == 0) prim_first = (uint32_t)best;
-      if (n_prim == 1) prim_second = (uint32_t)best;
-      last_primary_score = ch[best].score;
-      ++n_prim;
-    } else {
-      ch[best].state = 2;
+  uint32_t n_prim = 0, prim_first = 0, prim_second = 0, total_anchors = 0;
+  if (lane == 0) {
+    float last_primary_score = 0.0f;
+    for (;;) {
+      int best = -1;
+      for (uint32_t c = 0; c < nch; ++c)
+        if (ch[c].state == 0 && (best < 0 || chain_greater(ch[c].c, ch[best].c))) best = (int)c;
+      if (best < 0) break;
+      const CandRec cb = ch[best].c;
+      if (n_prim > 0 && cb.score < __fdiv_rn(last_primary_score, 3.0f)) break;
+      bool ok = true;
+      for (uint32_t c = 0; c < nch && ok; ++c) {
+        if (ch[c].state != 1 || (ch[c].c.bucket >> 1) != (cb.bucket >> 1)) continue;
+        const uint32_t mx = max(cb.start, ch[c].c.start), mn = min(cb.end, ch[c].c.end);
+        if (!(mx > mn)) ok = false;
+      }
+      if (ok) {
+        ch[best].state = 1;
+        ch[best].rank = n_prim;
+        if (n_prim == 0) prim_first = (uint32_t)best;
+        if (n_prim == 1) prim_second = (uint32_t)best;
+        last_primary_score = cb.score;
+        if (cb.owner == a.rank) total_anchors += cb.n;
+        ++n_prim;
+      } else {
+        ch[best].state = 2;
+      }
     }
   }
+  __syncwarp(full);
+  n_prim = __shfl_sync(full, n_prim, 0);
+  prim_first = __shfl_sync(full, prim_first, 0);
+  prim_second = __shfl_sync(full, prim_second, 0);
+  total_anchors = __shfl_sync(full, total_anchors, 0);
 
-  // ---- write survivors to the carry pool, primary order, anchors end -> start
+  // ---- survivors to the carry pool, primary order, anchors end -> start
   unsigned long long co = 0, ao = 0;
-  uint32_t total_anchors = 0;
-  for (uint32_t c = 0; c < nch; ++c)
-    if (ch[c].state == 1) total_anchors += ch[c].n;
   bool pool_ok = true;
   if (n_prim > 0) {
-    co = atomicAdd(&ctr->carry_chain_used[op], (unsigned long long)n_prim);
-    ao = atomicAdd(&ctr->carry_anchor_used[op], (unsigned long long)total_anchors);
+    if (lane == 0) {
+      co = atomicAdd(&ctr->carry_chain_used[op], (unsigned long long)n_prim);
+      ao = atomicAdd(&ctr->carry_anchor_used[op], (unsigned long long)total_anchors);
+    }
+    co = __shfl_sync(full, co, 0);
+    ao = __shfl_sync(full, ao, 0);
     if (co + n_prim > a.pool_chain_cap || ao + total_anchors > a.pool_anchor_cap) {
-      atomicOr(&ctr->error, 2u);
+      if (lane == 0) atomicOr(&ctr->error, 2u);
       pool_ok = false;
     }
   }
@@ -617,83 +723,108 @@ __global__ void __launch_bounds__(64) k_chain_select(SelectArgs a) {
   if (n_prim == 1) {
     mapq0 = 60;  // spatial_index.cc:255-258
   } else if (n_prim >= 2) {
-    const float ratio = __fdiv_rn(ch[prim_second].score, ch[prim_first].score);
+    const float ratio = __fdiv_rn(ch[prim_second].c.score, ch[prim_first].c.score);
     int mq = (int)__fmul_rn(40.0f, __fsub_rn(1.0f, ratio));
     mq = mq > 60 ? 60 : (mq < 0 ? 0 : mq);
     mapq0 = (uint32_t)(uint8_t)mq;
   }
   if (pool_ok && n_prim > 0) {
-    // ranks are 0..n_prim-1; emit in rank order
     uint32_t aoff = 0;
-    for (uint32_t r = 0; r < n_prim; ++r) {
+    for (uint32_t r = 0; r < n_prim; ++r) {  // ranks are 0..n_prim-1; emit in rank order
       uint32_t c = 0;
       while (!(ch[c].state == 1 && ch[c].rank == r)) ++c;
-      mean = __fadd_rn(mean, ch[c].score);
-      ChainRec rec;
-      rec.score = ch[c].score;
-      rec.contig = ch[c].contig;
-      rec.start = ch[c].start;
-      rec.end = ch[c].end;
-      rec.n_anchors = ch[c].n;
-      rec.mapq = r == 0 ? mapq0 : 0;
-      rec.dir = ch[c].dir;
-      rec.anchor_off = aoff;
-      a.pool_chain[op][co + r] = rec;
-      const uint32_t bucket = (ch[c].contig << 1) | (ch[c].dir ? 0u : 1u);
-      uint32_t idx = ch[c].end_idx;
-      CarryAnchor *dst = a.pool_anchor[op] + ao + aoff;
-      for (uint32_t k = 0; k < ch[c].n; ++k) {
-        CarryAnchor ca;
-        ca.target = kl.target(key[idx]);
-        ca.query = kl.query(key[idx]);
-        ca.dist = a.c.dist[idx];
-        ca.bucket = bucket;
-        dst[k] = ca;
-        idx = pred[idx] & 0x7FFFFFFFu;
+      const CandRec cc = ch[c].c;
+      mean = __fadd_rn(mean, cc.score);
+      const bool owned = cc.owner == a.rank;
+      if (lane == 0) {
+        ChainRec rec;
+        rec.score = cc.score;
+        rec.contig = cc.bucket >> 1;
+        rec.start = cc.start;
+        rec.end = cc.end;
+        rec.n_anchors = cc.n;
+        rec.mapq = r == 0 ? mapq0 : 0;
+        rec.dir = (cc.bucket & 1u) ^ 1u;
+        rec.anchor_off = owned ? aoff : 0xFFFFFFFFu;
+        a.pool_chain[op][co + r] = rec;
       }
-      aoff += ch[c].n;
+      if (owned) {
+        CarryAnchor *dst = a.pool_anchor[op] + ao + aoff;
+        for (uint32_t k = lane; k < cc.n; k += 32) {
+          const uint32_t idx = a.path[cc.path_off + k];
+          const uint64_t kk = a.c.key[idx];
+          CarryAnchor ca;
+          ca.target = kl.target(kk);
+          ca.query = kl.query(kk);
+          ca.dist = a.c.dist[idx];
+          ca.bucket = cc.bucket;
+          dst[k] = ca;
+        }
+        aoff += cc.n;
+      }
     }
     mean = __fdiv_rn(mean, (float)n_prim);
   }
+  __syncwarp(full);
 
   // ---- StreamingMap decision + tag sums on chains[0] (sigmap.cc:667-687, :701-745)
   st.n_chains = n_prim;
   st.chain_off = co;
   st.carry_off = ao;
-  st.carry_n = total_anchors;
+  st.carry_n = pool_ok ? total_anchors : 0u;
   st.pool = op;
   st.num_events += a.n_features[b];  // sigmap.cc:666
   st.stop = 0;
   st.mapped = 0;
   st.cm = 0;
+  st.owned0 = 0;
   st.s1 = st.s2 = st.sm = st.ad = st.at = st.aq = 0.0f;
+  st.q_first = st.q_last = 0;
   if (n_prim > 0 && pool_ok) {
-    const ChainTmp &c0 = ch[prim_first];
+    const CandRec c0 = ch[prim_first].c;
     const float s0 = c0.score;
-    const float s1 = n_prim > 1 ? ch[prim_second].score : 0.0f;
-    float ad = 0.0f, at = 0.0f, aq = 0.0f;
-    const CarryAnchor *an = a.pool_anchor[op] + ao;  // chain 0 is first
-    for (uint32_t k = 0; k < c0.n; ++k) {
-      ad = __fadd_rn(ad, an[k].dist);
-      if (k + 1 < c0.n) {
-        at = __fadd_rn(at, (float)(uint32_t)(an[k].target - an[k + 1].target));
-        aq = __fadd_rn(aq, (float)(uint32_t)(an[k].query - an[k + 1].query));
+    const float s1 = n_prim > 1 ? ch[prim_second].c.score : 0.0f;
+    if (c0.owner == a.rank) {
+      // sequential fp32 sums in anchor order (sigmap.cc:735-743), values fetched 32 at a time
+      const CarryAnchor *an = a.pool_anchor[op] + ao;  // chain 0 is first
+      float ad = 0.0f, at = 0.0f, aq = 0.0f;
+      for (uint32_t k0 = 0; k0 < c0.n; k0 += 32) {
+        const uint32_t k = k0 + lane;
+        float d = 0.0f, dt = 0.0f, dq = 0.0f;
+        if (k < c0.n) {
+          const CarryAnchor x = an[k];
+          d = x.dist;
+          if (k + 1 < c0.n) {
+            const CarryAnchor y = an[k + 1];
+            dt = (float)(uint32_t)(x.target - y.target);
+            dq = (float)(uint32_t)(x.query - y.query);
+          }
+        }
+        const int m = (int)min(32u, c0.n - k0);
+        for (int j = 0; j < m; ++j) {
+          ad = __fadd_rn(ad, __shfl_sync(full, d, j));
+          if (k0 + j + 1 < c0.n) {
+            at = __fadd_rn(at, __shfl_sync(full, dt, j));
+            aq = __fadd_rn(aq, __shfl_sync(full, dq, j));
+          }
+        }
       }
+      st.ad = __fdiv_rn(ad, (float)c0.n);
+      st.at = __fdiv_rn(at, (float)c0.n);
+      st.aq = __fdiv_rn(aq, (float)c0.n);
+      st.q_first = an[0].query;
+      st.q_last = an[c0.n - 1].query;
+      st.owned0 = 1;
     }
-    st.ad = __fdiv_rn(ad, (float)c0.n);
-    st.at = __fdiv_rn(at, (float)c0.n);
-    st.aq = __fdiv_rn(aq, (float)c0.n);
     st.s1 = s0;
     st.s2 = s1;
     st.sm = mean;
     st.cm = c0.n;
-    st.c0_contig = c0.contig;
+    st.c0_contig = c0.bucket >> 1;
     st.c0_start = c0.start;
     st.c0_end = c0.end;
-    st.c0_dir = c0.dir;
+    st.c0_dir = (c0.bucket & 1u) ^ 1u;
     st.c0_mapq = mapq0;
-    st.q_first = an[0].query;
-    st.q_last = an[c0.n - 1].query;
     if (n_prim >= 2) {
       const float ratio = __fdiv_rn(s0, s1);
       if (ratio >= a.prm.stop_mapping || s0 >= __fmul_rn(a.prm.stop_mapping_mean, mean)) st.stop = 1;
@@ -704,7 +835,7 @@ __global__ void __launch_bounds__(64) k_chain_select(SelectArgs a) {
       if (c0.n >= (uint32_t)a.prm.min_num_anchors_output) st.mapped = 1;
     }
   }
-  a.slots[slot] = st;
+  if (lane == 0) a.slots[slot] = st;
 }
 
 }  // namespace sb

@@ -35,14 +35,17 @@ __device__ __forceinline__ uint64_t spread10(uint32_t v) {
   return r;
 }
 
+// wsrc (contig-sharded index): offset of local window w's first value in val[]; nullptr = w
 __global__ void k_morton(const float *__restrict__ val, uint64_t n_windows, float vmin, float inv_span,
-                         uint64_t *__restrict__ code, uint32_t *__restrict__ widx) {
+                         uint64_t *__restrict__ code, uint32_t *__restrict__ widx,
+                         const uint32_t *__restrict__ wsrc) {
   uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= n_windows) return;
+  const uint64_t v0 = wsrc ? (uint64_t)wsrc[w] : w;
   uint64_t c = 0;
 #pragma unroll
   for (int d = 0; d < kDim; ++d) {
-    float t = (val[w + d] - vmin) * inv_span * 1024.0f;
+    float t = (val[v0 + d] - vmin) * inv_span * 1024.0f;
     int qv = (int)t;
     qv = qv < 0 ? 0 : (qv > 1023 ? 1023 : qv);
     c |= spread10((uint32_t)qv) << (kDim - 1 - d);
@@ -55,19 +58,21 @@ __global__ void k_morton(const float *__restrict__ val, uint64_t n_windows, floa
 __global__ void k_build_leaves(const float *__restrict__ val, const uint64_t *__restrict__ pos,
                                const uint32_t *__restrict__ order, uint64_t n_windows,
                                uint32_t n_leaves, float2 *__restrict__ leaf_vals,
-                               uint2 *__restrict__ leaf_tb, uint32_t *__restrict__ leaf_widx) {
+                               uint2 *__restrict__ leaf_tb, uint32_t *__restrict__ leaf_widx,
+                               const uint32_t *__restrict__ wsrc, const uint32_t *__restrict__ worig) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (uint64_t)n_leaves * kLeaf) return;
   const uint32_t leaf = (uint32_t)(i / kLeaf), sub = (uint32_t)(i % kLeaf);
   float2 *v = leaf_vals + (size_t)leaf * 3 * kLeaf + sub;
   if (i < n_windows) {
     const uint32_t w = order[i];
+    const uint64_t v0 = wsrc ? (uint64_t)wsrc[w] : (uint64_t)w;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) v[k * kLeaf] = make_float2(val[(uint64_t)w + 2 * k], val[(uint64_t)w + 2 * k + 1]);
+    for (int k = 0; k < 3; ++k) v[k * kLeaf] = make_float2(val[v0 + 2 * k], val[v0 + 2 * k + 1]);
     const uint64_t P = pos[w];
     // target = pos >> 1 (spatial_index.cc:380-381); bucket = contig*2 + strand
     leaf_tb[i] = make_uint2((uint32_t)(P >> 1), (uint32_t)((P >> 33) << 1) | (uint32_t)(P & 1));
-    leaf_widx[i] = w;
+    leaf_widx[i] = worig ? worig[w] : w;
   } else {
 #pragma unroll
     for (int k = 0; k < 3; ++k) v[k * kLeaf] = make_float2(kPadValue, kPadValue);
@@ -231,8 +236,8 @@ __device__ __forceinline__ uint32_t find_entry(const uint32_t *__restrict__ q_of
 // flight, and pushes the survivors onto the (empty) stack of the level below -- so a level
 // never holds more than the 64 children of one step.  Surviving leaves queue up and are
 // evaluated eight at a time the same way.
-template <bool STAGE>
-__global__ void __launch_bounds__(kSearchWarps * 32, 4)
+template <bool STAGE, int MINB = 4>
+__global__ void __launch_bounds__(kSearchWarps * 32, MINB)
 k_radius_search(const IndexView ix, const SearchArgs a) {
   extern __shared__ __align__(16) unsigned char s_dyn[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;

@@ -103,7 +103,7 @@ struct SlotState {
   uint32_t num_events;   // query offset of the next chunk (sigmap.cc:666)
   uint32_t n_chains;
   uint32_t pool;         // which carry pool holds this slot's chains/anchors
-  uint32_t pad0;
+  uint32_t owned0;       // 1: chain 0's anchors (and so ad/at/aq, q_first/q_last) are on this rank
   uint64_t chain_off;    // ChainRec index into pool_chain[pool]
   uint64_t carry_off;    // CarryAnchor index into pool_anchor[pool]
   uint32_t carry_n;
@@ -125,10 +125,12 @@ struct Counters {
   unsigned long long carry_anchor_used[2];
   unsigned long long carry_chain_used[2];
   unsigned long long sort_cursor;   // output position of the per-entry sort (k_seg_sort)
+  unsigned long long n_cand;        // sharded: chain candidates this rank appended to its exchange list
   unsigned int n_segments;
   unsigned int work;                // dynamic work counter for the search kernel
   unsigned int error;               // bit0 anchor overflow, bit1 carry overflow, bit2 chain scratch,
-                                    // bit3 run table overflow, bit4 entry too dense for k_seg_sort
+                                    // bit3 run table overflow, bit4 entry too dense for k_seg_sort,
+                                    // bit5 candidate exchange list overflow
   unsigned int max_entry_anchors;   // most anchors any one entry received this step
 };
 

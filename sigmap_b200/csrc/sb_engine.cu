@@ -24,6 +24,7 @@
 #include "k_events.cuh"
 #include "k_index.cuh"
 #include "sb_device.cuh"
+#include "sb_exchange.cuh"
 
 using namespace sb;
 
@@ -51,6 +52,7 @@ __global__ void k_reset_step(Counters *c) {
   c->n_segments = 0;
   c->work = 0;
   c->sort_cursor = 0;
+  c->n_cand = 0;
   c->max_entry_anchors = 0;
   c->error &= ~24u;  // per-step bits (run table overflow, dense entry); the others are per round
 }
@@ -189,6 +191,13 @@ struct Workspace {
   DevBuf<uint32_t> run_count, entry_total;
   DevBuf<unsigned char> cub_temp;
   DevBuf<ChainTmp> chain_tmp;
+  DevBuf<float> seg_max;
+  DevBuf<uint32_t> n_scratch;
+  // contig-sharded runs (sb_exchange.cuh)
+  DevBuf<CandRec> cand_list, cand_all;
+  DevBuf<unsigned long long> cand_counts;
+  DevBuf<double> ctl;
+  DevBuf<uint32_t> tags;
   // round readback
   DevBuf<uint32_t> ids;
   DevBuf<RoundInfo> round_info;
@@ -211,6 +220,7 @@ struct smb_ctx {
   int gshift = 0;
   uint32_t n_coarse = 1;
   bool seg_sort = true;           // per-entry shared-memory sort; SMB_SORT=global forces the radix sort
+  int search_minb = 4;            // CTAs per SM the search kernel is compiled for (SMB_SEARCH_MINB=4|5|6)
   std::vector<uint32_t> contig_len;
   // uploaded reads
   size_t n_reads = 0;
@@ -234,6 +244,11 @@ struct smb_ctx {
   uint64_t max_batch_anchors = 640ull << 20;  // x 32 B of sort/DP buffers = 20 GB of the 180 GB HBM
   uint64_t last_cap = 0;
   double est_anchors_per_chunk = 20000.0;
+  // contig-sharded index: the exchange backend (null = this context holds every contig)
+  std::unique_ptr<Exchange> ex;
+  std::shared_ptr<LocalGroup> local_group;
+  double *h_ctl = nullptr;  // pinned, 4 doubles
+  bool group_at_limit = false;
   // streaming
   SlotSpace *stream_slots = nullptr;
   smb_params stream_params{};
@@ -268,16 +283,18 @@ struct smb_batch {
 
 static int fail(smb_ctx *ctx, int code, const std::string &msg) {
   ctx->err = msg;
+  // a failed member must not leave its in-process shard peers waiting at a rendezvous
+  if (ctx->local_group) ctx->local_group->abort_all();
   return code;
 }
 
 // persistent grid of the search kernel: every CTA that fits on the device, no more
 static size_t search_smem(const smb_ctx *ctx) { return kSearchWarps * search_smem_per_warp(ctx->ix.n_levels); }
 
-template <bool STAGE>
+template <bool STAGE, int MINB = 4>
 static unsigned search_grid(smb_ctx *ctx) {
   int n = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_radius_search<STAGE>, kSearchWarps * 32,
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_radius_search<STAGE, MINB>, kSearchWarps * 32,
                                                     search_smem(ctx)) != cudaSuccess || n < 1)
     n = 4;
   int n_sm = 148;
@@ -286,11 +303,52 @@ static unsigned search_grid(smb_ctx *ctx) {
 }
 
 // ------------------------------------------------------------------ index build
-static int build_index(smb_ctx *ctx, const uint64_t *pos, const float *val, size_t n) {
+// owner == nullptr: every window of the cloud.  Otherwise (contig-sharded index) only the
+// windows whose first point lies on a contig with owner[contig] == rank; a window keeps its six
+// values even where it runs into the next contig / strand (Q2), so the shard holds exactly the
+// points the unsharded index holds for those contigs.
+static int build_index(smb_ctx *ctx, const uint64_t *pos, const float *val, size_t n,
+                       const uint32_t *owner = nullptr, uint32_t n_contigs = 0, uint32_t rank = 0) {
   if (n < (size_t)kDim) return fail(ctx, SMB_ERR_ARG, "point cloud smaller than the index dimension");
-  if (n - (kDim - 1) > 0xFFFFFFF0ull)
+  const uint64_t W_all = n - (kDim - 1);
+  // ---- which windows, and where their values start in the uploaded value array
+  std::vector<float> h_val;       // sharded: runs of owned values, each with 5 trailing values
+  std::vector<uint64_t> h_pos;    // sharded: position of every owned window
+  std::vector<uint32_t> h_wsrc, h_worig;
+  if (owner) {
+    for (uint64_t w = 0; w < W_all;) {
+      const uint64_t c = pos[w] >> 33;
+      if (c >= n_contigs) return fail(ctx, SMB_ERR_ARG, "point cloud names a contig beyond n_contigs");
+      if (owner[c] != rank) {
+        ++w;
+        continue;
+      }
+      uint64_t e = w + 1;  // maximal run of owned windows [w, e)
+      while (e < W_all && (pos[e] >> 33) < n_contigs && owner[pos[e] >> 33] == rank) ++e;
+      const size_t base = h_val.size();
+      if (base + (e - w) + kDim > 0xFFFFFFF0ull)
+        return fail(ctx, SMB_ERR_CAPACITY, "more than 2^32 window points on one shard: use more ranks");
+      h_val.insert(h_val.end(), val + w, val + e + (kDim - 1));
+      for (uint64_t x = w; x < e; ++x) {
+        h_pos.push_back(pos[x]);
+        h_wsrc.push_back((uint32_t)(base + (x - w)));
+        h_worig.push_back((uint32_t)x);
+      }
+      w = e;
+    }
+    if (h_pos.empty()) {  // a rank may own nothing (more ranks than contigs): keep one padding leaf
+      h_val.assign(kDim, kPadValue);
+      h_pos.push_back(~0ull);
+      h_wsrc.push_back(0);
+      h_worig.push_back(0xFFFFFFFFu);
+    }
+  } else if (W_all > 0xFFFFFFF0ull) {
     return fail(ctx, SMB_ERR_CAPACITY, "more than 2^32 window points: shard the index by contig");
-  const uint64_t W = n - (kDim - 1);
+  }
+  const uint64_t W = owner ? h_pos.size() : W_all;
+  const float *u_val = owner ? h_val.data() : val;
+  const uint64_t *u_pos = owner ? h_pos.data() : pos;
+  const size_t n_val = owner ? h_val.size() : n, n_pos = owner ? h_pos.size() : n;
   const uint32_t n_leaves = (uint32_t)((W + kLeaf - 1) / kLeaf);
   float vmin = val[0], vmax = val[0];
   uint32_t max_tpos = 0, max_bucket = 0;
@@ -308,17 +366,23 @@ static int build_index(smb_ctx *ctx, const uint64_t *pos, const float *val, size
   cudaStream_t s = ctx->stream;
   DevBuf<float> d_val;
   DevBuf<uint64_t> d_pos, code_a, code_b;
-  DevBuf<uint32_t> w_a, w_b;
+  DevBuf<uint32_t> w_a, w_b, d_wsrc, d_worig;
   DevBuf<unsigned char> tmp;
-  CK(d_val.ensure(n));
-  CK(d_pos.ensure(n));
+  CK(d_val.ensure(n_val));
+  CK(d_pos.ensure(n_pos));
   CK(code_a.ensure(W));
   CK(code_b.ensure(W));
   CK(w_a.ensure(W));
   CK(w_b.ensure(W));
-  CK(cudaMemcpyAsync(d_val.p, val, n * sizeof(float), cudaMemcpyHostToDevice, s));
-  CK(cudaMemcpyAsync(d_pos.p, pos, n * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
-  k_morton<<<(unsigned)((W + 255) / 256), 256, 0, s>>>(d_val.p, W, vmin, 1.0f / span, code_a.p, w_a.p);
+  CK(cudaMemcpyAsync(d_val.p, u_val, n_val * sizeof(float), cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(d_pos.p, u_pos, n_pos * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+  if (owner) {
+    CK(d_wsrc.ensure(W));
+    CK(d_worig.ensure(W));
+    CK(cudaMemcpyAsync(d_wsrc.p, h_wsrc.data(), W * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d_worig.p, h_worig.data(), W * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+  }
+  k_morton<<<(unsigned)((W + 255) / 256), 256, 0, s>>>(d_val.p, W, vmin, 1.0f / span, code_a.p, w_a.p, d_wsrc.p);
   LAUNCH_CHECK();
   size_t tb = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, tb, code_a.p, code_b.p, w_a.p, w_b.p, (uint64_t)W, 0, 60, s);
@@ -329,7 +393,7 @@ static int build_index(smb_ctx *ctx, const uint64_t *pos, const float *val, size
   CK(ctx->leaf_tb.ensure((size_t)n_leaves * kLeaf));
   CK(ctx->leaf_widx.ensure((size_t)n_leaves * kLeaf));
   k_build_leaves<<<(unsigned)(((uint64_t)n_leaves * kLeaf + 255) / 256), 256, 0, s>>>(
-      d_val.p, d_pos.p, w_b.p, W, n_leaves, ctx->leaf_vals.p, ctx->leaf_tb.p, ctx->leaf_widx.p);
+      d_val.p, d_pos.p, w_b.p, W, n_leaves, ctx->leaf_vals.p, ctx->leaf_tb.p, ctx->leaf_widx.p, d_wsrc.p, d_worig.p);
   LAUNCH_CHECK();
   IndexView ix{};
   ix.n_points = n;
@@ -365,6 +429,8 @@ static int build_index(smb_ctx *ctx, const uint64_t *pos, const float *val, size
   code_b.release();
   w_a.release();
   w_b.release();
+  d_wsrc.release();
+  d_worig.release();
   tmp.release();
   {
     // linear coordinate g = bucket_base[bucket] + target: monotone in the sort order, dense
@@ -378,7 +444,8 @@ static int build_index(smb_ctx *ctx, const uint64_t *pos, const float *val, size
     ctx->n_coarse = (uint32_t)(base.back() >> ctx->gshift) + 1;
   }
   ctx->ix = ix;
-  ctx->search_grid_main = search_grid<false>(ctx);
+  ctx->search_grid_main = ctx->search_minb == 6 ? search_grid<false, 6>(ctx)
+                          : ctx->search_minb == 5 ? search_grid<false, 5>(ctx) : search_grid<false, 4>(ctx);
   ctx->max_tpos = max_tpos;
   ctx->max_bucket = max_bucket;
   ctx->has_index = true;
@@ -556,7 +623,12 @@ static int run_step(smb_ctx *ctx, SlotSpace &sp, const StepEntries &en, StepSour
   sa.entry_total = w.entry_total.p;
   sa.runs_cap = kRunsCap;
   CK(cudaEventRecord(ctx->ev[2], s));
-  k_radius_search<false><<<ctx->search_grid_main, kSearchWarps * 32, search_smem(ctx), s>>>(ctx->ix, sa);
+  if (ctx->search_minb == 6)
+    k_radius_search<false, 6><<<ctx->search_grid_main, kSearchWarps * 32, search_smem(ctx), s>>>(ctx->ix, sa);
+  else if (ctx->search_minb == 5)
+    k_radius_search<false, 5><<<ctx->search_grid_main, kSearchWarps * 32, search_smem(ctx), s>>>(ctx->ix, sa);
+  else
+    k_radius_search<false, 4><<<ctx->search_grid_main, kSearchWarps * 32, search_smem(ctx), s>>>(ctx->ix, sa);
   LAUNCH_CHECK();
   ctx->stats.search_launches++;
   CK(cudaEventRecord(ctx->ev[3], s));
@@ -569,7 +641,28 @@ static int run_step(smb_ctx *ctx, SlotSpace &sp, const StepEntries &en, StepSour
   ctx->stats.ms_events += ms;
   cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]);
   ctx->stats.ms_search += ms;
-  if (n > cap) return 1;  // overflow: nothing has been committed to the slots yet
+  bool overflow = n > cap;
+  unsigned long long n_est = n;  // what the batch-size estimate is updated with
+  if (ctx->ex) {
+    // Sharded: every rank must take the same path through this step (the exchanges below are
+    // collective), so overflow and the estimate are agreed on first.
+    Workspace &wx = ctx->ws;
+    CK(wx.ctl.ensure(4));
+    ctx->h_ctl[0] = overflow ? 1.0 : 0.0;
+    ctx->h_ctl[1] = (overflow && ctx->last_cap >= ctx->max_batch_anchors) ? 1.0 : 0.0;
+    ctx->h_ctl[2] = (double)n;
+    ctx->h_ctl[3] = 0.0;
+    CK(cudaMemcpyAsync(wx.ctl.p, ctx->h_ctl, 4 * sizeof(double), cudaMemcpyHostToDevice, s));
+    int rc = ctx->ex->allreduce(wx.ctl.p, 4, EX_F64, EX_MAX, s, ctx->err);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(ctx->h_ctl, wx.ctl.p, 4 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    overflow = ctx->h_ctl[0] > 0.0;
+    ctx->group_at_limit = ctx->h_ctl[1] > 0.0;
+    n_est = (unsigned long long)ctx->h_ctl[2];
+    ctx->stats.exchanges++;
+  }
+  if (overflow) return 1;  // nothing has been committed to the slots yet
   ctx->stats.queries += ctx->h_ctr->n_queries;
   ctx->stats.hits += ctx->h_ctr->n_hits;
   ctx->stats.anchors += n;
@@ -643,15 +736,18 @@ static int run_step(smb_ctx *ctx, SlotSpace &sp, const StepEntries &en, StepSour
   if (n_slots64 >= (1ull << 31)) return fail(ctx, SMB_ERR_CAPACITY, "segment table too large: lower max_batch_chunks");
   ca.n_slots = (uint32_t)n_slots64;
   CK(w.seg.ensure(ca.n_slots));
+  CK(w.seg_max.ensure(ca.n_slots));
   ca.seg = w.seg.p;
+  ca.seg_max = w.seg_max.p;
   ca.ctr = ctx->d_ctr;
   CK(cudaMemsetAsync(w.seg.p, 0xFF, (size_t)ca.n_slots * sizeof(SegRec), s));
+  CK(cudaMemsetAsync(w.seg_max.p, 0, (size_t)ca.n_slots * sizeof(float), s));
+  const unsigned n_tiles = (unsigned)((n + kPrepTile - 1) / kPrepTile);
+  CK(w.link_list.ensure((size_t)std::max(n_tiles, 1u) * kPrepTile));
+  CK(w.link_count.ensure(std::max(n_tiles, 1u)));
+  ca.link_list = w.link_list.p;
+  ca.link_count = w.link_count.p;
   if (n > 0) {
-    const unsigned n_tiles = (unsigned)((n + kPrepTile - 1) / kPrepTile);
-    CK(w.link_list.ensure((size_t)n_tiles * kPrepTile));
-    CK(w.link_count.ensure(n_tiles));
-    ca.link_list = w.link_list.p;
-    ca.link_count = w.link_count.p;
     k_chain_prep<<<n_tiles, kPrepThreads, 0, s>>>(ca);
     LAUNCH_CHECK();
     k_chain_dp<<<(unsigned)(((uint64_t)ca.n_slots * 32 + kDpThreads - 1) / kDpThreads), kDpThreads, 0, s>>>(ca);
@@ -662,12 +758,15 @@ static int run_step(smb_ctx *ctx, SlotSpace &sp, const StepEntries &en, StepSour
   se.entry_slot = w.entry_slot.p;
   se.n_queries = w.n_queries.p;
   se.n_features = w.n_features.p;
-  se.absent = nullptr;
   se.slots = sp.slots.p;
   se.B = B;
   se.max_chains = std::min<uint32_t>(3u * (ctx->max_bucket + 1u), 4096u);
   CK(w.chain_tmp.ensure((size_t)B * se.max_chains));
+  CK(w.n_scratch.ensure(B));
   se.scratch = w.chain_tmp.p;
+  se.n_scratch = w.n_scratch.p;
+  se.path = w.link_list.p;  // the DP is done with its work lists: reuse them for the chain paths
+  se.rank = ctx->ex ? (uint32_t)ctx->ex->rank : 0u;
   se.out_pool = out_pool;
   for (int p = 0; p < 2; ++p) {
     se.pool_chain[p] = sp.pool_chain[p].p;
@@ -676,7 +775,53 @@ static int run_step(smb_ctx *ctx, SlotSpace &sp, const StepEntries &en, StepSour
   se.pool_chain_cap = sp.pool_chain[out_pool].cap;
   se.pool_anchor_cap = sp.pool_anchor[out_pool].cap;
   se.prm = prm;
-  k_chain_select<<<(B + 63) / 64, 64, 0, s>>>(se);
+  CK(cudaMemsetAsync(w.n_scratch.p, 0, B * sizeof(uint32_t), s));
+  if (ctx->ex) {
+    // exchange 2: the per-bucket running max of every rank's own contigs
+    int rc = ctx->ex->allreduce(w.seg_max.p, ca.n_slots, EX_F32, EX_MAX, s, ctx->err);
+    if (rc) return rc;
+    // a chain has >= 2 anchors of its own and a segment yields <= 3 of them
+    se.cand_cap = (uint32_t)std::min<uint64_t>(3ull * ca.n_slots, n / 2) + 1u;
+    CK(w.cand_list.ensure(se.cand_cap));
+    se.cand_list = w.cand_list.p;
+    ctx->stats.exchanges++;
+  }
+  if (n > 0) {
+    k_sel_trace<<<(unsigned)(((uint64_t)ca.n_slots * 32 + kTraceThreads - 1) / kTraceThreads), kTraceThreads, 0, s>>>(se);
+    LAUNCH_CHECK();
+  }
+  if (ctx->ex) {
+    // exchange 3: candidate counts, then the candidate records padded to the largest count
+    const uint32_t world = (uint32_t)ctx->ex->world;
+    CK(w.cand_counts.ensure(world + 1));
+    int rc = ctx->ex->allgather(&ctx->d_ctr->n_cand, w.cand_counts.p, sizeof(unsigned long long), s, ctx->err);
+    if (rc) return rc;
+    std::vector<unsigned long long> h_counts(world);
+    CK(cudaMemcpyAsync(h_counts.data(), w.cand_counts.p, world * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    unsigned long long per_rank = 0;
+    for (uint32_t r = 0; r < world; ++r) per_rank = std::max(per_rank, h_counts[r]);
+    if (per_rank > 0) {
+      // my own list must be able to serve a padded send of per_rank records
+      if (w.cand_list.cap < per_rank) {
+        DevBuf<CandRec> grown;
+        CK(grown.ensure(per_rank));
+        CK(cudaMemcpyAsync(grown.p, w.cand_list.p, std::min<size_t>(w.cand_list.cap, h_counts[ctx->ex->rank]) * sizeof(CandRec), cudaMemcpyDeviceToDevice, s));
+        CK(cudaStreamSynchronize(s));
+        w.cand_list.release();
+        w.cand_list = grown;
+        se.cand_list = w.cand_list.p;
+      }
+      CK(w.cand_all.ensure((size_t)per_rank * world));
+      rc = ctx->ex->allgather(w.cand_list.p, w.cand_all.p, (size_t)per_rank * sizeof(CandRec), s, ctx->err);
+      if (rc) return rc;
+      const uint64_t total = per_rank * world;
+      k_sel_scatter<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(se, w.cand_all.p, w.cand_counts.p, world, (uint32_t)per_rank);
+      LAUNCH_CHECK();
+    }
+    ctx->stats.exchanges += 2;
+  }
+  k_sel_final<<<(unsigned)(((uint64_t)B * 32 + kFinalThreads - 1) / kFinalThreads), kFinalThreads, 0, s>>>(se);
   LAUNCH_CHECK();
   CK(cudaEventRecord(ctx->ev[2], s));
   CK(cudaMemcpyAsync(ctx->h_ctr, ctx->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
@@ -689,7 +834,8 @@ static int run_step(smb_ctx *ctx, SlotSpace &sp, const StepEntries &en, StepSour
   ctx->stats.linked += ctx->h_ctr->n_linked;
   if (ctx->h_ctr->error & 2u) return fail(ctx, SMB_ERR_CAPACITY, "carry pool overflow");
   if (ctx->h_ctr->error & 4u) return fail(ctx, SMB_ERR_CAPACITY, "per-read chain scratch overflow");
-  if (Bpres) ctx->est_anchors_per_chunk = 0.5 * ctx->est_anchors_per_chunk + 0.5 * ((double)n / Bpres);
+  if (ctx->h_ctr->error & 32u) return fail(ctx, SMB_ERR_CAPACITY, "chain candidate exchange list overflow");
+  if (Bpres) ctx->est_anchors_per_chunk = 0.5 * ctx->est_anchors_per_chunk + 0.5 * ((double)n_est / Bpres);
   return SMB_OK;
 }
 
@@ -788,7 +934,7 @@ static int run_round(smb_ctx *ctx, SlotSpace &sp, const std::vector<uint32_t> &p
       rc = run_step(ctx, sp, en, src, prm, out_pool);
       if (rc == 1) {  // anchor buffer overflow: grow the buffers, or halve the step at the limit
         ctx->est_anchors_per_chunk *= 2.0;
-        if (ctx->last_cap >= ctx->max_batch_anchors) {
+        if (ctx->ex ? ctx->group_at_limit : ctx->last_cap >= ctx->max_batch_anchors) {
           if (count <= 1) return fail(ctx, SMB_ERR_CAPACITY, "one chunk overflows max_batch_anchors");
           count = (count + 1) / 2;
         }
@@ -801,6 +947,45 @@ static int run_round(smb_ctx *ctx, SlotSpace &sp, const std::vector<uint32_t> &p
     at += count;
   }
   sp.round++;
+  return SMB_OK;
+}
+
+// Contig-sharded runs: ad/at/aq and the query span of chain 0 are computed by the rank that holds
+// chain 0's anchors (SlotState::owned0); everybody else contributes zeros, so a SUM all-reduce
+// of the bit patterns hands every rank the owner's values.  flags bit0 (5000-hit cap) is OR-ed.
+static int merge_owner_tags(smb_ctx *ctx, std::vector<SlotState> &st, size_t n) {
+  if (!ctx->ex || n == 0) return SMB_OK;
+  std::vector<uint32_t> h(n * 6);
+  auto bits = [](float f) { uint32_t u; memcpy(&u, &f, 4); return u; };
+  for (size_t r = 0; r < n; ++r) {
+    const SlotState &x = st[r];
+    const bool own = x.n_chains > 0 && x.owned0;
+    h[r * 6 + 0] = own ? bits(x.ad) : 0u;
+    h[r * 6 + 1] = own ? bits(x.at) : 0u;
+    h[r * 6 + 2] = own ? bits(x.aq) : 0u;
+    h[r * 6 + 3] = own ? x.q_first : 0u;
+    h[r * 6 + 4] = own ? x.q_last : 0u;
+    h[r * 6 + 5] = x.flags & 1u;
+  }
+  Workspace &w = ctx->ws;
+  cudaStream_t s = ctx->stream;
+  CK(w.tags.ensure(n * 6));
+  CK(cudaMemcpyAsync(w.tags.p, h.data(), n * 6 * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+  int rc = ctx->ex->allreduce(w.tags.p, n * 6, EX_U32, EX_SUM, s, ctx->err);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(h.data(), w.tags.p, n * 6 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  ctx->stats.exchanges++;
+  auto flt = [](uint32_t u) { float f; memcpy(&f, &u, 4); return f; };
+  for (size_t r = 0; r < n; ++r) {
+    SlotState &x = st[r];
+    x.ad = flt(h[r * 6 + 0]);
+    x.at = flt(h[r * 6 + 1]);
+    x.aq = flt(h[r * 6 + 2]);
+    x.q_first = h[r * 6 + 3];
+    x.q_last = h[r * 6 + 4];
+    x.flags = (x.flags & ~1u) | (h[r * 6 + 5] ? 1u : 0u);
+  }
   return SMB_OK;
 }
 
@@ -893,6 +1078,7 @@ int smb_create(smb_ctx **out, int device) {
   if ((e = cudaMalloc((void **)&ctx->d_ctr, sizeof(Counters))) != cudaSuccess) return bail("cudaMalloc", e);
   if ((e = cudaMemset(ctx->d_ctr, 0, sizeof(Counters))) != cudaSuccess) return bail("cudaMemset", e);
   if ((e = cudaMallocHost((void **)&ctx->h_ctr, sizeof(Counters))) != cudaSuccess) return bail("cudaMallocHost", e);
+  if ((e = cudaMallocHost((void **)&ctx->h_ctl, 4 * sizeof(double))) != cudaSuccess) return bail("cudaMallocHost", e);
   for (auto &ev : ctx->ev)
     if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail("cudaEventCreate", e);
   for (auto &ev : ctx->timer)
@@ -902,6 +1088,10 @@ int smb_create(smb_ctx **out, int device) {
                                 (int)kSortSmemBytes)) != cudaSuccess)
     return bail("cudaFuncSetAttribute(k_seg_sort)", e);
   if (const char *env = getenv("SMB_SORT")) ctx->seg_sort = strcmp(env, "global") != 0;
+  if (const char *env = getenv("SMB_SEARCH_MINB")) {
+    const int v = atoi(env);
+    if (v == 5 || v == 6) ctx->search_minb = v;
+  }
   *out = ctx;
   return SMB_OK;
 }
@@ -922,6 +1112,10 @@ void smb_destroy(smb_ctx *ctx) {
   w.means.release(); w.features.release(); w.key_a.release(); w.key_b.release(); w.dist_a.release();
   w.dist_b.release(); w.score.release(); w.coef.release(); w.pred.release(); w.seg.release(); w.runs.release(); w.run_count.release(); w.entry_total.release(); w.link_list.release(); w.link_count.release(); w.cub_temp.release();
   w.chain_tmp.release(); w.ids.release(); w.round_info.release();
+  w.seg_max.release(); w.n_scratch.release(); w.cand_list.release(); w.cand_all.release();
+  w.cand_counts.release(); w.ctl.release(); w.tags.release();
+  ctx->ex.reset();
+  ctx->local_group.reset();
   ctx->leaf_vals.release(); ctx->leaf_tb.release(); ctx->leaf_widx.release(); ctx->bucket_base.release();
   for (auto &l : ctx->level) l.release();
   ctx->raw.release(); ctx->kept.release(); ctx->d_read_off.release(); ctx->d_kept_off.release();
@@ -930,6 +1124,7 @@ void smb_destroy(smb_ctx *ctx) {
   for (auto &ev : ctx->timer) if (ev) cudaEventDestroy(ev);
   if (ctx->d_ctr) cudaFree(ctx->d_ctr);
   if (ctx->h_ctr) cudaFreeHost(ctx->h_ctr);
+  if (ctx->h_ctl) cudaFreeHost(ctx->h_ctl);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -997,6 +1192,95 @@ int smb_index_set_contigs(smb_ctx *ctx, const uint32_t *lengths, uint32_t n_cont
   return SMB_OK;
 }
 
+int smb_index_set_points_sharded(smb_ctx *ctx, const uint64_t *pos, const float *val, size_t n,
+                                 const uint32_t *contig_owner, uint32_t n_contigs) {
+  CK(cudaSetDevice(ctx->device));
+  if (!ctx->ex) return fail(ctx, SMB_ERR_STATE, "join a shard group first (smb_shard_local_group / smb_shard_nccl_init)");
+  for (uint32_t c = 0; c < n_contigs; ++c)
+    if (contig_owner[c] >= (uint32_t)ctx->ex->world) return fail(ctx, SMB_ERR_ARG, "contig owner out of range");
+  return build_index(ctx, pos, val, n, contig_owner, n_contigs, (uint32_t)ctx->ex->rank);
+}
+
+// ---------------------------------------------------------- contig-sharded runs
+int smbh_assign_contigs(const uint32_t *lengths, uint32_t n_contigs, uint32_t world, uint32_t *owner) {
+  if (world == 0) return SMB_ERR_ARG;
+  // longest-processing-time bin packing: contigs by decreasing length onto the lightest rank
+  std::vector<uint32_t> order(n_contigs);
+  for (uint32_t c = 0; c < n_contigs; ++c) order[c] = c;
+  std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return lengths[x] > lengths[y]; });
+  std::vector<uint64_t> load(world, 0);
+  for (uint32_t c : order) {
+    uint32_t best = 0;
+    for (uint32_t r = 1; r < world; ++r)
+      if (load[r] < load[best]) best = r;
+    owner[c] = best;
+    load[best] += lengths[c];
+  }
+  return SMB_OK;
+}
+
+int smb_shard_local_group(smb_ctx *const *ctxs, uint32_t n) {
+  if (n == 0) return SMB_ERR_ARG;
+  auto g = std::make_shared<LocalGroup>();
+  g->world = (int)n;
+  g->send.assign(n, nullptr);
+  g->device.resize(n);
+  for (uint32_t r = 0; r < n; ++r) g->device[r] = ctxs[r]->device;
+  for (uint32_t r = 0; r < n; ++r) {
+    // peers on other GPUs: direct loads over NVLink when the driver allows it
+    cudaSetDevice(ctxs[r]->device);
+    for (uint32_t q = 0; q < n; ++q) {
+      int can = 0;
+      if (ctxs[q]->device != ctxs[r]->device &&
+          cudaDeviceCanAccessPeer(&can, ctxs[r]->device, ctxs[q]->device) == cudaSuccess && can)
+        if (cudaDeviceEnablePeerAccess(ctxs[q]->device, 0) != cudaSuccess) cudaGetLastError();
+    }
+    auto ex = std::make_unique<LocalExchange>();
+    ex->rank = (int)r;
+    ex->world = (int)n;
+    ex->g = g;
+    ex->device = ctxs[r]->device;
+    ctxs[r]->ex = std::move(ex);
+    ctxs[r]->local_group = g;
+  }
+  return SMB_OK;
+}
+
+int smb_shard_nccl_unique_id(char *id128) {
+  NcclApi &api = NcclApi::get();
+  if (!api.load()) {
+    g_create_error = api.error;
+    return SMB_ERR_STATE;
+  }
+  NcclApi::unique_id id;
+  const int rc = api.GetUniqueId(&id);
+  if (rc != 0) {
+    g_create_error = std::string("ncclGetUniqueId: ") + api.GetErrorString(rc);
+    return SMB_ERR_CUDA;
+  }
+  memcpy(id128, id.internal, 128);
+  return SMB_OK;
+}
+
+int smb_shard_nccl_init(smb_ctx *ctx, int rank, int world, const char *id128) {
+  CK(cudaSetDevice(ctx->device));
+  if (world < 1 || rank < 0 || rank >= world) return fail(ctx, SMB_ERR_ARG, "bad rank / world");
+  NcclApi &api = NcclApi::get();
+  if (!api.load()) return fail(ctx, SMB_ERR_STATE, api.error);
+  NcclApi::unique_id id;
+  memcpy(id.internal, id128, 128);
+  auto ex = std::make_unique<NcclExchange>();
+  ex->rank = rank;
+  ex->world = world;
+  const int rc = api.CommInitRank(&ex->comm, world, id, rank);
+  if (rc != 0) return fail(ctx, SMB_ERR_CUDA, std::string("ncclCommInitRank: ") + api.GetErrorString(rc));
+  ctx->ex = std::move(ex);
+  return SMB_OK;
+}
+
+int smb_shard_rank(const smb_ctx *ctx) { return ctx->ex ? ctx->ex->rank : 0; }
+int smb_shard_world(const smb_ctx *ctx) { return ctx->ex ? ctx->ex->world : 1; }
+
 uint64_t smb_index_num_points(const smb_ctx *ctx) { return ctx->has_index ? ctx->ix.n_points : 0; }
 uint32_t smb_index_num_contigs(const smb_ctx *ctx) { return (uint32_t)ctx->contig_len.size(); }
 
@@ -1062,7 +1346,18 @@ static int filter_reads(smb_ctx *ctx) {
 
 extern "C" {
 
+static int map_uploaded_impl(smb_ctx *ctx, const smb_params *prm_in, smb_mapping *out);
+
 int smb_map_uploaded(smb_ctx *ctx, const smb_params *prm_in, smb_mapping *out) {
+  const int rc = map_uploaded_impl(ctx, prm_in, out);
+  // a failed member must not leave its in-process peers waiting at a rendezvous
+  if (rc && ctx->local_group) ctx->local_group->abort_all();
+  return rc;
+}
+
+}  // extern "C"
+
+static int map_uploaded_impl(smb_ctx *ctx, const smb_params *prm_in, smb_mapping *out) {
   CK(cudaSetDevice(ctx->device));
   if (!ctx->has_index) return fail(ctx, SMB_ERR_STATE, "no index loaded");
   smb_params prm = *prm_in;
@@ -1160,10 +1455,14 @@ int smb_map_uploaded(smb_ctx *ctx, const smb_params *prm_in, smb_mapping *out) {
     CK(cudaMemcpyAsync(st.data(), sp.slots.p, R * sizeof(SlotState), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->stats.d2h_bytes += R * sizeof(SlotState);
+    rc = merge_owner_tags(ctx, st, R);
+    if (rc) return rc;
   }
   for (size_t r = 0; r < R; ++r) make_row(ctx, st[r], ctx->h_kept_len[r], chunks_used[r], &out[r]);
   return SMB_OK;
 }
+
+extern "C" {
 
 int smb_map_reads(smb_ctx *ctx, const int16_t *raw, const uint64_t *read_off, const float *dig,
                   const float *range, const float *offset, size_t n_reads, const smb_params *params,
@@ -1413,6 +1712,7 @@ int smb_batch_get_anchors(smb_batch *b, uint32_t slot, uint32_t chain, smb_ancho
   if (chain >= st.n_chains) return fail(ctx, SMB_ERR_ARG, "chain out of range");
   ChainRec rec;
   CK(cudaMemcpy(&rec, b->sp.pool_chain[st.pool].p + st.chain_off + chain, sizeof(ChainRec), cudaMemcpyDeviceToHost));
+  if (rec.anchor_off == 0xFFFFFFFFu) return fail(ctx, SMB_ERR_STATE, "the chain's anchors live on the rank that owns its contig");
   const uint32_t n = std::min(cap, rec.n_anchors);
   std::vector<CarryAnchor> an(std::max(n, 1u));
   if (n) CK(cudaMemcpy(an.data(), b->sp.pool_anchor[st.pool].p + st.carry_off + rec.anchor_off, n * sizeof(CarryAnchor), cudaMemcpyDeviceToHost));
@@ -1535,6 +1835,8 @@ int smb_stream_round(smb_ctx *ctx, const uint32_t *channels, uint32_t n, const i
   std::vector<SlotState> st(sp.n_slots ? sp.n_slots : 1);
   CK(cudaMemcpy(st.data(), sp.slots.p, sp.n_slots * sizeof(SlotState), cudaMemcpyDeviceToHost));
   ctx->stats.d2h_bytes += sp.n_slots * sizeof(SlotState);
+  rc = merge_owner_tags(ctx, st, sp.n_slots);
+  if (rc) return rc;
   for (uint32_t i = 0; i < n; ++i) {
     const uint32_t ch = channels[i];
     const bool mapped_chunk = seen[ch] != 0;

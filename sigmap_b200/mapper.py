@@ -80,6 +80,25 @@ class Mapper:
         self._check(F.lib.smb_index_set_points(self._ctx, F.ptr(pos, F.u64p), F.ptr(val, F.f32p),
                                                len(pos)), "smb_index_set_points")
 
+    def set_index_sharded(self, pos, val, contig_owner):
+        """Contig-sharded index: keep only the windows of contigs with contig_owner[c] == this
+        context's shard rank (join a group first: shard.ContigShardGroup / shard.nccl_join)."""
+        pos = np.ascontiguousarray(pos, np.uint64)
+        val = np.ascontiguousarray(val, np.float32)
+        owner = np.ascontiguousarray(contig_owner, np.uint32)
+        self._check(F.lib.smb_index_set_points_sharded(self._ctx, F.ptr(pos, F.u64p),
+                                                       F.ptr(val, F.f32p), len(pos),
+                                                       F.ptr(owner, F.u32p), len(owner)),
+                    "smb_index_set_points_sharded")
+
+    @property
+    def shard_rank(self):
+        return F.lib.smb_shard_rank(self._ctx)
+
+    @property
+    def shard_world(self):
+        return F.lib.smb_shard_world(self._ctx)
+
     def set_contigs(self, lengths):
         lengths = np.ascontiguousarray(lengths, np.uint32)
         self.contig_lengths = lengths

@@ -1,9 +1,17 @@
-"""Read sharding across GPUs (mode 1): reads are independent
-(sigmap.cc:630-866 touches only its own read and the read-only index), so ranks map disjoint
-slices of the read set against a replicated index and the only exchange is the final gather of
-the fixed-size result rows.  No data-path collective.
+"""Multi-GPU modes of the mapping path.
 
+Mode 1, read sharding: reads are independent (sigmap.cc:630-866 touches only its own read and
+the read-only index), so ranks map disjoint slices of the read set against a replicated index and
+the only exchange is the final gather of the fixed-size result rows.  No data-path collective.
 Works on any torch.distributed backend (nccl on the GPU box, gloo in the CPU tests).
+
+Mode 2, contig-sharded index (references whose index exceeds one GPU): contigs are bin-packed
+over the ranks (`assign_contigs`), every rank maps every read against its own contigs, and the
+library's three small collectives per pipeline step (sb_exchange.cuh) make every rank return the
+rows of the unsharded run.  `nccl_join` sets this up for one-process-per-GPU runs (NCCL over
+NVLink, unique id broadcast through torch.distributed); `ContigShardGroup` does the same for
+several contexts inside one process (one host thread per context), which is how the path is
+parity-tested on a single GPU.
 """
 import ctypes as C
 
@@ -76,3 +84,88 @@ def reduce_scalar(x, op, dist=None, device="cpu"):
     t = torch.tensor([float(x)], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX if op == "max" else dist.ReduceOp.SUM)
     return float(t.item())
+
+
+# ------------------------------------------------------------------ mode 2: contig-sharded index
+def assign_contigs(lengths, world):
+    """owner[c] = rank holding contig c: longest contigs first onto the lightest rank
+    (smbh_assign_contigs; deterministic, so every rank computes the same table)."""
+    from . import _ffi as F
+    lengths = np.ascontiguousarray(lengths, np.uint32)
+    owner = np.zeros(len(lengths), np.uint32)
+    rc = F.lib.smbh_assign_contigs(F.ptr(lengths, F.u32p), len(lengths), int(world),
+                                   F.ptr(owner, F.u32p))
+    if rc != 0:
+        raise ValueError("smbh_assign_contigs: world must be >= 1")
+    return owner
+
+
+def nccl_join(mapper, dist):
+    """Make `mapper` rank dist.get_rank() of a contig-shard group whose collectives are NCCL calls
+    on the mapper's own stream.  The NCCL unique id travels through torch.distributed (any
+    backend); afterwards torch is out of the data path."""
+    from . import _ffi as F
+    rank, world = dist.get_rank(), dist.get_world_size()
+    box = [None]
+    if rank == 0:
+        buf = C.create_string_buffer(128)
+        rc = F.lib.smb_shard_nccl_unique_id(buf)
+        if rc != 0:
+            raise RuntimeError(f"smb_shard_nccl_unique_id failed ({rc}): "
+                               f"{F.lib.smb_last_error(None).decode()}")
+        box[0] = buf.raw
+    dist.broadcast_object_list(box, src=0)
+    mapper._check(F.lib.smb_shard_nccl_init(mapper._ctx, rank, world, box[0]), "smb_shard_nccl_init")
+
+
+class ContigShardGroup:
+    """`world` contexts in this process (devices[i] may repeat: shards of one GPU), joined into a
+    local shard group.  Collective calls run one host thread per rank."""
+
+    def __init__(self, devices):
+        from . import _ffi as F
+        from .mapper import Mapper
+        self.mappers = [Mapper(d) for d in devices]
+        arr = (C.c_void_p * len(self.mappers))(*[m._ctx for m in self.mappers])
+        rc = F.lib.smb_shard_local_group(arr, len(self.mappers))
+        if rc != 0:
+            raise RuntimeError(f"smb_shard_local_group failed ({rc})")
+
+    @property
+    def world(self):
+        return len(self.mappers)
+
+    def _each(self, fn):
+        import threading
+        out, err = [None] * self.world, [None] * self.world
+
+        def run(r):
+            try:
+                out[r] = fn(self.mappers[r])
+            except Exception as e:  # noqa: BLE001 - re-raised below
+                err[r] = e
+
+        ts = [threading.Thread(target=run, args=(r,)) for r in range(self.world)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        for e in err:
+            if e is not None:
+                raise e
+        return out
+
+    def set_index(self, pos, val, contig_lengths, owner=None):
+        owner = assign_contigs(contig_lengths, self.world) if owner is None else owner
+        self.owner = np.ascontiguousarray(owner, np.uint32)
+        for m in self.mappers:
+            m.set_index_sharded(pos, val, self.owner)
+            m.set_contigs(contig_lengths)
+
+    def map_reads(self, reads, params=None):
+        """rows of every rank (list of lists); they are identical by construction."""
+        return self._each(lambda m: m.map_reads(reads, params))
+
+    def close(self):
+        for m in self.mappers:
+            m.close()

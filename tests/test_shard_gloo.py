@@ -23,6 +23,27 @@ def test_block_range_partitions_exactly():
             assert max(sizes) - min(sizes) <= 1
 
 
+def test_assign_contigs_balanced_and_deterministic():
+    """Contig-sharded index: longest-first bin packing onto the lightest rank."""
+    from sigmap_b200.shard import assign_contigs
+    rng = np.random.default_rng(5)
+    human = [248956422, 242193529, 198295559, 190214555, 181538259, 170805979, 159345973, 145138636,
+             138394717, 133797422, 135086622, 133275309, 114364328, 107043718, 101991189, 90338345,
+             83257441, 80373285, 58617616, 64444167, 46709983, 50818468, 156040895, 57227415]
+    for lengths, world in ((human, 8), (human, 3), (rng.integers(1000, 10 ** 6, 40).tolist(), 5),
+                           ([10, 10, 10], 8), ([7], 1)):
+        owner = assign_contigs(lengths, world)
+        assert owner.shape == (len(lengths),) and owner.max() < world
+        assert np.array_equal(owner, assign_contigs(lengths, world))
+        load = np.bincount(owner, weights=np.asarray(lengths, float), minlength=world)
+        # LPT bound: no rank above 4/3 of the ideal split unless one contig alone exceeds it
+        assert load.max() <= max(max(lengths), 4.0 / 3.0 * sum(lengths) / world + 1)
+        if len(lengths) >= world:
+            assert (load > 0).all()
+    with pytest.raises(ValueError):
+        assign_contigs([5, 6], 0)
+
+
 def test_shard_reads_slices(golden, host):
     from sigmap_b200.shard import shard_reads
     reads = golden.reads(host)
