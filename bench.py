@@ -251,17 +251,22 @@ def stream_latency(mapper, reads, n_channels, rounds, warm=3):
     channels = np.arange(n_channels, dtype=np.uint32)
     off = (np.arange(n_channels + 1, dtype=np.uint64) * chunk).astype(np.uint32)
     samples = np.zeros(n_channels * chunk, np.int16)
-    lat, stops = [], 0
+    lat, stops, detail = [], 0, []
     for rd in range(warm + rounds):
         for ch in range(n_channels):
             o = int(reads.read_off[cur[ch]]) + at[ch]
             samples[ch * chunk:(ch + 1) * chunk] = reads.raw[o:o + chunk]
+        before = mapper.stats()
         t0 = time.perf_counter()
         dec, _ = mapper.stream_round_arrays(channels, samples, off)
         dt = time.perf_counter() - t0
         if rd >= warm:
             lat.append(dt * 1000.0)
             stops += int(dec.sum())
+            after = mapper.stats()
+            detail.append({"round": rd - warm, "ms": round(dt * 1000.0, 3),
+                           **{k: round(after[k] - before[k], 3) for k in
+                              ("ms_events", "ms_search", "ms_sort", "ms_chain", "steps", "chunks", "anchors")}})
         for ch in range(n_channels):
             at[ch] += chunk
             r = cur[ch]
@@ -273,6 +278,7 @@ def stream_latency(mapper, reads, n_channels, rounds, warm=3):
     return {"metric": "per-chunk latency, read-until mode", "unit": "ms", "p50": q(0.5), "p90": q(0.9),
             "max": lat[-1], "channels": n_channels, "rounds": rounds, "chunks": rounds * n_channels,
             "stop_decisions": stops, "chunk_samples": chunk,
+            "slowest_rounds": sorted(detail, key=lambda d: -d["ms"])[:3],
             "samples_per_s": rounds * n_channels * chunk / (sum(lat) / 1000.0),
             "timed": "smb_stream_round call, host buffers in -> decisions out (host clock)"}
 

@@ -16,6 +16,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 #include <string>
 #include <vector>
 
@@ -51,6 +52,7 @@ __global__ void k_reset_step(Counters *c) {
   c->n_linked = 0;
   c->n_segments = 0;
   c->work = 0;
+  c->dp_cursor = 0;
   c->sort_cursor = 0;
   c->n_cand = 0;
   c->max_entry_anchors = 0;
@@ -185,7 +187,8 @@ struct Workspace {
   // anchors
   DevBuf<uint64_t> key_a, key_b;
   DevBuf<float> dist_a, dist_b, score, coef;
-  DevBuf<uint32_t> pred, link_list, link_count;
+  DevBuf<uint32_t> pred, link_list, link_count, head_list, head_count, head_base, sub_start;
+  DevBuf<SubRec> sub;
   DevBuf<SegRec> seg;
   DevBuf<RunRec> runs;
   DevBuf<uint32_t> run_count, entry_total;
@@ -216,6 +219,7 @@ struct smb_ctx {
   DevBuf<uint32_t> leaf_widx;
   uint32_t max_tpos = 0, max_bucket = 0;
   unsigned search_grid_main = 148 * 4;
+  unsigned dp_grid = 148 * 8;     // persistent grid of the chaining DP: every CTA that fits
   DevBuf<uint64_t> bucket_base;   // linear coordinate of every bucket's target 0 (k_sort.cuh)
   int gshift = 0;
   uint32_t n_coarse = 1;
@@ -748,9 +752,31 @@ static int run_step(smb_ctx *ctx, SlotSpace &sp, const StepEntries &en, StepSour
   ca.link_list = w.link_list.p;
   ca.link_count = w.link_count.p;
   if (n > 0) {
+    // DP ranges: at most one per segment plus one per 32 anchors (k_chain_prep)
+    const uint64_t sub_cap = n / 32 + std::min<uint64_t>(ca.n_slots, n) + 2;
+    CK(w.head_list.ensure((size_t)n_tiles * kHeadsPerTile));
+    CK(w.head_count.ensure(n_tiles + 1));
+    CK(w.head_base.ensure(n_tiles + 1));
+    CK(w.sub_start.ensure(sub_cap + 1));
+    CK(w.sub.ensure(sub_cap));
+    ca.head_list = w.head_list.p;
+    ca.head_count = w.head_count.p;
+    ca.head_base = w.head_base.p;
+    ca.n_tiles = n_tiles;
+    ca.sub_start = w.sub_start.p;
+    ca.sub = w.sub.p;
     k_chain_prep<<<n_tiles, kPrepThreads, 0, s>>>(ca);
     LAUNCH_CHECK();
-    k_chain_dp<<<(unsigned)(((uint64_t)ca.n_slots * 32 + kDpThreads - 1) / kDpThreads), kDpThreads, 0, s>>>(ca);
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, w.head_count.p, w.head_base.p, (int)(n_tiles + 1), s);
+    CK(w.cub_temp.ensure(tb));
+    CK(cub::DeviceScan::ExclusiveSum(w.cub_temp.p, tb, w.head_count.p, w.head_base.p, (int)(n_tiles + 1), s));
+    ctx->stats.launches += 2;
+    k_head_flatten<<<n_tiles, 128, 0, s>>>(ca);
+    LAUNCH_CHECK();
+    k_chain_dp<<<ctx->dp_grid, kDpThreads, 0, s>>>(ca);
+    LAUNCH_CHECK();
+    k_dp_combine<<<(ca.n_slots + 127) / 128, 128, 0, s>>>(ca);
     LAUNCH_CHECK();
   }
   SelectArgs se{};
@@ -1087,6 +1113,12 @@ int smb_create(smb_ctx **out, int device) {
   if ((e = cudaFuncSetAttribute(k_seg_sort, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)kSortSmemBytes)) != cudaSuccess)
     return bail("cudaFuncSetAttribute(k_seg_sort)", e);
+  {
+    int nb = 0, n_sm = 148;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_chain_dp, kDpThreads, 0) != cudaSuccess || nb < 1) nb = 8;
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device);
+    ctx->dp_grid = (unsigned)(nb * n_sm);
+  }
   if (const char *env = getenv("SMB_SORT")) ctx->seg_sort = strcmp(env, "global") != 0;
   if (const char *env = getenv("SMB_SEARCH_MINB")) {
     const int v = atoi(env);
@@ -1114,6 +1146,7 @@ void smb_destroy(smb_ctx *ctx) {
   w.chain_tmp.release(); w.ids.release(); w.round_info.release();
   w.seg_max.release(); w.n_scratch.release(); w.cand_list.release(); w.cand_all.release();
   w.cand_counts.release(); w.ctl.release(); w.tags.release();
+  w.head_list.release(); w.head_count.release(); w.head_base.release(); w.sub_start.release(); w.sub.release();
   ctx->ex.reset();
   ctx->local_group.reset();
   ctx->leaf_vals.release(); ctx->leaf_tb.release(); ctx->leaf_widx.release(); ctx->bucket_base.release();
