@@ -69,6 +69,8 @@ struct ChainArgs {
   uint32_t *head_base;   // [n_tiles + 1]; head_base[n_tiles] = number of DP ranges
   uint32_t n_tiles;
   uint32_t *sub_start;   // [n_subs + 1] first anchor of every DP range, ascending; last = n
+  uint32_t *head_link;   // [n_tiles * kHeadsPerTile] linked anchors of the tile before each head
+  uint32_t *sub_link;    // [n_subs + 1] the same, flattened: where the range starts in its tile's link list
   SubRec *sub;           // [n_subs]
   Counters *ctr;
 };
@@ -267,8 +269,8 @@ __global__ void __launch_bounds__(kPrepThreads) k_chain_prep(ChainArgs a) {
       if (w < wid) before += t;
       total += t;
     }
-    if (linked)
-      a.link_list[(size_t)blockIdx.x * kPrepTile + base + before + __popc(m & ((1u << lane) - 1u))] = i;
+    const uint32_t link_pos = base + before + __popc(m & ((1u << lane) - 1u));  // linked ones before me
+    if (linked) a.link_list[(size_t)blockIdx.x * kPrepTile + link_pos] = i;
     // DP ranges start at every segment start and at the first target gap of each 32-anchor group
     // (one per group keeps the ranges from getting tiny: <= n/32 + segments of them)
     const unsigned gm = __ballot_sync(0xffffffffu, gap_head);
@@ -286,6 +288,7 @@ __global__ void __launch_bounds__(kPrepThreads) k_chain_prep(ChainArgs a) {
     if (head) {
       const uint32_t rank = hbase + hbefore + __popc(hm & ((1u << lane) - 1u));
       a.head_list[(size_t)blockIdx.x * kHeadsPerTile + rank] = i;
+      a.head_link[(size_t)blockIdx.x * kHeadsPerTile + rank] = link_pos;
       if (seg_head) a.seg[my_seg].sub0 = blockIdx.x * kPrepTile + rank;
     }
     __syncthreads();
@@ -308,14 +311,21 @@ __global__ void __launch_bounds__(kPrepThreads) k_chain_prep(ChainArgs a) {
 __global__ void k_head_flatten(ChainArgs a) {
   const uint32_t tile = blockIdx.x;
   const uint32_t base = a.head_base[tile], cnt = a.head_count[tile];
-  for (uint32_t k = threadIdx.x; k < cnt; k += blockDim.x)
+  for (uint32_t k = threadIdx.x; k < cnt; k += blockDim.x) {
     a.sub_start[base + k] = a.head_list[(size_t)tile * kHeadsPerTile + k];
-  if (tile == a.n_tiles - 1 && threadIdx.x == 0) a.sub_start[a.head_base[a.n_tiles]] = (uint32_t)a.n;
+    a.sub_link[base + k] = a.head_link[(size_t)tile * kHeadsPerTile + k];
+  }
+  if (tile == a.n_tiles - 1 && threadIdx.x == 0) {
+    // sentinel: the last range ends at anchor n, i.e. after the last tile's whole link list
+    const uint32_t total = a.head_base[a.n_tiles];
+    a.sub_start[total] = (uint32_t)a.n;
+    a.sub_link[total] = (a.n % kPrepTile) ? a.link_count[tile] : 0u;
+  }
 }
 
 constexpr int kDpThreads = 128;
 constexpr int kDpFreePasses = 2;  // thread-parallel passes before the in-order cooperative path
-constexpr int kDpGrab = 4;        // DP ranges per grab of the work cursor
+constexpr int kDpGrab = 8;        // DP ranges per grab of the work cursor
 
 // A warp owns a segment and takes its linked anchors 32 at a time, one per lane.
 //  * Thread-parallel passes: every lane runs the reference's lookback for its own anchor.  An
@@ -345,9 +355,15 @@ __global__ void __launch_bounds__(kDpThreads) k_chain_dp(ChainArgs a) {
   id0 = __shfl_sync(full, id0, 0);
   if (id0 >= n_subs) break;
   const uint32_t id1 = min(id0 + (uint32_t)kDpGrab, n_subs);
-  uint32_t bound = lane <= kDpGrab && id0 + lane <= n_subs ? a.sub_start[id0 + lane] : 0u;
+  const bool has_bound = lane <= kDpGrab && id0 + lane <= n_subs;
+  const uint32_t bound = has_bound ? a.sub_start[id0 + lane] : 0u;
+  const uint32_t blink = has_bound ? a.sub_link[id0 + lane] : 0u;
   for (uint32_t id = id0; id < id1; ++id) {
   const uint32_t s = __shfl_sync(full, bound, (int)(id - id0)), e = __shfl_sync(full, bound, (int)(id - id0) + 1);
+  // the range's linked anchors: link lists of tiles [s / tile, e / tile], from off_s in the first
+  // to off_e (exclusive) in the last
+  const uint32_t off_s = __shfl_sync(full, blink, (int)(id - id0)), off_e = __shfl_sync(full, blink, (int)(id - id0) + 1);
+  const uint32_t tile_s = s / kPrepTile, tile_e = e / kPrepTile;
 
   // max over the linked anchors only: the others score <= 6, and every comparison this max
   // feeds has a candidate score >= min_chaining_score = 10 on the other side (:545-567)
@@ -356,14 +372,13 @@ __global__ void __launch_bounds__(kDpThreads) k_chain_dp(ChainArgs a) {
   uint32_t ti0 = 0, ti1 = 0, ti2 = 0;
   int ntop = 0;
 
-  for (uint32_t tile = s / kPrepTile; tile * kPrepTile < e; ++tile) {
-    const uint32_t cnt = a.link_count[tile];
+  for (uint32_t tile = tile_s; tile <= tile_e; ++tile) {
+    const uint32_t cnt = tile == tile_e ? off_e : a.link_count[tile];
     const uint32_t *list = a.link_list + (size_t)tile * kPrepTile;
-    for (uint32_t c0 = 0; c0 < cnt; c0 += 32) {
+    for (uint32_t c0 = tile == tile_s ? off_s : 0u; c0 < cnt; c0 += 32) {
       const uint32_t c = c0 + lane;
       uint32_t i = c < cnt ? list[c] : 0xFFFFFFFFu;
-      const bool valid = c < cnt && i >= s && i < e;
-      if (!__ballot_sync(full, valid)) continue;
+      const bool valid = c < cnt;
       int32_t ti = 0, qi = 0;
       float ci = 0.0f, init = 0.0f, M = 0.0f;
       uint32_t lo = 0;

@@ -28,9 +28,12 @@
 namespace sb {
 
 constexpr int kRunsCap = 512;        // runs recorded per entry (a run = one flush of <= 128 hits)
-constexpr int kSortThreads = 1024;
-constexpr int kSortCap = 10240;      // anchors of one part held in shared memory
-constexpr int kSortBins = 8192;      // fine bins per part
+// Two shapes of the kernel (template parameters CAP = anchors of one part held in shared memory,
+// THREADS, BINS = fine bins per part):
+//   <10240, 1024, 8192>  one 200 KB CTA per SM: fewest passes over an entry's runs
+//   < 5120,  512, 4096>  two 100 KB CTAs per SM: one CTA's barrier / DRAM waits overlap the
+//                        other's work, at the price of twice the parts per entry
+constexpr int kSortCapBig = 10240, kSortCapSmall = 5120;
 constexpr int kCoarseBins = 256;
 constexpr int kSmallBin = 24;        // bins up to this size: insertion sort by one thread
 constexpr int kBigBinCap = 512;      // dense bins queued for the warp-wide rank sort
@@ -50,11 +53,14 @@ struct SegSortArgs {
   Counters *ctr;                // sort_cursor (output position), error bit 4 (dense coarse bin)
 };
 
-constexpr size_t kSortSmemBytes = (size_t)kSortCap * (8 + 4 + 2 + 2) + (size_t)kSortBins * 4 +
-                                  (size_t)kCoarseBins * 4 + (size_t)(kCoarseBins + 2) * 4 +
-                                  (size_t)kBigBinCap * 4 + 64 * 4;
+constexpr size_t sort_smem_bytes(int cap, int bins) {
+  return (size_t)cap * (8 + 4 + 2 + 2) + (size_t)bins * 4 + (size_t)kCoarseBins * 4 +
+         (size_t)(kCoarseBins + 2) * 4 + (size_t)kBigBinCap * 4 + 64 * 4;
+}
 
-__global__ void __launch_bounds__(kSortThreads, 1) k_seg_sort(const SegSortArgs a) {
+template <int kSortCap, int kSortThreads, int kSortBins>
+__global__ void __launch_bounds__(kSortThreads, kSortThreads == 1024 ? 1 : 2) k_seg_sort(const SegSortArgs a) {
+  static_assert(kSortBins % kSortThreads == 0, "bins per thread");
   extern __shared__ __align__(16) unsigned char s_raw[];
   uint64_t *s_key = reinterpret_cast<uint64_t *>(s_raw);
   float *s_dist = reinterpret_cast<float *>(s_key + kSortCap);
@@ -81,6 +87,8 @@ __global__ void __launch_bounds__(kSortThreads, 1) k_seg_sort(const SegSortArgs 
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) mine += __shfl_xor_sync(full, mine, d);
   if (tid < kCoarseBins) s_coarse[tid] = 0;
+  if (tid < 32) s_misc[tid] = 0;
+  __syncthreads();
   if (lane == 0) s_misc[wid] = mine;
   __syncthreads();
   if (wid == 0) {
@@ -153,9 +161,11 @@ __global__ void __launch_bounds__(kSortThreads, 1) k_seg_sort(const SegSortArgs 
       for (uint32_t i0 = 0; i0 < run.count; i0 += 32) {
         const uint32_t i = i0 + lane;
         uint64_t k = 0, g = 0;
+        float dv = 0.0f;
         bool in = false;
         if (i < run.count) {
           k = a.key_in[run.start + i];
+          dv = a.dist_in[run.start + i];  // with the key load in flight, not after it
           g = coord(k);
           const uint32_t cb = (uint32_t)(g >> a.gshift);
           in = cb >= c_lo && cb < c_hi;
@@ -169,7 +179,7 @@ __global__ void __launch_bounds__(kSortThreads, 1) k_seg_sort(const SegSortArgs 
           const uint32_t slot = base + __popc(m & lt);
           if (slot < (uint32_t)kSortCap) {  // always true: part sizes are exact
             s_key[slot] = k;
-            s_dist[slot] = a.dist_in[run.start + i];
+            s_dist[slot] = dv;
             atomicAdd(&s_bins[(uint32_t)((g - g_lo) >> fshift)], 1u);
           }
         }
@@ -195,7 +205,7 @@ __global__ void __launch_bounds__(kSortThreads, 1) k_seg_sort(const SegSortArgs 
       if (lane == 31) s_misc[wid] = incl;
       __syncthreads();
       if (wid == 0) {
-        const uint32_t w = s_misc[lane];
+        const uint32_t w = lane < kSortThreads / 32 ? s_misc[lane] : 0u;
         uint32_t in2 = w;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {

@@ -187,7 +187,7 @@ struct Workspace {
   // anchors
   DevBuf<uint64_t> key_a, key_b;
   DevBuf<float> dist_a, dist_b, score, coef;
-  DevBuf<uint32_t> pred, link_list, link_count, head_list, head_count, head_base, sub_start;
+  DevBuf<uint32_t> pred, link_list, link_count, head_list, head_count, head_base, sub_start, head_link, sub_link;
   DevBuf<SubRec> sub;
   DevBuf<SegRec> seg;
   DevBuf<RunRec> runs;
@@ -225,6 +225,7 @@ struct smb_ctx {
   uint32_t n_coarse = 1;
   bool seg_sort = true;           // per-entry shared-memory sort; SMB_SORT=global forces the radix sort
   int search_minb = 4;            // CTAs per SM the search kernel is compiled for (SMB_SEARCH_MINB=4|5|6)
+  bool sort_small = false;        // SMB_SORT=small: two 100 KB sort CTAs per SM instead of one 200 KB CTA
   std::vector<uint32_t> contig_len;
   // uploaded reads
   size_t n_reads = 0;
@@ -684,7 +685,7 @@ static int run_step(smb_ctx *ctx, SlotSpace &sp, const StepEntries &en, StepSour
   // per-entry sort in shared memory (k_sort.cuh) when every entry is small enough for a few
   // passes over its runs and the run table did not overflow
   if (!sorted && want_seg && !(ctx->h_ctr->error & 8u) &&
-      ctx->h_ctr->max_entry_anchors <= 8u * (unsigned)kSortCap) {
+      ctx->h_ctr->max_entry_anchors <= 8u * (unsigned)(ctx->sort_small ? kSortCapSmall : kSortCapBig)) {
     SegSortArgs ss{};
     ss.key_in = w.key_a.p;
     ss.dist_in = w.dist_a.p;
@@ -698,7 +699,10 @@ static int run_step(smb_ctx *ctx, SlotSpace &sp, const StepEntries &en, StepSour
     ss.gshift = ctx->gshift;
     ss.n_coarse = ctx->n_coarse;
     ss.ctr = ctx->d_ctr;
-    k_seg_sort<<<B, kSortThreads, kSortSmemBytes, s>>>(ss);
+    if (ctx->sort_small)
+      k_seg_sort<kSortCapSmall, 512, 4096><<<B, 512, sort_smem_bytes(kSortCapSmall, 4096), s>>>(ss);
+    else
+      k_seg_sort<kSortCapBig, 1024, 8192><<<B, 1024, sort_smem_bytes(kSortCapBig, 8192), s>>>(ss);
     LAUNCH_CHECK();
     CK(cudaMemcpyAsync(ctx->h_ctr, ctx->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
@@ -758,12 +762,16 @@ static int run_step(smb_ctx *ctx, SlotSpace &sp, const StepEntries &en, StepSour
     CK(w.head_count.ensure(n_tiles + 1));
     CK(w.head_base.ensure(n_tiles + 1));
     CK(w.sub_start.ensure(sub_cap + 1));
+    CK(w.head_link.ensure((size_t)n_tiles * kHeadsPerTile));
+    CK(w.sub_link.ensure(sub_cap + 1));
     CK(w.sub.ensure(sub_cap));
     ca.head_list = w.head_list.p;
     ca.head_count = w.head_count.p;
     ca.head_base = w.head_base.p;
     ca.n_tiles = n_tiles;
     ca.sub_start = w.sub_start.p;
+    ca.head_link = w.head_link.p;
+    ca.sub_link = w.sub_link.p;
     ca.sub = w.sub.p;
     k_chain_prep<<<n_tiles, kPrepThreads, 0, s>>>(ca);
     LAUNCH_CHECK();
@@ -1110,8 +1118,10 @@ int smb_create(smb_ctx **out, int device) {
   for (auto &ev : ctx->timer)
     if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail("cudaEventCreate", e);
   // the per-entry sort keeps a whole part of an entry in shared memory (200 KB of the 227 KB)
-  if ((e = cudaFuncSetAttribute(k_seg_sort, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)kSortSmemBytes)) != cudaSuccess)
+  if ((e = cudaFuncSetAttribute(k_seg_sort<kSortCapBig, 1024, 8192>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)sort_smem_bytes(kSortCapBig, 8192))) != cudaSuccess ||
+      (e = cudaFuncSetAttribute(k_seg_sort<kSortCapSmall, 512, 4096>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)sort_smem_bytes(kSortCapSmall, 4096))) != cudaSuccess)
     return bail("cudaFuncSetAttribute(k_seg_sort)", e);
   {
     int nb = 0, n_sm = 148;
@@ -1119,7 +1129,10 @@ int smb_create(smb_ctx **out, int device) {
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device);
     ctx->dp_grid = (unsigned)(nb * n_sm);
   }
-  if (const char *env = getenv("SMB_SORT")) ctx->seg_sort = strcmp(env, "global") != 0;
+  if (const char *env = getenv("SMB_SORT")) {
+    ctx->seg_sort = strcmp(env, "global") != 0;
+    ctx->sort_small = strcmp(env, "small") == 0;
+  }
   if (const char *env = getenv("SMB_SEARCH_MINB")) {
     const int v = atoi(env);
     if (v == 5 || v == 6) ctx->search_minb = v;
@@ -1146,7 +1159,7 @@ void smb_destroy(smb_ctx *ctx) {
   w.chain_tmp.release(); w.ids.release(); w.round_info.release();
   w.seg_max.release(); w.n_scratch.release(); w.cand_list.release(); w.cand_all.release();
   w.cand_counts.release(); w.ctl.release(); w.tags.release();
-  w.head_list.release(); w.head_count.release(); w.head_base.release(); w.sub_start.release(); w.sub.release();
+  w.head_list.release(); w.head_count.release(); w.head_base.release(); w.sub_start.release(); w.sub.release(); w.head_link.release(); w.sub_link.release();
   ctx->ex.reset();
   ctx->local_group.reset();
   ctx->leaf_vals.release(); ctx->leaf_tb.release(); ctx->leaf_widx.release(); ctx->bucket_base.release();
