@@ -325,7 +325,9 @@ __global__ void k_head_flatten(ChainArgs a) {
 
 constexpr int kDpThreads = 128;
 constexpr int kDpFreePasses = 2;  // thread-parallel passes before the in-order cooperative path
-constexpr int kDpGrab = 8;        // DP ranges per grab of the work cursor
+constexpr int kDpGrab = 1;        // DP ranges per grab of the work cursor (ranges are as large as
+                                  // segments at the reference's anchor density: one at a time)
+constexpr int kDpGroup = 4;       // predecessors fetched together in the thread-parallel lookback
 
 // A warp owns a segment and takes its linked anchors 32 at a time, one per lane.
 //  * Thread-parallel passes: every lane runs the reference's lookback for its own anchor.  An
@@ -398,28 +400,46 @@ __global__ void __launch_bounds__(kDpThreads) k_chain_dp(ChainArgs a) {
           uint32_t best = i;
           int S = 0;  // num_skips
           bool defer = false;
-          for (uint32_t j = i; j-- > lo;) {
-            const uint64_t kj = key[j];
-            const int32_t pt = (int32_t)kl.target(kj), pq = (int32_t)kl.query(kj);
-            if (pq == qi || pt == ti) continue;
-            if (pt + kMaxTargetGap < ti) break;
-            const int32_t dt = ti - pt, dq = qi - pq;
-            if (dq < 0) continue;
-            float cur = 0.0f;
-            if (gap_compatible(dt, dq)) {
-              if (pred[j] & kPending) {
-                defer = true;
+          // predecessors four at a time: the key loads of a group are independent, so the walk
+          // pays one memory round trip per group instead of one per predecessor
+          bool done = false;
+          for (uint32_t jb = i; jb > lo && !done;) {
+            const uint32_t m = min(jb - lo, (uint32_t)kDpGroup);
+            uint64_t kk[kDpGroup];
+#pragma unroll
+            for (int u = 0; u < kDpGroup; ++u) kk[u] = (uint32_t)u < m ? key[jb - 1u - (uint32_t)u] : 0ull;
+#pragma unroll
+            for (int u = 0; u < kDpGroup; ++u) {
+              if (done || (uint32_t)u >= m) break;
+              const uint32_t j = jb - 1u - (uint32_t)u;
+              const uint64_t kj = kk[u];
+              const int32_t pt = (int32_t)kl.target(kj), pq = (int32_t)kl.query(kj);
+              if (pq == qi || pt == ti) continue;
+              if (pt + kMaxTargetGap < ti) {
+                done = true;
                 break;
               }
-              cur = __fadd_rn(score[j], __fmul_rn((float)min(min(dt, dq), kDim), ci));
+              const int32_t dt = ti - pt, dq = qi - pq;
+              if (dq < 0) continue;
+              float cur = 0.0f;
+              if (gap_compatible(dt, dq)) {
+                if (pred[j] & kPending) {
+                  defer = true;
+                  done = true;
+                  break;
+                }
+                cur = __fadd_rn(score[j], __fmul_rn((float)min(min(dt, dq), kDim), ci));
+              }
+              if (cur > M) {
+                M = cur;
+                best = j;
+                --S;
+              } else if (++S > kMaxSkips) {
+                done = true;
+                break;
+              }
             }
-            if (cur > M) {
-              M = cur;
-              best = j;
-              --S;
-            } else if (++S > kMaxSkips) {
-              break;
-            }
+            jb -= m;
           }
           if (!defer) {
             score[i] = M;

@@ -107,8 +107,17 @@ __global__ void __launch_bounds__(kSortThreads, kSortThreads == 1024 ? 1 : 2) k_
   if (total > (uint32_t)kSortCap) {
     for (uint32_t r = wid; r < nr; r += kSortThreads / 32) {
       const RunRec run = runs[r];
-      for (uint32_t i = lane; i < run.count; i += 32)
-        atomicAdd(&s_coarse[(uint32_t)(coord(a.key_in[run.start + i]) >> a.gshift)], 1u);
+      for (uint32_t i0 = 0; i0 < run.count; i0 += 4 * 32) {  // a run is <= 128 hits: one trip
+        uint64_t kq[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const uint32_t i = i0 + u * 32 + lane;
+          kq[u] = i < run.count ? a.key_in[run.start + i] : ~0ull;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (kq[u] != ~0ull) atomicAdd(&s_coarse[(uint32_t)(coord(kq[u]) >> a.gshift)], 1u);
+      }
     }
     __syncthreads();
     if (tid == 0) {
@@ -158,29 +167,39 @@ __global__ void __launch_bounds__(kSortThreads, kSortThreads == 1024 ? 1 : 2) k_
     // ---- gather the part's anchors + fine histogram
     for (uint32_t r = wid; r < nr; r += kSortThreads / 32) {
       const RunRec run = runs[r];
-      for (uint32_t i0 = 0; i0 < run.count; i0 += 32) {
-        const uint32_t i = i0 + lane;
-        uint64_t k = 0, g = 0;
-        float dv = 0.0f;
-        bool in = false;
-        if (i < run.count) {
-          k = a.key_in[run.start + i];
-          dv = a.dist_in[run.start + i];  // with the key load in flight, not after it
-          g = coord(k);
-          const uint32_t cb = (uint32_t)(g >> a.gshift);
-          in = cb >= c_lo && cb < c_hi;
+      for (uint32_t i0 = 0; i0 < run.count; i0 += 4 * 32) {  // a run is <= 128 hits: one trip,
+        uint64_t kq[4];                                       // its eight loads in flight together
+        float dq[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const uint32_t i = i0 + u * 32 + lane;
+          const bool has = i < run.count;
+          kq[u] = has ? a.key_in[run.start + i] : ~0ull;
+          dq[u] = has ? a.dist_in[run.start + i] : 0.0f;
         }
-        const unsigned m = __ballot_sync(full, in);
-        if (!m) continue;
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(&s_misc[32], (uint32_t)__popc(m));
-        base = __shfl_sync(full, base, 0);
-        if (in) {
-          const uint32_t slot = base + __popc(m & lt);
-          if (slot < (uint32_t)kSortCap) {  // always true: part sizes are exact
-            s_key[slot] = k;
-            s_dist[slot] = dv;
-            atomicAdd(&s_bins[(uint32_t)((g - g_lo) >> fshift)], 1u);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (i0 + u * 32 >= run.count) break;
+          const uint64_t k = kq[u];
+          uint64_t g = 0;
+          bool in = false;
+          if (k != ~0ull) {
+            g = coord(k);
+            const uint32_t cb = (uint32_t)(g >> a.gshift);
+            in = cb >= c_lo && cb < c_hi;
+          }
+          const unsigned m = __ballot_sync(full, in);
+          if (!m) continue;
+          uint32_t base = 0;
+          if (lane == 0) base = atomicAdd(&s_misc[32], (uint32_t)__popc(m));
+          base = __shfl_sync(full, base, 0);
+          if (in) {
+            const uint32_t slot = base + __popc(m & lt);
+            if (slot < (uint32_t)kSortCap) {  // always true: part sizes are exact
+              s_key[slot] = k;
+              s_dist[slot] = dq[u];
+              atomicAdd(&s_bins[(uint32_t)((g - g_lo) >> fshift)], 1u);
+            }
           }
         }
       }

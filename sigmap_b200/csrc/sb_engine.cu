@@ -224,7 +224,7 @@ struct smb_ctx {
   int gshift = 0;
   uint32_t n_coarse = 1;
   bool seg_sort = true;           // per-entry shared-memory sort; SMB_SORT=global forces the radix sort
-  int search_minb = 4;            // CTAs per SM the search kernel is compiled for (SMB_SEARCH_MINB=4|5|6)
+  bool search_bfs = false;        // SMB_SEARCH=bfs: level-order traversal (fuller 8-node steps)
   bool sort_small = false;        // SMB_SORT=small: two 100 KB sort CTAs per SM instead of one 200 KB CTA
   std::vector<uint32_t> contig_len;
   // uploaded reads
@@ -296,10 +296,10 @@ static int fail(smb_ctx *ctx, int code, const std::string &msg) {
 // persistent grid of the search kernel: every CTA that fits on the device, no more
 static size_t search_smem(const smb_ctx *ctx) { return kSearchWarps * search_smem_per_warp(ctx->ix.n_levels); }
 
-template <bool STAGE, int MINB = 4>
+template <bool STAGE, bool BFS = false>
 static unsigned search_grid(smb_ctx *ctx) {
   int n = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_radius_search<STAGE, MINB>, kSearchWarps * 32,
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_radius_search<STAGE, BFS>, kSearchWarps * 32,
                                                     search_smem(ctx)) != cudaSuccess || n < 1)
     n = 4;
   int n_sm = 148;
@@ -449,8 +449,7 @@ static int build_index(smb_ctx *ctx, const uint64_t *pos, const float *val, size
     ctx->n_coarse = (uint32_t)(base.back() >> ctx->gshift) + 1;
   }
   ctx->ix = ix;
-  ctx->search_grid_main = ctx->search_minb == 6 ? search_grid<false, 6>(ctx)
-                          : ctx->search_minb == 5 ? search_grid<false, 5>(ctx) : search_grid<false, 4>(ctx);
+  ctx->search_grid_main = ctx->search_bfs ? search_grid<false, true>(ctx) : search_grid<false, false>(ctx);
   ctx->max_tpos = max_tpos;
   ctx->max_bucket = max_bucket;
   ctx->has_index = true;
@@ -628,12 +627,10 @@ static int run_step(smb_ctx *ctx, SlotSpace &sp, const StepEntries &en, StepSour
   sa.entry_total = w.entry_total.p;
   sa.runs_cap = kRunsCap;
   CK(cudaEventRecord(ctx->ev[2], s));
-  if (ctx->search_minb == 6)
-    k_radius_search<false, 6><<<ctx->search_grid_main, kSearchWarps * 32, search_smem(ctx), s>>>(ctx->ix, sa);
-  else if (ctx->search_minb == 5)
-    k_radius_search<false, 5><<<ctx->search_grid_main, kSearchWarps * 32, search_smem(ctx), s>>>(ctx->ix, sa);
+  if (ctx->search_bfs)
+    k_radius_search<false, true><<<ctx->search_grid_main, kSearchWarps * 32, search_smem(ctx), s>>>(ctx->ix, sa);
   else
-    k_radius_search<false, 4><<<ctx->search_grid_main, kSearchWarps * 32, search_smem(ctx), s>>>(ctx->ix, sa);
+    k_radius_search<false, false><<<ctx->search_grid_main, kSearchWarps * 32, search_smem(ctx), s>>>(ctx->ix, sa);
   LAUNCH_CHECK();
   ctx->stats.search_launches++;
   CK(cudaEventRecord(ctx->ev[3], s));
@@ -1133,10 +1130,7 @@ int smb_create(smb_ctx **out, int device) {
     ctx->seg_sort = strcmp(env, "global") != 0;
     ctx->sort_small = strcmp(env, "small") == 0;
   }
-  if (const char *env = getenv("SMB_SEARCH_MINB")) {
-    const int v = atoi(env);
-    if (v == 5 || v == 6) ctx->search_minb = v;
-  }
+  if (const char *env = getenv("SMB_SEARCH")) ctx->search_bfs = strcmp(env, "bfs") == 0;
   *out = ctx;
   return SMB_OK;
 }
@@ -1622,7 +1616,10 @@ int smb_stage_radius(smb_ctx *ctx, const float *queries, size_t nq, float radius
   sa.out_dist = d_a.p;
   sa.cap = dcap;
   sa.ctr = ctx->d_ctr;
-  k_radius_search<true><<<search_grid<true>(ctx), kSearchWarps * 32, search_smem(ctx), s>>>(ctx->ix, sa);
+  if (ctx->search_bfs)
+    k_radius_search<true, true><<<search_grid<true, true>(ctx), kSearchWarps * 32, search_smem(ctx), s>>>(ctx->ix, sa);
+  else
+    k_radius_search<true, false><<<search_grid<true, false>(ctx), kSearchWarps * 32, search_smem(ctx), s>>>(ctx->ix, sa);
   LAUNCH_CHECK();
   CK(cudaMemcpyAsync(ctx->h_ctr, ctx->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
