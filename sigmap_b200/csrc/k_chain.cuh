@@ -35,20 +35,9 @@ struct SegRec {
   float max;          // max chaining score over the segment's linked anchors (see k_chain_dp)
   float top_s[3];     // best three local end candidates: score desc, index desc
   uint32_t top_i[3];
-  uint32_t sub0;      // the segment's first DP range: tile * kPrepTile + rank among the tile's heads
-};
-
-// DP range = a run of anchors no later anchor can look back into (k_chain_prep): what one warp
-// of k_chain_dp settles, with the same summary a whole segment gets.
-struct SubRec {
-  float max;
-  uint32_t ntop;
-  float top_s[3];
-  uint32_t top_i[3];
 };
 constexpr uint32_t kSegEmpty = 0xFFFFFFFFu;
 constexpr int kPrepTile = 1024;  // anchors per k_chain_prep block = per compacted work list tile
-constexpr int kHeadsPerTile = kPrepTile;  // worst case: every anchor of a tile starts a segment
 
 struct ChainArgs {
   const uint64_t *key;   // sorted
@@ -64,14 +53,6 @@ struct ChainArgs {
   uint32_t n_slots;      // B << bbits
   uint32_t *link_list;   // [n_tiles * kPrepTile] indices of linked anchors, ascending per tile
   uint32_t *link_count;  // [n_tiles]
-  uint32_t *head_list;   // [n_tiles * kHeadsPerTile] first anchors of the DP ranges, ascending per tile
-  uint32_t *head_count;  // [n_tiles + 1] (last = 0); head_base = its exclusive scan
-  uint32_t *head_base;   // [n_tiles + 1]; head_base[n_tiles] = number of DP ranges
-  uint32_t n_tiles;
-  uint32_t *sub_start;   // [n_subs + 1] first anchor of every DP range, ascending; last = n
-  uint32_t *head_link;   // [n_tiles * kHeadsPerTile] linked anchors of the tile before each head
-  uint32_t *sub_link;    // [n_subs + 1] the same, flattened: where the range starts in its tile's link list
-  SubRec *sub;           // [n_subs]
   Counters *ctr;
 };
 
@@ -178,8 +159,8 @@ constexpr uint32_t kPending = 0x40000000u;  // pred[] bit: linked anchor not yet
 __global__ void __launch_bounds__(kPrepThreads) k_chain_prep(ChainArgs a) {
   // the tile's anchors and the kPrepHalo before it, unpacked: {segment id, target, query, -}
   __shared__ int4 s_a[kPrepHalo + kPrepTile];
-  __shared__ uint32_t warp_base[kPrepThreads / 32], warp_heads[kPrepThreads / 32];
-  __shared__ uint32_t tile_count, tile_heads;
+  __shared__ uint32_t warp_base[kPrepThreads / 32];
+  __shared__ uint32_t tile_count;
   const uint32_t n = (uint32_t)a.n;  // < 2^30
   const uint32_t tile0 = blockIdx.x * kPrepTile;
   const KeyLayout kl = a.kl;
@@ -194,34 +175,23 @@ __global__ void __launch_bounds__(kPrepThreads) k_chain_prep(ChainArgs a) {
     }
     s_a[x] = v;
   }
-  if (threadIdx.x == 0) {
-    tile_count = 0;
-    tile_heads = 0;
-  }
+  if (threadIdx.x == 0) tile_count = 0;
   __syncthreads();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   for (int sub = 0; sub < kPrepTile / kPrepThreads; ++sub) {
     const int local = sub * kPrepThreads + threadIdx.x;
     const uint32_t i = tile0 + local;
     bool linked = false;
-    bool seg_head = false, gap_head = false;
-    uint32_t my_seg = 0;
     if (i < n) {
       const int me = kPrepHalo + local;
       const int4 mine = s_a[me];
       const uint32_t sg = (uint32_t)mine.x;
       const int32_t ti = mine.y, qi = mine.z;
-      my_seg = sg;
       if (sg < a.n_slots) {
-        const int4 prev = s_a[me - 1];
-        const uint32_t sp = (uint32_t)prev.x;  // 0xFFFFFFFF before the first anchor
+        const uint32_t sp = (uint32_t)s_a[me - 1].x;  // 0xFFFFFFFF before the first anchor
         if (i == 0 || sp != sg) {
-          seg_head = true;
           a.seg[sg].start = i;
           if (i > 0 && sp < a.n_slots) a.seg[sp].end = i;
-        } else if (prev.y + kMaxTargetGap < ti) {
-          // the lookback of this and of every later anchor stops before `prev` (:480)
-          gap_head = true;
         }
         if (i == n - 1) a.seg[sg].end = n;
       }
@@ -269,64 +239,20 @@ __global__ void __launch_bounds__(kPrepThreads) k_chain_prep(ChainArgs a) {
       if (w < wid) before += t;
       total += t;
     }
-    const uint32_t link_pos = base + before + __popc(m & ((1u << lane) - 1u));  // linked ones before me
-    if (linked) a.link_list[(size_t)blockIdx.x * kPrepTile + link_pos] = i;
-    // DP ranges start at every segment start and at the first target gap of each 32-anchor group
-    // (one per group keeps the ranges from getting tiny: <= n/32 + segments of them)
-    const unsigned gm = __ballot_sync(0xffffffffu, gap_head);
-    const bool head = seg_head || (gap_head && (gm & ((1u << lane) - 1u)) == 0u);
-    const unsigned hm = __ballot_sync(0xffffffffu, head);
-    if (lane == 0) warp_heads[wid] = __popc(hm);
+    if (linked)
+      a.link_list[(size_t)blockIdx.x * kPrepTile + base + before + __popc(m & ((1u << lane) - 1u))] = i;
     __syncthreads();
-    const uint32_t hbase = tile_heads;
-    uint32_t hbefore = 0, htotal = 0;
-    for (int w = 0; w < kPrepThreads / 32; ++w) {
-      const uint32_t t = warp_heads[w];
-      if (w < wid) hbefore += t;
-      htotal += t;
-    }
-    if (head) {
-      const uint32_t rank = hbase + hbefore + __popc(hm & ((1u << lane) - 1u));
-      a.head_list[(size_t)blockIdx.x * kHeadsPerTile + rank] = i;
-      a.head_link[(size_t)blockIdx.x * kHeadsPerTile + rank] = link_pos;
-      if (seg_head) a.seg[my_seg].sub0 = blockIdx.x * kPrepTile + rank;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      tile_count = base + total;
-      tile_heads = hbase + htotal;
-    }
+    if (threadIdx.x == 0) tile_count = base + total;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
     a.link_count[blockIdx.x] = tile_count;
-    a.head_count[blockIdx.x] = tile_heads;
-    if (blockIdx.x == 0) a.head_count[a.n_tiles] = 0;
     if (tile_count) atomicAdd(&a.ctr->n_linked, (unsigned long long)tile_count);
-  }
-}
-
-// head lists of the tiles -> one ascending array of range starts (head_base = exclusive scan of
-// head_count, done by cub in between)
-__global__ void k_head_flatten(ChainArgs a) {
-  const uint32_t tile = blockIdx.x;
-  const uint32_t base = a.head_base[tile], cnt = a.head_count[tile];
-  for (uint32_t k = threadIdx.x; k < cnt; k += blockDim.x) {
-    a.sub_start[base + k] = a.head_list[(size_t)tile * kHeadsPerTile + k];
-    a.sub_link[base + k] = a.head_link[(size_t)tile * kHeadsPerTile + k];
-  }
-  if (tile == a.n_tiles - 1 && threadIdx.x == 0) {
-    // sentinel: the last range ends at anchor n, i.e. after the last tile's whole link list
-    const uint32_t total = a.head_base[a.n_tiles];
-    a.sub_start[total] = (uint32_t)a.n;
-    a.sub_link[total] = (a.n % kPrepTile) ? a.link_count[tile] : 0u;
   }
 }
 
 constexpr int kDpThreads = 128;
 constexpr int kDpFreePasses = 2;  // thread-parallel passes before the in-order cooperative path
-constexpr int kDpGrab = 1;        // DP ranges per grab of the work cursor (ranges are as large as
-                                  // segments at the reference's anchor density: one at a time)
 constexpr int kDpGroup = 4;       // predecessors fetched together in the thread-parallel lookback
 
 // A warp owns a segment and takes its linked anchors 32 at a time, one per lane.
@@ -343,29 +269,15 @@ __global__ void __launch_bounds__(kDpThreads) k_chain_dp(ChainArgs a) {
   const int lane = threadIdx.x & 31;
   const unsigned full = 0xffffffffu;
   const unsigned le = (2u << lane) - 1u;  // lanes 0..lane
+  const uint32_t slot = (blockIdx.x * kDpThreads + threadIdx.x) / 32;
+  if (slot >= a.n_slots) return;
+  SegRec r = a.seg[slot];
+  if (r.start == kSegEmpty) return;
+  const uint32_t s = r.start, e = r.end;
   const KeyLayout kl = a.kl;
   const uint64_t *key = a.key;
   float *score = a.score;
   uint32_t *pred = a.pred;
-  const uint32_t n_subs = a.head_base[a.n_tiles];
-
-  // persistent warps take DP ranges from a shared cursor, kDpGrab at a time: ranges differ
-  // wildly in cost (background vs the read's true locus), so static assignment leaves a tail
-  for (;;) {
-  uint32_t id0 = 0;
-  if (lane == 0) id0 = atomicAdd(&a.ctr->dp_cursor, (unsigned)kDpGrab);
-  id0 = __shfl_sync(full, id0, 0);
-  if (id0 >= n_subs) break;
-  const uint32_t id1 = min(id0 + (uint32_t)kDpGrab, n_subs);
-  const bool has_bound = lane <= kDpGrab && id0 + lane <= n_subs;
-  const uint32_t bound = has_bound ? a.sub_start[id0 + lane] : 0u;
-  const uint32_t blink = has_bound ? a.sub_link[id0 + lane] : 0u;
-  for (uint32_t id = id0; id < id1; ++id) {
-  const uint32_t s = __shfl_sync(full, bound, (int)(id - id0)), e = __shfl_sync(full, bound, (int)(id - id0) + 1);
-  // the range's linked anchors: link lists of tiles [s / tile, e / tile], from off_s in the first
-  // to off_e (exclusive) in the last
-  const uint32_t off_s = __shfl_sync(full, blink, (int)(id - id0)), off_e = __shfl_sync(full, blink, (int)(id - id0) + 1);
-  const uint32_t tile_s = s / kPrepTile, tile_e = e / kPrepTile;
 
   // max over the linked anchors only: the others score <= 6, and every comparison this max
   // feeds has a candidate score >= min_chaining_score = 10 on the other side (:545-567)
@@ -374,13 +286,14 @@ __global__ void __launch_bounds__(kDpThreads) k_chain_dp(ChainArgs a) {
   uint32_t ti0 = 0, ti1 = 0, ti2 = 0;
   int ntop = 0;
 
-  for (uint32_t tile = tile_s; tile <= tile_e; ++tile) {
-    const uint32_t cnt = tile == tile_e ? off_e : a.link_count[tile];
+  for (uint32_t tile = s / kPrepTile; tile * kPrepTile < e; ++tile) {
+    const uint32_t cnt = a.link_count[tile];
     const uint32_t *list = a.link_list + (size_t)tile * kPrepTile;
-    for (uint32_t c0 = tile == tile_s ? off_s : 0u; c0 < cnt; c0 += 32) {
+    for (uint32_t c0 = 0; c0 < cnt; c0 += 32) {
       const uint32_t c = c0 + lane;
       uint32_t i = c < cnt ? list[c] : 0xFFFFFFFFu;
-      const bool valid = c < cnt;
+      const bool valid = c < cnt && i >= s && i < e;
+      if (!__ballot_sync(full, valid)) continue;
       int32_t ti = 0, qi = 0;
       float ci = 0.0f, init = 0.0f, M = 0.0f;
       uint32_t lo = 0;
@@ -542,60 +455,13 @@ __global__ void __launch_bounds__(kDpThreads) k_chain_dp(ChainArgs a) {
     }
   }
   if (lane == 0) {
-    SubRec r;
     r.ntop = (uint32_t)ntop;
     r.max = runmax;
     r.top_s[0] = ts0; r.top_s[1] = ts1; r.top_s[2] = ts2;
     r.top_i[0] = ti0; r.top_i[1] = ti1; r.top_i[2] = ti2;
-    a.sub[id] = r;
+    a.seg[slot] = r;
+    a.seg_max[slot] = runmax;
   }
-  }  // ranges of this grab
-  }  // grabs
-}
-
-// A segment's summary from its DP ranges, in order: the running max before range k is the max
-// of the earlier ranges, and -- exactly like the earlier-buckets term in k_sel_trace -- it only
-// removes a suffix of the range's own candidate list (score <= max/2, :545-549).  The segment
-// keeps the best three of what survives, score desc then index desc (compare(), :11-20).
-__global__ void k_dp_combine(ChainArgs a) {
-  const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
-  if (slot >= a.n_slots) return;
-  SegRec r = a.seg[slot];
-  if (r.start == kSegEmpty) return;
-  const uint32_t n_subs = a.head_base[a.n_tiles];
-  uint32_t id = a.head_base[r.sub0 / kPrepTile] + r.sub0 % kPrepTile;
-  float P = 0.0f;
-  float ts[3] = {0.f, 0.f, 0.f};
-  uint32_t ti[3] = {0u, 0u, 0u};
-  int ntop = 0;
-  for (; id < n_subs && a.sub_start[id] < r.end; ++id) {
-    const SubRec sr = a.sub[id];
-    const float half = __fdiv_rn(P, 2.0f);
-    for (uint32_t k = 0; k < sr.ntop && k < 3u; ++k) {
-      const float sc = sr.top_s[k];
-      const uint32_t ix = sr.top_i[k];
-      if (!(sc > half)) break;
-      int at = ntop;  // position among the kept ones
-      while (at > 0 && (sc > ts[at - 1] || (sc == ts[at - 1] && ix > ti[at - 1]))) --at;
-      if (at >= 3) continue;
-      for (int m = min(ntop, 2); m > at; --m) {
-        ts[m] = ts[m - 1];
-        ti[m] = ti[m - 1];
-      }
-      ts[at] = sc;
-      ti[at] = ix;
-      if (ntop < 3) ++ntop;
-    }
-    P = fmaxf(P, sr.max);
-  }
-  r.ntop = (uint32_t)ntop;
-  r.max = P;
-  for (int k = 0; k < 3; ++k) {
-    r.top_s[k] = ts[k];
-    r.top_i[k] = ti[k];
-  }
-  a.seg[slot] = r;
-  a.seg_max[slot] = P;
 }
 
 // ---------------------------------------------------------------------------------------

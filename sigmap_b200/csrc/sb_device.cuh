@@ -128,7 +128,6 @@ struct Counters {
   unsigned long long n_cand;        // sharded: chain candidates this rank appended to its exchange list
   unsigned int n_segments;
   unsigned int work;                // dynamic work counter for the search kernel
-  unsigned int dp_cursor;           // dynamic work counter for the chaining DP (DP ranges)
   unsigned int error;               // bit0 anchor overflow, bit1 carry overflow, bit2 chain scratch,
                                     // bit3 run table overflow, bit4 entry too dense for k_seg_sort,
                                     // bit5 candidate exchange list overflow

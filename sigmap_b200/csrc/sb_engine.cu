@@ -16,7 +16,6 @@
 #include <cstdlib>
 #include <cstring>
 #include <cub/device/device_radix_sort.cuh>
-#include <cub/device/device_scan.cuh>
 #include <string>
 #include <vector>
 
@@ -52,7 +51,6 @@ __global__ void k_reset_step(Counters *c) {
   c->n_linked = 0;
   c->n_segments = 0;
   c->work = 0;
-  c->dp_cursor = 0;
   c->sort_cursor = 0;
   c->n_cand = 0;
   c->max_entry_anchors = 0;
@@ -187,8 +185,7 @@ struct Workspace {
   // anchors
   DevBuf<uint64_t> key_a, key_b;
   DevBuf<float> dist_a, dist_b, score, coef;
-  DevBuf<uint32_t> pred, link_list, link_count, head_list, head_count, head_base, sub_start, head_link, sub_link;
-  DevBuf<SubRec> sub;
+  DevBuf<uint32_t> pred, link_list, link_count;
   DevBuf<SegRec> seg;
   DevBuf<RunRec> runs;
   DevBuf<uint32_t> run_count, entry_total;
@@ -219,12 +216,11 @@ struct smb_ctx {
   DevBuf<uint32_t> leaf_widx;
   uint32_t max_tpos = 0, max_bucket = 0;
   unsigned search_grid_main = 148 * 4;
-  unsigned dp_grid = 148 * 8;     // persistent grid of the chaining DP: every CTA that fits
   DevBuf<uint64_t> bucket_base;   // linear coordinate of every bucket's target 0 (k_sort.cuh)
   int gshift = 0;
   uint32_t n_coarse = 1;
   bool seg_sort = true;           // per-entry shared-memory sort; SMB_SORT=global forces the radix sort
-  bool search_bfs = false;        // SMB_SEARCH=bfs: level-order traversal (fuller 8-node steps)
+  bool search_bfs = true;         // level-order traversal (fuller 8-node steps); SMB_SEARCH=dfs: depth-first
   bool sort_small = false;        // SMB_SORT=small: two 100 KB sort CTAs per SM instead of one 200 KB CTA
   std::vector<uint32_t> contig_len;
   // uploaded reads
@@ -753,35 +749,9 @@ static int run_step(smb_ctx *ctx, SlotSpace &sp, const StepEntries &en, StepSour
   ca.link_list = w.link_list.p;
   ca.link_count = w.link_count.p;
   if (n > 0) {
-    // DP ranges: at most one per segment plus one per 32 anchors (k_chain_prep)
-    const uint64_t sub_cap = n / 32 + std::min<uint64_t>(ca.n_slots, n) + 2;
-    CK(w.head_list.ensure((size_t)n_tiles * kHeadsPerTile));
-    CK(w.head_count.ensure(n_tiles + 1));
-    CK(w.head_base.ensure(n_tiles + 1));
-    CK(w.sub_start.ensure(sub_cap + 1));
-    CK(w.head_link.ensure((size_t)n_tiles * kHeadsPerTile));
-    CK(w.sub_link.ensure(sub_cap + 1));
-    CK(w.sub.ensure(sub_cap));
-    ca.head_list = w.head_list.p;
-    ca.head_count = w.head_count.p;
-    ca.head_base = w.head_base.p;
-    ca.n_tiles = n_tiles;
-    ca.sub_start = w.sub_start.p;
-    ca.head_link = w.head_link.p;
-    ca.sub_link = w.sub_link.p;
-    ca.sub = w.sub.p;
     k_chain_prep<<<n_tiles, kPrepThreads, 0, s>>>(ca);
     LAUNCH_CHECK();
-    size_t tb = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, tb, w.head_count.p, w.head_base.p, (int)(n_tiles + 1), s);
-    CK(w.cub_temp.ensure(tb));
-    CK(cub::DeviceScan::ExclusiveSum(w.cub_temp.p, tb, w.head_count.p, w.head_base.p, (int)(n_tiles + 1), s));
-    ctx->stats.launches += 2;
-    k_head_flatten<<<n_tiles, 128, 0, s>>>(ca);
-    LAUNCH_CHECK();
-    k_chain_dp<<<ctx->dp_grid, kDpThreads, 0, s>>>(ca);
-    LAUNCH_CHECK();
-    k_dp_combine<<<(ca.n_slots + 127) / 128, 128, 0, s>>>(ca);
+    k_chain_dp<<<(unsigned)(((uint64_t)ca.n_slots * 32 + kDpThreads - 1) / kDpThreads), kDpThreads, 0, s>>>(ca);
     LAUNCH_CHECK();
   }
   SelectArgs se{};
@@ -1120,17 +1090,11 @@ int smb_create(smb_ctx **out, int device) {
       (e = cudaFuncSetAttribute(k_seg_sort<kSortCapSmall, 512, 4096>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)sort_smem_bytes(kSortCapSmall, 4096))) != cudaSuccess)
     return bail("cudaFuncSetAttribute(k_seg_sort)", e);
-  {
-    int nb = 0, n_sm = 148;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_chain_dp, kDpThreads, 0) != cudaSuccess || nb < 1) nb = 8;
-    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device);
-    ctx->dp_grid = (unsigned)(nb * n_sm);
-  }
   if (const char *env = getenv("SMB_SORT")) {
     ctx->seg_sort = strcmp(env, "global") != 0;
     ctx->sort_small = strcmp(env, "small") == 0;
   }
-  if (const char *env = getenv("SMB_SEARCH")) ctx->search_bfs = strcmp(env, "bfs") == 0;
+  if (const char *env = getenv("SMB_SEARCH")) ctx->search_bfs = strcmp(env, "dfs") != 0;
   *out = ctx;
   return SMB_OK;
 }
@@ -1153,7 +1117,6 @@ void smb_destroy(smb_ctx *ctx) {
   w.chain_tmp.release(); w.ids.release(); w.round_info.release();
   w.seg_max.release(); w.n_scratch.release(); w.cand_list.release(); w.cand_all.release();
   w.cand_counts.release(); w.ctl.release(); w.tags.release();
-  w.head_list.release(); w.head_count.release(); w.head_base.release(); w.sub_start.release(); w.sub.release(); w.head_link.release(); w.sub_link.release();
   ctx->ex.reset();
   ctx->local_group.reset();
   ctx->leaf_vals.release(); ctx->leaf_tb.release(); ctx->leaf_widx.release(); ctx->bucket_base.release();

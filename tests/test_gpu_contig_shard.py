@@ -107,3 +107,22 @@ def test_shard_holds_only_its_contigs(multi, whole, port):
         assert seen == len(idx) > 0
     finally:
         g.close()
+
+
+def test_nccl_two_ranks_when_two_gpus():
+    """The same check over the NCCL backend, one process per GPU (needs >= 2 GPUs: skipped on the
+    single-GPU test box; run with `gpurun --gpus 2`)."""
+    import os
+    import subprocess
+    import sys
+
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29517",
+                        os.path.join(root, "tools", "shard_nccl_check.py")],
+                       capture_output=True, text=True, timeout=600, env=dict(os.environ, CHECK_READS="120"))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "PASS" in r.stdout
