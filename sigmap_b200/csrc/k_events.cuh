@@ -204,18 +204,41 @@ struct Det {
   bool valid;
 };
 
-__global__ void __launch_bounds__(128)
-k_ev_features(const float *__restrict__ t1, const float *__restrict__ t2,
-              const float *__restrict__ ps, float *__restrict__ means, float *__restrict__ features,
-              uint32_t *__restrict__ n_features, uint32_t *__restrict__ n_raw_events,
-              uint32_t *__restrict__ peaks_out /* optional, chunk-major kFeatCap */, uint32_t B,
-              uint32_t Bp, Counters *__restrict__ ctr) {
-  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= B) return;
+// Where the detector reads its per-sample inputs: the transposed global arrays of the
+// thread-per-chunk path, or the shared-memory rows of the warp-per-chunk path.
+struct EvGlobalSrc {
+  const float *t1, *t2, *ps;
+  uint32_t Bp, b;
+  __device__ __forceinline__ void load8(int base, float *a, float *c) const {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      a[k] = __ldg(t1 + (size_t)(base + k) * Bp + b);
+      c[k] = __ldg(t2 + (size_t)(base + k) * Bp + b);
+    }
+  }
+  __device__ __forceinline__ float prefix(unsigned long long i) const { return __ldg(ps + (size_t)i * Bp + b); }
+};
+struct EvSharedSrc {
+  const float *t1, *t2, *ps;
+  __device__ __forceinline__ void load8(int base, float *a, float *c) const {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      a[k] = t1[base + k];
+      c[k] = t2[base + k];
+    }
+  }
+  __device__ __forceinline__ float prefix(unsigned long long i) const { return ps[i]; }
+};
+
+// One thread, one chunk: peaks -> events -> z-scores -> compressed features.
+template <class Src>
+__device__ __forceinline__ void ev_detect_features(const Src &src, float *__restrict__ my_means,
+                                                   float *__restrict__ my_feat,
+                                                   uint32_t *__restrict__ my_peaks /* optional */,
+                                                   uint32_t &nf_out, uint32_t &ne_out) {
   Det sd = {4.30265f, FLT_MAX, 3, -1, 0, false};  // event.h:31-37 defaults
   Det ld = {2.57058f, FLT_MAX, 6, -1, 0, false};
   const float peak_height = 1.0f;
-  float *my_means = means + (size_t)b * kFeatCap;
   uint32_t np = 0;
   int prev_peak = 0, prev_prev_peak = 0;
   auto emit = [&](int pos) {
@@ -223,9 +246,9 @@ k_ev_features(const float *__restrict__ t1, const float *__restrict__ t2,
     if (np < (uint32_t)kFeatCap) {
       unsigned long long s = np == 0 ? 0ull : (unsigned long long)prev_peak;
       unsigned long long len = (unsigned long long)pos - s;  // unsigned wrap as in the reference
-      float d = __fsub_rn(__ldg(ps + (size_t)pos * Bp + b), __ldg(ps + (size_t)s * Bp + b));
+      float d = __fsub_rn(src.prefix((unsigned long long)pos), src.prefix(s));
       my_means[np] = __fdiv_rn(d, (float)len);
-      if (peaks_out) peaks_out[(size_t)b * kFeatCap + np] = (uint32_t)pos;
+      if (my_peaks) my_peaks[np] = (uint32_t)pos;
     }
     prev_prev_peak = prev_peak;
     prev_peak = pos;
@@ -233,11 +256,7 @@ k_ev_features(const float *__restrict__ t1, const float *__restrict__ t2,
   };
   for (int base = 0; base < kChunk; base += 8) {
     float a[8], c[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      a[k] = __ldg(t1 + (size_t)(base + k) * Bp + b);
-      c[k] = __ldg(t2 + (size_t)(base + k) * Bp + b);
-    }
+    src.load8(base, a, c);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const int i = base + k;
@@ -305,7 +324,7 @@ k_ev_features(const float *__restrict__ t1, const float *__restrict__ t2,
     {
       unsigned long long s = (unsigned long long)prev_prev_peak;  // peaks[ne-2]
       unsigned long long len = (unsigned long long)kChunk - s;
-      float d = __fsub_rn(__ldg(ps + (size_t)kChunk * Bp + b), __ldg(ps + (size_t)s * Bp + b));
+      float d = __fsub_rn(src.prefix((unsigned long long)kChunk), src.prefix(s));
       my_means[ne - 1] = __fdiv_rn(d, (float)len);
     }
     double mean = 0.0;
@@ -317,7 +336,6 @@ k_ev_features(const float *__restrict__ t1, const float *__restrict__ t2,
       ss = __dadd_rn(ss, __dmul_rn(d, d));
     }
     const double sdv = __dsqrt_rn(__ddiv_rn(ss, (double)(ne - 1)));
-    float *my_feat = features + (size_t)b * kFeatCap;
     float last = 0.0f;
     for (uint32_t k = 0; k < ne; ++k) {
       float z = (float)__ddiv_rn(__dsub_rn((double)my_means[k], mean), sdv);
@@ -327,11 +345,142 @@ k_ev_features(const float *__restrict__ t1, const float *__restrict__ t2,
       }
     }
   }
+  nf_out = nf;
+  ne_out = ne;
+}
+
+__global__ void __launch_bounds__(128)
+k_ev_features(const float *__restrict__ t1, const float *__restrict__ t2,
+              const float *__restrict__ ps, float *__restrict__ means, float *__restrict__ features,
+              uint32_t *__restrict__ n_features, uint32_t *__restrict__ n_raw_events,
+              uint32_t *__restrict__ peaks_out /* optional, chunk-major kFeatCap */, uint32_t B,
+              uint32_t Bp, Counters *__restrict__ ctr) {
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const EvGlobalSrc src{t1, t2, ps, Bp, b};
+  uint32_t nf = 0, ne = 0;
+  ev_detect_features(src, means + (size_t)b * kFeatCap, features + (size_t)b * kFeatCap,
+                     peaks_out ? peaks_out + (size_t)b * kFeatCap : nullptr, nf, ne);
   n_features[b] = nf;
   if (n_raw_events) n_raw_events[b] = ne;
   if (ctr) {
     atomicAdd(&ctr->n_events_raw, (unsigned long long)ne);
     atomicAdd(&ctr->n_events_kept, (unsigned long long)nf);
+  }
+}
+
+// ---------------------------------------------------------------- small batches: warp per chunk
+// The read-until path maps a few hundred chunks per round; with one THREAD per chunk that is a
+// handful of warps whose 32 lanes diverge through the detector and wait on global memory every
+// step.  Here one WARP owns a chunk and keeps it in shared memory: all lanes load and convert
+// the samples and compute the t-statistics; the two order-dependent parts (the fp32 prefix sums
+// and the detector / z-score / compression tail) run on lane 0 alone with the same expressions
+// as the thread-per-chunk kernels, so results are bit-identical.
+//   rows: ps[0..4000], pss[0..4000] (overwritten in place by t2, one tile behind), t1[0..4000]
+constexpr int kEvRow = kChunk + 8;  // floats per shared row (16-byte multiple)
+constexpr size_t kEvWarpSmem = (size_t)3 * kEvRow * sizeof(float);
+
+template <bool RAW>
+__global__ void __launch_bounds__(32)
+k_ev_chunk_warp(const void *__restrict__ src, const uint64_t *__restrict__ chunk_start,
+                const float *__restrict__ chunk_offset, const float *__restrict__ chunk_scale,
+                float *__restrict__ means, float *__restrict__ features,
+                uint32_t *__restrict__ n_features, uint32_t *__restrict__ n_raw_events,
+                uint32_t *__restrict__ peaks_out /* optional */, uint32_t B,
+                Counters *__restrict__ ctr) {
+  extern __shared__ __align__(16) float s_ev[];
+  const uint32_t b = blockIdx.x;
+  if (b >= B) return;
+  const int lane = threadIdx.x;
+  float *ps = s_ev, *pss = s_ev + kEvRow, *t1 = s_ev + 2 * kEvRow;
+  // ---- samples -> ps[i+1] = x_i, pss[i+1] = x_i * x_i (all lanes)
+  if (RAW) {
+    const int4 *in = reinterpret_cast<const int4 *>(static_cast<const int16_t *>(src) + chunk_start[b]);
+    const float off = chunk_offset[b], scale = chunk_scale[b];
+    for (int i = lane; i < kChunk / 8; i += 32) {
+      const int4 w = __ldg(in + i);
+      __align__(16) int16_t v[8];
+      *reinterpret_cast<int4 *>(v) = w;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float x = raw_to_pa(v[k], off, scale);
+        ps[1 + 8 * i + k] = x;
+        pss[1 + 8 * i + k] = __fmul_rn(x, x);
+      }
+    }
+  } else {
+    const float4 *in = reinterpret_cast<const float4 *>(static_cast<const float *>(src) + chunk_start[b]);
+    for (int i = lane; i < kChunk / 4; i += 32) {
+      const float4 w = __ldg(in + i);
+      const float v[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        ps[1 + 4 * i + k] = v[k];
+        pss[1 + 4 * i + k] = __fmul_rn(v[k], v[k]);
+      }
+    }
+  }
+  __syncwarp();
+  // ---- sequential fp32 prefix sums, in place (event.h:58-68)
+  if (lane == 0) {
+    float s = 0.0f, q = 0.0f;
+    ps[0] = 0.0f;
+    pss[0] = 0.0f;
+    for (int i = 1; i <= kChunk; i += 8) {
+      float x[8], y[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        x[k] = ps[i + k];
+        y[k] = pss[i + k];
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        s = __fadd_rn(s, x[k]);
+        q = __fadd_rn(q, y[k]);
+        ps[i + k] = s;
+        pss[i + k] = q;
+      }
+    }
+  }
+  __syncwarp();
+  // ---- t-statistics, 32 positions per tile; t2 replaces pss one tile behind the reads
+  {
+    float held = 0.0f;
+    int held_i = -1;
+    for (int base = 0; base <= kChunk; base += 32) {
+      const int i = base + lane;
+      float a = 0.0f, c = 0.0f;
+      if (i <= kChunk) {
+        // zeros on [0,w) and (n-w, n]  (event.h:85-87,112-114)
+        if (i >= 3 && i <= kChunk - 3) a = tstat_at(ps, pss, i, 3);
+        if (i >= 6 && i <= kChunk - 6) c = tstat_at(ps, pss, i, 6);
+      }
+      __syncwarp();  // this tile's reads of pss[base-6 .. base+37] are done
+      if (held_i >= 0) pss[held_i] = held;  // previous tile: [base-32, base)
+      if (i <= kChunk) {
+        t1[i] = a;
+        held = c;
+        held_i = i;
+      } else {
+        held_i = -1;
+      }
+      __syncwarp();
+    }
+    if (held_i >= 0) pss[held_i] = held;
+    __syncwarp();
+  }
+  // ---- detector and tail on lane 0
+  if (lane == 0) {
+    const EvSharedSrc ssrc{t1, pss, ps};
+    uint32_t nf = 0, ne = 0;
+    ev_detect_features(ssrc, means + (size_t)b * kFeatCap, features + (size_t)b * kFeatCap,
+                       peaks_out ? peaks_out + (size_t)b * kFeatCap : nullptr, nf, ne);
+    n_features[b] = nf;
+    if (n_raw_events) n_raw_events[b] = ne;
+    if (ctr) {
+      atomicAdd(&ctr->n_events_raw, (unsigned long long)ne);
+      atomicAdd(&ctr->n_events_kept, (unsigned long long)nf);
+    }
   }
 }
 

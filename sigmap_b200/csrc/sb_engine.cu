@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -175,8 +176,13 @@ struct Workspace {
   // per-entry
   DevBuf<uint32_t> entry_slot, n_features, n_raw_events, n_queries, q_off, feat_row;
   // event lookahead block of the offline path: features of chunks [r0, r1) of the active reads
-  DevBuf<float> feat_cache;
-  DevBuf<uint32_t> nf_cache, nraw_cache;
+  // (two of them: the next block is computed on the event stream while this one is being mapped)
+  DevBuf<float> feat_cache[2];
+  DevBuf<uint32_t> nf_cache[2], nraw_cache[2];
+  int cache_cur = 0;
+  // chunk table of the lookahead blocks (the event stream's own copies)
+  DevBuf<uint64_t> blk_chunk_start;
+  DevBuf<float> blk_chunk_offset, blk_chunk_scale;
   DevBuf<uint8_t> absent;
   DevBuf<uint64_t> chunk_start;
   DevBuf<float> chunk_offset, chunk_scale;
@@ -222,6 +228,12 @@ struct smb_ctx {
   bool seg_sort = true;           // per-entry shared-memory sort; SMB_SORT=global forces the radix sort
   bool search_bfs = true;         // level-order traversal (fuller 8-node steps); SMB_SEARCH=dfs: depth-first
   bool sort_small = false;        // SMB_SORT=small: two 100 KB sort CTAs per SM instead of one 200 KB CTA
+  cudaStream_t stream_ev = nullptr;  // lookahead event blocks run here, next to the mapping rounds
+  cudaEvent_t ev_blk_t0[2] = {}, ev_blk_t1[2] = {};
+  bool ev_overlap = true;            // SMB_EVENTS_OVERLAP=0: compute every block when it is needed
+  double ev_survival_hint = 0.0;     // share of reads that went past their first chunk in the last call
+  uint32_t ev_warp_max = 2048;    // event batches up to this many chunks run warp-per-chunk in shared memory
+                                  // (SMB_EVENTS=thread: never, =warp: always)
   std::vector<uint32_t> contig_len;
   // uploaded reads
   size_t n_reads = 0;
@@ -256,6 +268,13 @@ struct smb_ctx {
   std::vector<std::vector<int16_t>> stream_pending;  // kept samples not yet forming a chunk
   std::vector<float> stream_offset, stream_scale;
   std::vector<uint32_t> stream_chunks, stream_kept;
+  // raw values kept by the (30, 200) pA filter form an interval [lo, hi] per channel (the
+  // conversion is monotone in the raw value); lo > hi: nothing kept; generic: test every sample
+  std::vector<int32_t> stream_lo, stream_hi;
+  std::vector<uint8_t> stream_generic;
+  int16_t *h_stream_stage = nullptr;  // pinned: this round's chunks, channel after channel
+  size_t h_stream_stage_cap = 0;
+  DevBuf<int16_t> d_stream_stage;
 };
 
 struct smb_batch {
@@ -478,25 +497,50 @@ static int ensure_event_ws(smb_ctx *ctx, uint32_t B) {
   return SMB_OK;
 }
 
+struct ChunkTable {  // device arrays describing the chunks of one event launch
+  const uint64_t *start;
+  const float *offset, *scale;
+};
+
 static int run_events(smb_ctx *ctx, StepSource src, const void *samples, uint32_t B,
                       uint32_t *d_peaks_out, float *d_features = nullptr, uint32_t *d_n_features = nullptr,
-                      uint32_t *d_n_raw = nullptr) {
+                      uint32_t *d_n_raw = nullptr, cudaStream_t s = nullptr, const ChunkTable *table = nullptr) {
   Workspace &w = ctx->ws;
-  cudaStream_t s = ctx->stream;
+  if (!s) s = ctx->stream;
+  const ChunkTable own{w.chunk_start.p, w.chunk_offset.p, w.chunk_scale.p};
+  const ChunkTable &ct = table ? *table : own;
   const uint32_t Bp = (B + 31) & ~31u;
+  // small batches (read-until rounds, the thin last rounds of a read set): a warp per chunk in
+  // shared memory; the stage hook that returns the t-statistics needs the global arrays
+  if (B <= ctx->ev_warp_max && !d_peaks_out) {
+    CK(w.means.ensure((size_t)B * kFeatCap));
+    if (!d_n_raw) CK(w.n_raw_events.ensure(B));
+    float *feat = d_features ? d_features : w.features.p;
+    uint32_t *nfeat = d_n_features ? d_n_features : w.n_features.p;
+    uint32_t *nraw = d_n_raw ? d_n_raw : w.n_raw_events.p;
+    Counters *ctr = d_n_raw ? nullptr : ctx->d_ctr;
+    if (src == SRC_RAW_KEPT)
+      k_ev_chunk_warp<true><<<B, 32, kEvWarpSmem, s>>>(samples, ct.start, ct.offset, ct.scale,
+                                                       w.means.p, feat, nfeat, nraw, nullptr, B, ctr);
+    else
+      k_ev_chunk_warp<false><<<B, 32, kEvWarpSmem, s>>>(samples, ct.start, nullptr, nullptr, w.means.p,
+                                                        feat, nfeat, nraw, nullptr, B, ctr);
+    LAUNCH_CHECK();
+    return SMB_OK;
+  }
   int rc = ensure_event_ws(ctx, B);
   if (rc) return rc;
   if (src == SRC_RAW_KEPT)
-    k_ev_prefix<true><<<(B + 127) / 128, 128, 0, s>>>(samples, w.chunk_start.p, w.chunk_offset.p,
-                                                      w.chunk_scale.p, w.ps.p, w.pss.p, B, Bp);
+    k_ev_prefix<true><<<(B + 127) / 128, 128, 0, s>>>(samples, ct.start, ct.offset, ct.scale, w.ps.p, w.pss.p,
+                                                      B, Bp);
   else
-    k_ev_prefix<false><<<(B + 127) / 128, 128, 0, s>>>(samples, w.chunk_start.p, nullptr, nullptr,
+    k_ev_prefix<false><<<(B + 127) / 128, 128, 0, s>>>(samples, ct.start, nullptr, nullptr,
                                                        w.ps.p, w.pss.p, B, Bp);
   LAUNCH_CHECK();
   dim3 g((B + 127) / 128, (kChunk + 1 + kStrip - 1) / kStrip);
   k_ev_tstat<<<g, 128, 0, s>>>(w.ps.p, w.pss.p, w.t1.p, w.t2.p, B, Bp);
   LAUNCH_CHECK();
-  CK(w.n_raw_events.ensure(B));
+  if (!d_n_raw) CK(w.n_raw_events.ensure(B));
   k_ev_features<<<(B + 127) / 128, 128, 0, s>>>(w.t1.p, w.t2.p, w.ps.p, w.means.p,
                                                 d_features ? d_features : w.features.p,
                                                 d_n_features ? d_n_features : w.n_features.p,
@@ -558,7 +602,7 @@ static int run_step(smb_ctx *ctx, SlotSpace &sp, const StepEntries &en, StepSour
       k_scatter_features<<<Bpres, 256, 0, s>>>(en.d_features, en.d_feat_off, Bpres, w.features.p, w.n_features.p);
       LAUNCH_CHECK();
     } else if (src == SRC_CACHED) {
-      k_gather_nfeat<<<(Bpres + 255) / 256, 256, 0, s>>>(w.nf_cache.p, w.nraw_cache.p, w.feat_row.p, Bpres,
+      k_gather_nfeat<<<(Bpres + 255) / 256, 256, 0, s>>>(w.nf_cache[w.cache_cur].p, w.nraw_cache[w.cache_cur].p, w.feat_row.p, Bpres,
                                                          w.n_features.p, ctx->d_ctr);
       LAUNCH_CHECK();
     } else {
@@ -604,7 +648,7 @@ static int run_step(smb_ctx *ctx, SlotSpace &sp, const StepEntries &en, StepSour
                                                      w.entry_total.p, (uint32_t)kRunsCap);
   LAUNCH_CHECK();
   SearchArgs sa{};
-  sa.features = src == SRC_CACHED ? w.feat_cache.p : w.features.p;
+  sa.features = src == SRC_CACHED ? w.feat_cache[w.cache_cur].p : w.features.p;
   sa.feat_row = w.feat_row.p;
   sa.q_off = w.q_off.p;
   sa.entry_slot = w.entry_slot.p;
@@ -1095,6 +1139,21 @@ int smb_create(smb_ctx **out, int device) {
     ctx->sort_small = strcmp(env, "small") == 0;
   }
   if (const char *env = getenv("SMB_SEARCH")) ctx->search_bfs = strcmp(env, "dfs") != 0;
+  if ((e = cudaFuncSetAttribute(k_ev_chunk_warp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)kEvWarpSmem)) != cudaSuccess ||
+      (e = cudaFuncSetAttribute(k_ev_chunk_warp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)kEvWarpSmem)) != cudaSuccess)
+    return bail("cudaFuncSetAttribute(k_ev_chunk_warp)", e);
+  if ((e = cudaStreamCreateWithFlags(&ctx->stream_ev, cudaStreamNonBlocking)) != cudaSuccess)
+    return bail("cudaStreamCreate", e);
+  for (int c = 0; c < 2; ++c)
+    if ((e = cudaEventCreate(&ctx->ev_blk_t0[c])) != cudaSuccess || (e = cudaEventCreate(&ctx->ev_blk_t1[c])) != cudaSuccess)
+      return bail("cudaEventCreate", e);
+  if (const char *env = getenv("SMB_EVENTS_OVERLAP")) ctx->ev_overlap = strcmp(env, "0") != 0;
+  if (const char *env = getenv("SMB_EVENTS")) {
+    if (!strcmp(env, "thread")) ctx->ev_warp_max = 0;
+    else if (!strcmp(env, "warp")) ctx->ev_warp_max = 0xFFFFFFFFu;
+  }
   *out = ctx;
   return SMB_OK;
 }
@@ -1103,14 +1162,13 @@ void smb_destroy(smb_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  if (ctx->stream_slots) {
-    slots_release(*ctx->stream_slots);
-    delete ctx->stream_slots;
-  }
+  if (ctx->stream_ev) cudaStreamSynchronize(ctx->stream_ev);
+  smb_stream_close(ctx);
   slots_release(ctx->map_slots);
   Workspace &w = ctx->ws;
   w.entry_slot.release(); w.n_features.release(); w.n_raw_events.release(); w.n_queries.release();
-  w.q_off.release(); w.feat_row.release(); w.feat_cache.release(); w.nf_cache.release(); w.nraw_cache.release(); w.absent.release(); w.chunk_start.release(); w.chunk_offset.release();
+  w.q_off.release(); w.feat_row.release(); for (int c = 0; c < 2; ++c) { w.feat_cache[c].release(); w.nf_cache[c].release(); w.nraw_cache[c].release(); }
+  w.blk_chunk_start.release(); w.blk_chunk_offset.release(); w.blk_chunk_scale.release(); w.absent.release(); w.chunk_start.release(); w.chunk_offset.release();
   w.chunk_scale.release(); w.ps.release(); w.pss.release(); w.t1.release(); w.t2.release();
   w.means.release(); w.features.release(); w.key_a.release(); w.key_b.release(); w.dist_a.release();
   w.dist_b.release(); w.score.release(); w.coef.release(); w.pred.release(); w.seg.release(); w.runs.release(); w.run_count.release(); w.entry_total.release(); w.link_list.release(); w.link_count.release(); w.cub_temp.release();
@@ -1125,6 +1183,9 @@ void smb_destroy(smb_ctx *ctx) {
   ctx->d_dig.release(); ctx->d_range.release(); ctx->d_offset.release(); ctx->d_kept_len.release();
   for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
   for (auto &ev : ctx->timer) if (ev) cudaEventDestroy(ev);
+  for (auto &ev : ctx->ev_blk_t0) if (ev) cudaEventDestroy(ev);
+  for (auto &ev : ctx->ev_blk_t1) if (ev) cudaEventDestroy(ev);
+  if (ctx->stream_ev) cudaStreamDestroy(ctx->stream_ev);
   if (ctx->d_ctr) cudaFree(ctx->d_ctr);
   if (ctx->h_ctr) cudaFreeHost(ctx->h_ctr);
   if (ctx->h_ctl) cudaFreeHost(ctx->h_ctl);
@@ -1382,56 +1443,117 @@ static int map_uploaded_impl(smb_ctx *ctx, const smb_params *prm_in, smb_mapping
   uint32_t round = 0;
   // Event detection does not depend on the mapping state, only on the raw signal, and its
   // kernels are one-thread-per-chunk sequential scans that want as many chunks per launch as
-  // possible.  So events run in LOOKAHEAD BLOCKS: chunks [ev_r0, ev_r1) of every read active
-  // at ev_r0 in one launch, cached as feature rows; the block is several rounds deep only
-  // while most reads survive from round to round (full-read mapping), one round deep when
-  // the stop rules retire most reads after their first chunk.
+  // possible.  So events run in LOOKAHEAD BLOCKS: chunks [r0, r1) of every read active at r0 in
+  // one launch, cached as feature rows; the block is several rounds deep only while most reads
+  // survive from round to round (full-read mapping), one round deep when the stop rules retire
+  // most reads after their first chunk.  The kernels are latency-bound and leave the SMs almost
+  // idle, so the NEXT block is computed on the event stream while the rounds of the current one
+  // are being mapped (two feature caches); a block is handed over with a host wait on its event.
   const uint32_t kEvRowCap = 96u << 10;
-  uint32_t ev_r0 = 0, ev_r1 = 0;
-  std::vector<uint32_t> row_base(R, 0);
+  struct EvBlock {
+    uint32_t r0 = 0, r1 = 0;
+    bool ready = false;                 // launched, not yet consumed
+    std::vector<uint32_t> row_base;     // per read: first row of the read in the block's cache
+    std::vector<uint64_t> cs;           // host chunk table (kept alive until the block is consumed)
+    std::vector<float> co, csc;
+  } blk[2];
+  int cur = 0;            // block being mapped (blk[cur].r0 <= round < blk[cur].r1 once consumed)
+  bool have_next = false; // blk[1 - cur] holds a launched block for round == blk[cur].r1
   size_t prev_active = 0;
   auto chunk_limit = [&](uint32_t r) { return std::min<uint32_t>(n_chunks[r], (uint32_t)prm.max_num_chunks); };
+  // enqueue the events of chunks [r0, r0 + depth) of `who` on the event stream, into cache `c`
+  auto launch_block = [&](int c, uint32_t r0, uint32_t depth, const std::vector<uint32_t> &who) -> int {
+    EvBlock &b = blk[c];
+    Workspace &w = ctx->ws;
+    cudaStream_t s = ctx->stream_ev;
+    b.r0 = r0;
+    b.r1 = r0 + depth;
+    b.row_base.assign(R, 0);
+    b.cs.clear();
+    b.co.clear();
+    b.csc.clear();
+    for (uint32_t r : who) {
+      b.row_base[r] = (uint32_t)b.cs.size();
+      const uint32_t lim = std::min(chunk_limit(r), b.r1);
+      for (uint32_t ch = r0; ch < lim; ++ch) {
+        b.cs.push_back(ctx->h_kept_off[r] + (uint64_t)kChunk * ch);
+        b.co.push_back(ctx->h_offset[r]);
+        b.csc.push_back(ctx->h_scale[r]);
+      }
+    }
+    const uint32_t rows = (uint32_t)b.cs.size();
+    CK(cudaEventRecord(ctx->ev_blk_t0[c], s));
+    if (rows) {
+      CK(w.blk_chunk_start.ensure(rows));
+      CK(w.blk_chunk_offset.ensure(rows));
+      CK(w.blk_chunk_scale.ensure(rows));
+      CK(w.feat_cache[c].ensure((size_t)rows * kFeatCap));
+      CK(w.nf_cache[c].ensure(rows));
+      CK(w.nraw_cache[c].ensure(rows));
+      CK(cudaMemcpyAsync(w.blk_chunk_start.p, b.cs.data(), rows * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+      CK(cudaMemcpyAsync(w.blk_chunk_offset.p, b.co.data(), rows * sizeof(float), cudaMemcpyHostToDevice, s));
+      CK(cudaMemcpyAsync(w.blk_chunk_scale.p, b.csc.data(), rows * sizeof(float), cudaMemcpyHostToDevice, s));
+      ctx->stats.h2d_bytes += rows * 16ull;
+      const ChunkTable ct{w.blk_chunk_start.p, w.blk_chunk_offset.p, w.blk_chunk_scale.p};
+      int rc2 = run_events(ctx, SRC_RAW_KEPT, ctx->kept.p, rows, nullptr, w.feat_cache[c].p, w.nf_cache[c].p,
+                           w.nraw_cache[c].p, s, &ct);
+      if (rc2) return rc2;
+    }
+    CK(cudaEventRecord(ctx->ev_blk_t1[c], s));
+    b.ready = true;
+    return SMB_OK;
+  };
+  // wait for block `c` and make it the one the rounds read
+  auto consume_block = [&](int c) -> int {
+    CK(cudaEventSynchronize(ctx->ev_blk_t1[c]));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev_blk_t0[c], ctx->ev_blk_t1[c]);
+    ctx->stats.ms_events += ms;
+    blk[c].ready = false;
+    cur = c;
+    ctx->ws.cache_cur = c;
+    return SMB_OK;
+  };
+  const uint32_t first_active = (uint32_t)active.size();
+  uint32_t after_first = first_active;
   while (!active.empty()) {
-    if (round >= ev_r1) {
-      uint32_t depth = 1;
-      if (round > 0 && active.size() * 2 > prev_active)
-        depth = (uint32_t)std::min<size_t>(8, std::max<size_t>(1, kEvRowCap / active.size()));
-      ev_r0 = round;
-      ev_r1 = round + depth;
-      std::vector<uint64_t> cs;
-      std::vector<float> co, csc;
-      for (uint32_t r : active) {
-        row_base[r] = (uint32_t)cs.size();
-        const uint32_t lim = std::min(chunk_limit(r), ev_r1);
-        for (uint32_t c = round; c < lim; ++c) {
-          cs.push_back(ctx->h_kept_off[r] + (uint64_t)kChunk * c);
-          co.push_back(ctx->h_offset[r]);
-          csc.push_back(ctx->h_scale[r]);
+    if (round >= blk[cur].r1) {
+      if (have_next && blk[1 - cur].r0 == round) {
+        rc = consume_block(1 - cur);
+        if (rc) return rc;
+      } else {
+        uint32_t depth = 1;
+        if (round > 0 && active.size() * 2 > prev_active)
+          depth = (uint32_t)std::min<size_t>(8, std::max<size_t>(1, kEvRowCap / active.size()));
+        const int c = round == 0 ? 0 : 1 - cur;
+        rc = launch_block(c, round, depth, active);
+        if (rc) return rc;
+        rc = consume_block(c);
+        if (rc) return rc;
+      }
+      have_next = false;
+    }
+    // the block after this one, while this one is being mapped: worth it only while most reads
+    // go on from round to round (known from the previous round; for round 0 from the last call)
+    if (ctx->ev_overlap && !have_next) {
+      const bool surviving = round > 0 ? active.size() * 2 > prev_active : ctx->ev_survival_hint > 0.5;
+      if (surviving) {
+        const uint32_t r0n = blk[cur].r1;
+        std::vector<uint32_t> who;
+        who.reserve(active.size());
+        for (uint32_t r : active)
+          if (chunk_limit(r) > r0n) who.push_back(r);
+        if (!who.empty()) {
+          const uint32_t depth = (uint32_t)std::min<size_t>(8, std::max<size_t>(1, kEvRowCap / who.size()));
+          rc = launch_block(1 - cur, r0n, depth, who);
+          if (rc) return rc;
+          have_next = true;
         }
       }
-      const uint32_t rows = (uint32_t)cs.size();
-      Workspace &w = ctx->ws;
-      cudaStream_t s = ctx->stream;
-      CK(w.chunk_start.ensure(rows));
-      CK(w.chunk_offset.ensure(rows));
-      CK(w.chunk_scale.ensure(rows));
-      CK(w.feat_cache.ensure((size_t)rows * kFeatCap));
-      CK(w.nf_cache.ensure(rows));
-      CK(w.nraw_cache.ensure(rows));
-      CK(cudaMemcpyAsync(w.chunk_start.p, cs.data(), rows * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
-      CK(cudaMemcpyAsync(w.chunk_offset.p, co.data(), rows * sizeof(float), cudaMemcpyHostToDevice, s));
-      CK(cudaMemcpyAsync(w.chunk_scale.p, csc.data(), rows * sizeof(float), cudaMemcpyHostToDevice, s));
-      ctx->stats.h2d_bytes += rows * 16ull;
-      CK(cudaEventRecord(ctx->ev[5], s));
-      rc = run_events(ctx, SRC_RAW_KEPT, ctx->kept.p, rows, nullptr, w.feat_cache.p, w.nf_cache.p, w.nraw_cache.p);
-      if (rc) return rc;
-      CK(cudaEventRecord(ctx->ev[4], s));
-      CK(cudaStreamSynchronize(s));  // cs/co/csc go out of scope; also gives the event time
-      float ms = 0;
-      cudaEventElapsedTime(&ms, ctx->ev[5], ctx->ev[4]);
-      ctx->stats.ms_events += ms;
     }
     prev_active = active.size();
+    const std::vector<uint32_t> &row_base = blk[cur].row_base;
+    const uint32_t ev_r0 = blk[cur].r0;
     auto fill = [&](StepEntries &en, size_t first, uint32_t count) {
       en.feat_row.resize(count);
       for (uint32_t i = 0; i < count; ++i) en.feat_row[i] = row_base[active[first + i]] + (round - ev_r0);
@@ -1450,8 +1572,12 @@ static int map_uploaded_impl(smb_ctx *ctx, const smb_params *prm_in, smb_mapping
       if (!info[i].stop && more) next.push_back(r);
     }
     active.swap(next);
+    if (round == 0) after_first = (uint32_t)active.size();
     ++round;
   }
+  // a block launched for rounds that never came (every read stopped) must not outlive the call
+  if (blk[0].ready || blk[1].ready) CK(cudaStreamSynchronize(ctx->stream_ev));
+  if (first_active) ctx->ev_survival_hint = (double)after_first / (double)first_active;
   // final rows
   std::vector<SlotState> st(std::max<size_t>(R, 1));
   if (R) {
@@ -1743,6 +1869,9 @@ int smb_stream_open(smb_ctx *ctx, uint32_t n_channels, const smb_params *params)
   ctx->stream_scale.assign(n_channels, 1.f);
   ctx->stream_chunks.assign(n_channels, 0);
   ctx->stream_kept.assign(n_channels, 0);
+  ctx->stream_lo.assign(n_channels, 0);
+  ctx->stream_hi.assign(n_channels, -1);
+  ctx->stream_generic.assign(n_channels, 1);
   return SMB_OK;
 }
 
@@ -1754,7 +1883,52 @@ int smb_stream_close(smb_ctx *ctx) {
     delete ctx->stream_slots;
     ctx->stream_slots = nullptr;
   }
+  if (ctx->h_stream_stage) {
+    cudaFreeHost(ctx->h_stream_stage);
+    ctx->h_stream_stage = nullptr;
+    ctx->h_stream_stage_cap = 0;
+  }
+  ctx->d_stream_stage.release();
   return SMB_OK;
+}
+
+// the K1 filter of one raw value on the host: same fp32 expression as raw_to_pa()
+static inline bool host_keep(int raw, float off, float scale) {
+  volatile float sum = (float)raw + off;  // volatile: two separately rounded fp32 operations
+  volatile float pa = sum * scale;
+  return pa > 30.0f && pa < 200.0f;
+}
+
+// Raw values kept on a channel.  For finite offset and finite positive scale the conversion
+// fl(fl(raw + offset) * scale) is non-decreasing in raw, so "pA > 30" holds from some raw value
+// upwards and "pA < 200" up to some raw value: two binary searches over the int16 range.
+static void stream_keep_interval(float off, float scale, int32_t &lo, int32_t &hi, uint8_t &generic) {
+  generic = !(scale > 0.0f) || !std::isfinite(scale) || !std::isfinite(off);
+  lo = 0;
+  hi = -1;
+  if (generic) return;
+  auto above30 = [&](int raw) {
+    volatile float sum = (float)raw + off;
+    volatile float pa = sum * scale;
+    return pa > 30.0f;
+  };
+  auto below200 = [&](int raw) {
+    volatile float sum = (float)raw + off;
+    volatile float pa = sum * scale;
+    return pa < 200.0f;
+  };
+  int a = -32768, b = 32768;  // first raw in [a, b) with above30, b if none
+  while (a < b) {
+    const int m = a + (b - a) / 2;
+    if (above30(m)) b = m; else a = m + 1;
+  }
+  lo = a;
+  a = -32769, b = 32767;      // last raw in (a, b] with below200, a if none
+  while (a < b) {
+    const int m = b - (b - a) / 2;
+    if (below200(m)) a = m; else b = m - 1;
+  }
+  hi = a;
 }
 
 int smb_stream_begin_read(smb_ctx *ctx, uint32_t ch, float dig, float range, float offset) {
@@ -1769,6 +1943,8 @@ int smb_stream_begin_read(smb_ctx *ctx, uint32_t ch, float dig, float range, flo
   ctx->stream_scale[ch] = range / dig;
   ctx->stream_chunks[ch] = 0;
   ctx->stream_kept[ch] = 0;
+  stream_keep_interval(offset, ctx->stream_scale[ch], ctx->stream_lo[ch], ctx->stream_hi[ch],
+                       ctx->stream_generic[ch]);
   return SMB_OK;
 }
 
@@ -1778,23 +1954,48 @@ int smb_stream_round(smb_ctx *ctx, const uint32_t *channels, uint32_t n, const i
   CK(cudaSetDevice(ctx->device));
   SlotSpace &sp = *ctx->stream_slots;
   const smb_params &prm = ctx->stream_params;
-  // host-side range filter of the incoming samples (same expression as K1) and chunk cutting
+  // host-side range filter of the incoming samples (same decisions as K1) and chunk cutting;
+  // completed chunks go straight into the pinned staging buffer
+  if ((size_t)n * kChunk > ctx->h_stream_stage_cap) {
+    if (ctx->h_stream_stage) cudaFreeHost(ctx->h_stream_stage);
+    ctx->h_stream_stage = nullptr;
+    ctx->h_stream_stage_cap = 0;
+    const size_t want = (size_t)std::max(n, sp.n_slots) * kChunk;
+    CK(cudaMallocHost((void **)&ctx->h_stream_stage, want * sizeof(int16_t)));
+    ctx->h_stream_stage_cap = want;
+  }
   std::vector<uint32_t> present;
-  std::vector<int16_t> chunk_samples;
+  present.reserve(n);
   for (uint32_t i = 0; i < n; ++i) {
     const uint32_t ch = channels[i];
     if (ch >= sp.n_slots) return fail(ctx, SMB_ERR_ARG, "bad channel");
     std::vector<int16_t> &pend = ctx->stream_pending[ch];
-    const float off = ctx->stream_offset[ch], scale = ctx->stream_scale[ch];
-    for (uint32_t k = sample_off[i]; k < sample_off[i + 1]; ++k) {
-      volatile float sum = (float)samples[k] + off;
-      volatile float pa = sum * scale;
-      if (pa > 30.0f && pa < 200.0f) pend.push_back(samples[k]);
+    const int16_t *in = samples + sample_off[i];
+    const size_t cnt = sample_off[i + 1] - sample_off[i];
+    if (ctx->stream_generic[ch]) {
+      const float off = ctx->stream_offset[ch], scale = ctx->stream_scale[ch];
+      for (size_t k = 0; k < cnt; ++k)
+        if (host_keep(in[k], off, scale)) pend.push_back(in[k]);
+    } else {
+      const int lo = ctx->stream_lo[ch], hi = ctx->stream_hi[ch];
+      int outside = 0;
+      for (size_t k = 0; k < cnt; ++k) outside |= (in[k] < lo) | (in[k] > hi);
+      if (!outside) {
+        pend.insert(pend.end(), in, in + cnt);
+      } else {
+        const size_t old = pend.size();
+        pend.resize(old + cnt);
+        int16_t *w = pend.data() + old;
+        for (size_t k = 0; k < cnt; ++k) {
+          *w = in[k];
+          w += (in[k] >= lo) & (in[k] <= hi);
+        }
+        pend.resize((size_t)(w - pend.data()));
+      }
     }
-    ctx->stream_kept[ch] += 0;
     if (pend.size() >= (size_t)kChunk && ctx->stream_chunks[ch] < (uint32_t)prm.max_num_chunks) {
+      memcpy(ctx->h_stream_stage + present.size() * kChunk, pend.data(), kChunk * sizeof(int16_t));
       present.push_back(ch);
-      chunk_samples.insert(chunk_samples.end(), pend.begin(), pend.begin() + kChunk);
       pend.erase(pend.begin(), pend.begin() + kChunk);
     }
   }
@@ -1805,12 +2006,14 @@ int smb_stream_round(smb_ctx *ctx, const uint32_t *channels, uint32_t n, const i
   for (uint32_t ch = 0; ch < sp.n_slots; ++ch)
     if (!seen[ch] && sp.h_nchains[ch] > 0) absent.push_back(ch);
   if (!present.empty() || !absent.empty()) {
-    DevBuf<int16_t> d_s;
-    CK(d_s.ensure(std::max<size_t>(chunk_samples.size(), 8)));
-    CK(cudaMemcpyAsync(d_s.p, chunk_samples.data(), chunk_samples.size() * sizeof(int16_t), cudaMemcpyHostToDevice, ctx->stream));
-    ctx->stats.h2d_bytes += chunk_samples.size() * 2;
+    const size_t n_stage = present.size() * kChunk;
+    CK(ctx->d_stream_stage.ensure(std::max<size_t>(n_stage, 8)));
+    if (n_stage)
+      CK(cudaMemcpyAsync(ctx->d_stream_stage.p, ctx->h_stream_stage, n_stage * sizeof(int16_t),
+                         cudaMemcpyHostToDevice, ctx->stream));
+    ctx->stats.h2d_bytes += n_stage * 2;
     auto fill = [&](StepEntries &en, size_t first, uint32_t count) {
-      en.samples = d_s.p;
+      en.samples = ctx->d_stream_stage.p;
       en.chunk_start.resize(count);
       en.offset.resize(count);
       en.scale.resize(count);
@@ -1828,8 +2031,6 @@ int smb_stream_round(smb_ctx *ctx, const uint32_t *channels, uint32_t n, const i
       ctx->stream_chunks[ch]++;
       ctx->stream_kept[ch] += kChunk;
     }
-    cudaStreamSynchronize(ctx->stream);
-    d_s.release();
   }
   // decisions + provisional rows for the channels named in this call
   std::vector<uint32_t> ids(channels, channels + n);

@@ -270,3 +270,78 @@ def test_streaming_rounds_match_offline(mapper, small):
             m = done[ch]
             assert (m.mapped, m.contig, m.strand_plus, m.t_start, m.frag_len, m.chunks) == \
                    (off.mapped, off.contig, off.strand_plus, off.t_start, off.frag_len, off.chunks)
+
+
+def test_streaming_filter_boundaries_match_offline(mapper, host, small):
+    """Samples outside (30, 200) pA -- including the raw values either side of both thresholds --
+    are dropped by the read-until path (host interval filter) exactly as by the offline K1 kernel."""
+    n = 8
+    rng = np.random.default_rng(11)
+    raws, off_ = [], [0]
+    edge = np.array([159, 160, 161, 162, 1128, 1129, 1130, 1131, -32768, 32767, 0, -11], np.int16)
+    for r in range(n):
+        raw = small.reads.read(r).copy()
+        where = rng.choice(len(raw), size=len(raw) // 200, replace=False)
+        raw[where] = rng.choice(edge, size=len(where))
+        raws.append(raw)
+        off_.append(off_[-1] + len(raw))
+    spiked = host.ReadSet([f"s{r}" for r in range(n)], np.concatenate(raws), np.array(off_, np.uint64),
+                          host.DIGITISATION, host.RANGE, host.OFFSET, small.reads.truth[:n])
+    offline = mapper.map_reads(spiked)
+    kept = [len(mapper.raw_to_pa(raws[r], DIG, OFF, RNG)) for r in range(n)]
+    assert all(k < len(raws[r]) for r, k in enumerate(kept))  # the filter really dropped samples
+    mapper.stream_open(n)
+    for ch in range(n):
+        mapper.stream_begin_read(ch, DIG, RNG, OFF)
+    cursor, done = [0] * n, {}
+    for _ in range(200):
+        chans, slices = [], []
+        for ch in range(n):
+            if ch in done or cursor[ch] >= len(raws[ch]):
+                continue
+            take = int(rng.integers(1500, 6000))
+            chans.append(ch)
+            slices.append(raws[ch][cursor[ch]:cursor[ch] + take])
+            cursor[ch] += take
+        if not chans:
+            break
+        dec, maps = mapper.stream_round(chans, slices)
+        for ch, d, m in zip(chans, dec, maps):
+            if d:
+                done[ch] = m
+    mapper.stream_close()
+    assert done
+    for ch, m in done.items():
+        o = offline[ch]
+        assert (m.mapped, m.contig, m.strand_plus, m.t_start, m.frag_len, m.chunks) == \
+               (o.mapped, o.contig, o.strand_plus, o.t_start, o.frag_len, o.chunks)
+
+
+def test_event_kernels_thread_and_warp_per_chunk_agree(mapper, port, small, monkeypatch):
+    """The two event paths (thread per chunk over transposed global arrays; warp per chunk in
+    shared memory for small batches) give bit-identical features and PAF rows."""
+    from sigmap_b200.mapper import Mapper
+    chunks = []
+    for r in range(12):
+        pa = small.pa(port, r)
+        for c in range(min(len(pa) // 4000, 3)):
+            chunks.append(pa[c * 4000:(c + 1) * 4000])
+    chunks.append(np.full(4000, 90.0, np.float32))                      # no peaks at all
+    chunks.append(np.tile(np.array([60.0, 120.0], np.float32), 2000))   # a peak every sample
+    chunks = np.stack(chunks)
+    base_feat = mapper.GenerateEvents(chunks)
+    base_rows = mapper.paf_lines(small.reads, mapper.map_reads(small.reads), small.ref.names)
+    for mode in ("thread", "warp"):
+        monkeypatch.setenv("SMB_EVENTS", mode)
+        m = Mapper(0)
+        try:
+            m.set_index(small.pos, small.val)
+            m.set_contigs(small.ref.lengths)
+            got = m.GenerateEvents(chunks)
+            assert len(got) == len(base_feat)
+            for g, e in zip(got, base_feat):
+                assert g.shape == e.shape and np.array_equal(bits(g), bits(e)), mode
+            rows = m.paf_lines(small.reads, m.map_reads(small.reads), small.ref.names)
+            assert [paf_cols(l) for l in rows] == [paf_cols(l) for l in base_rows], mode
+        finally:
+            m.close()
