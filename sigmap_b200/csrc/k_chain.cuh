@@ -8,15 +8,18 @@
 //
 //   k_inject_carry   anchors of the previous chunk's surviving chains re-enter the buckets
 //                    (spatial_index.cc:303-322), before the search appends its hits
-//   k_mark_segments  heads of (entry, bucket) runs in the sorted array
-//   k_chain_dp       the banded chaining DP (spatial_index.cc:434-540), one thread per
-//                    (entry, bucket) segment -- buckets are independent until the running
-//                    global max is applied
-//   k_chain_select   one thread per entry: running max across buckets in order, top-3 end
-//                    candidates, traceback with used-flags, primary chains, MAPQ
-//                    (spatial_index.cc:542-576, :165-274), then StreamingMap's stop / output
-//                    decision and tag sums (sigmap.cc:667-745); survivors' anchors go to the
-//                    carry pool for the next chunk.
+//   k_fix_ties       (radix-sort path only) equal-target runs ordered by query
+//   k_chain_prep     thread per anchor: coefficient, initial score, segment bounds and the
+//                    position-only link test; linked anchors compacted into per-tile work lists
+//   k_chain_dp       the banded chaining DP (spatial_index.cc:434-540), one WARP per
+//                    (entry, bucket) segment over the linked anchors only -- buckets are
+//                    independent until the running global max is applied
+//   k_sel_trace      warp per segment: running max of the earlier buckets, traceback of the
+//                    segment's <= 3 end candidates with used-flags (spatial_index.cc:165-220)
+//   k_sel_scatter    contig-sharded runs: candidates gathered from the other ranks
+//   k_sel_final      warp per entry: primary chains, MAPQ (spatial_index.cc:222-274), then
+//                    StreamingMap's stop / output decision and tag sums (sigmap.cc:667-745);
+//                    survivors' anchors go to the carry pool for the next chunk.
 // All float arithmetic mirrors the reference expression by expression (no FMA).
 #ifndef SB_K_CHAIN_CUH
 #define SB_K_CHAIN_CUH

@@ -1,7 +1,11 @@
 // sb_cli.cc -- `sigmap` command-line driver on top of the C ABI: the drop-in for the
 // reference's `sigmap -i` / `sigmap -m` (flags of sigmap.cc:1331-1377, same files in and
 // out).  Host-side only: parses flags, reads FASTA / .pt / BLOW5, calls smb_map_reads, writes
-// the modified PAF.  Extra flags: --gpu N (device ordinal).  `-t` is accepted for
+// the modified PAF.  Extra flags: --gpu N (device ordinal), or --gpus LIST (several devices,
+// one context and one host thread each) with --shard reads (each device maps its own slice of
+// the reads against a full copy of the index; default) or --shard contigs (the index is
+// partitioned by contig, every device maps every read, chains merged by the library's
+// collectives -- for references whose index exceeds one GPU).  `-t` is accepted for
 // compatibility (the GPU path does not use host mapping threads).
 //
 // Differences kept on purpose and documented in DESIGN.md: `-i` writes <prefix>.pt only (the
@@ -16,6 +20,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/sigmap_b200.h"
@@ -62,6 +67,8 @@ struct Args {
   bool index = false, map = false, help = false;
   std::string ref, model, ref_index, sig_dir, output;
   int dimension = 6, max_leaf = 20, threads = 1, gpu = 0;
+  std::vector<int> gpus;       // --gpus 0,1,2,...: empty = the single device --gpu
+  bool shard_contigs = false;  // --shard contigs
   smb_params prm;
 };
 
@@ -73,7 +80,10 @@ const char *kHelp =
     " Mapping options:\n  -m, --map              Map signal data\n"
     "      --step-size INT    Seeding step size in reads [2]\n"
     "  -t, --num-threads INT  # threads for mapping [1] (accepted, unused on GPU)\n"
-    "      --gpu INT          CUDA device ordinal [0]\n\n"
+    "      --gpu INT          CUDA device ordinal [0]\n"
+    "      --gpus LIST        several devices, e.g. 0,1,2,3 (one context per entry)\n"
+    "      --shard MODE       with --gpus: reads (split the reads, index replicated; default)\n"
+    "                         or contigs (split the index by contig, chains merged)\n\n"
     " Input options:\n  -r, --ref FILE         Reference file\n  -p, --pore-model FILE  Pore model file\n"
     "  -x, --ref-index FILE   Reference index file\n  -s, --sig-dir DIR      Signal data directory\n\n"
     " Output options:\n  -o, --output arg       Output file\n\n"
@@ -111,6 +121,20 @@ Args parse(int argc, char **argv) {
     else if (o == "-l" || o == "--max-leaf") a.max_leaf = atoi(val().c_str());
     else if (o == "-t" || o == "--num-threads") a.threads = atoi(val().c_str());
     else if (o == "--gpu") a.gpu = atoi(val().c_str());
+    else if (o == "--gpus") {
+      const std::string list = val();
+      for (size_t at = 0; at <= list.size();) {
+        size_t comma = list.find(',', at);
+        if (comma == std::string::npos) comma = list.size();
+        if (comma > at) a.gpus.push_back(atoi(list.substr(at, comma - at).c_str()));
+        at = comma + 1;
+      }
+      if (a.gpus.empty()) die("--gpus needs a list of device ordinals");
+    } else if (o == "--shard") {
+      const std::string m = val();
+      if (m == "contigs") a.shard_contigs = true;
+      else if (m != "reads") die("--shard must be reads or contigs");
+    }
     else if (o == "-r" || o == "--ref") a.ref = val();
     else if (o == "-p" || o == "--pore-model") a.model = val();
     else if (o == "-x" || o == "--ref-index") a.ref_index = val();
@@ -174,25 +198,89 @@ int map_reads(const Args &a) {
   fprintf(stderr, "Loaded %zu reads in %fs.\n", reads.n, now() - t0);
   smbh_fasta fa;
   if (smbh_fasta_load(a.ref.c_str(), &fa)) die("Cannot find sequence file!");
-  smb_ctx *ctx = nullptr;
-  if (smb_create(&ctx, a.gpu)) die(std::string("smb_create: ") + smb_last_error(nullptr));
+  const std::vector<int> devs = a.gpus.empty() ? std::vector<int>{a.gpu} : a.gpus;
+  const size_t G = devs.size();
+  std::vector<smb_ctx *> ctxs(G, nullptr);
+  for (size_t g = 0; g < G; ++g)
+    if (smb_create(&ctxs[g], devs[g])) die(std::string("smb_create: ") + smb_last_error(nullptr));
   t0 = now();
-  if (smb_index_load(ctx, a.ref_index.c_str())) die(std::string("smb_index_load: ") + smb_last_error(ctx));
-  smb_index_set_contigs(ctx, fa.lengths, fa.n);
+  const bool by_contig = a.shard_contigs && G > 1;
+  if (by_contig) {
+    // every context gets the windows of its own contigs out of the same point cloud
+    uint64_t *pos = nullptr;
+    float *val = nullptr;
+    size_t n_points = 0;
+    int dim = 0, max_leaf = 0;
+    if (smbh_pt_read(a.ref_index.c_str(), &pos, &val, &n_points, &dim, &max_leaf)) die("Cannot read index file!");
+    std::vector<uint32_t> owner(std::max(fa.n, 1u), 0);
+    smbh_assign_contigs(fa.lengths, fa.n, (uint32_t)G, owner.data());
+    if (smb_shard_local_group(ctxs.data(), (uint32_t)G)) die(std::string("smb_shard_local_group: ") + smb_last_error(ctxs[0]));
+    std::vector<std::string> err(G);
+    std::vector<std::thread> th;
+    for (size_t g = 0; g < G; ++g)
+      th.emplace_back([&, g] {
+        if (smb_index_set_points_sharded(ctxs[g], pos, val, n_points, owner.data(), fa.n) ||
+            smb_index_set_contigs(ctxs[g], fa.lengths, fa.n))
+          err[g] = smb_last_error(ctxs[g]);
+      });
+    for (auto &t : th) t.join();
+    for (size_t g = 0; g < G; ++g)
+      if (!err[g].empty()) die("index shard " + std::to_string(g) + ": " + err[g]);
+    smbh_free(pos);
+    smbh_free(val);
+  } else {
+    for (size_t g = 0; g < G; ++g) {
+      if (smb_index_load(ctxs[g], a.ref_index.c_str())) die(std::string("smb_index_load: ") + smb_last_error(ctxs[g]));
+      smb_index_set_contigs(ctxs[g], fa.lengths, fa.n);
+    }
+  }
   fprintf(stderr, "Loaded index successfully in %fs.\n", now() - t0);
   std::vector<smb_mapping> rows(reads.n ? reads.n : 1);
   t0 = now();
   uint64_t zero_off[1] = {0};
-  if (smb_map_reads(ctx, reads.raw, reads.n ? reads.read_off : zero_off, reads.digitisation, reads.range,
-                    reads.offset, reads.n, &a.prm, rows.data()))
-    die(std::string("smb_map_reads: ") + smb_last_error(ctx));
+  if (G == 1) {
+    if (smb_map_reads(ctxs[0], reads.raw, reads.n ? reads.read_off : zero_off, reads.digitisation, reads.range,
+                      reads.offset, reads.n, &a.prm, rows.data()))
+      die(std::string("smb_map_reads: ") + smb_last_error(ctxs[0]));
+  } else {
+    // reads: context g maps the g-th block of the reads; contigs: every context maps every read
+    // (all calls identical, as the collectives require) and context 0's rows are the result
+    std::vector<std::string> err(G);
+    std::vector<std::vector<smb_mapping>> all(by_contig ? G : 0);
+    std::vector<std::thread> th;
+    for (size_t g = 0; g < G; ++g)
+      th.emplace_back([&, g] {
+        size_t lo = 0, hi = reads.n;
+        if (!by_contig) {
+          lo = reads.n * g / G;
+          hi = reads.n * (g + 1) / G;
+        }
+        const size_t cnt = hi - lo;
+        std::vector<uint64_t> off(cnt + 1, 0);
+        for (size_t r = 0; r <= cnt && reads.n; ++r) off[r] = reads.read_off[lo + r] - reads.read_off[lo];
+        smb_mapping *dst = rows.data() + lo;
+        if (by_contig && g > 0) {
+          all[g].resize(cnt ? cnt : 1);
+          dst = all[g].data();
+        }
+        const int16_t *raw = reads.n ? reads.raw + reads.read_off[lo] : reads.raw;
+        if (smb_map_reads(ctxs[g], raw, off.data(), reads.digitisation + lo, reads.range + lo, reads.offset + lo,
+                          cnt, &a.prm, dst))
+          err[g] = smb_last_error(ctxs[g]);
+      });
+    for (auto &t : th) t.join();
+    for (size_t g = 0; g < G; ++g)
+      if (!err[g].empty()) die("smb_map_reads on device " + std::to_string(devs[g]) + ": " + err[g]);
+  }
   const double dt = now() - t0;
   fprintf(stderr, "Finished mapping in %f, # reads: %zu\n", dt, reads.n);
-  smb_stats st;
-  smb_stats_get(ctx, &st);
-  fprintf(stderr, "GPU: %.3f ms kernels (events %.3f, search %.3f, sort %.3f, chain %.3f), %llu samples, %llu queries, %llu hits\n",
-          st.ms_total, st.ms_events, st.ms_search, st.ms_sort, st.ms_chain, (unsigned long long)st.samples,
-          (unsigned long long)st.queries, (unsigned long long)st.hits);
+  for (size_t g = 0; g < G; ++g) {
+    smb_stats st;
+    smb_stats_get(ctxs[g], &st);
+    fprintf(stderr, "GPU %d: %.3f ms kernels (events %.3f, search %.3f, sort %.3f, chain %.3f), %llu samples, %llu queries, %llu hits\n",
+            devs[g], st.ms_total, st.ms_events, st.ms_search, st.ms_sort, st.ms_chain, (unsigned long long)st.samples,
+            (unsigned long long)st.queries, (unsigned long long)st.hits);
+  }
   // rows grouped by contig (unmapped under contig 0), arrival order inside: sigmap.cc:197-241
   FILE *out = fopen(a.output.c_str(), "w");
   if (!out) die("Cannot open output file!");
@@ -210,7 +298,7 @@ int map_reads(const Args &a) {
     }
   }
   fclose(out);
-  smb_destroy(ctx);
+  for (smb_ctx *c : ctxs) smb_destroy(c);
   smbh_reads_free(&reads);
   smbh_fasta_free(&fa);
   return 0;

@@ -5,8 +5,9 @@
 // thread walking one read chunk by chunk, all still-active reads advance together in ROUNDS;
 // round k maps chunk k of every active read as one batch (split into steps that fit the
 // anchor buffers):
-//   events (3 kernels) -> query table -> carry re-injection + radius search -> device radix
-//   sort by (entry, bucket, target, query) -> chaining DP -> per-read selection/decision.
+//   events (lookahead blocks on their own stream) -> query table -> carry re-injection +
+//   radius search -> per-entry shared-memory sort by (bucket, target, query) -> chain prep ->
+//   chaining DP -> traceback -> per-read selection/decision.
 // The only host<->device traffic per step is a counter readback (anchor count) and, per
 // round, 12 bytes per active read (stop flag, kept events, chain count).
 #include <cuda_runtime.h>

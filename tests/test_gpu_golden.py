@@ -141,3 +141,20 @@ def test_cli_dropin_matches_reference_cli(ref, small, tmp_path):
     rr = ref.cli(["-m", "-r", small.fasta, "-p", MODEL_PATH, "-x", str(tmp_path / "refidx"), "-s", small.sigdir,
                   "-o", rout, "-t", "1"])
     assert [l.split("\t")[0] for l in open(out)] == [l.split("\t")[0] for l in open(rout)]
+
+
+@pytest.mark.parametrize("shard", ["reads", "contigs"])
+def test_cli_multi_device_modes_match_single_device(small, tmp_path, shard):
+    """`sigmap -m --gpus LIST --shard reads|contigs` (one context and host thread per entry; the
+    list may repeat a device, which is how a one-GPU box tests it) prints the single-device PAF."""
+    from sigmap_b200.host import MODEL_PATH
+    exe = os.path.join(ROOT, "sigmap_b200", "bin", "sigmap")
+    base = ["-m", "-r", small.fasta, "-p", MODEL_PATH, "-x", small.prefix, "-s", small.sigdir]
+    one, many = str(tmp_path / "one.paf"), str(tmp_path / "many.paf")
+    r = subprocess.run([exe, *base, "-o", one], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-400:]
+    r = subprocess.run([exe, *base, "-o", many, "--gpus", "0,0,0", "--shard", shard],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-400:]
+    assert r.stderr.count("GPU 0:") == 3
+    assert [paf_cols(l) for l in open(many)] == [paf_cols(l) for l in open(one)]
