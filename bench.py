@@ -431,7 +431,8 @@ def main():
                      "wall_ms_per_step": 1000.0 * t_wall / max(args.steps, 1),
                      "counters_per_step": {k: int(st[k] // max(args.steps, 1)) for k in
                                            ("samples", "events", "queries", "hits", "anchors",
-                                            "capped_queries", "chunks", "steps", "linked")}},
+                                            "capped_queries", "chunks", "steps", "linked",
+                                            "seg_sort_steps", "part_sort_steps")}},
         "latency": latency,
         "mapped_reads": n_mapped, "truth_concordant_reads": ok, "setup_s": t_setup,
     }

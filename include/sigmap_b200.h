@@ -104,6 +104,7 @@ typedef struct smb_stats {
   uint64_t seg_sort_steps; /* steps whose anchors were sorted per entry in shared memory
                               (the others fell back to the global radix sort) */
   uint64_t exchanges;      /* collectives issued by a contig-sharded run (0 otherwise) */
+  uint64_t part_sort_steps; /* of seg_sort_steps: sorted one CTA per (entry, part) from pre-routed runs */
 } smb_stats;
 
 /* ------------------------------------------------------------------ context */

@@ -112,6 +112,7 @@ class Stats(C.Structure):
         ("linked", C.c_uint64),
         ("seg_sort_steps", C.c_uint64),
         ("exchanges", C.c_uint64),
+        ("part_sort_steps", C.c_uint64),
     ]
 
 

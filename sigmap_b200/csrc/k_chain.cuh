@@ -59,37 +59,83 @@ struct ChainArgs {
   Counters *ctr;
 };
 
-__global__ void k_inject_carry(const uint32_t *__restrict__ entry_slot, const uint32_t *__restrict__ n_queries,
-                               const SlotState *__restrict__ slots, const CarryAnchor *__restrict__ pool0,
-                               const CarryAnchor *__restrict__ pool1, uint32_t B, KeyLayout kl,
-                               uint64_t *__restrict__ out_key, float *__restrict__ out_dist,
-                               unsigned long long cap, Counters *__restrict__ ctr, RunRec *__restrict__ runs,
-                               uint32_t *__restrict__ run_count, uint32_t *__restrict__ entry_total,
-                               uint32_t runs_cap) {
+constexpr int kCarryThreads = 256;
+constexpr int kCarryMaxParts = 32;  // = kMaxParts of k_index.cuh
+
+// runs == nullptr: no run lists (radix-sort path).  Otherwise the carried anchors of an entry are
+// routed, 32 at a time, to the entry's n_parts coordinate ranges exactly like the hits of a search
+// flush (k_index.cuh): one run per part touched.
+__global__ void __launch_bounds__(kCarryThreads)
+k_inject_carry(const uint32_t *__restrict__ entry_slot, const uint32_t *__restrict__ n_queries,
+               const SlotState *__restrict__ slots, const CarryAnchor *__restrict__ pool0,
+               const CarryAnchor *__restrict__ pool1, uint32_t B, KeyLayout kl,
+               uint64_t *__restrict__ out_key, float *__restrict__ out_dist,
+               unsigned long long cap, Counters *__restrict__ ctr, RunRec *__restrict__ runs,
+               uint32_t *__restrict__ run_count, uint32_t *__restrict__ entry_total,
+               uint32_t runs_cap, uint32_t n_parts, float inv_span, const uint64_t *__restrict__ bucket_base) {
+  __shared__ uint32_t s_cnt[kCarryThreads / 32][kCarryMaxParts];
   const uint32_t b = (blockIdx.x * blockDim.x + threadIdx.x) / 32, lane = threadIdx.x & 31;
+  const unsigned full = 0xffffffffu;
   if (b >= B) return;
   if (n_queries[b] == 0) return;  // GenerateChains is not called for this entry
   const SlotState st = slots[entry_slot[b]];
   if (st.carry_n == 0) return;
   const CarryAnchor *src = (st.pool ? pool1 : pool0) + st.carry_off;
-  unsigned long long base = 0;
-  if (lane == 0) {
-    base = atomicAdd(&ctr->n_anchors, (unsigned long long)st.carry_n);
-    if (runs) {  // the carried anchors are one run of this entry (k_sort.cuh)
-      const uint32_t r = atomicAdd(&run_count[b], 1u);
-      if (r < runs_cap) runs[(size_t)b * runs_cap + r] = RunRec{(uint32_t)base, st.carry_n};
-      else atomicOr(&ctr->error, 8u);
-      const uint32_t t = atomicAdd(&entry_total[b], st.carry_n) + st.carry_n;
-      atomicMax(&ctr->max_entry_anchors, t);
+  if (!runs) {
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(&ctr->n_anchors, (unsigned long long)st.carry_n);
+    base = __shfl_sync(full, base, 0);
+    for (uint32_t i = lane; i < st.carry_n; i += 32) {
+      const CarryAnchor c = src[i];
+      if (base + i < cap) {
+        out_key[base + i] = kl.pack(b, c.bucket, c.target, c.query);
+        out_dist[base + i] = c.dist;
+      }
     }
+    return;
   }
-  base = __shfl_sync(0xffffffffu, base, 0);
-  for (uint32_t i = lane; i < st.carry_n; i += 32) {
-    const CarryAnchor c = src[i];
-    if (base + i < cap) {
-      out_key[base + i] = kl.pack(b, c.bucket, c.target, c.query);
-      out_dist[base + i] = c.dist;
+  uint32_t *pcnt = s_cnt[(threadIdx.x >> 5)];
+  for (uint32_t i0 = 0; i0 < st.carry_n; i0 += 32) {
+    const uint32_t i = i0 + lane;
+    const bool valid = i < st.carry_n;
+    const uint32_t batch = min(32u, st.carry_n - i0);
+    pcnt[lane] = 0;
+    __syncwarp();
+    CarryAnchor c = CarryAnchor{0u, 0u, 0.0f, 0u};
+    uint32_t part = 0, rank = 0;
+    if (valid) {
+      c = src[i];
+      part = part_of(bucket_base[c.bucket] + c.target, inv_span, n_parts);
+      rank = atomicAdd(&pcnt[part], 1u);
     }
+    __syncwarp();
+    const uint32_t mine = pcnt[lane];
+    uint32_t incl = mine;
+#pragma unroll
+    for (int d = 1; d < kCarryMaxParts; d <<= 1) {
+      const uint32_t t = __shfl_up_sync(full, incl, d);
+      if (lane >= (uint32_t)d) incl += t;
+    }
+    const uint32_t excl = incl - mine;
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(&ctr->n_anchors, (unsigned long long)batch);
+    base = __shfl_sync(full, base, 0);
+    if (mine) {
+      const size_t list = (size_t)b * n_parts + lane;
+      const uint32_t r = atomicAdd(&run_count[list], 1u);
+      if (r < runs_cap) runs[list * runs_cap + r] = RunRec{(uint32_t)(base + excl), mine};
+      else atomicOr(&ctr->error, 8u);
+      atomicAdd(&entry_total[list], mine);
+    }
+    const uint32_t off = __shfl_sync(full, excl, (int)part);
+    if (valid) {
+      const unsigned long long o = base + off + rank;
+      if (o < cap) {
+        out_key[o] = kl.pack(b, c.bucket, c.target, c.query);
+        out_dist[o] = c.dist;
+      }
+    }
+    __syncwarp();
   }
 }
 

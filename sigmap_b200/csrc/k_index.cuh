@@ -166,12 +166,14 @@ constexpr int kSearchWarps = 8;          // warps per CTA
 constexpr int kLevelCap = 128;           // entries per level stack: 64 waiting + the children of one 8-node step
 constexpr int kLeafQueueCap = 128;       // < 8 left over + 64 pushed per step
 constexpr int kStageCap = 128;           // staged hits per warp before one global reservation
-constexpr int kSearchGrab = 4;           // queries per grab of the dynamic work counter
+constexpr int kSearchGrab = 8;           // queries per grab of the dynamic work counter
+constexpr int kMaxParts = 32;            // parts per entry the flush can route to (k_part_sort)
 
 // dynamic shared memory per warp: staging (key part, point id, d2), leaf queue, level counts,
 // and one 64-entry stack per node level
 __host__ __device__ inline size_t search_smem_per_warp(int n_levels) {
-  return (size_t)kStageCap * 16 + (size_t)kLeafQueueCap * 4 + 16 * 4 + (size_t)n_levels * kLevelCap * 4;
+  return (size_t)kStageCap * 16 + (size_t)kLeafQueueCap * 4 + 16 * 4 + kMaxParts * 4 +
+         (size_t)n_levels * kLevelCap * 4;
 }
 
 struct SearchArgs {
@@ -191,12 +193,30 @@ struct SearchArgs {
   unsigned long long cap;      // capacity of out_key/out_dist
   Counters *ctr;
   SlotState *slots_mut;        // to flag capped queries
-  // pipeline mode: where each entry's hits went (k_sort.cuh); runs == nullptr disables it
-  RunRec *runs;                // [B][runs_cap]
-  uint32_t *run_count;         // [B]
-  uint32_t *entry_total;       // [B] anchors per entry so far
+  // pipeline mode: where each entry's hits went (k_sort.cuh); runs == nullptr disables it.
+  // Every flush routes its hits to the n_parts coordinate ranges ("parts": part_of(g) with
+  // g = bucket_base[bucket] + target) of the entry and records one run per part it touched.
+  RunRec *runs;                // [B * n_parts][runs_cap]
+  uint32_t *run_count;         // [B * n_parts]
+  uint32_t *entry_total;       // [B * n_parts] anchors per (entry, part) so far
   uint32_t runs_cap;
+  uint32_t n_parts;            // 1..kMaxParts
+  float inv_span;              // 1 / coordinates per part
+  const uint64_t *bucket_base;
+  uint32_t grab;               // queries per grab of the work counter (0 = kSearchGrab)
+  int prefetch;                // 0: none; 1: children/leaves pushed on a stack are prefetched into L2; 2: into L1
 };
+
+// the records a step has just decided to visit are requested now, so the step that pops them
+// finds them on chip instead of paying the DRAM round trip itself
+__device__ __forceinline__ void prefetch_lines(const void *p, int n_lines, int mode) {
+  const char *c = static_cast<const char *>(p);
+  if (mode == 1) {
+    for (int i = 0; i < n_lines; ++i) asm volatile("prefetch.global.L2 [%0];" ::"l"(c + 128 * i));
+  } else {
+    for (int i = 0; i < n_lines; ++i) asm volatile("prefetch.global.L1 [%0];" ::"l"(c + 128 * i));
+  }
+}
 
 __device__ __forceinline__ float exact_d2(const float q[kDim], const float v[kDim]) {
   float e[kDim];
@@ -256,10 +276,13 @@ k_radius_search(const IndexView ix, const SearchArgs a) {
   float *st_dist = reinterpret_cast<float *>(mine + kStageCap * 12);
   uint32_t *leafq = reinterpret_cast<uint32_t *>(mine + kStageCap * 16);
   uint32_t *lcnt = leafq + kLeafQueueCap;          // [16] nodes waiting per level
-  uint32_t *lstk = lcnt + 16;                      // [n_levels][kLevelCap]
+  uint32_t *pcnt = lcnt + 16;                      // [kMaxParts] hits per part of the flush in progress
+  uint32_t *lstk = pcnt + kMaxParts;               // [n_levels][kLevelCap]
   const uint32_t nq = STAGE ? a.n_queries : a.q_off[a.B];
   const float r2 = a.radius;
   const float r2_prune = r2 * 1.0001f + 1e-12f;
+  const int pf = a.prefetch;
+  const uint32_t grab = a.grab ? a.grab : (uint32_t)kSearchGrab;
   const int top_level = n_levels - 1;
   const uint32_t n_top = ix.level_count[top_level];  // <= 8
   int staged = 0;
@@ -272,33 +295,79 @@ k_radius_search(const IndexView ix, const SearchArgs a) {
   // loads of a pass in flight (they are off the traversal's critical path here)
   auto flush = [&]() {
     if (staged == 0) return;
-    unsigned long long base = 0;
-    if (lane == 0) {
-      base = atomicAdd(&a.ctr->n_anchors, (unsigned long long)staged);
-      if (!STAGE && a.runs) {  // all staged hits belong to staged_entry
-        const uint32_t r = atomicAdd(&a.run_count[staged_entry], 1u);
-        if (r < a.runs_cap) a.runs[(size_t)staged_entry * a.runs_cap + r] = RunRec{(uint32_t)base, (uint32_t)staged};
-        else atomicOr(&a.ctr->error, 8u);
-        const uint32_t t = atomicAdd(&a.entry_total[staged_entry], (uint32_t)staged) + (uint32_t)staged;
-        atomicMax(&a.ctr->max_entry_anchors, t);
+    if (STAGE || !a.runs) {
+      unsigned long long base = 0;
+      if (lane == 0) base = atomicAdd(&a.ctr->n_anchors, (unsigned long long)staged);
+      base = __shfl_sync(full, base, 0);
+#pragma unroll
+      for (int i0 = 0; i0 < kStageCap; i0 += 32) {
+        const int i = i0 + lane;
+        if (i < staged) {
+          const unsigned long long o = base + i;
+          const uint32_t pid = st_pid[i];
+          uint64_t key;
+          if (STAGE) {
+            key = st_qk[i] | __ldg(ix.leaf_widx + pid);
+          } else {
+            const uint2 tb = __ldg(ix.leaf_tb + pid);
+            key = st_qk[i] | ((uint64_t)tb.y << a.key.sh_b()) | ((uint64_t)tb.x << a.key.sh_t());
+          }
+          if (o < a.cap) {
+            a.out_key[o] = key;
+            a.out_dist[o] = st_dist[i];
+          }
+        }
+      }
+      __syncwarp();
+      staged = 0;
+      return;
+    }
+    // all staged hits belong to staged_entry; route them to its parts
+    pcnt[lane] = 0;
+    __syncwarp();
+    uint64_t key[kStageCap / 32];
+    uint32_t where[kStageCap / 32];  // part << 8 | rank inside the part (this flush)
+#pragma unroll
+    for (int u = 0; u < kStageCap / 32; ++u) {
+      const int i = u * 32 + lane;
+      key[u] = 0;
+      where[u] = 0;
+      if (i < staged) {
+        const uint2 tb = __ldg(ix.leaf_tb + st_pid[i]);
+        key[u] = st_qk[i] | ((uint64_t)tb.y << a.key.sh_b()) | ((uint64_t)tb.x << a.key.sh_t());
+        const uint32_t part = part_of(__ldg(a.bucket_base + tb.y) + tb.x, a.inv_span, a.n_parts);
+        where[u] = (part << 8) | atomicAdd(&pcnt[part], 1u);
       }
     }
-    base = __shfl_sync(full, base, 0);
+    __syncwarp();
+    const uint32_t mine = pcnt[lane];  // lane p: hits of part p
+    uint32_t incl = mine;
 #pragma unroll
-    for (int i0 = 0; i0 < kStageCap; i0 += 32) {
-      const int i = i0 + lane;
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t t = __shfl_up_sync(full, incl, d);
+      if (lane >= d) incl += t;
+    }
+    const uint32_t excl = incl - mine;
+    // both reservations are issued before either result is used: one round trip, not two
+    const size_t list = (size_t)staged_entry * a.n_parts + lane;
+    uint32_t r = 0;
+    if (mine) r = atomicAdd(&a.run_count[list], 1u);
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(&a.ctr->n_anchors, (unsigned long long)staged);
+    base = __shfl_sync(full, base, 0);
+    if (mine) {
+      if (r < a.runs_cap) a.runs[list * a.runs_cap + r] = RunRec{(uint32_t)(base + excl), mine};
+      else atomicOr(&a.ctr->error, 8u);
+      atomicAdd(&a.entry_total[list], mine);
+    }
+#pragma unroll
+    for (int u = 0; u < kStageCap / 32; ++u) {
+      const int i = u * 32 + lane;
+      const uint32_t off = __shfl_sync(full, excl, (int)(where[u] >> 8));
       if (i < staged) {
-        const unsigned long long o = base + i;
-        const uint32_t pid = st_pid[i];
-        uint64_t key;
-        if (STAGE) {
-          key = st_qk[i] | __ldg(ix.leaf_widx + pid);
-        } else {
-          const uint2 tb = __ldg(ix.leaf_tb + pid);
-          key = st_qk[i] | ((uint64_t)tb.y << a.key.sh_b()) | ((uint64_t)tb.x << a.key.sh_t());
-        }
+        const unsigned long long o = base + off + (where[u] & 0xFFu);
         if (o < a.cap) {
-          a.out_key[o] = key;
+          a.out_key[o] = key[u];
           a.out_dist[o] = st_dist[i];
         }
       }
@@ -309,10 +378,10 @@ k_radius_search(const IndexView ix, const SearchArgs a) {
 
   for (;;) {
     uint32_t q0 = 0;
-    if (lane == 0) q0 = atomicAdd(&a.ctr->work, (unsigned)kSearchGrab);
+    if (lane == 0) q0 = atomicAdd(&a.ctr->work, grab);
     q0 = __shfl_sync(full, q0, 0);
     if (q0 >= nq) break;
-    const uint32_t q1 = min(q0 + (uint32_t)kSearchGrab, nq);
+    const uint32_t q1 = min(q0 + grab, nq);
     for (uint32_t qi = q0; qi < q1; ++qi) {
       // ---- locate the query
       float q[kDim];
@@ -444,6 +513,10 @@ k_radius_search(const IndexView ix, const SearchArgs a) {
               uint32_t *dst = lstk + (L - 1) * kLevelCap + below;
               if (mA & (1u << lane)) dst[__popc(mA & lt)] = nodeA * kFan + sub;
               if (mB & (1u << lane)) dst[nA + __popc(mB & lt)] = nodeB * kFan + sub;
+              if (pf) {
+                if (mA & (1u << lane)) prefetch_lines(ix.level_node[L - 1] + (size_t)(nodeA * kFan + sub) * (3 * kFan), 3, pf);
+                if (mB & (1u << lane)) prefetch_lines(ix.level_node[L - 1] + (size_t)(nodeB * kFan + sub) * (3 * kFan), 3, pf);
+              }
               __syncwarp();  // every lane has read lcnt before lane 0 rewrites it
               if (lane == 0) {
                 lcnt[L] = (uint32_t)c;
@@ -453,6 +526,10 @@ k_radius_search(const IndexView ix, const SearchArgs a) {
             } else {
               if (mA & (1u << lane)) leafq[nleaf + __popc(mA & lt)] = nodeA * kFan + sub;
               if (mB & (1u << lane)) leafq[nleaf + nA + __popc(mB & lt)] = nodeB * kFan + sub;
+              if (pf) {
+                if (mA & (1u << lane)) prefetch_lines(ix.leaf_vals + (size_t)(nodeA * kFan + sub) * (3 * kLeaf), 2, pf);
+                if (mB & (1u << lane)) prefetch_lines(ix.leaf_vals + (size_t)(nodeB * kFan + sub) * (3 * kLeaf), 2, pf);
+              }
               nleaf += nA + nB;
               __syncwarp();
               if (lane == 0) lcnt[0] = (uint32_t)c;

@@ -34,6 +34,9 @@ constexpr int kRunsCap = 512;        // runs recorded per entry (a run = one flu
 //   < 5120,  512, 4096>  two 100 KB CTAs per SM: one CTA's barrier / DRAM waits overlap the
 //                        other's work, at the price of twice the parts per entry
 constexpr int kSortCapBig = 10240, kSortCapSmall = 5120;
+// k_part_sort shapes: <5120, 512, 4096> two 105 KB CTAs per SM; <2304, 256, 2304> four 52 KB CTAs
+constexpr int kPartSortCap = 5120;   // anchors of one (entry, part) held by a k_part_sort CTA
+constexpr int kPartSortCapSmall = 2304;
 constexpr int kCoarseBins = 256;
 constexpr int kSmallBin = 24;        // bins up to this size: insertion sort by one thread
 constexpr int kBigBinCap = 512;      // dense bins queued for the warp-wide rank sort
@@ -43,8 +46,9 @@ struct SegSortArgs {
   const float *dist_in;
   uint64_t *key_out;
   float *dist_out;
-  const RunRec *runs;           // [B][kRunsCap]
-  const uint32_t *run_count;    // [B]
+  const RunRec *runs;           // [B * n_parts][kRunsCap]
+  const uint32_t *run_count;    // [B * n_parts]
+  uint32_t n_parts;             // run lists per entry (k_part_sort's partition; 1 = one list)
   uint32_t B;
   KeyLayout kl;
   const uint64_t *bucket_base;  // [n_buckets + 1] linear coordinate of target 0 of each bucket
@@ -76,14 +80,20 @@ __global__ void __launch_bounds__(kSortThreads, kSortThreads == 1024 ? 1 : 2) k_
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const unsigned full = 0xffffffffu;
   const unsigned lt = (1u << lane) - 1u;
-  const uint32_t nr = min(a.run_count[entry], (uint32_t)kRunsCap);
-  if (nr == 0) return;
-  const RunRec *runs = a.runs + (size_t)entry * kRunsCap;
+  // the entry's runs: the lists of its n_parts parts, addressed as one virtual list of
+  // n_parts * kRunsCap slots (slot v = list v / kRunsCap, run v % kRunsCap; unused slots skipped)
+  const RunRec *runs = a.runs + (size_t)entry * a.n_parts * kRunsCap;
+  const uint32_t *rcount = a.run_count + (size_t)entry * a.n_parts;
+  const uint32_t nr = a.n_parts == 1 ? min(rcount[0], (uint32_t)kRunsCap) : a.n_parts * (uint32_t)kRunsCap;
+  auto run_at = [&](uint32_t v) -> RunRec {
+    const uint32_t used = min(rcount[v / kRunsCap], (uint32_t)kRunsCap);
+    return (v % kRunsCap) < used ? runs[v] : RunRec{0u, 0u};
+  };
   const KeyLayout kl = a.kl;
 
   // ---- total anchors of the entry
   uint32_t mine = 0;
-  for (uint32_t r = tid; r < nr; r += kSortThreads) mine += runs[r].count;
+  for (uint32_t r = tid; r < nr; r += kSortThreads) mine += run_at(r).count;
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) mine += __shfl_xor_sync(full, mine, d);
   if (tid < kCoarseBins) s_coarse[tid] = 0;
@@ -106,7 +116,7 @@ __global__ void __launch_bounds__(kSortThreads, kSortThreads == 1024 ? 1 : 2) k_
   // ---- pass 0: coarse histogram and the split into parts that fit shared memory
   if (total > (uint32_t)kSortCap) {
     for (uint32_t r = wid; r < nr; r += kSortThreads / 32) {
-      const RunRec run = runs[r];
+      const RunRec run = run_at(r);
       for (uint32_t i0 = 0; i0 < run.count; i0 += 4 * 32) {  // a run is <= 128 hits: one trip
         uint64_t kq[4];
 #pragma unroll
@@ -166,7 +176,7 @@ __global__ void __launch_bounds__(kSortThreads, kSortThreads == 1024 ? 1 : 2) k_
 
     // ---- gather the part's anchors + fine histogram
     for (uint32_t r = wid; r < nr; r += kSortThreads / 32) {
-      const RunRec run = runs[r];
+      const RunRec run = run_at(r);
       for (uint32_t i0 = 0; i0 < run.count; i0 += 4 * 32) {  // a run is <= 128 hits: one trip,
         uint64_t kq[4];                                       // its eight loads in flight together
         float dq[4];
@@ -297,6 +307,278 @@ __global__ void __launch_bounds__(kSortThreads, kSortThreads == 1024 ? 1 : 2) k_
 
     // ---- write the part back, sorted
     for (uint32_t pos = tid; pos < n; pos += kSortThreads) {
+      const uint32_t slot = s_order[pos];
+      a.key_out[out + pos] = s_key[slot];
+      a.dist_out[out + pos] = s_dist[slot];
+    }
+    out += n;
+    __syncthreads();
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------
+// k_part_sort: the same sort when the producers (search flush, carry injection) have already
+// routed every anchor to one of n_parts equal-width coordinate ranges of its entry ("parts",
+// part_of(g)) and recorded one run list and one exact count per (entry, part).  One CTA per
+// (entry, part): no coarse pass, nothing read twice, nothing filtered; output positions come
+// from an exclusive scan of the counts, so the result is globally ordered by
+// (entry, bucket, target, query).  Two 100 KB CTAs share an SM and cover each other's barriers.
+//   gather   the part's anchors are addressed as one flat range [0, n) through the scanned run
+//            counts: a warp takes four runs at a time, lanes the anchors of a run, slot = run
+//            offset + i, no atomics; the loads of the four runs are in flight together
+//   then     fine histogram -> scan -> counting-sort scatter -> per-bin order -> write-back,
+//            as in k_seg_sort.
+struct PartSortArgs {
+  const uint64_t *key_in;
+  const float *dist_in;
+  uint64_t *key_out;
+  float *dist_out;
+  const RunRec *runs;           // [B * n_parts][kRunsCap]
+  const uint32_t *run_count;    // [B * n_parts]
+  const uint32_t *part_total;   // [B * n_parts] anchors of the part (<= CAP, checked by the host)
+  const uint32_t *out_base;     // [B * n_parts] exclusive scan of part_total
+  uint32_t n_parts;
+  uint64_t span;                // coordinates per part (part boundaries are fuzzy by float rounding:
+                                // the fine bins clamp, which keeps them monotone in g)
+  KeyLayout kl;
+  const uint64_t *bucket_base;
+  uint32_t n_buckets;
+  Counters *ctr;                // error bit 4: a sub-range of an oversize part overflowed
+};
+
+constexpr size_t part_sort_smem_bytes(int cap, int bins) {
+  return (size_t)cap * (8 + 4 + 2 + 2) + (size_t)bins * 4 + (size_t)kRunsCap * 8 + (size_t)kBigBinCap * 4 + 64 * 4;
+}
+
+// largest anchor count of any (entry, part): the host picks the sort kernel with it
+__global__ void k_max_u32(const uint32_t *__restrict__ v, size_t n, unsigned int *__restrict__ out) {
+  uint32_t m = 0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    m = max(m, v[i]);
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, d));
+  if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+}
+
+template <int CAP, int THREADS, int BINS>
+__global__ void __launch_bounds__(THREADS, THREADS >= 1024 ? 1 : (THREADS >= 512 ? 2 : 4)) k_part_sort(const PartSortArgs a) {
+  static_assert(BINS % THREADS == 0, "bins per thread");
+  static_assert(THREADS <= 1024 && THREADS % 32 == 0, "block shape");
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  uint64_t *s_key = reinterpret_cast<uint64_t *>(s_raw);
+  float *s_dist = reinterpret_cast<float *>(s_key + CAP);
+  uint32_t *s_bins = reinterpret_cast<uint32_t *>(s_dist + CAP);
+  uint32_t *s_run_start = s_bins + BINS;          // [kRunsCap]
+  uint32_t *s_run_off = s_run_start + kRunsCap;   // [kRunsCap] exclusive scan of the run counts
+  uint32_t *s_big = s_run_off + kRunsCap;         // [kBigBinCap]
+  uint32_t *s_misc = s_big + kBigBinCap;          // [64]: 0..31 warp sums, 32 kept, 33 nbig
+  uint16_t *s_order = reinterpret_cast<uint16_t *>(s_misc + 64);
+  uint16_t *s_order2 = s_order + CAP;
+
+  const uint32_t idx = blockIdx.x;
+  const uint32_t n_all = a.part_total[idx];
+  if (n_all == 0) return;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const unsigned full = 0xffffffffu;
+  const uint32_t nr = min(a.run_count[idx], (uint32_t)kRunsCap);
+  const RunRec *runs = a.runs + (size_t)idx * kRunsCap;
+  const KeyLayout kl = a.kl;
+  unsigned long long out = a.out_base[idx];
+  const uint64_t g_part = (uint64_t)(idx % a.n_parts) * a.span;
+  // A part that fits the CTA is sorted in one go (slot = position in the flat run range, no
+  // filtering).  The rare oversize part is cut into n_sub coordinate sub-ranges sized for half
+  // the capacity, each gathered by filtering the whole part; a sub-range that still overflows
+  // raises error bit 4 and the host redoes the step's sort with the generic kernels.
+  const uint32_t n_sub = n_all <= (uint32_t)CAP ? 1u : (2u * n_all + CAP - 1u) / (uint32_t)CAP;
+  const uint64_t sub_span = (a.span + n_sub - 1) / n_sub;
+  int fshift = 0;
+  while ((sub_span >> fshift) >= (uint64_t)BINS) ++fshift;
+  // bucket bases: from shared memory when the genome has <= 64 buckets (32 contigs x 2 strands)
+  __shared__ uint64_t s_bb[64];
+  const bool bb_local = a.n_buckets <= 64u;
+  if (bb_local && tid < (int)a.n_buckets) s_bb[tid] = a.bucket_base[tid];
+  auto coord = [&](uint64_t k) -> uint64_t {
+    const uint32_t b = kl.bucket(k);
+    return (bb_local ? s_bb[b] : __ldg(a.bucket_base + b)) + kl.target(k);
+  };
+
+  // ---- run table -> shared memory, exclusive scan of the counts (kPer consecutive runs a thread)
+  {
+    constexpr int kPer = (kRunsCap + THREADS - 1) / THREADS;
+    uint32_t cnt[kPer], sum = 0;
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) {
+      const uint32_t r = (uint32_t)tid * kPer + j;
+      RunRec rec = RunRec{0u, 0u};
+      if (r < nr) rec = runs[r];
+      if (r < (uint32_t)kRunsCap) s_run_start[r] = rec.start;
+      cnt[j] = rec.count;
+      sum += rec.count;
+    }
+    uint32_t incl = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t t = __shfl_up_sync(full, incl, d);
+      if (lane >= d) incl += t;
+    }
+    if (lane == 31) s_misc[wid] = incl;
+    __syncthreads();
+    uint32_t at = incl - sum;
+    for (int w = 0; w < wid; ++w) at += s_misc[w];
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) {
+      const uint32_t r = (uint32_t)tid * kPer + j;
+      if (r < (uint32_t)kRunsCap) s_run_off[r] = at;
+      at += cnt[j];
+    }
+  }
+
+  for (uint32_t sub = 0; sub < n_sub; ++sub) {
+    const uint64_t g_lo = g_part + (uint64_t)sub * sub_span;
+    // the first / last sub-range are open-ended: part boundaries are fuzzy (part_of)
+    const uint64_t f_lo = sub == 0 ? 0ull : g_lo;
+    const uint64_t f_hi = sub + 1 == n_sub ? ~0ull : g_lo + sub_span;
+    for (int b = tid; b < BINS; b += THREADS) s_bins[b] = 0;
+    if (tid == 0) {
+      s_misc[32] = 0;
+      s_misc[33] = 0;
+    }
+    __syncthreads();
+
+    // ---- gather + fine histogram: a warp takes four runs at a time, lanes the consecutive
+    // anchors of a run (slot = run offset + i), all loads of the four runs in flight together
+    auto place = [&](uint32_t h, uint64_t k, float d) {
+      const uint64_t g = coord(k);
+      uint32_t slot = h;
+      if (n_sub > 1) slot = (g >= f_lo && g < f_hi) ? atomicAdd(&s_misc[32], 1u) : 0xFFFFFFFFu;
+      if (slot < (uint32_t)CAP) {
+        const uint32_t bin = g >= g_lo ? (uint32_t)min((g - g_lo) >> fshift, (uint64_t)(BINS - 1)) : 0u;
+        s_key[slot] = k;
+        s_dist[slot] = d;
+        s_order2[slot] = (uint16_t)bin;  // kept for the scatter below
+        atomicAdd(&s_bins[bin], 1u);
+      }
+    };
+    for (uint32_t r0 = (uint32_t)wid * 4u; r0 < nr; r0 += (THREADS / 32) * 4u) {
+      uint32_t st[4], of[4], cn[4];
+      uint64_t kq[4];
+      float dq[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t r = r0 + u;
+        st[u] = 0;
+        of[u] = 0;
+        cn[u] = 0;
+        if (r < nr) {
+          st[u] = s_run_start[r];
+          of[u] = s_run_off[r];
+          cn[u] = (r + 1 < nr ? s_run_off[r + 1] : n_all) - of[u];
+        }
+        kq[u] = ~0ull;
+        dq[u] = 0.0f;
+        if ((uint32_t)lane < cn[u]) {
+          kq[u] = a.key_in[st[u] + lane];
+          dq[u] = a.dist_in[st[u] + lane];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if ((uint32_t)lane < cn[u]) place(of[u] + lane, kq[u], dq[u]);
+        for (uint32_t i = 32u + lane; i < cn[u]; i += 32u)  // runs longer than a warp: rare
+          place(of[u] + i, a.key_in[st[u] + i], a.dist_in[st[u] + i]);
+      }
+    }
+    __syncthreads();
+    uint32_t n = n_all;
+    if (n_sub > 1) {
+      n = s_misc[32];
+      if (n > (uint32_t)CAP) {
+        if (tid == 0) atomicOr(&a.ctr->error, 16u);
+        n = CAP;
+      }
+    }
+
+    // ---- exclusive scan of the fine histogram (consecutive bins per thread)
+    {
+      uint32_t v[BINS / THREADS], sum = 0;
+#pragma unroll
+      for (int j = 0; j < BINS / THREADS; ++j) {
+        v[j] = s_bins[tid * (BINS / THREADS) + j];
+        sum += v[j];
+      }
+      uint32_t incl = sum;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(full, incl, d);
+        if (lane >= d) incl += t;
+      }
+      if (lane == 31) s_misc[wid] = incl;
+      __syncthreads();
+      uint32_t wbase = 0;
+      for (int w = 0; w < wid; ++w) wbase += s_misc[w];
+      uint32_t run_sum = wbase + incl - sum;
+#pragma unroll
+      for (int j = 0; j < BINS / THREADS; ++j) {
+        s_bins[tid * (BINS / THREADS) + j] = run_sum;
+        run_sum += v[j];
+      }
+    }
+    __syncthreads();
+
+    // ---- counting-sort scatter of the slots; afterwards s_bins[b] = end of bin b
+    for (uint32_t slot = tid; slot < n; slot += THREADS)
+      s_order[atomicAdd(&s_bins[s_order2[slot]], 1u)] = (uint16_t)slot;
+    __syncthreads();
+
+    // ---- order every bin by the full key (bucket | target | query)
+    for (int b = tid; b < BINS; b += THREADS) {
+      const uint32_t lo = b ? s_bins[b - 1] : 0u, hi = s_bins[b];
+      const uint32_t m = hi - lo;
+      if (m < 2) continue;
+      bool by_thread = m <= (uint32_t)kSmallBin;
+      if (!by_thread) {
+        const uint32_t at = atomicAdd(&s_misc[33], 1u);
+        if (at < (uint32_t)kBigBinCap) s_big[at] = (uint32_t)b;
+        else by_thread = true;  // queue full: slow but correct
+      }
+      if (by_thread) {
+        for (uint32_t x = lo + 1; x < hi; ++x) {
+          const uint16_t ox = s_order[x];
+          const uint64_t kx = s_key[ox];
+          uint32_t y = x;
+          while (y > lo && s_key[s_order[y - 1]] > kx) {
+            s_order[y] = s_order[y - 1];
+            --y;
+          }
+          s_order[y] = ox;
+        }
+      }
+    }
+    __syncthreads();
+    const uint32_t nbig = min(s_misc[33], (uint32_t)kBigBinCap);
+    for (uint32_t bi = wid; bi < nbig; bi += THREADS / 32) {
+      const uint32_t b = s_big[bi];
+      const uint32_t lo = b ? s_bins[b - 1] : 0u, hi = s_bins[b];
+      const uint32_t m = hi - lo;
+      for (uint32_t x = lane; x < m; x += 32) {
+        const uint16_t ox = s_order[lo + x];
+        const uint64_t kx = s_key[ox];
+        uint32_t rank = 0;
+        for (uint32_t y = 0; y < m; ++y) {
+          const uint64_t ky = s_key[s_order[lo + y]];
+          rank += (ky < kx || (ky == kx && y < x)) ? 1u : 0u;
+        }
+        s_order2[lo + rank] = ox;
+      }
+      __syncwarp();
+      for (uint32_t x = lane; x < m; x += 32) s_order[lo + x] = s_order2[lo + x];
+    }
+    __syncthreads();
+
+    // ---- write the sub-range back, sorted
+    for (uint32_t pos = tid; pos < n; pos += THREADS) {
       const uint32_t slot = s_order[pos];
       a.key_out[out + pos] = s_key[slot];
       a.dist_out[out + pos] = s_dist[slot];

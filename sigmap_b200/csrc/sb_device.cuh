@@ -134,6 +134,14 @@ struct Counters {
   unsigned int max_entry_anchors;   // most anchors any one entry received this step
 };
 
+// Part of an entry that linear coordinate g = bucket_base[bucket] + target belongs to
+// (k_sort.cuh, k_part_sort).  Any function that is monotone in g gives contiguous parts; float
+// rounding only moves the boundaries by a few hundred positions, identically for every producer.
+__host__ __device__ __forceinline__ uint32_t part_of(uint64_t g, float inv_span, uint32_t n_parts) {
+  const uint32_t p = (uint32_t)((float)g * inv_span);
+  return p < n_parts ? p : n_parts - 1u;
+}
+
 // where one flush of the search kernel (or the carry injection) wrote hits of one entry
 struct RunRec {
   uint32_t start, count;

@@ -18,6 +18,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 #include <string>
 #include <vector>
 
@@ -29,6 +30,8 @@
 #include "sb_exchange.cuh"
 
 using namespace sb;
+
+static_assert(kCarryMaxParts == kMaxParts, "one part limit for every run producer");
 
 namespace {
 thread_local std::string g_create_error;
@@ -107,6 +110,8 @@ __global__ void k_query_table(const uint32_t *__restrict__ n_features, uint32_t 
     ctr->n_queries = carry;
   }
 }
+
+__global__ void k_clear_error_bits(Counters *c, unsigned int bits) { c->error &= ~bits; }
 
 struct RoundInfo {
   uint32_t stop, num_events, n_chains;
@@ -195,7 +200,7 @@ struct Workspace {
   DevBuf<uint32_t> pred, link_list, link_count;
   DevBuf<SegRec> seg;
   DevBuf<RunRec> runs;
-  DevBuf<uint32_t> run_count, entry_total;
+  DevBuf<uint32_t> run_count, entry_total, part_base;
   DevBuf<unsigned char> cub_temp;
   DevBuf<ChainTmp> chain_tmp;
   DevBuf<float> seg_max;
@@ -226,7 +231,13 @@ struct smb_ctx {
   DevBuf<uint64_t> bucket_base;   // linear coordinate of every bucket's target 0 (k_sort.cuh)
   int gshift = 0;
   uint32_t n_coarse = 1;
+  uint64_t g_total = 1;           // linear coordinates of the whole index (sum of the bucket spans)
+  double part_fill = 0.70;        // share of a k_part_sort CTA's capacity an average part should fill
+  bool part_small = false;        // SMB_PART=small: four 52 KB k_part_sort CTAs per SM instead of two 105 KB ones
+  bool part_sort = true;          // SMB_SORT=entry: always the one-CTA-per-entry sort (k_seg_sort)
   bool seg_sort = true;           // per-entry shared-memory sort; SMB_SORT=global forces the radix sort
+  uint32_t search_grab = 0;       // SMB_GRAB=n: queries per grab of the search work counter (0 = default)
+  int search_prefetch = 0;        // SMB_PREFETCH=1/2: prefetch pushed children into L2 / L1 (k_index.cuh)
   bool search_bfs = true;         // level-order traversal (fuller 8-node steps); SMB_SEARCH=dfs: depth-first
   bool sort_small = false;        // SMB_SORT=small: two 100 KB sort CTAs per SM instead of one 200 KB CTA
   cudaStream_t stream_ev = nullptr;  // lookahead event blocks run here, next to the mapping rounds
@@ -460,6 +471,7 @@ static int build_index(smb_ctx *ctx, const uint64_t *pos, const float *val, size
     for (size_t b = 0; b < bucket_span.size(); ++b) base[b + 1] = base[b] + bucket_span[b];
     CK(ctx->bucket_base.ensure(base.size()));
     CK(cudaMemcpy(ctx->bucket_base.p, base.data(), base.size() * sizeof(uint64_t), cudaMemcpyHostToDevice));
+    ctx->g_total = base.back();
     ctx->gshift = 0;
     while ((base.back() >> ctx->gshift) >= (uint64_t)kCoarseBins) ++ctx->gshift;
     ctx->n_coarse = (uint32_t)(base.back() >> ctx->gshift) + 1;
@@ -635,18 +647,37 @@ static int run_step(smb_ctx *ctx, SlotSpace &sp, const StepEntries &en, StepSour
   CK(w.coef.ensure(cap));
   CK(w.pred.ensure(cap));
   const bool want_seg = ctx->seg_sort;
-  if (want_seg) {
-    CK(w.runs.ensure((size_t)B * kRunsCap));
-    CK(w.run_count.ensure(B));
-    CK(w.entry_total.ensure(B));
-    CK(cudaMemsetAsync(w.run_count.p, 0, B * sizeof(uint32_t), s));
-    CK(cudaMemsetAsync(w.entry_total.p, 0, B * sizeof(uint32_t), s));
+  // parts per entry (k_sort.cuh): equal coordinate ranges sized so that a part of an average
+  // entry fills part_fill (70 %) of one k_part_sort CTA; more than kMaxParts -> one list, k_seg_sort
+  uint32_t n_parts = 1;
+  uint64_t span = std::max<uint64_t>(ctx->g_total, 1);
+  const int part_cap = ctx->part_small ? kPartSortCapSmall : kPartSortCap;
+  if (want_seg && ctx->part_sort) {
+    const double per_coord = std::max(ctx->est_anchors_per_chunk, 1.0) / (double)std::max<uint64_t>(ctx->g_total, 1);
+    const double want = ctx->part_fill * (double)part_cap / per_coord;
+    if (want < (double)ctx->g_total) {
+      const uint64_t sp2 = std::max<uint64_t>((uint64_t)want, 1);
+      const uint64_t np = (ctx->g_total + sp2 - 1) / sp2;
+      if (np <= (uint64_t)kMaxParts) {
+        n_parts = (uint32_t)np;
+        span = sp2;
+      }
+    }
   }
-  k_inject_carry<<<(B * 32 + 255) / 256, 256, 0, s>>>(w.entry_slot.p, w.n_queries.p, sp.slots.p,
-                                                     sp.pool_anchor[0].p, sp.pool_anchor[1].p, B, kl,
-                                                     w.key_a.p, w.dist_a.p, cap, ctx->d_ctr,
-                                                     want_seg ? w.runs.p : nullptr, w.run_count.p,
-                                                     w.entry_total.p, (uint32_t)kRunsCap);
+  const float inv_span = 1.0f / (float)span;
+  const size_t n_lists = (size_t)B * n_parts;
+  if (want_seg) {
+    CK(w.runs.ensure(n_lists * kRunsCap));
+    CK(w.run_count.ensure(n_lists));
+    CK(w.entry_total.ensure(n_lists));
+    CK(w.part_base.ensure(n_lists + 1));
+    CK(cudaMemsetAsync(w.run_count.p, 0, n_lists * sizeof(uint32_t), s));
+    CK(cudaMemsetAsync(w.entry_total.p, 0, n_lists * sizeof(uint32_t), s));
+  }
+  k_inject_carry<<<(B * 32 + kCarryThreads - 1) / kCarryThreads, kCarryThreads, 0, s>>>(
+      w.entry_slot.p, w.n_queries.p, sp.slots.p, sp.pool_anchor[0].p, sp.pool_anchor[1].p, B, kl, w.key_a.p,
+      w.dist_a.p, cap, ctx->d_ctr, want_seg ? w.runs.p : nullptr, w.run_count.p, w.entry_total.p,
+      (uint32_t)kRunsCap, n_parts, inv_span, ctx->bucket_base.p);
   LAUNCH_CHECK();
   SearchArgs sa{};
   sa.features = src == SRC_CACHED ? w.feat_cache[w.cache_cur].p : w.features.p;
@@ -667,6 +698,11 @@ static int run_step(smb_ctx *ctx, SlotSpace &sp, const StepEntries &en, StepSour
   sa.run_count = w.run_count.p;
   sa.entry_total = w.entry_total.p;
   sa.runs_cap = kRunsCap;
+  sa.n_parts = n_parts;
+  sa.inv_span = inv_span;
+  sa.bucket_base = ctx->bucket_base.p;
+  sa.prefetch = ctx->search_prefetch;
+  sa.grab = ctx->search_grab;
   CK(cudaEventRecord(ctx->ev[2], s));
   if (ctx->search_bfs)
     k_radius_search<false, true><<<ctx->search_grid_main, kSearchWarps * 32, search_smem(ctx), s>>>(ctx->ix, sa);
@@ -675,6 +711,10 @@ static int run_step(smb_ctx *ctx, SlotSpace &sp, const StepEntries &en, StepSour
   LAUNCH_CHECK();
   ctx->stats.search_launches++;
   CK(cudaEventRecord(ctx->ev[3], s));
+  if (want_seg) {
+    k_max_u32<<<148, 256, 0, s>>>(w.entry_total.p, n_lists, &ctx->d_ctr->max_entry_anchors);
+    LAUNCH_CHECK();
+  }
   CK(cudaMemcpyAsync(ctx->h_ctr, ctx->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
   ctx->stats.d2h_bytes += sizeof(Counters);
@@ -720,10 +760,53 @@ static int run_step(smb_ctx *ctx, SlotSpace &sp, const StepEntries &en, StepSour
   const uint64_t *keys = w.key_a.p;
   const float *dists = w.dist_a.p;
   bool sorted = n <= 1;
-  // per-entry sort in shared memory (k_sort.cuh) when every entry is small enough for a few
-  // passes over its runs and the run table did not overflow
-  if (!sorted && want_seg && !(ctx->h_ctr->error & 8u) &&
-      ctx->h_ctr->max_entry_anchors <= 8u * (unsigned)(ctx->sort_small ? kSortCapSmall : kSortCapBig)) {
+  // per-entry sort in shared memory (k_sort.cuh) when the run tables did not overflow:
+  // one CTA per (entry, part) if every part fits one CTA, else one CTA per entry working through
+  // the entry in several passes
+  const bool runs_ok = !sorted && want_seg && !(ctx->h_ctr->error & 8u);
+  if (runs_ok && ctx->part_sort && ctx->h_ctr->max_entry_anchors <= 8u * (unsigned)part_cap) {
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, w.entry_total.p, w.part_base.p, (int)n_lists, s);
+    CK(w.cub_temp.ensure(tb));
+    CK(cub::DeviceScan::ExclusiveSum(w.cub_temp.p, tb, w.entry_total.p, w.part_base.p, (int)n_lists, s));
+    ctx->stats.launches += 2;
+    PartSortArgs ps{};
+    ps.key_in = w.key_a.p;
+    ps.dist_in = w.dist_a.p;
+    ps.key_out = w.key_b.p;
+    ps.dist_out = w.dist_b.p;
+    ps.runs = w.runs.p;
+    ps.run_count = w.run_count.p;
+    ps.part_total = w.entry_total.p;
+    ps.out_base = w.part_base.p;
+    ps.n_parts = n_parts;
+    ps.span = span;
+    ps.kl = kl;
+    ps.bucket_base = ctx->bucket_base.p;
+    ps.n_buckets = ctx->max_bucket + 1u;
+    ps.ctr = ctx->d_ctr;
+    if (ctx->part_small)
+      k_part_sort<kPartSortCapSmall, 256, 2304><<<(unsigned)n_lists, 256, part_sort_smem_bytes(kPartSortCapSmall, 2304), s>>>(ps);
+    else
+      k_part_sort<kPartSortCap, 512, 4096><<<(unsigned)n_lists, 512, part_sort_smem_bytes(kPartSortCap, 4096), s>>>(ps);
+    LAUNCH_CHECK();
+    CK(cudaMemcpyAsync(ctx->h_ctr, ctx->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    ctx->stats.d2h_bytes += sizeof(Counters);
+    if (!(ctx->h_ctr->error & 16u)) {
+      sorted = true;
+      ctx->stats.seg_sort_steps++;
+      ctx->stats.part_sort_steps++;
+      keys = w.key_b.p;
+      dists = w.dist_b.p;
+    } else {
+      k_clear_error_bits<<<1, 1, 0, s>>>(ctx->d_ctr, 16u);  // the generic kernel reports through the same bit
+      LAUNCH_CHECK();
+      ctx->h_ctr->error &= ~16u;
+    }
+  }
+  if (!sorted && runs_ok &&
+      (uint64_t)ctx->h_ctr->max_entry_anchors * n_parts <= 8ull * (unsigned)(ctx->sort_small ? kSortCapSmall : kSortCapBig)) {
     SegSortArgs ss{};
     ss.key_in = w.key_a.p;
     ss.dist_in = w.dist_a.p;
@@ -731,6 +814,7 @@ static int run_step(smb_ctx *ctx, SlotSpace &sp, const StepEntries &en, StepSour
     ss.dist_out = w.dist_b.p;
     ss.runs = w.runs.p;
     ss.run_count = w.run_count.p;
+    ss.n_parts = n_parts;
     ss.B = B;
     ss.kl = kl;
     ss.bucket_base = ctx->bucket_base.p;
@@ -1135,11 +1219,21 @@ int smb_create(smb_ctx **out, int device) {
       (e = cudaFuncSetAttribute(k_seg_sort<kSortCapSmall, 512, 4096>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)sort_smem_bytes(kSortCapSmall, 4096))) != cudaSuccess)
     return bail("cudaFuncSetAttribute(k_seg_sort)", e);
+  if ((e = cudaFuncSetAttribute(k_part_sort<kPartSortCap, 512, 4096>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)part_sort_smem_bytes(kPartSortCap, 4096))) != cudaSuccess ||
+      (e = cudaFuncSetAttribute(k_part_sort<kPartSortCapSmall, 256, 2304>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)part_sort_smem_bytes(kPartSortCapSmall, 2304))) != cudaSuccess)
+    return bail("cudaFuncSetAttribute(k_part_sort)", e);
   if (const char *env = getenv("SMB_SORT")) {
     ctx->seg_sort = strcmp(env, "global") != 0;
     ctx->sort_small = strcmp(env, "small") == 0;
+    ctx->part_sort = strcmp(env, "entry") != 0 && !ctx->sort_small;
   }
   if (const char *env = getenv("SMB_SEARCH")) ctx->search_bfs = strcmp(env, "dfs") != 0;
+  if (const char *env = getenv("SMB_PREFETCH")) ctx->search_prefetch = atoi(env);
+  if (const char *env = getenv("SMB_GRAB")) ctx->search_grab = (uint32_t)std::max(atoi(env), 0);
+  if (const char *env = getenv("SMB_PART_FILL")) ctx->part_fill = atof(env);
+  if (const char *env = getenv("SMB_PART")) ctx->part_small = strcmp(env, "small") == 0;
   if ((e = cudaFuncSetAttribute(k_ev_chunk_warp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)kEvWarpSmem)) != cudaSuccess ||
       (e = cudaFuncSetAttribute(k_ev_chunk_warp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1172,7 +1266,7 @@ void smb_destroy(smb_ctx *ctx) {
   w.blk_chunk_start.release(); w.blk_chunk_offset.release(); w.blk_chunk_scale.release(); w.absent.release(); w.chunk_start.release(); w.chunk_offset.release();
   w.chunk_scale.release(); w.ps.release(); w.pss.release(); w.t1.release(); w.t2.release();
   w.means.release(); w.features.release(); w.key_a.release(); w.key_b.release(); w.dist_a.release();
-  w.dist_b.release(); w.score.release(); w.coef.release(); w.pred.release(); w.seg.release(); w.runs.release(); w.run_count.release(); w.entry_total.release(); w.link_list.release(); w.link_count.release(); w.cub_temp.release();
+  w.dist_b.release(); w.score.release(); w.coef.release(); w.pred.release(); w.seg.release(); w.runs.release(); w.run_count.release(); w.entry_total.release(); w.part_base.release(); w.link_list.release(); w.link_count.release(); w.cub_temp.release();
   w.chain_tmp.release(); w.ids.release(); w.round_info.release();
   w.seg_max.release(); w.n_scratch.release(); w.cand_list.release(); w.cand_all.release();
   w.cand_counts.release(); w.ctl.release(); w.tags.release();

@@ -20,6 +20,6 @@ for V in "$@"; do
 import json,sys
 for l in open(sys.argv[1]):
     if l.startswith('{'):
-        d=json.loads(l); print(d['value']/1e9, d['ms_per_step'], d['pipeline']['kernel_ms_per_step'])
+        d=json.loads(l); c=d['pipeline']['counters_per_step']; print(round(d['value']/1e9,4), round(d['ms_per_step'],1), {k:round(v,1) for k,v in d['pipeline']['kernel_ms_per_step'].items()}, 'steps', c.get('steps'), 'seg', c.get('seg_sort_steps'), 'part', c.get('part_sort_steps'))
 PY
 done
