@@ -314,12 +314,9 @@ constexpr int kDpGroup = 4;       // predecessors fetched together in the thread
 //    previous one) is settled in order by the whole warp: lanes load 32 consecutive predecessors
 //    coalesced, score one each, and the sequential rules (continue/break, running best, +-1 skip
 //    counter with its > 25 break) are resolved with a prefix-max scan and ballots.
-__global__ void __launch_bounds__(kDpThreads) k_chain_dp(ChainArgs a) {
-  const int lane = threadIdx.x & 31;
+__device__ __forceinline__ void dp_segment(const ChainArgs &a, const uint32_t slot, const int lane) {
   const unsigned full = 0xffffffffu;
   const unsigned le = (2u << lane) - 1u;  // lanes 0..lane
-  const uint32_t slot = (blockIdx.x * kDpThreads + threadIdx.x) / 32;
-  if (slot >= a.n_slots) return;
   SegRec r = a.seg[slot];
   if (r.start == kSegEmpty) return;
   const uint32_t s = r.start, e = r.end;
@@ -510,6 +507,25 @@ __global__ void __launch_bounds__(kDpThreads) k_chain_dp(ChainArgs a) {
     r.top_i[0] = ti0; r.top_i[1] = ti1; r.top_i[2] = ti2;
     a.seg[slot] = r;
     a.seg_max[slot] = runmax;
+  }
+}
+
+// Segments differ a lot in how many linked anchors they hold, so a fixed warp <-> segment
+// assignment leaves most warps of a block idle behind its slowest one: persistent warps take
+// segments from a work cursor instead (dynamic = 0: warp w handles segment w).
+__global__ void __launch_bounds__(kDpThreads) k_chain_dp(ChainArgs a, int dynamic) {
+  const int lane = threadIdx.x & 31;
+  if (!dynamic) {
+    const uint32_t slot = (blockIdx.x * kDpThreads + threadIdx.x) / 32;
+    if (slot < a.n_slots) dp_segment(a, slot, lane);
+    return;
+  }
+  for (;;) {
+    uint32_t slot = 0;
+    if (lane == 0) slot = atomicAdd(&a.ctr->dp_cursor, 1u);
+    slot = __shfl_sync(0xffffffffu, slot, 0);
+    if (slot >= a.n_slots) break;
+    dp_segment(a, slot, lane);
   }
 }
 

@@ -19,6 +19,8 @@
 #ifndef SB_K_INDEX_CUH
 #define SB_K_INDEX_CUH
 
+#include <cuda_fp16.h>
+
 #include "sb_device.cuh"
 
 namespace sb {
@@ -81,28 +83,44 @@ __global__ void k_build_leaves(const float *__restrict__ val, const uint64_t *__
   }
 }
 
-// box [lo, hi] -> centre + outward-rounded half extent, stored as child `j` of node record `rec`
-__device__ __forceinline__ void store_child_box(float4 *rec, int j, const float *lo, const float *hi, bool real) {
-  float c[kDim], h[kDim];
+// box [lo, hi] -> twelve binary16 numbers, lo rounded down and hi rounded up, so the stored box
+// always contains the fp32 one (values beyond the binary16 range become +-inf: never pruned);
+// stored as child `j` of node record `rec`.  A padding child is the empty box (+inf, -inf).
+__device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
+  return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
+}
+__device__ __forceinline__ float2 unpack_h2(uint32_t v) {
+  return make_float2(__half2float(__ushort_as_half((unsigned short)(v & 0xFFFFu))),
+                     __half2float(__ushort_as_half((unsigned short)(v >> 16))));
+}
+__device__ __forceinline__ void store_child_box(uint2 *rec, int j, const float *lo, const float *hi, bool real) {
+  __half l[kDim], h[kDim];
 #pragma unroll
   for (int d = 0; d < kDim; ++d) {
     if (real) {
-      c[d] = 0.5f * (lo[d] + hi[d]);
-      const float e = fmaxf(hi[d] - c[d], c[d] - lo[d]);
-      h[d] = e + 1.0e-6f * e + 1.0e-6f;  // covers the fp32 rounding of c, e and of the test itself
+      l[d] = __float2half_rd(lo[d]);
+      h[d] = __float2half_ru(hi[d]);
     } else {
-      c[d] = 0.0f;
-      h[d] = kPadExtent;
+      l[d] = __ushort_as_half((unsigned short)0x7C00);  // +inf
+      h[d] = __ushort_as_half((unsigned short)0xFC00);  // -inf
     }
   }
-  rec[j] = make_float4(c[0], c[1], c[2], c[3]);
-  rec[kFan + j] = make_float4(c[4], c[5], h[0], h[1]);
-  rec[2 * kFan + j] = make_float4(h[2], h[3], h[4], h[5]);
+  rec[j] = make_uint2(pack_h2(l[0], l[1]), pack_h2(l[2], l[3]));
+  rec[kFan + j] = make_uint2(pack_h2(l[4], l[5]), pack_h2(h[0], h[1]));
+  rec[2 * kFan + j] = make_uint2(pack_h2(h[2], h[3]), pack_h2(h[4], h[5]));
+}
+// child `j` of a node record -> lo[6], hi[6]
+__device__ __forceinline__ void load_child_box(const uint2 *rec, int j, float *lo, float *hi) {
+  const uint2 a = rec[j], b = rec[kFan + j], c = rec[2 * kFan + j];
+  const float2 l01 = unpack_h2(a.x), l23 = unpack_h2(a.y), l45 = unpack_h2(b.x);
+  const float2 h01 = unpack_h2(b.y), h23 = unpack_h2(c.x), h45 = unpack_h2(c.y);
+  lo[0] = l01.x; lo[1] = l01.y; lo[2] = l23.x; lo[3] = l23.y; lo[4] = l45.x; lo[5] = l45.y;
+  hi[0] = h01.x; hi[1] = h01.y; hi[2] = h23.x; hi[3] = h23.y; hi[4] = h45.x; hi[5] = h45.y;
 }
 
 // level-0 nodes: thread (n, j) boxes leaf 8n + j
 __global__ void k_nodes_level0(const float2 *__restrict__ leaf_vals, const uint2 *__restrict__ leaf_tb,
-                               uint32_t n_leaves, uint32_t n_nodes, float4 *__restrict__ nodes) {
+                               uint32_t n_leaves, uint32_t n_nodes, uint2 *__restrict__ nodes) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_nodes * kFan) return;
   const uint32_t n = t / kFan, j = t % kFan, leaf = t;
@@ -131,8 +149,8 @@ __global__ void k_nodes_level0(const float2 *__restrict__ leaf_vals, const uint2
 }
 
 // level l+1 from level l: thread (n, j) boxes child node 8n + j of the level below
-__global__ void k_nodes_up(const float4 *__restrict__ child, uint32_t n_child, uint32_t n_nodes,
-                           float4 *__restrict__ nodes) {
+__global__ void k_nodes_up(const uint2 *__restrict__ child, uint32_t n_child, uint32_t n_nodes,
+                           uint2 *__restrict__ nodes) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_nodes * kFan) return;
   const uint32_t n = t / kFan, j = t % kFan, m = t;
@@ -144,17 +162,16 @@ __global__ void k_nodes_up(const float4 *__restrict__ child, uint32_t n_child, u
   }
   bool real = false;
   if (m < n_child) {
-    const float4 *rec = child + (size_t)m * 3 * kFan;
+    const uint2 *rec = child + (size_t)m * 3 * kFan;
     for (int p = 0; p < kFan; ++p) {
-      const float4 a = rec[p], b = rec[kFan + p], c = rec[2 * kFan + p];
-      if (b.z < 0.0f) continue;  // padding child
+      float cl[kDim], ch[kDim];
+      load_child_box(rec, p, cl, ch);
+      if (cl[0] > ch[0]) continue;  // padding child (empty box)
       real = true;
-      const float cc[kDim] = {a.x, a.y, a.z, a.w, b.x, b.y};
-      const float hh[kDim] = {b.z, b.w, c.x, c.y, c.z, c.w};
 #pragma unroll
       for (int d = 0; d < kDim; ++d) {
-        lo[d] = fminf(lo[d], cc[d] - hh[d]);
-        hi[d] = fmaxf(hi[d], cc[d] + hh[d]);
+        lo[d] = fminf(lo[d], cl[d]);
+        hi[d] = fmaxf(hi[d], ch[d]);
       }
     }
   }
@@ -204,19 +221,7 @@ struct SearchArgs {
   float inv_span;              // 1 / coordinates per part
   const uint64_t *bucket_base;
   uint32_t grab;               // queries per grab of the work counter (0 = kSearchGrab)
-  int prefetch;                // 0: none; 1: children/leaves pushed on a stack are prefetched into L2; 2: into L1
 };
-
-// the records a step has just decided to visit are requested now, so the step that pops them
-// finds them on chip instead of paying the DRAM round trip itself
-__device__ __forceinline__ void prefetch_lines(const void *p, int n_lines, int mode) {
-  const char *c = static_cast<const char *>(p);
-  if (mode == 1) {
-    for (int i = 0; i < n_lines; ++i) asm volatile("prefetch.global.L2 [%0];" ::"l"(c + 128 * i));
-  } else {
-    for (int i = 0; i < n_lines; ++i) asm volatile("prefetch.global.L1 [%0];" ::"l"(c + 128 * i));
-  }
-}
 
 __device__ __forceinline__ float exact_d2(const float q[kDim], const float v[kDim]) {
   float e[kDim];
@@ -281,7 +286,6 @@ k_radius_search(const IndexView ix, const SearchArgs a) {
   const uint32_t nq = STAGE ? a.n_queries : a.q_off[a.B];
   const float r2 = a.radius;
   const float r2_prune = r2 * 1.0001f + 1e-12f;
-  const int pf = a.prefetch;
   const uint32_t grab = a.grab ? a.grab : (uint32_t)kSearchGrab;
   const int top_level = n_levels - 1;
   const uint32_t n_top = ix.level_count[top_level];  // <= 8
@@ -485,25 +489,36 @@ k_radius_search(const IndexView ix, const SearchArgs a) {
           const uint32_t nodeA = hasA ? stk[c - 1 - grp] : 0u;
           const uint32_t nodeB = hasB ? stk[c - 5 - grp] : 0u;
           c -= take;
-          const float4 *base = ix.level_node[L] + sub;
-          const float4 *ra = base + (size_t)nodeA * (3 * kFan);
-          const float4 *rb = base + (size_t)nodeB * (3 * kFan);
-          const float4 a0 = __ldg(ra), a1 = __ldg(ra + kFan), a2 = __ldg(ra + 2 * kFan);
-          const float4 b0 = __ldg(rb), b1 = __ldg(rb + kFan), b2 = __ldg(rb + 2 * kFan);
-          // boxes only prune (with slack), so this distance may use FMA; the accept test may not
-          float sa, sb, t;
-          t = fmaxf(fabsf(q[0] - a0.x) - a1.z, 0.0f); sa = t * t;
-          t = fmaxf(fabsf(q[1] - a0.y) - a1.w, 0.0f); sa = __fmaf_rn(t, t, sa);
-          t = fmaxf(fabsf(q[2] - a0.z) - a2.x, 0.0f); sa = __fmaf_rn(t, t, sa);
-          t = fmaxf(fabsf(q[3] - a0.w) - a2.y, 0.0f); sa = __fmaf_rn(t, t, sa);
-          t = fmaxf(fabsf(q[4] - a1.x) - a2.z, 0.0f); sa = __fmaf_rn(t, t, sa);
-          t = fmaxf(fabsf(q[5] - a1.y) - a2.w, 0.0f); sa = __fmaf_rn(t, t, sa);
-          t = fmaxf(fabsf(q[0] - b0.x) - b1.z, 0.0f); sb = t * t;
-          t = fmaxf(fabsf(q[1] - b0.y) - b1.w, 0.0f); sb = __fmaf_rn(t, t, sb);
-          t = fmaxf(fabsf(q[2] - b0.z) - b2.x, 0.0f); sb = __fmaf_rn(t, t, sb);
-          t = fmaxf(fabsf(q[3] - b0.w) - b2.y, 0.0f); sb = __fmaf_rn(t, t, sb);
-          t = fmaxf(fabsf(q[4] - b1.x) - b2.z, 0.0f); sb = __fmaf_rn(t, t, sb);
-          t = fmaxf(fabsf(q[5] - b1.y) - b2.w, 0.0f); sb = __fmaf_rn(t, t, sb);
+          const uint2 *base = ix.level_node[L] + sub;
+          const uint2 *ra = base + (size_t)nodeA * (3 * kFan);
+          const uint2 *rb = base + (size_t)nodeB * (3 * kFan);
+          const uint2 a0 = __ldg(ra), a1 = __ldg(ra + kFan), a2 = __ldg(ra + 2 * kFan);
+          const uint2 b0 = __ldg(rb), b1 = __ldg(rb + kFan), b2 = __ldg(rb + 2 * kFan);
+          // boxes only prune (stored rounded outwards, tested with slack), so this distance may
+          // use FMA; the accept test may not
+          float sa = 0.0f, sb = 0.0f;
+          {
+            const float2 l01 = unpack_h2(a0.x), l23 = unpack_h2(a0.y), l45 = unpack_h2(a1.x);
+            const float2 h01 = unpack_h2(a1.y), h23 = unpack_h2(a2.x), h45 = unpack_h2(a2.y);
+            const float lo[kDim] = {l01.x, l01.y, l23.x, l23.y, l45.x, l45.y};
+            const float hi[kDim] = {h01.x, h01.y, h23.x, h23.y, h45.x, h45.y};
+#pragma unroll
+            for (int d = 0; d < kDim; ++d) {
+              const float t = fmaxf(fmaxf(lo[d] - q[d], q[d] - hi[d]), 0.0f);
+              sa = __fmaf_rn(t, t, sa);
+            }
+          }
+          {
+            const float2 l01 = unpack_h2(b0.x), l23 = unpack_h2(b0.y), l45 = unpack_h2(b1.x);
+            const float2 h01 = unpack_h2(b1.y), h23 = unpack_h2(b2.x), h45 = unpack_h2(b2.y);
+            const float lo[kDim] = {l01.x, l01.y, l23.x, l23.y, l45.x, l45.y};
+            const float hi[kDim] = {h01.x, h01.y, h23.x, h23.y, h45.x, h45.y};
+#pragma unroll
+            for (int d = 0; d < kDim; ++d) {
+              const float t = fmaxf(fmaxf(lo[d] - q[d], q[d] - hi[d]), 0.0f);
+              sb = __fmaf_rn(t, t, sb);
+            }
+          }
           const uint32_t mA = __ballot_sync(full, hasA && sa <= r2_prune);
           const uint32_t mB = __ballot_sync(full, hasB && sb <= r2_prune);
           const int nA = __popc(mA), nB = __popc(mB);
@@ -513,10 +528,6 @@ k_radius_search(const IndexView ix, const SearchArgs a) {
               uint32_t *dst = lstk + (L - 1) * kLevelCap + below;
               if (mA & (1u << lane)) dst[__popc(mA & lt)] = nodeA * kFan + sub;
               if (mB & (1u << lane)) dst[nA + __popc(mB & lt)] = nodeB * kFan + sub;
-              if (pf) {
-                if (mA & (1u << lane)) prefetch_lines(ix.level_node[L - 1] + (size_t)(nodeA * kFan + sub) * (3 * kFan), 3, pf);
-                if (mB & (1u << lane)) prefetch_lines(ix.level_node[L - 1] + (size_t)(nodeB * kFan + sub) * (3 * kFan), 3, pf);
-              }
               __syncwarp();  // every lane has read lcnt before lane 0 rewrites it
               if (lane == 0) {
                 lcnt[L] = (uint32_t)c;
@@ -526,10 +537,6 @@ k_radius_search(const IndexView ix, const SearchArgs a) {
             } else {
               if (mA & (1u << lane)) leafq[nleaf + __popc(mA & lt)] = nodeA * kFan + sub;
               if (mB & (1u << lane)) leafq[nleaf + nA + __popc(mB & lt)] = nodeB * kFan + sub;
-              if (pf) {
-                if (mA & (1u << lane)) prefetch_lines(ix.leaf_vals + (size_t)(nodeA * kFan + sub) * (3 * kLeaf), 2, pf);
-                if (mB & (1u << lane)) prefetch_lines(ix.leaf_vals + (size_t)(nodeB * kFan + sub) * (3 * kLeaf), 2, pf);
-              }
               nleaf += nA + nB;
               __syncwarp();
               if (lane == 0) lcnt[0] = (uint32_t)c;

@@ -51,8 +51,9 @@ struct DevBuf {
 // children (level 0: leaves 8n..8n+7, level l: nodes 8n..8n+7 of level l-1), pointer-free.
 // A warp works on FOUR nodes (or leaves) per step, one 8-lane group each, so records are laid
 // out for 8 lanes:
-//   node  = [3][8 children] float4: (c0 c1 c2 c3) (c4 c5 h0 h1) (h2 h3 h4 h5), box = centre +-
-//           half extent, 384 bytes, three fully coalesced 128-byte loads per lane group;
+//   node  = [3][8 children] x four binary16: (lo0 lo1 lo2 lo3) (lo4 lo5 hi0 hi1) (hi2 hi3 hi4 hi5),
+//           box corners rounded outwards, 192 bytes, three coalesced 64-byte loads per lane
+//           group -- the search is bound by L2 bandwidth, and node records are most of it;
 //   leaf  = [3][8 points] float2: (v0 v1) (v2 v3) (v4 v5), 192 bytes.
 struct IndexView {
   uint64_t n_points;    // N (point cloud size); windows W = N - 5
@@ -60,7 +61,7 @@ struct IndexView {
   uint32_t n_leaves;    // ceil(W / 8)
   int n_levels;         // node levels; the top level has <= 8 nodes
   uint32_t level_count[kMaxLevels];  // nodes per level
-  const float4 *level_node[kMaxLevels];
+  const uint2 *level_node[kMaxLevels];
   const float2 *leaf_vals;    // [n_leaves][3][8]
   const uint2 *leaf_tb;       // [n_leaves*8] {target position (pos >> 1, low 32 bits),
                               //               contig*2 + strand (0 = '+'), ~0u = padding}
@@ -131,7 +132,8 @@ struct Counters {
   unsigned int error;               // bit0 anchor overflow, bit1 carry overflow, bit2 chain scratch,
                                     // bit3 run table overflow, bit4 entry too dense for k_seg_sort,
                                     // bit5 candidate exchange list overflow
-  unsigned int max_entry_anchors;   // most anchors any one entry received this step
+  unsigned int max_entry_anchors;   // most anchors any one (entry, part) received this step
+  unsigned int dp_cursor;           // next segment of the chaining DP's work queue
 };
 
 // Part of an entry that linear coordinate g = bucket_base[bucket] + target belongs to

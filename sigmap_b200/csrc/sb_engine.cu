@@ -59,6 +59,7 @@ __global__ void k_reset_step(Counters *c) {
   c->sort_cursor = 0;
   c->n_cand = 0;
   c->max_entry_anchors = 0;
+  c->dp_cursor = 0;
   c->error &= ~24u;  // per-step bits (run table overflow, dense entry); the others are per round
 }
 
@@ -223,7 +224,7 @@ struct smb_ctx {
   bool has_index = false;
   IndexView ix{};
   DevBuf<float2> leaf_vals;
-  DevBuf<float4> level[kMaxLevels];
+  DevBuf<uint2> level[kMaxLevels];
   DevBuf<uint2> leaf_tb;
   DevBuf<uint32_t> leaf_widx;
   uint32_t max_tpos = 0, max_bucket = 0;
@@ -233,11 +234,12 @@ struct smb_ctx {
   uint32_t n_coarse = 1;
   uint64_t g_total = 1;           // linear coordinates of the whole index (sum of the bucket spans)
   double part_fill = 0.70;        // share of a k_part_sort CTA's capacity an average part should fill
+  bool dp_dynamic = true;         // SMB_DP=static: warp w of the DP grid handles segment w
+  unsigned dp_grid = 148 * 8;     // persistent DP grid: every block that fits on the device
   bool part_small = false;        // SMB_PART=small: four 52 KB k_part_sort CTAs per SM instead of two 105 KB ones
   bool part_sort = true;          // SMB_SORT=entry: always the one-CTA-per-entry sort (k_seg_sort)
   bool seg_sort = true;           // per-entry shared-memory sort; SMB_SORT=global forces the radix sort
   uint32_t search_grab = 0;       // SMB_GRAB=n: queries per grab of the search work counter (0 = default)
-  int search_prefetch = 0;        // SMB_PREFETCH=1/2: prefetch pushed children into L2 / L1 (k_index.cuh)
   bool search_bfs = true;         // level-order traversal (fuller 8-node steps); SMB_SEARCH=dfs: depth-first
   bool sort_small = false;        // SMB_SORT=small: two 100 KB sort CTAs per SM instead of one 200 KB CTA
   cudaStream_t stream_ev = nullptr;  // lookahead event blocks run here, next to the mapping rounds
@@ -701,7 +703,6 @@ static int run_step(smb_ctx *ctx, SlotSpace &sp, const StepEntries &en, StepSour
   sa.n_parts = n_parts;
   sa.inv_span = inv_span;
   sa.bucket_base = ctx->bucket_base.p;
-  sa.prefetch = ctx->search_prefetch;
   sa.grab = ctx->search_grab;
   CK(cudaEventRecord(ctx->ev[2], s));
   if (ctx->search_bfs)
@@ -880,7 +881,11 @@ static int run_step(smb_ctx *ctx, SlotSpace &sp, const StepEntries &en, StepSour
   if (n > 0) {
     k_chain_prep<<<n_tiles, kPrepThreads, 0, s>>>(ca);
     LAUNCH_CHECK();
-    k_chain_dp<<<(unsigned)(((uint64_t)ca.n_slots * 32 + kDpThreads - 1) / kDpThreads), kDpThreads, 0, s>>>(ca);
+    const unsigned dp_blocks = (unsigned)(((uint64_t)ca.n_slots * 32 + kDpThreads - 1) / kDpThreads);
+    if (ctx->dp_dynamic)
+      k_chain_dp<<<std::min(dp_blocks, ctx->dp_grid), kDpThreads, 0, s>>>(ca, 1);
+    else
+      k_chain_dp<<<dp_blocks, kDpThreads, 0, s>>>(ca, 0);
     LAUNCH_CHECK();
   }
   SelectArgs se{};
@@ -1230,10 +1235,17 @@ int smb_create(smb_ctx **out, int device) {
     ctx->part_sort = strcmp(env, "entry") != 0 && !ctx->sort_small;
   }
   if (const char *env = getenv("SMB_SEARCH")) ctx->search_bfs = strcmp(env, "dfs") != 0;
-  if (const char *env = getenv("SMB_PREFETCH")) ctx->search_prefetch = atoi(env);
   if (const char *env = getenv("SMB_GRAB")) ctx->search_grab = (uint32_t)std::max(atoi(env), 0);
   if (const char *env = getenv("SMB_PART_FILL")) ctx->part_fill = atof(env);
   if (const char *env = getenv("SMB_PART")) ctx->part_small = strcmp(env, "small") == 0;
+  if (const char *env = getenv("SMB_DP")) ctx->dp_dynamic = strcmp(env, "static") != 0;
+  {
+    int per_sm = 0, n_sm = 148;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_chain_dp, kDpThreads, 0) != cudaSuccess || per_sm < 1)
+      per_sm = 8;
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device);
+    ctx->dp_grid = (unsigned)(per_sm * n_sm);
+  }
   if ((e = cudaFuncSetAttribute(k_ev_chunk_warp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)kEvWarpSmem)) != cudaSuccess ||
       (e = cudaFuncSetAttribute(k_ev_chunk_warp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
