@@ -205,11 +205,11 @@ constexpr int kPrepHalo = 128;     // predecessors staged in shared memory ahead
 constexpr int kPrepThreads = 256;  // kPrepTile / kPrepThreads anchors per thread
 constexpr uint32_t kPending = 0x40000000u;  // pred[] bit: linked anchor not yet settled by the DP
 
-__global__ void __launch_bounds__(kPrepThreads) k_chain_prep(ChainArgs a) {
+__global__ void __launch_bounds__(kPrepThreads, 8) k_chain_prep(ChainArgs a) {
   // the tile's anchors and the kPrepHalo before it, unpacked: {segment id, target, query, -}
   __shared__ int4 s_a[kPrepHalo + kPrepTile];
-  __shared__ uint32_t warp_base[kPrepThreads / 32];
-  __shared__ uint32_t tile_count;
+  constexpr int kSubTiles = kPrepTile / kPrepThreads;
+  __shared__ uint32_t warp_cnt[kSubTiles][kPrepThreads / 32];  // linked anchors per (sub-tile, warp)
   const uint32_t n = (uint32_t)a.n;  // < 2^30
   const uint32_t tile0 = blockIdx.x * kPrepTile;
   const KeyLayout kl = a.kl;
@@ -224,10 +224,11 @@ __global__ void __launch_bounds__(kPrepThreads) k_chain_prep(ChainArgs a) {
     }
     s_a[x] = v;
   }
-  if (threadIdx.x == 0) tile_count = 0;
   __syncthreads();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  for (int sub = 0; sub < kPrepTile / kPrepThreads; ++sub) {
+  unsigned link_mask[kSubTiles];  // my warp's linked lanes, per sub-tile
+#pragma unroll
+  for (int sub = 0; sub < kSubTiles; ++sub) {
     const int local = sub * kPrepThreads + threadIdx.x;
     const uint32_t i = tile0 + local;
     bool linked = false;
@@ -277,26 +278,33 @@ __global__ void __launch_bounds__(kPrepThreads) k_chain_prep(ChainArgs a) {
       a.score[i] = __fmul_rn(ci, (float)kDim);
       a.pred[i] = linked ? (i | kPending) : i;
     }
-    // ordered compaction of the linked anchors (sub-tiles are consecutive index ranges)
-    const unsigned m = __ballot_sync(0xffffffffu, linked);
-    if (lane == 0) warp_base[wid] = __popc(m);
-    __syncthreads();
-    const uint32_t base = tile_count;
-    uint32_t before = 0, total = 0;
-    for (int w = 0; w < kPrepThreads / 32; ++w) {
-      const uint32_t t = warp_base[w];
-      if (w < wid) before += t;
-      total += t;
-    }
-    if (linked)
-      a.link_list[(size_t)blockIdx.x * kPrepTile + base + before + __popc(m & ((1u << lane) - 1u))] = i;
-    __syncthreads();
-    if (threadIdx.x == 0) tile_count = base + total;
+    link_mask[sub] = __ballot_sync(0xffffffffu, linked);
+    if (lane == 0) warp_cnt[sub][wid] = __popc(link_mask[sub]);
   }
+  // ordered compaction of the linked anchors: index order is (sub-tile, warp, lane), so one
+  // barrier and a walk over the 32 counts place every one of them
   __syncthreads();
+  uint32_t at = 0, total = 0;
+#pragma unroll
+  for (int sub = 0; sub < kSubTiles; ++sub) {
+    uint32_t before = 0, sub_total = 0;
+#pragma unroll
+    for (int w = 0; w < kPrepThreads / 32; ++w) {
+      const uint32_t t = warp_cnt[sub][w];
+      if (w < wid) before += t;
+      sub_total += t;
+    }
+    const unsigned m = link_mask[sub];
+    if (m & (1u << lane)) {
+      const uint32_t i = tile0 + sub * kPrepThreads + threadIdx.x;
+      a.link_list[(size_t)blockIdx.x * kPrepTile + at + before + __popc(m & ((1u << lane) - 1u))] = i;
+    }
+    at += sub_total;
+    total += sub_total;
+  }
   if (threadIdx.x == 0) {
-    a.link_count[blockIdx.x] = tile_count;
-    if (tile_count) atomicAdd(&a.ctr->n_linked, (unsigned long long)tile_count);
+    a.link_count[blockIdx.x] = total;
+    if (total) atomicAdd(&a.ctr->n_linked, (unsigned long long)total);
   }
 }
 
