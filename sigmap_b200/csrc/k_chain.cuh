@@ -57,6 +57,7 @@ struct ChainArgs {
   uint32_t *link_list;   // [n_tiles * kPrepTile] indices of linked anchors, ascending per tile
   uint32_t *link_count;  // [n_tiles]
   Counters *ctr;
+  int dp_passes;         // thread-parallel passes of k_chain_dp before the in-order cooperative path
 };
 
 constexpr int kCarryThreads = 256;
@@ -309,7 +310,7 @@ __global__ void __launch_bounds__(kPrepThreads, 8) k_chain_prep(ChainArgs a) {
 }
 
 constexpr int kDpThreads = 128;
-constexpr int kDpFreePasses = 2;  // thread-parallel passes before the in-order cooperative path
+constexpr int kDpFreePasses = 1;  // thread-parallel passes before the in-order cooperative path (measured: 1 < 2 < 4)
 constexpr int kDpGroup = 4;       // predecessors fetched together in the thread-parallel lookback
 
 // A warp owns a segment and takes its linked anchors 32 at a time, one per lane.
@@ -361,7 +362,7 @@ __device__ __forceinline__ void dp_segment(const ChainArgs &a, const uint32_t sl
       }
       bool todo = valid;
       // ---- thread-parallel passes
-      for (int pass = 0; pass < kDpFreePasses; ++pass) {
+      for (int pass = 0; pass < a.dp_passes; ++pass) {
         if (todo) {
           M = init;
           uint32_t best = i;

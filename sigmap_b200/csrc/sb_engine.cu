@@ -234,6 +234,7 @@ struct smb_ctx {
   uint32_t n_coarse = 1;
   uint64_t g_total = 1;           // linear coordinates of the whole index (sum of the bucket spans)
   double part_fill = 0.70;        // share of a k_part_sort CTA's capacity an average part should fill
+  int dp_passes = kDpFreePasses;  // SMB_DP_PASSES=n
   bool dp_dynamic = true;         // SMB_DP=static: warp w of the DP grid handles segment w
   unsigned dp_grid = 148 * 8;     // persistent DP grid: every block that fits on the device
   bool part_small = false;        // SMB_PART=small: four 52 KB k_part_sort CTAs per SM instead of two 105 KB ones
@@ -871,6 +872,7 @@ static int run_step(smb_ctx *ctx, SlotSpace &sp, const StepEntries &en, StepSour
   ca.seg = w.seg.p;
   ca.seg_max = w.seg_max.p;
   ca.ctr = ctx->d_ctr;
+  ca.dp_passes = ctx->dp_passes;
   CK(cudaMemsetAsync(w.seg.p, 0xFF, (size_t)ca.n_slots * sizeof(SegRec), s));
   CK(cudaMemsetAsync(w.seg_max.p, 0, (size_t)ca.n_slots * sizeof(float), s));
   const unsigned n_tiles = (unsigned)((n + kPrepTile - 1) / kPrepTile);
@@ -1239,6 +1241,7 @@ int smb_create(smb_ctx **out, int device) {
   if (const char *env = getenv("SMB_PART_FILL")) ctx->part_fill = atof(env);
   if (const char *env = getenv("SMB_PART")) ctx->part_small = strcmp(env, "small") == 0;
   if (const char *env = getenv("SMB_DP")) ctx->dp_dynamic = strcmp(env, "static") != 0;
+  if (const char *env = getenv("SMB_DP_PASSES")) ctx->dp_passes = std::max(atoi(env), 0);
   {
     int per_sm = 0, n_sm = 148;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_chain_dp, kDpThreads, 0) != cudaSuccess || per_sm < 1)
