@@ -20,7 +20,7 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --
     > $OUT/launches_bench.log 2>&1
 python profiles/summarize_launches.py $OUT/launches.csv > $OUT/launches_summary.txt 2>&1
 head -30 $OUT/launches_summary.txt
-bash tools/gpu_prof.sh $TAG 'k_radius_search|k_chain_dp|k_chain_prep|k_chain_select|k_seg_sort|k_ev_features' 60 12 \
-    k_radius_search k_chain_dp k_seg_sort k_chain_select k_chain_prep k_ev_features > $OUT/prof.log 2>&1
+bash tools/gpu_prof.sh $TAG 'k_radius_search|k_chain_dp|k_chain_prep|k_sel_trace|k_sel_final|k_part_sort|k_ev_features' 70 14 \
+    k_radius_search k_chain_dp k_part_sort k_chain_prep k_ev_features > $OUT/prof.log 2>&1
 tail -20 $OUT/summary.md
 fi
