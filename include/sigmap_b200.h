@@ -250,6 +250,9 @@ int smbh_fasta_write(const char *path, const char *const *names, const char *con
  * Call with pos == NULL to get the count. */
 size_t smbh_build_point_cloud(const char *const *seqs, const uint32_t *lengths, uint32_t n,
                               const float *level_mean, uint64_t *pos, float *val);
+/* The same in one pass: *pos / *val are allocated by the library (release with smbh_free). */
+int smbh_build_point_cloud_alloc(const char *const *seqs, const uint32_t *lengths, uint32_t n,
+                                 const float *level_mean, uint64_t **pos, float **val, size_t *count);
 /* .pt file of SpatialIndex::Save (spatial_index.cc:105-123) */
 int smbh_pt_write(const char *prefix, const uint64_t *pos, const float *val, size_t n,
                   int dim, int max_leaf);

@@ -188,6 +188,8 @@ PROTOTYPES = {
     "smbh_fasta_free": (None, [C.POINTER(Fasta)]),
     "smbh_fasta_write": (C.c_int, [C.c_char_p, charpp, charpp, u32p, C.c_uint32]),
     "smbh_build_point_cloud": (C.c_size_t, [charpp, u32p, C.c_uint32, f32p, u64p, f32p]),
+    "smbh_build_point_cloud_alloc": (C.c_int, [charpp, u32p, C.c_uint32, f32p, C.POINTER(u64p), C.POINTER(f32p),
+                                              C.POINTER(C.c_size_t)]),
     "smbh_pt_write": (C.c_int, [C.c_char_p, u64p, f32p, C.c_size_t, C.c_int, C.c_int]),
     "smbh_pt_read": (C.c_int, [C.c_char_p, C.POINTER(u64p), C.POINTER(f32p),
                                C.POINTER(C.c_size_t), C.POINTER(C.c_int), C.POINTER(C.c_int)]),

@@ -9,6 +9,7 @@
 //   point selection: skip masked, skip |dz| <= 0.01 vs last     spatial_index.cc:33-57
 //   order: all + strands by contig, then all - strands          spatial_index.cc:82-93
 //   packed position ((contig<<32 | p) << 1) | strand            spatial_index.cc:47-51
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -18,12 +19,27 @@
 #include "../../include/sigmap_b200.h"
 #include "sb_host.h"
 
+// Everything position-parallel runs on all host cores (OpenMP): the reverse complement, the
+// expected levels, the 11-mer census and masking, the final division of the z-scores.  What the
+// reference's arithmetic makes order-dependent stays sequential and identical: the double
+// accumulators of the z-normalisation and the `last kept value` chain of the point selection.
+// A 3.1 Gbp reference is ~6.2 G positions; at one core this stage took ~18 minutes.
 namespace {
 
 constexpr int kK = 6;                    // pore-model k
 constexpr int kMaskK = SMB_DIM + kK - 1; // 11-mers are masked (sigmap.cc:1014)
 constexpr float kMaskFreq = 0.0002f;
 constexpr double kMinDelta = 0.01;       // spatial_index.cc:46
+constexpr uint32_t kChunk = 1u << 20;    // positions per parallel work item
+
+struct Codes {  // A=0 C=1 G=2 T=3 (either case), anything else -1: sb::base_code as a table
+  signed char t[256];
+  Codes() {
+    for (int c = 0; c < 256; ++c) t[c] = (signed char)sb::base_code((char)c);
+  }
+  int operator()(char c) const { return t[(unsigned char)c]; }
+};
+const Codes kCode;
 
 struct StrandView {
   std::string owned;  // reverse complement when needed
@@ -31,38 +47,50 @@ struct StrandView {
   uint32_t len;
 };
 
-StrandView make_strand(const char *seq, uint32_t len, int strand) {
-  StrandView v;
+void make_strand(StrandView &v, const char *seq, uint32_t len, int strand) {
+  v.len = len;
   if (strand == 0) {
     v.s = seq;
-    v.len = len;
-    return v;
+    return;
   }
   v.owned.resize(len);
-  for (uint32_t i = 0; i < len; ++i) {  // sequence_batch.h:66-77
-    int c = sb::base_code(seq[len - 1 - i]);
-    v.owned[i] = c < 0 ? 'N' : "ACGT"[3 ^ c];
+  char *out = &v.owned[0];
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < (int64_t)len; ++i) {  // sequence_batch.h:66-77
+    const int c = kCode(seq[len - 1 - i]);
+    out[i] = c < 0 ? 'N' : "ACGT"[3 ^ c];
   }
   v.s = v.owned.c_str();  // NUL-terminated like std::string::data() in the reference
-  v.len = len;
-  return v;
 }
 
 // Expected current per position.  Position 0 hashes bases 0..5; position p >= 1 shifts in
-// base p+6 (not p+5), so the last position shifts in the terminating NUL, read as 'A'.
+// base p+6 (not p+5), so the last position shifts in the terminating NUL, read as 'A'.  From
+// p = 6 on the hash therefore holds bases p+1..p+6, which lets chunks start anywhere.
 void expected_levels(const StrandView &v, const float *level_mean, std::vector<float> &out) {
   const uint32_t L = v.len - kK + 1, mask = (1u << (2 * kK)) - 1;
   out.resize(L);
+  auto code0 = [&](uint32_t i) {  // ambiguous bases (and the NUL) hash as 'A'
+    const int c = kCode(v.s[i]);
+    return (uint32_t)(c < 0 ? 0 : c);
+  };
   uint32_t h = 0;
-  for (uint32_t i = 0; i < (uint32_t)kK; ++i) {
-    int c = i < L ? sb::base_code(v.s[i]) : -1;
-    h = ((h << 2) | (uint32_t)(c < 0 ? 0 : c)) & mask;
-  }
+  for (uint32_t i = 0; i < (uint32_t)kK; ++i) h = ((h << 2) | (i < L ? code0(i) : 0u)) & mask;
   out[0] = level_mean[h];
-  for (uint32_t p = 1; p < L; ++p) {
-    int c = sb::base_code(v.s[p + kK]);
-    h = ((h << 2) | (uint32_t)(c < 0 ? 0 : c)) & mask;
+  const uint32_t head = L < 7u ? L : 7u;
+  for (uint32_t p = 1; p < head; ++p) {
+    h = ((h << 2) | code0(p + kK)) & mask;
     out[p] = level_mean[h];
+  }
+  float *o = out.data();
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int64_t a = 7; a < (int64_t)L; a += kChunk) {
+    const uint32_t b = (uint32_t)std::min<int64_t>(L, a + kChunk);
+    uint32_t g = 0;
+    for (uint32_t i = (uint32_t)a + 1; i < (uint32_t)a + kK; ++i) g = (g << 2) | code0(i);  // bases a+1..a+5
+    for (uint32_t q = (uint32_t)a; q < b; ++q) {  // g holds bases q+1..q+5: shift in base q+6
+      g = ((g << 2) | code0(q + kK)) & mask;      // now bases q+1..q+6
+      o[q] = level_mean[g];
+    }
   }
 }
 
@@ -74,58 +102,80 @@ void znormalise(std::vector<float> &x) {
   double ss = 0;
   for (size_t i = 0; i < n; ++i) ss += (x[i] - mean) * (x[i] - mean);
   const double sd = std::sqrt(ss / (n - 1));
-  for (size_t i = 0; i < n; ++i) x[i] = (float)((x[i] - mean) / sd);
+  float *p = x.data();
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < (int64_t)n; ++i) p[i] = (float)((p[i] - mean) / sd);
 }
 
-// Walks a strand's k-mers; fn(pos_of_kmer_start, canonical_kmer) for complete k-mers and
-// fn_amb(pos) where the window *ending* at an ambiguous base starts.
+// Walks the k-mers STARTING in [a, b) of a strand; fn(pos_of_kmer_start, canonical_kmer) for
+// complete k-mers and fn_amb(pos) where the window *ending* at an ambiguous base starts.
+// Equivalent to one walk over the whole strand restricted to those starts: the run counter and
+// both hashes only depend on the last 11 bases.
 template <class F, class G>
-void walk_kmers(const StrandView &v, F fn, G fn_amb) {
+void walk_kmers(const StrandView &v, uint32_t a, uint32_t b, F fn, G fn_amb) {
   const uint64_t m = (1ull << (2 * kMaskK)) - 1, shift = 2ull * (kMaskK - 1);
   uint64_t fw = 0, rv = 0;
   int run = 0;
-  for (uint32_t p = 0; p < v.len; ++p) {
-    int c = sb::base_code(v.s[p]);
+  const uint64_t end = std::min<uint64_t>(v.len, (uint64_t)b + kMaskK - 1);
+  for (uint64_t p = a; p < end; ++p) {
+    const int c = kCode(v.s[p]);
     if (c >= 0) {
       fw = ((fw << 2) | (uint64_t)c) & m;
       rv = (rv >> 2) | ((uint64_t)(3 ^ c) << shift);
-      if (++run >= kMaskK) fn(p + 1 - kMaskK, fw < rv ? fw : rv);
+      if (++run >= kMaskK) fn((uint32_t)(p + 1 - kMaskK), fw < rv ? fw : rv);
     } else {
       run = 0;
       fw = rv = 0;
-      if (p >= (uint32_t)kMaskK - 1) fn_amb(p + 1 - kMaskK);
+      if (p >= (uint64_t)a + kMaskK - 1) fn_amb((uint32_t)(p + 1 - kMaskK));
     }
   }
 }
 
-}  // namespace
-
-extern "C" size_t smbh_build_point_cloud(const char *const *seqs, const uint32_t *lengths,
-                                         uint32_t n, const float *level_mean, uint64_t *pos,
-                                         float *val) {
+size_t build_cloud(const char *const *seqs, const uint32_t *lengths, uint32_t n, const float *level_mean,
+                   uint64_t *pos, float *val) {
   // k-mer census over the + strands (canonical, so the - strand adds nothing new)
   std::vector<uint32_t> hist((size_t)1 << (2 * kMaskK), 0);
+  uint32_t *H = hist.data();
   uint64_t total = 0;
   for (uint32_t s = 0; s < n; ++s) {
-    StrandView v = make_strand(seqs[s], lengths[s], 0);
-    walk_kmers(v, [&](uint32_t, uint64_t k) { ++hist[k]; ++total; }, [](uint32_t) {});
+    StrandView v;
+    make_strand(v, seqs[s], lengths[s], 0);
+    uint64_t part = 0;
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : part)
+    for (int64_t a = 0; a < (int64_t)v.len; a += kChunk) {
+      uint64_t mine = 0;
+      walk_kmers(v, (uint32_t)a, (uint32_t)std::min<int64_t>(v.len, a + kChunk),
+                 [&](uint32_t, uint64_t k) {
+#pragma omp atomic
+                   ++H[k];
+                   ++mine;
+                 },
+                 [](uint32_t) {});
+      part += mine;
+    }
+    total += part;
   }
   size_t count = 0;
   bool any = false;
   float last = 0;
   std::vector<float> z;
   std::vector<unsigned char> masked;
+  StrandView v;
   for (int strand = 0; strand < 2; ++strand) {
     for (uint32_t s = 0; s < n; ++s) {
       if (lengths[s] < (uint32_t)kMaskK) continue;
-      StrandView v = make_strand(seqs[s], lengths[s], strand);
+      make_strand(v, seqs[s], lengths[s], strand);
       expected_levels(v, level_mean, z);
       znormalise(z);
-      masked.assign(v.len - kMaskK + 1, 0);
-      walk_kmers(
-          v,
-          [&](uint32_t p, uint64_t k) { masked[p] = ((float)hist[k] / (float)total) > kMaskFreq; },
-          [&](uint32_t p) { masked[p] = 1; });
+      const uint32_t n_starts = v.len - kMaskK + 1;
+      masked.assign(n_starts, 0);
+      unsigned char *M = masked.data();
+#pragma omp parallel for schedule(dynamic, 1)
+      for (int64_t a = 0; a < (int64_t)n_starts; a += kChunk)
+        walk_kmers(
+            v, (uint32_t)a, (uint32_t)std::min<int64_t>(n_starts, a + kChunk),
+            [&](uint32_t p, uint64_t k) { M[p] = ((float)H[k] / (float)total) > kMaskFreq; },
+            [&](uint32_t p) { M[p] = 1; });
       const uint32_t n_windows = (uint32_t)z.size() - SMB_DIM + 1;
       for (uint32_t p = 0; p < n_windows; ++p) {
         if (masked[p]) continue;
@@ -142,4 +192,36 @@ extern "C" size_t smbh_build_point_cloud(const char *const *seqs, const uint32_t
     }
   }
   return count;
+}
+
+}  // namespace
+
+extern "C" size_t smbh_build_point_cloud(const char *const *seqs, const uint32_t *lengths,
+                                         uint32_t n, const float *level_mean, uint64_t *pos,
+                                         float *val) {
+  return build_cloud(seqs, lengths, n, level_mean, pos, val);
+}
+
+// One pass instead of count + fill: the arrays are allocated at the upper bound (one point per
+// window; untouched pages cost nothing) and trimmed.  Release with smbh_free.
+extern "C" int smbh_build_point_cloud_alloc(const char *const *seqs, const uint32_t *lengths, uint32_t n,
+                                            const float *level_mean, uint64_t **pos, float **val,
+                                            size_t *count) {
+  size_t upper = 1;
+  for (uint32_t s = 0; s < n; ++s)
+    if (lengths[s] >= (uint32_t)kMaskK) upper += 2 * (size_t)(lengths[s] - kMaskK + 1);
+  uint64_t *P = (uint64_t *)malloc(upper * sizeof(uint64_t));
+  float *V = (float *)malloc(upper * sizeof(float));
+  if (!P || !V) {
+    free(P);
+    free(V);
+    return SMB_ERR_IO;
+  }
+  const size_t c = build_cloud(seqs, lengths, n, level_mean, P, V);
+  uint64_t *P2 = (uint64_t *)realloc(P, std::max<size_t>(c, 1) * sizeof(uint64_t));
+  float *V2 = (float *)realloc(V, std::max<size_t>(c, 1) * sizeof(float));
+  *pos = P2 ? P2 : P;
+  *val = V2 ? V2 : V;
+  *count = c;
+  return SMB_OK;
 }

@@ -166,13 +166,16 @@ int build_index(const Args &a) {
   if (smbh_pore_model_load(a.model.c_str(), mean.data(), stdv.data())) die("Cannot load pore model!");
   smbh_fasta fa;
   if (smbh_fasta_load(a.ref.c_str(), &fa)) die("Cannot find sequence file!");
-  size_t n = smbh_build_point_cloud(fa.seqs, fa.lengths, fa.n, mean.data(), nullptr, nullptr);
-  std::vector<uint64_t> pos(n);
-  std::vector<float> val(n);
-  smbh_build_point_cloud(fa.seqs, fa.lengths, fa.n, mean.data(), pos.data(), val.data());
+  uint64_t *pos = nullptr;
+  float *val = nullptr;
+  size_t n = 0;
+  if (smbh_build_point_cloud_alloc(fa.seqs, fa.lengths, fa.n, mean.data(), &pos, &val, &n))
+    die("Out of memory while collecting points!");
   fprintf(stderr, "Collected %zu points.\n", n);
-  if (smbh_pt_write(a.output.c_str(), pos.data(), val.data(), n, a.dimension, a.max_leaf))
+  if (smbh_pt_write(a.output.c_str(), pos, val, n, a.dimension, a.max_leaf))
     die("Cannot write index file!");
+  smbh_free(pos);
+  smbh_free(val);
   smbh_fasta_free(&fa);
   fprintf(stderr, "Built index successfully in %fs.\n", now() - t0);
   return 0;

@@ -135,12 +135,16 @@ def sim_reads(seed, ref, n_reads, first_read=0, min_bases=2000, max_bases=9000, 
 
 def build_point_cloud(ref, level_mean):
     """Reference -> (pos uint64[n], val float32[n]) = the content of the reference's .pt."""
-    n = F.lib.smbh_build_point_cloud(ref.seq_ptrs, F.ptr(ref.lengths, F.u32p), ref.n,
-                                     F.ptr(level_mean, F.f32p), None, None)
-    pos = np.zeros(n, np.uint64)
-    val = np.zeros(n, np.float32)
-    F.lib.smbh_build_point_cloud(ref.seq_ptrs, F.ptr(ref.lengths, F.u32p), ref.n,
-                                 F.ptr(level_mean, F.f32p), F.ptr(pos, F.u64p), F.ptr(val, F.f32p))
+    pp, vp, n = F.u64p(), F.f32p(), C.c_size_t()
+    _check(F.lib.smbh_build_point_cloud_alloc(ref.seq_ptrs, F.ptr(ref.lengths, F.u32p), ref.n,
+                                              F.ptr(level_mean, F.f32p), C.byref(pp), C.byref(vp),
+                                              C.byref(n)), "smbh_build_point_cloud_alloc")
+    try:
+        pos = np.ctypeslib.as_array(pp, (max(n.value, 1),))[:n.value].copy()
+        val = np.ctypeslib.as_array(vp, (max(n.value, 1),))[:n.value].copy()
+    finally:
+        F.lib.smbh_free(pp)
+        F.lib.smbh_free(vp)
     return pos, val
 
 
