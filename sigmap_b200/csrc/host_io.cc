@@ -6,6 +6,10 @@
 //   pore model  pore_model.cc:11-47      .pt   spatial_index.cc:105-147
 //   FASTA       sequence_batch.cc (kseq) BLOW5 slow5lib 0.2.0 (extern/slow5lib/src/slow5.c)
 //   PAF         output_tools.h:200-210,336-354 + sigmap.cc:731-745
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <zlib.h>
 
 #include <cstdio>
@@ -301,94 +305,118 @@ static bool inflate_all(const unsigned char *src, size_t n, std::vector<unsigned
   return ret == Z_STREAM_END;
 }
 
+// The file is mapped, the record boundaries are found in one sequential walk over the 8-byte
+// length prefixes, and everything per record -- inflating zlib records, parsing the header,
+// copying the samples to their final place -- runs on all host cores.  The raw samples are
+// copied exactly once, into an array sized from the record headers.
 int smbh_blow5_read(const char *path, smbh_reads *out) {
-  FILE *f = fopen(path, "rb");
-  if (!f) return SMB_ERR_IO;
-  unsigned char head[68];
-  if (fread(head, 1, 68, f) != 68 || memcmp(head, "BLOW5\1", 6) != 0) {
-    fclose(f);
+  const int fd = open(path, O_RDONLY);
+  if (fd < 0) return SMB_ERR_IO;
+  struct stat st;
+  if (fstat(fd, &st) != 0 || st.st_size < 68) {
+    close(fd);
     return SMB_ERR_IO;
   }
-  int method = head[9];
+  const size_t fsize = (size_t)st.st_size;
+  void *map = mmap(nullptr, fsize, PROT_READ, MAP_PRIVATE, fd, 0);
+  close(fd);
+  if (map == MAP_FAILED) return SMB_ERR_IO;
+  const unsigned char *base = static_cast<const unsigned char *>(map);
+  struct Unmap {
+    void *p;
+    size_t n;
+    ~Unmap() { munmap(p, n); }
+  } unmap{map, fsize};
+  if (memcmp(base, "BLOW5\1", 6) != 0) return SMB_ERR_IO;
+  const int method = base[9];
   uint32_t hl;
-  memcpy(&hl, head + 64, 4);
-  if (method > 1 || fseek(f, hl, SEEK_CUR) != 0) {
-    fclose(f);
-    return SMB_ERR_IO;
-  }
-  std::vector<std::string> names;
-  std::vector<int16_t> raw;
-  std::vector<uint64_t> offs;
-  std::vector<float> dig, rng, off;
-  std::vector<unsigned char> rec, plain;
+  memcpy(&hl, base + 64, 4);
+  if (method > 1 || (size_t)68 + hl > fsize) return SMB_ERR_IO;
+
+  // ---- record boundaries
+  std::vector<size_t> rec_at;
+  std::vector<uint64_t> rec_len;
+  size_t at = (size_t)68 + hl;
   for (;;) {
-    unsigned char lenb[8];
-    size_t got = fread(lenb, 1, 5, f);
-    if (got == 5 && memcmp(lenb, "5WOLB", 5) == 0) {
-      int c = fgetc(f);
-      if (c == EOF) break;
-      ungetc(c, f);
-    }
-    if (got != 5 || fread(lenb + 5, 1, 3, f) != 3) {
-      fclose(f);
-      return SMB_ERR_IO;  // truncated (no EOF marker)
-    }
+    if (at + 5 <= fsize && memcmp(base + at, "5WOLB", 5) == 0 && at + 5 == fsize) break;  // EOF marker
+    if (at + 8 > fsize) return SMB_ERR_IO;  // truncated (no EOF marker)
     uint64_t rl;
-    memcpy(&rl, lenb, 8);
-    rec.resize(rl);
-    if (fread(rec.data(), 1, rl, f) != rl) {
-      fclose(f);
-      return SMB_ERR_IO;
-    }
-    const unsigned char *p = rec.data();
-    size_t pn = rec.size();
+    memcpy(&rl, base + at, 8);
+    if (rl > fsize - at - 8) return SMB_ERR_IO;
+    rec_at.push_back(at + 8);
+    rec_len.push_back(rl);
+    at += 8 + rl;
+  }
+  const size_t nrec = rec_at.size();
+
+  // ---- per record: plain bytes (inflated when needed) and the header fields
+  std::vector<std::vector<unsigned char>> plain(method == 1 ? nrec : 0);
+  std::vector<const unsigned char *> body(nrec, nullptr);  // first sample
+  std::vector<const unsigned char *> name_at(nrec, nullptr);
+  std::vector<uint16_t> name_len(nrec, 0);
+  std::vector<uint64_t> ns(nrec, 0);
+  std::vector<float> dig(nrec), rng(nrec), off(nrec);
+  int bad = 0;
+#pragma omp parallel for schedule(dynamic, 16) reduction(| : bad)
+  for (int64_t i = 0; i < (int64_t)nrec; ++i) {
+    const unsigned char *p = base + rec_at[i];
+    size_t pn = rec_len[i];
     if (method == 1) {
-      if (!inflate_all(rec.data(), rec.size(), plain)) {
-        fclose(f);
-        return SMB_ERR_IO;
+      if (!inflate_all(p, pn, plain[i])) {
+        bad |= 1;
+        continue;
       }
-      p = plain.data();
-      pn = plain.size();
+      p = plain[i].data();
+      pn = plain[i].size();
     }
-    if (pn < 2) { fclose(f); return SMB_ERR_IO; }
+    if (pn < 2) { bad |= 1; continue; }
     uint16_t idl;
     memcpy(&idl, p, 2);
-    if (pn < (size_t)2 + idl + 4 + 32 + 8) { fclose(f); return SMB_ERR_IO; }
-    names.emplace_back((const char *)p + 2, idl);
+    if (pn < (size_t)2 + idl + 4 + 32 + 8) { bad |= 1; continue; }
     const unsigned char *q = p + 2 + idl + 4;
     double d4[4];
     memcpy(d4, q, 32);
-    uint64_t ns;
-    memcpy(&ns, q + 32, 8);
-    if (pn < (size_t)2 + idl + 4 + 32 + 8 + 2 * ns) { fclose(f); return SMB_ERR_IO; }
+    uint64_t n;
+    memcpy(&n, q + 32, 8);
+    if (n > (pn - ((size_t)2 + idl + 4 + 32 + 8)) / 2) { bad |= 1; continue; }
+    name_at[i] = p + 2;
+    name_len[i] = idl;
     // signal_batch.cc:187-191 narrows the doubles to float
-    dig.push_back((float)d4[0]);
-    off.push_back((float)d4[1]);
-    rng.push_back((float)d4[2]);
-    offs.push_back(raw.size());
-    size_t base = raw.size();
-    raw.resize(base + ns);
-    memcpy(raw.data() + base, q + 40, 2 * ns);
+    dig[i] = (float)d4[0];
+    off[i] = (float)d4[1];
+    rng[i] = (float)d4[2];
+    ns[i] = n;
+    body[i] = q + 40;
   }
-  fclose(f);
-  // append to *out
-  size_t n0 = out->n, n1 = n0 + names.size();
-  uint64_t s0 = n0 ? out->read_off[n0] : 0;
+  if (bad) return SMB_ERR_IO;
+
+  // ---- append to *out
+  const size_t n0 = out->n, n1 = n0 + nrec;
+  const uint64_t s0 = n0 ? out->read_off[n0] : 0;
+  uint64_t added = 0;
+  for (size_t i = 0; i < nrec; ++i) added += ns[i];
   out->names = (char **)realloc(out->names, (n1 + 1) * sizeof(char *));
   out->read_off = (uint64_t *)realloc(out->read_off, (n1 + 1) * sizeof(uint64_t));
   out->digitisation = (float *)realloc(out->digitisation, (n1 + 1) * sizeof(float));
   out->range = (float *)realloc(out->range, (n1 + 1) * sizeof(float));
   out->offset = (float *)realloc(out->offset, (n1 + 1) * sizeof(float));
-  out->raw = (int16_t *)realloc(out->raw, (s0 + raw.size() + 1) * sizeof(int16_t));
-  memcpy(out->raw + s0, raw.data(), raw.size() * sizeof(int16_t));
-  for (size_t i = 0; i < names.size(); ++i) {
-    out->names[n0 + i] = strdup(names[i].c_str());
-    out->read_off[n0 + i] = s0 + offs[i];
+  out->raw = (int16_t *)realloc(out->raw, (s0 + added + 1) * sizeof(int16_t));
+  if (!out->names || !out->read_off || !out->digitisation || !out->range || !out->offset || !out->raw)
+    return SMB_ERR_IO;
+  uint64_t run = s0;
+  for (size_t i = 0; i < nrec; ++i) {
+    out->read_off[n0 + i] = run;
+    run += ns[i];
+  }
+  out->read_off[n1] = run;
+#pragma omp parallel for schedule(dynamic, 16)
+  for (int64_t i = 0; i < (int64_t)nrec; ++i) {
+    memcpy(out->raw + out->read_off[n0 + i], body[i], 2 * ns[i]);
+    out->names[n0 + i] = strndup((const char *)name_at[i], name_len[i]);
     out->digitisation[n0 + i] = dig[i];
     out->range[n0 + i] = rng[i];
     out->offset[n0 + i] = off[i];
   }
-  out->read_off[n1] = s0 + raw.size();
   out->n = n1;
   return SMB_OK;
 }

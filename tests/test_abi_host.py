@@ -111,6 +111,58 @@ def test_blow5_round_trip_and_reference_reader(host, model, ref, tmp_path):
     assert np.array_equal(part.truth, reads.truth[3:])
 
 
+def test_blow5_zlib_records_truncation_and_append(host, model, tmp_path):
+    """zlib-compressed records (slow5lib's default) read like plain ones; a truncated file is an
+    error, not a short read set; reading a second file appends."""
+    import struct
+    import zlib
+    g = host.sim_reference(4, [30000])
+    reads = host.sim_reads(11, g, 7, min_bases=300, max_bases=900, model=model)
+    plain = str(tmp_path / "plain.blow5")
+    reads.write_blow5(plain)
+    data = open(plain, "rb").read()
+    hdr_len = struct.unpack_from("<I", data, 64)[0]
+    at, recs = 68 + hdr_len, []
+    while data[at:at + 5] != b"5WOLB" or at + 5 != len(data):
+        n = struct.unpack_from("<Q", data, at)[0]
+        recs.append(data[at + 8:at + 8 + n])
+        at += 8 + n
+    assert len(recs) == reads.n
+    head = bytearray(data[:68 + hdr_len])
+    head[9] = 1  # record compression: zlib
+    packed = str(tmp_path / "zlib.blow5")
+    with open(packed, "wb") as f:
+        f.write(head)
+        for r in recs:
+            c = zlib.compress(r)
+            f.write(struct.pack("<Q", len(c)) + c)
+        f.write(b"5WOLB")
+    back = host.ReadSet.read_blow5(packed)
+    assert back.names == reads.names and np.array_equal(back.raw, reads.raw)
+    assert np.array_equal(back.read_off, reads.read_off)
+    assert np.array_equal(bits(back.offset), bits(reads.offset))
+    # truncated: no EOF marker / cut inside a record
+    for cut in (len(data) - 5, len(data) - 400):
+        bad = str(tmp_path / f"cut{cut}.blow5")
+        open(bad, "wb").write(data[:cut])
+        with pytest.raises(Exception):
+            host.ReadSet.read_blow5(bad)
+    # appending two files through the C ABI (what the CLI does for a signal directory)
+    from sigmap_b200 import _ffi as F
+    import ctypes as C
+    r = F.Reads()
+    assert F.lib.smbh_blow5_read(plain.encode(), C.byref(r)) == 0
+    assert F.lib.smbh_blow5_read(packed.encode(), C.byref(r)) == 0
+    try:
+        assert r.n == 2 * reads.n
+        off = np.ctypeslib.as_array(r.read_off, (r.n + 1,))
+        raw = np.ctypeslib.as_array(r.raw, (int(off[-1]),))
+        assert np.array_equal(raw, np.concatenate([reads.raw, reads.raw]))
+        assert [r.names[i].decode() for i in range(r.n)] == reads.names * 2
+    finally:
+        F.lib.smbh_reads_free(C.byref(r))
+
+
 def test_format_paf_rows(host):
     from sigmap_b200 import _ffi
     m = _ffi.Mapping(mapped=1, read_len=22979, q_start=58, q_end=432, strand_plus=1, contig=0,
