@@ -77,36 +77,68 @@ int smbh_fasta_load(const char *path, smbh_fasta *out) {
   gzFile f = gzopen(path, "r");
   if (!f) return SMB_ERR_IO;
   std::vector<std::string> names, seqs;
-  std::vector<char> buf(1 << 20);
-  std::string cur_line;
-  bool in_seq = false;
-  auto handle_line = [&](const std::string &l) {
-    if (l.empty()) return;
-    if (l[0] == '>') {
-      size_t e = 1;
-      while (e < l.size() && l[e] != ' ' && l[e] != '\t') ++e;  // kseq: name ends at whitespace
-      names.push_back(l.substr(1, e - 1));
-      seqs.emplace_back();
-      in_seq = true;
-    } else if (in_seq) {
-      std::string &s = seqs.back();
-      for (char c : l)
-        if (c > ' ') s.push_back(c);
+  std::vector<char> buf(4 << 20);
+  // Line-wise over whole buffer segments (memchr + append) rather than byte by byte.  '\n' and
+  // '\r' both end a line, a '>' at a line start opens a record whose name ends at the first
+  // whitespace (kseq), every byte <= ' ' inside sequence lines is dropped, text before the first
+  // header is ignored.
+  std::string header;
+  bool at_line_start = true, in_header = false, in_seq = false;
+  auto finish_header = [&]() {
+    size_t e = 0;
+    while (e < header.size() && (unsigned char)header[e] > ' ') ++e;
+    names.push_back(header.substr(0, e));
+    seqs.emplace_back();
+    in_seq = true;
+    in_header = false;
+  };
+  auto append_bases = [&](const char *p, size_t n) {
+    std::string &s = seqs.back();
+    bool clean = true;
+    for (size_t k = 0; k < n; ++k) clean &= (unsigned char)p[k] > ' ';
+    if (clean) {
+      s.append(p, n);
+    } else {
+      for (size_t k = 0; k < n; ++k)
+        if ((unsigned char)p[k] > ' ') s.push_back(p[k]);
     }
   };
   int got;
   while ((got = gzread(f, buf.data(), (unsigned)buf.size())) > 0) {
-    for (int i = 0; i < got; ++i) {
-      char c = buf[i];
-      if (c == '\n' || c == '\r') {
-        handle_line(cur_line);
-        cur_line.clear();
+    const char *b = buf.data();
+    size_t i = 0;
+    const size_t n = (size_t)got;
+    while (i < n) {
+      if (at_line_start) {
+        at_line_start = false;
+        if (b[i] == '\n' || b[i] == '\r') {  // empty line
+          at_line_start = true;
+          ++i;
+          continue;
+        }
+        if (b[i] == '>') {
+          in_header = true;
+          header.clear();
+          ++i;
+          continue;
+        }
+      }
+      const char *nl = (const char *)memchr(b + i, '\n', n - i);
+      size_t e = nl ? (size_t)(nl - b) : n;
+      const char *cr = (const char *)memchr(b + i, '\r', e - i);
+      if (cr) e = (size_t)(cr - b);
+      if (in_header) header.append(b + i, e - i);
+      else if (in_seq) append_bases(b + i, e - i);
+      if (e < n) {  // a line terminator at e
+        if (in_header) finish_header();
+        at_line_start = true;
+        i = e + 1;
       } else {
-        cur_line.push_back(c);
+        i = e;
       }
     }
   }
-  handle_line(cur_line);
+  if (in_header) finish_header();
   gzclose(f);
   // sequence_batch.cc:22-25: zero-length records are skipped
   std::vector<size_t> keep;
