@@ -397,10 +397,12 @@ def main():
     alg_bytes = (24.0 * st["queries"] + 44.0 * st["hits"]) / L   # SURVEY.md 8(d) per-unit figures
     dur_s = st["ms_search"] / 1000.0 / L
     achieved = alg_bytes / dur_s / 1e9 if dur_s > 0 else 0.0
-    traffic = None
+    traffic, ncu_note = None, None
     tpath = os.path.join(ROOT, "profiles", "search_traffic.json")
-    if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+    if os.path.exists(tpath):  # one ncu --set full capture of a whole step (tools/gpu_traffic.sh)
+        tj = json.load(open(tpath))
+        traffic = tj.get("dram_bytes_per_launch")
+        ncu_note = {"limiter": tj.get("limiter"), **(tj.get("ncu") or {})}
     pipeline_bytes = (2.0 * st["samples"] + 8.0 * st["events"] + 24.0 * st["queries"] +
                       44.0 * st["hits"] + 44.0 * st["anchors"])
 
@@ -423,7 +425,8 @@ def main():
         "roofline": {"bound": "hbm", "kernel": "k_radius_search", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
-                     "avg_launch_ms": dur_s * 1000.0, "launches": int(st["search_launches"])},
+                     "avg_launch_ms": dur_s * 1000.0, "launches": int(st["search_launches"]),
+                     "ncu": ncu_note},
         "pipeline": {"algorithmic_GBps": pipeline_bytes / (ms / 1000.0) / 1e9 / max(world, 1),
                      "frac_of_hbm": pipeline_bytes / (ms / 1000.0) / 1e9 / max(world, 1) / peak,
                      "kernel_ms_per_step": {k: st[k] / max(args.steps, 1) for k in
