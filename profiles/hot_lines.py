@@ -68,7 +68,20 @@ def main():
     top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
     name, ix, rows = sass_rows(rep, kernel, launch)
     base = re.sub(r"\(.*", "", name).split("::")[-1].split("<")[0]
-    tmpl = "ILb1" if "(bool)1" in name else ("ILb0" if "(bool)0" in name else "")
+    # template arguments -> their Itanium mangling, e.g. <(bool)0, (bool)1> -> ILb0ELb1EE,
+    # <(int)5120, (int)512, (int)4096> -> ILi5120ELi512ELi4096EE: picks the right instantiation
+    tmpl = ""
+    m = re.search(re.escape(base) + r"<([^>]*)>", name)
+    if m:
+        parts = []
+        for a in m.group(1).split(","):
+            k = re.match(r"\s*\((bool|int|unsigned int)\)(-?\d+)", a)
+            if not k:
+                parts = None
+                break
+            parts.append({"bool": "Lb", "int": "Li", "unsigned int": "Lj"}[k.group(1)] + k.group(2))
+        if parts:
+            tmpl = "I" + "E".join(parts) + "EE"
     table = line_table(lambda l: base in l and tmpl in l)
     if len(table) != len(rows):
         print(f"# warning: {len(rows)} SASS rows in the report vs {len(table)} in the cubin "
