@@ -266,7 +266,15 @@ __device__ __forceinline__ uint32_t find_entry(const uint32_t *__restrict__ q_of
 // as the stack below has room for the 64 children of a step (else on the lowest one, whose child
 // stack is empty), so every level is consumed in full groups of eight nodes with at most one
 // partial group per level -- measured on the 4.6 Mbp index: 17.9 steps per query instead of 21.1.
-template <bool STAGE, bool BFS = false>
+//
+// BOX16 = true (experimental, SMB_BOX=half): the box test itself runs in packed binary16 -- two
+// dimensions per instruction, no unpacking of the stored corners.  It stays conservative through a
+// per-query threshold: with qh = round16(q) (|qh - q| <= 2^-11 |q|) every per-dimension distance
+// computed in binary16 is at most (T_d + 2^-11 |q_d|)(1 + 2^-11) where T_d is the exact distance
+// to the stored box, so a box within r of q gives a sum of squares of at most
+// (r + 2^-11 |q|_2)^2 (1 + 2^-11)^8; anything above that is pruned.  Overflow gives +inf (pruned,
+// correctly: such a box is farther than 65504 - |q|), inf - inf gives NaN, which max() drops.
+template <bool STAGE, bool BFS = false, bool BOX16 = false>
 __global__ void __launch_bounds__(kSearchWarps * 32, 4)
 k_radius_search(const IndexView ix, const SearchArgs a) {
   extern __shared__ __align__(16) unsigned char s_dyn[];
@@ -411,6 +419,18 @@ k_radius_search(const IndexView ix, const SearchArgs a) {
         for (int d = 0; d < kDim; ++d) q[d] = __ldg(f + d);
         qk = a.key.pack(entry, 0u, 0u, p + ev_off);
       }
+      __half2 qh01, qh23, qh45;
+      float theta16 = 0.0f;
+      if (BOX16) {
+        qh01 = __floats2half2_rn(q[0], q[1]);
+        qh23 = __floats2half2_rn(q[2], q[3]);
+        qh45 = __floats2half2_rn(q[4], q[5]);
+        float qq = 0.0f;
+#pragma unroll
+        for (int d = 0; d < kDim; ++d) qq = __fmaf_rn(q[d], q[d], qq);
+        const float reach = sqrtf(r2) + 4.8828125e-4f * sqrtf(qq) * 1.001f;  // r + 2^-11 |q|_2
+        theta16 = reach * reach * 1.0045f;                                   // (1 + 2^-11)^8 < 1.004
+      }
       uint32_t qhits = 0;
       bool capped = false;
       // L = lowest level with nodes waiting (n_levels when none), c = how many wait there
@@ -497,7 +517,21 @@ k_radius_search(const IndexView ix, const SearchArgs a) {
           // boxes only prune (stored rounded outwards, tested with slack), so this distance may
           // use FMA; the accept test may not
           float sa = 0.0f, sb = 0.0f;
-          {
+          if (BOX16) {
+            const __half2 zero = __float2half2_rn(0.0f);
+            auto as_h2 = [](uint32_t v) { return *reinterpret_cast<const __half2 *>(&v); };
+            auto box_d2 = [&](const uint2 r0, const uint2 r1, const uint2 r2_) -> float {
+              const __half2 t01 = __hmax2(__hmax2(__hsub2(as_h2(r0.x), qh01), __hsub2(qh01, as_h2(r1.y))), zero);
+              const __half2 t23 = __hmax2(__hmax2(__hsub2(as_h2(r0.y), qh23), __hsub2(qh23, as_h2(r2_.x))), zero);
+              const __half2 t45 = __hmax2(__hmax2(__hsub2(as_h2(r1.x), qh45), __hsub2(qh45, as_h2(r2_.y))), zero);
+              __half2 acc = __hmul2(t01, t01);
+              acc = __hfma2(t23, t23, acc);
+              acc = __hfma2(t45, t45, acc);
+              return __low2float(acc) + __high2float(acc);
+            };
+            sa = box_d2(a0, a1, a2);
+            sb = box_d2(b0, b1, b2);
+          } else {
             const float2 l01 = unpack_h2(a0.x), l23 = unpack_h2(a0.y), l45 = unpack_h2(a1.x);
             const float2 h01 = unpack_h2(a1.y), h23 = unpack_h2(a2.x), h45 = unpack_h2(a2.y);
             const float lo[kDim] = {l01.x, l01.y, l23.x, l23.y, l45.x, l45.y};
@@ -508,7 +542,7 @@ k_radius_search(const IndexView ix, const SearchArgs a) {
               sa = __fmaf_rn(t, t, sa);
             }
           }
-          {
+          if (!BOX16) {
             const float2 l01 = unpack_h2(b0.x), l23 = unpack_h2(b0.y), l45 = unpack_h2(b1.x);
             const float2 h01 = unpack_h2(b1.y), h23 = unpack_h2(b2.x), h45 = unpack_h2(b2.y);
             const float lo[kDim] = {l01.x, l01.y, l23.x, l23.y, l45.x, l45.y};
@@ -519,8 +553,9 @@ k_radius_search(const IndexView ix, const SearchArgs a) {
               sb = __fmaf_rn(t, t, sb);
             }
           }
-          const uint32_t mA = __ballot_sync(full, hasA && sa <= r2_prune);
-          const uint32_t mB = __ballot_sync(full, hasB && sb <= r2_prune);
+          const float prune_at = BOX16 ? theta16 : r2_prune;
+          const uint32_t mA = __ballot_sync(full, hasA && sa <= prune_at);
+          const uint32_t mB = __ballot_sync(full, hasB && sb <= prune_at);
           const int nA = __popc(mA), nB = __popc(mB);
           if (BFS) {
             if (L > 0) {

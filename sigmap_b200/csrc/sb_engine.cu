@@ -241,6 +241,7 @@ struct smb_ctx {
   bool part_sort = true;          // SMB_SORT=entry: always the one-CTA-per-entry sort (k_seg_sort)
   bool seg_sort = true;           // per-entry shared-memory sort; SMB_SORT=global forces the radix sort
   uint32_t search_grab = 0;       // SMB_GRAB=n: queries per grab of the search work counter (0 = default)
+  bool search_box16 = false;      // SMB_BOX=half: experimental packed-binary16 box test (k_index.cuh), BFS only
   bool search_bfs = true;         // level-order traversal (fuller 8-node steps); SMB_SEARCH=dfs: depth-first
   bool sort_small = false;        // SMB_SORT=small: two 100 KB sort CTAs per SM instead of one 200 KB CTA
   cudaStream_t stream_ev = nullptr;  // lookahead event blocks run here, next to the mapping rounds
@@ -326,10 +327,10 @@ static int fail(smb_ctx *ctx, int code, const std::string &msg) {
 // persistent grid of the search kernel: every CTA that fits on the device, no more
 static size_t search_smem(const smb_ctx *ctx) { return kSearchWarps * search_smem_per_warp(ctx->ix.n_levels); }
 
-template <bool STAGE, bool BFS = false>
+template <bool STAGE, bool BFS = false, bool BOX16 = false>
 static unsigned search_grid(smb_ctx *ctx) {
   int n = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_radius_search<STAGE, BFS>, kSearchWarps * 32,
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_radius_search<STAGE, BFS, BOX16>, kSearchWarps * 32,
                                                     search_smem(ctx)) != cudaSuccess || n < 1)
     n = 4;
   int n_sm = 148;
@@ -706,7 +707,9 @@ static int run_step(smb_ctx *ctx, SlotSpace &sp, const StepEntries &en, StepSour
   sa.bucket_base = ctx->bucket_base.p;
   sa.grab = ctx->search_grab;
   CK(cudaEventRecord(ctx->ev[2], s));
-  if (ctx->search_bfs)
+  if (ctx->search_bfs && ctx->search_box16)
+    k_radius_search<false, true, true><<<ctx->search_grid_main, kSearchWarps * 32, search_smem(ctx), s>>>(ctx->ix, sa);
+  else if (ctx->search_bfs)
     k_radius_search<false, true><<<ctx->search_grid_main, kSearchWarps * 32, search_smem(ctx), s>>>(ctx->ix, sa);
   else
     k_radius_search<false, false><<<ctx->search_grid_main, kSearchWarps * 32, search_smem(ctx), s>>>(ctx->ix, sa);
@@ -1237,6 +1240,7 @@ int smb_create(smb_ctx **out, int device) {
     ctx->part_sort = strcmp(env, "entry") != 0 && !ctx->sort_small;
   }
   if (const char *env = getenv("SMB_SEARCH")) ctx->search_bfs = strcmp(env, "dfs") != 0;
+  if (const char *env = getenv("SMB_BOX")) ctx->search_box16 = strcmp(env, "half") == 0;
   if (const char *env = getenv("SMB_GRAB")) ctx->search_grab = (uint32_t)std::max(atoi(env), 0);
   if (const char *env = getenv("SMB_PART_FILL")) ctx->part_fill = atof(env);
   if (const char *env = getenv("SMB_PART")) ctx->part_small = strcmp(env, "small") == 0;
@@ -1815,7 +1819,9 @@ int smb_stage_radius(smb_ctx *ctx, const float *queries, size_t nq, float radius
   sa.out_dist = d_a.p;
   sa.cap = dcap;
   sa.ctr = ctx->d_ctr;
-  if (ctx->search_bfs)
+  if (ctx->search_bfs && ctx->search_box16)
+    k_radius_search<true, true, true><<<search_grid<true, true, true>(ctx), kSearchWarps * 32, search_smem(ctx), s>>>(ctx->ix, sa);
+  else if (ctx->search_bfs)
     k_radius_search<true, true><<<search_grid<true, true>(ctx), kSearchWarps * 32, search_smem(ctx), s>>>(ctx->ix, sa);
   else
     k_radius_search<true, false><<<search_grid<true, false>(ctx), kSearchWarps * 32, search_smem(ctx), s>>>(ctx->ix, sa);
