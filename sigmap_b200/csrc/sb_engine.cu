@@ -1229,6 +1229,18 @@ int smb_create(smb_ctx **out, int device) {
       (e = cudaFuncSetAttribute(k_seg_sort<kSortCapSmall, 512, 4096>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)sort_smem_bytes(kSortCapSmall, 4096))) != cudaSuccess)
     return bail("cudaFuncSetAttribute(k_seg_sort)", e);
+  // the search keeps one stack per index level in shared memory: from 7 levels on (> 16.7 M
+  // points, i.e. references beyond ~8 Mbp) a CTA needs more than the 48 KB a kernel gets by default
+  {
+    const int need = (int)(kSearchWarps * search_smem_per_warp(kMaxLevels));
+    if ((e = cudaFuncSetAttribute(k_radius_search<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, need)) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(k_radius_search<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, need)) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(k_radius_search<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, need)) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(k_radius_search<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, need)) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(k_radius_search<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, need)) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(k_radius_search<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, need)) != cudaSuccess)
+      return bail("cudaFuncSetAttribute(k_radius_search)", e);
+  }
   if ((e = cudaFuncSetAttribute(k_part_sort<kPartSortCap, 512, 4096>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)part_sort_smem_bytes(kPartSortCap, 4096))) != cudaSuccess ||
       (e = cudaFuncSetAttribute(k_part_sort<kPartSortCapSmall, 256, 2304>, cudaFuncAttributeMaxDynamicSharedMemorySize,
