@@ -294,6 +294,11 @@ def main():
     if args.impl == "reference":
         run_reference(args)
         return
+    # torchrun pins OMP_NUM_THREADS=1 in every worker; the host-side setup (simulator, point
+    # cloud) is OpenMP code and would crawl: give each rank its share of the cores instead
+    w_env = int(os.environ.get("WORLD_SIZE", "1"))
+    if w_env > 1 and os.environ.get("OMP_NUM_THREADS", "1") == "1":
+        os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // w_env))
     rank, world, local, dist = dist_setup(args.gpus)
     import torch
     from sigmap_b200.mapper import Mapper, default_params, full_read_params
