@@ -36,3 +36,5 @@ echo "== bench config 3 (12 Mbp x 16 contigs, 100 000 reads, default stop rules)
 ( timeout 600 python bench.py --ref-bp 12000000 --contigs 16 --reads 100000 --mode default --steps 1 --warmup 1 \
     --no-cpu-baseline --stream-rounds 0 ) > $OUT/bench_c3.json 2> $OUT/bench_c3.err
 summ $OUT/bench_c3.json; tail -2 $OUT/bench_c3.err
+echo "== CUDA vs oracle on noisy, multi-contig, spiked reads"
+( timeout 600 python tools/check_noisy_gpu.py ) > $OUT/noisy.log 2>&1; tail -3 $OUT/noisy.log
