@@ -232,15 +232,16 @@ class Mapper:
 
     def stream_round_arrays(self, channels, samples, off):
         """One round from pre-packed host arrays: channels u32[n], samples i16[off[n]], off u32[n+1]
-        -> (stop decisions u8[n], provisional rows).  This is the call whose duration is the
-        per-chunk latency of read-until mode (submit -> decision)."""
+        -> (stop decisions u8[n], provisional rows: a ctypes array of Mapping, rows [0, n) valid).
+        This is the call whose duration is the per-chunk latency of read-until mode
+        (submit -> decision), so nothing per-row happens on the Python side."""
         n = len(channels)
         dec = np.zeros(max(n, 1), np.uint8)
         maps = (F.Mapping * max(n, 1))()
         self._check(F.lib.smb_stream_round(self._ctx, F.ptr(channels, F.u32p), n,
                                            F.ptr(samples, F.i16p), F.ptr(off, F.u32p),
                                            F.ptr(dec, F.u8p), maps), "smb_stream_round")
-        return dec[:n].copy(), [maps[i] for i in range(n)]
+        return dec[:n], maps
 
     def stream_close(self):
         self._check(F.lib.smb_stream_close(self._ctx), "smb_stream_close")
