@@ -105,6 +105,9 @@ typedef struct smb_stats {
                               (the others fell back to the global radix sort) */
   uint64_t exchanges;      /* collectives issued by a contig-sharded run (0 otherwise) */
   uint64_t part_sort_steps; /* of seg_sort_steps: sorted one CTA per (entry, part) from pre-routed runs */
+  uint64_t overflow_queries; /* queries whose frontier outgrew the lean search kernel's slots and went
+                                through the general one (every query does with option search=general) */
+  uint64_t sync_points;     /* host waits on the device inside the mapping calls */
 } smb_stats;
 
 /* ------------------------------------------------------------------ context */
@@ -121,6 +124,13 @@ int smb_timer_start(smb_ctx *ctx);
 int smb_timer_stop(smb_ctx *ctx, double *ms);
 /* tuning: max chunks per pipeline step and anchor capacity per step (0 = keep default) */
 int smb_set_limits(smb_ctx *ctx, uint32_t max_batch_chunks, uint64_t max_batch_anchors);
+
+/* Run-time switches for A/B measurements and for tests that have to reach the fallback paths:
+ * name = an SMB_<NAME> environment variable without the prefix (smb_create reads those once),
+ * e.g. ("sort", "part|entry|small|global"), ("search", "lean|general"), ("front_cap", "72"),
+ * ("runs_cap", "64"), ("dp", "dynamic|static"), ("events", "auto|thread|warp").  Results never
+ * depend on them (every path is held to the same parity tests); only speed does. */
+int smb_set_option(smb_ctx *ctx, const char *name, const char *value);
 
 /* -------------------------------------------------------------------- index */
 /* Replaces SpatialIndex::Load (spatial_index.cc:132-163).  Reads <prefix>.pt (the point

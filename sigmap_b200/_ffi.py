@@ -113,6 +113,8 @@ class Stats(C.Structure):
         ("seg_sort_steps", C.c_uint64),
         ("exchanges", C.c_uint64),
         ("part_sort_steps", C.c_uint64),
+        ("overflow_queries", C.c_uint64),
+        ("sync_points", C.c_uint64),
     ]
 
 
@@ -144,6 +146,7 @@ PROTOTYPES = {
     "smb_timer_start": (C.c_int, [C.c_void_p]),
     "smb_timer_stop": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "smb_set_limits": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint64]),
+    "smb_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_char_p]),
     "smb_index_load": (C.c_int, [C.c_void_p, C.c_char_p]),
     "smb_index_set_points": (C.c_int, [C.c_void_p, u64p, f32p, C.c_size_t]),
     "smb_index_set_contigs": (C.c_int, [C.c_void_p, u32p, C.c_uint32]),

@@ -56,16 +56,17 @@ __global__ void k_morton(const float *__restrict__ val, uint64_t n_windows, floa
   widx[w] = (uint32_t)w;
 }
 
-// sorted rank i -> leaf arrays; one thread per slot of the padded leaf array
+// sorted rank i -> leaf records; one thread per slot of the padded leaf array
 __global__ void k_build_leaves(const float *__restrict__ val, const uint64_t *__restrict__ pos,
                                const uint32_t *__restrict__ order, uint64_t n_windows,
-                               uint32_t n_leaves, float2 *__restrict__ leaf_vals,
-                               uint2 *__restrict__ leaf_tb, uint32_t *__restrict__ leaf_widx,
+                               uint32_t n_leaves, uint2 *__restrict__ leaves,
+                               uint32_t *__restrict__ leaf_widx,
                                const uint32_t *__restrict__ wsrc, const uint32_t *__restrict__ worig) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (uint64_t)n_leaves * kLeaf) return;
   const uint32_t leaf = (uint32_t)(i / kLeaf), sub = (uint32_t)(i % kLeaf);
-  float2 *v = leaf_vals + (size_t)leaf * 3 * kLeaf + sub;
+  uint2 *rec = leaves + (size_t)leaf * kLeafRec + sub;
+  float2 *v = reinterpret_cast<float2 *>(rec);
   if (i < n_windows) {
     const uint32_t w = order[i];
     const uint64_t v0 = wsrc ? (uint64_t)wsrc[w] : (uint64_t)w;
@@ -73,12 +74,12 @@ __global__ void k_build_leaves(const float *__restrict__ val, const uint64_t *__
     for (int k = 0; k < 3; ++k) v[k * kLeaf] = make_float2(val[v0 + 2 * k], val[v0 + 2 * k + 1]);
     const uint64_t P = pos[w];
     // target = pos >> 1 (spatial_index.cc:380-381); bucket = contig*2 + strand
-    leaf_tb[i] = make_uint2((uint32_t)(P >> 1), (uint32_t)((P >> 33) << 1) | (uint32_t)(P & 1));
+    rec[3 * kLeaf] = make_uint2((uint32_t)(P >> 1), (uint32_t)((P >> 33) << 1) | (uint32_t)(P & 1));
     leaf_widx[i] = worig ? worig[w] : w;
   } else {
 #pragma unroll
     for (int k = 0; k < 3; ++k) v[k * kLeaf] = make_float2(kPadValue, kPadValue);
-    leaf_tb[i] = make_uint2(0u, 0xFFFFFFFFu);
+    rec[3 * kLeaf] = make_uint2(0u, 0xFFFFFFFFu);
     leaf_widx[i] = 0xFFFFFFFFu;
   }
 }
@@ -119,8 +120,8 @@ __device__ __forceinline__ void load_child_box(const uint2 *rec, int j, float *l
 }
 
 // level-0 nodes: thread (n, j) boxes leaf 8n + j
-__global__ void k_nodes_level0(const float2 *__restrict__ leaf_vals, const uint2 *__restrict__ leaf_tb,
-                               uint32_t n_leaves, uint32_t n_nodes, uint2 *__restrict__ nodes) {
+__global__ void k_nodes_level0(const uint2 *__restrict__ leaves, uint32_t n_leaves, uint32_t n_nodes,
+                               uint2 *__restrict__ nodes) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_nodes * kFan) return;
   const uint32_t n = t / kFan, j = t % kFan, leaf = t;
@@ -132,12 +133,14 @@ __global__ void k_nodes_level0(const float2 *__restrict__ leaf_vals, const uint2
   }
   bool real = false;
   if (leaf < n_leaves) {
+    const uint2 *rec = leaves + (size_t)leaf * kLeafRec;
     for (int p = 0; p < kLeaf; ++p) {
-      if (leaf_tb[(size_t)leaf * kLeaf + p].y == 0xFFFFFFFFu) continue;
+      if (rec[3 * kLeaf + p].y == 0xFFFFFFFFu) continue;
       real = true;
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
-        const float2 v = leaf_vals[((size_t)leaf * 3 + k) * kLeaf + p];
+        const uint2 raw = rec[k * kLeaf + p];
+        const float2 v = make_float2(__uint_as_float(raw.x), __uint_as_float(raw.y));
         lo[2 * k] = fminf(lo[2 * k], v.x);
         hi[2 * k] = fmaxf(hi[2 * k], v.x);
         lo[2 * k + 1] = fminf(lo[2 * k + 1], v.y);
@@ -179,18 +182,48 @@ __global__ void k_nodes_up(const uint2 *__restrict__ child, uint32_t n_child, ui
 }
 
 // ------------------------------------------------------------------ search
-constexpr int kSearchWarps = 8;          // warps per CTA
+//
+// Two kernels share the work of radiusSearch (spatial_index.cc:366):
+//
+//   k_search_lean     the fast path, one 1024-thread CTA per SM.  Queries arrive sorted by the
+//                     Morton code of the query point (k_query_keys + a radix sort), so the warps
+//                     in flight walk the same corner of the index and nodes / leaves come from
+//                     L1/L2 instead of DRAM.  The node levels every query walks (the prefix of
+//                     nodes[] that fits 64 KB) are staged in shared memory with one TMA bulk copy
+//                     (cp.async.bulk + mbarrier).  A warp owns a query and walks the hierarchy
+//                     level by level: the frontier of one level sits in shared memory, every step
+//                     tests the 64 child boxes of eight frontier nodes (two per 8-lane group, packed
+//                     binary16 arithmetic) and appends the survivors to the next level's frontier;
+//                     the last frontier holds leaves, evaluated the same way with the exact fp32
+//                     expression.  No stacks, no per-level bookkeeping.  A query whose frontier would
+//                     outgrow its kFrontCap slots is handed, untouched, to
+//   k_radius_search   the general kernel (one small stack per level, any frontier size, the 5 000-hit
+//                     cap of spatial_index.cc:371-372), which works through the list of such queries.
+//                     A frontier of kFrontCap leaves holds 2 048 points, so a query that can reach the
+//                     cap always takes this path: the cap rule lives in one place.
+constexpr int kSearchWarps = 8;          // warps per CTA (general kernel)
 constexpr int kLevelCap = 128;           // entries per level stack: 64 waiting + the children of one 8-node step
 constexpr int kLeafQueueCap = 128;       // < 8 left over + 64 pushed per step
 constexpr int kStageCap = 128;           // staged hits per warp before one global reservation
 constexpr int kSearchGrab = 8;           // queries per grab of the dynamic work counter
 constexpr int kMaxParts = 32;            // parts per entry the flush can route to (k_part_sort)
+constexpr int kLeanWarps = 32;           // lean kernel: one 1024-thread CTA per SM
+constexpr int kFrontCap = 256;           // lean kernel: frontier slots (nodes of a level / leaves) per query
+constexpr int kLeanStage = 192;          // lean kernel: staged hits per warp
+constexpr int kLeanGrab = 4;             // lean kernel: sorted queries per grab
+constexpr int kQueryBits = 12;           // query payload = entry << kQueryBits | query number inside the entry
 
-// dynamic shared memory per warp: staging (key part, point id, d2), leaf queue, level counts,
-// and one 64-entry stack per node level
+// dynamic shared memory per warp of the general kernel: staging (key part, point id, d2), leaf
+// queue, level counts, and one stack per node level
 __host__ __device__ inline size_t search_smem_per_warp(int n_levels) {
   return (size_t)kStageCap * 16 + (size_t)kLeafQueueCap * 4 + 16 * 4 + kMaxParts * 4 +
          (size_t)n_levels * kLevelCap * 4;
+}
+// lean kernel, per warp: staged keys (8 B) and distances, two frontiers, per-part counts
+constexpr size_t kLeanWarpSmem = (size_t)kLeanStage * 12 + 2 * (size_t)kFrontCap * 4 + kMaxParts * 4;
+__host__ __device__ inline size_t lean_top_region(uint32_t smem_bytes) { return ((size_t)smem_bytes + 127) & ~(size_t)127; }
+__host__ __device__ inline size_t lean_smem(uint32_t smem_bytes) {
+  return lean_top_region(smem_bytes) + (size_t)kLeanWarps * kLeanWarpSmem;
 }
 
 struct SearchArgs {
@@ -220,7 +253,20 @@ struct SearchArgs {
   uint32_t n_parts;            // 1..kMaxParts
   float inv_span;              // 1 / coordinates per part
   const uint64_t *bucket_base;
-  uint32_t grab;               // queries per grab of the work counter (0 = kSearchGrab)
+  uint32_t n_buckets;
+  uint32_t grab;               // queries per grab of the work counter (0 = default)
+  unsigned int *work;          // the work counter of this launch
+  // lean kernel: queries in Morton order.  order[k] = payload of the k-th query (pipeline:
+  // entry << kQueryBits | query number; stage: query id); nullptr = natural order.
+  const uint32_t *order;
+  uint32_t nq_cap;             // pipeline: capacity of order[] (sized from an estimate; more queries
+                               // than that raise error bit 6 and the host redoes the step)
+  const uint2 *entry_info;     // pipeline: {feature row, query offset (num_events)} per entry
+  uint32_t front_cap;          // frontier slots a query may use (<= kFrontCap; tests lower it)
+  uint32_t *ovf_list;          // payloads of the queries left to the general kernel
+  // general kernel: qlist != nullptr -> work through qlist[0 .. *qlist_n) instead of all queries
+  const uint32_t *qlist;
+  const unsigned int *qlist_n;
 };
 
 __device__ __forceinline__ float exact_d2(const float q[kDim], const float v[kDim]) {
@@ -252,31 +298,425 @@ __device__ __forceinline__ uint32_t find_entry(const uint32_t *__restrict__ q_of
   return lo;
 }
 
+// ---- Morton order of the queries (lean kernel).  One block per batch entry; key = 24-bit Morton
+// code (6 dims x 4 bits) of the query point in the index's own quantisation, payload =
+// entry << kQueryBits | query number.  Also fills entry_info.
+__device__ __forceinline__ uint32_t morton24(const float *q, float vmin, float inv_span) {
+  uint32_t c = 0;
+#pragma unroll
+  for (int d = 0; d < kDim; ++d) {
+    int v = (int)((q[d] - vmin) * inv_span * 16.0f);
+    v = v < 0 ? 0 : (v > 15 ? 15 : v);
+#pragma unroll
+    for (int b = 0; b < 4; ++b) c |= (uint32_t)((v >> b) & 1) << (kDim * b + (kDim - 1 - d));
+  }
+  return c;
+}
+
+__global__ void k_query_keys(const float *__restrict__ features, const uint32_t *__restrict__ feat_row,
+                             const uint32_t *__restrict__ q_off, const uint32_t *__restrict__ entry_slot,
+                             const SlotState *__restrict__ slots, uint32_t B, int step, float vmin,
+                             float inv_span, uint32_t *__restrict__ key, uint32_t *__restrict__ payload,
+                             uint2 *__restrict__ entry_info, uint32_t nq_cap) {
+  const uint32_t b = blockIdx.x;
+  if (b >= B) return;
+  const uint32_t q0 = q_off[b], nq = q_off[b + 1] - q0;
+  const uint32_t frow = feat_row[b];
+  if (threadIdx.x == 0) entry_info[b] = make_uint2(frow, slots[entry_slot[b]].num_events);
+  const float *f = features + (size_t)frow * kFeatCap;
+  for (uint32_t k = threadIdx.x; k < nq && q0 + k < nq_cap; k += blockDim.x) {
+    const uint32_t p = (uint32_t)step * (k + 1u);  // seeds at step, 2*step, ... (Q3)
+    float q[kDim];
+#pragma unroll
+    for (int d = 0; d < kDim; ++d) q[d] = f[p + d];
+    key[q0 + k] = morton24(q, vmin, inv_span);
+    payload[q0 + k] = (b << kQueryBits) | k;
+  }
+}
+
+// stage mode: Morton keys of explicit queries, payload = query id
+__global__ void k_query_keys_stage(const float *__restrict__ queries, uint32_t nq, float vmin, float inv_span,
+                                   uint32_t *__restrict__ key, uint32_t *__restrict__ payload) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nq) return;
+  float q[kDim];
+#pragma unroll
+  for (int d = 0; d < kDim; ++d) q[d] = queries[(size_t)i * kDim + d];
+  key[i] = morton24(q, vmin, inv_span);
+  payload[i] = i;
+}
+
+// ---- hits -> global memory.  `n` staged (key, d2) pairs of ONE batch entry: one reservation of
+// output space, the hits grouped by coordinate part inside it, one run record per part touched.
+// Not inlined: it is called from three places of two kernels and is off the traversal's path.
+template <int CAP>
+__device__ __noinline__ void flush_routed(const SearchArgs &a, const uint64_t *__restrict__ st_key,
+                                          const float *__restrict__ st_dist, uint32_t *__restrict__ pcnt,
+                                          const uint64_t *__restrict__ s_bb, int n, uint32_t entry) {
+  const int lane = threadIdx.x & 31;
+  const unsigned full = 0xffffffffu;
+  pcnt[lane] = 0;
+  __syncwarp();
+  uint64_t key[CAP / 32];
+  uint32_t where[CAP / 32];  // part << 8 | rank inside the part (this flush)
+#pragma unroll
+  for (int u = 0; u < CAP / 32; ++u) {
+    const int i = u * 32 + lane;
+    key[u] = 0;
+    where[u] = 0;
+    if (i < n) {
+      key[u] = st_key[i];
+      const uint32_t b = a.key.bucket(key[u]);
+      const uint64_t base = s_bb ? s_bb[b] : __ldg(a.bucket_base + b);
+      const uint32_t part = part_of(base + a.key.target(key[u]), a.inv_span, a.n_parts);
+      where[u] = (part << 8) | atomicAdd(&pcnt[part], 1u);
+    }
+  }
+  __syncwarp();
+  const uint32_t mine = pcnt[lane];  // lane p: hits of part p
+  uint32_t incl = mine;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t t = __shfl_up_sync(full, incl, d);
+    if (lane >= d) incl += t;
+  }
+  const uint32_t excl = incl - mine;
+  // both reservations are issued before either result is used: one round trip, not two
+  const size_t list = (size_t)entry * a.n_parts + lane;
+  uint32_t r = 0;
+  if (mine) r = atomicAdd(&a.run_count[list], 1u);
+  unsigned long long base = 0;
+  if (lane == 0) base = atomicAdd(&a.ctr->n_anchors, (unsigned long long)n);
+  base = __shfl_sync(full, base, 0);
+  if (mine) {
+    if (r < a.runs_cap) a.runs[list * a.runs_cap + r] = RunRec{(uint32_t)(base + excl), mine};
+    else atomicOr(&a.ctr->error, 8u);
+    atomicAdd(&a.entry_total[list], mine);
+  }
+#pragma unroll
+  for (int u = 0; u < CAP / 32; ++u) {
+    const int i = u * 32 + lane;
+    const uint32_t off = __shfl_sync(full, excl, (int)(where[u] >> 8));
+    if (i < n) {
+      const unsigned long long o = base + off + (where[u] & 0xFFu);
+      if (o < a.cap) {
+        a.out_key[o] = key[u];
+        a.out_dist[o] = st_dist[i];
+      }
+    }
+  }
+  __syncwarp();
+}
+
+// the same without routing (stage mode; pipeline mode on the radix-sort path)
+template <int CAP>
+__device__ __noinline__ void flush_plain(const SearchArgs &a, const uint64_t *__restrict__ st_key,
+                                         const float *__restrict__ st_dist, int n) {
+  const int lane = threadIdx.x & 31;
+  unsigned long long base = 0;
+  if (lane == 0) base = atomicAdd(&a.ctr->n_anchors, (unsigned long long)n);
+  base = __shfl_sync(0xffffffffu, base, 0);
+#pragma unroll
+  for (int i0 = 0; i0 < CAP; i0 += 32) {
+    const int i = i0 + lane;
+    if (i < n) {
+      const unsigned long long o = base + i;
+      if (o < a.cap) {
+        a.out_key[o] = st_key[i];
+        a.out_dist[o] = st_dist[i];
+      }
+    }
+  }
+  __syncwarp();
+}
+
+// ---- the packed binary16 box test.  It stays conservative through a per-query threshold: with
+// qh = round16(q) (|qh - q| <= 2^-11 |q|) every per-dimension distance computed in binary16 is at
+// most (T_d + 2^-11 |q_d|)(1 + 2^-11) where T_d is the exact distance to the stored box (itself
+// rounded outwards), so a box within r of q gives a sum of squares of at most
+// (r + 2^-11 |q|_2)^2 (1 + 2^-11)^8; anything above that is pruned.  Overflow gives +inf (pruned,
+// correctly: such a box is farther than 65504 - |q|), inf - inf gives NaN, which max() drops.
+struct QueryH {
+  __half2 q01, q23, q45;
+  float theta;
+};
+__device__ __forceinline__ QueryH make_query_h(const float q[kDim], float r2) {
+  QueryH h;
+  h.q01 = __floats2half2_rn(q[0], q[1]);
+  h.q23 = __floats2half2_rn(q[2], q[3]);
+  h.q45 = __floats2half2_rn(q[4], q[5]);
+  float qq = 0.0f;
+#pragma unroll
+  for (int d = 0; d < kDim; ++d) qq = __fmaf_rn(q[d], q[d], qq);
+  const float reach = sqrtf(r2) + 4.8828125e-4f * sqrtf(qq) * 1.001f;  // r + 2^-11 |q|_2
+  h.theta = reach * reach * 1.0045f + 1e-6f;                            // (1 + 2^-11)^8 < 1.004; + underflow slack
+  return h;
+}
+__device__ __forceinline__ float box_d2_h(const uint2 r0, const uint2 r1, const uint2 r2, const QueryH &h) {
+  auto as_h2 = [](uint32_t v) { return *reinterpret_cast<const __half2 *>(&v); };
+  const __half2 zero = __float2half2_rn(0.0f);
+  const __half2 t01 = __hmax2(__hmax2(__hsub2(as_h2(r0.x), h.q01), __hsub2(h.q01, as_h2(r1.y))), zero);
+  const __half2 t23 = __hmax2(__hmax2(__hsub2(as_h2(r0.y), h.q23), __hsub2(h.q23, as_h2(r2.x))), zero);
+  const __half2 t45 = __hmax2(__hmax2(__hsub2(as_h2(r1.x), h.q45), __hsub2(h.q45, as_h2(r2.y))), zero);
+  __half2 acc = __hmul2(t01, t01);
+  acc = __hfma2(t23, t23, acc);
+  acc = __hfma2(t45, t45, acc);
+  return __low2float(acc) + __high2float(acc);
+}
+
+// ---- TMA bulk copy global -> shared, completion on an mbarrier (sm_90+: UBLKCP)
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+// One level of the lean traversal: the nf frontier nodes in src[] -> the surviving children in
+// dst[]; returns their number, or -1 when dst would outgrow front_cap.  SMEM: the level's records
+// are in shared memory.
+template <bool SMEM>
+__device__ __forceinline__ int lean_node_level(const uint2 *__restrict__ lvl, const uint32_t *__restrict__ src,
+                                               uint32_t *__restrict__ dst, int nf, int front_cap, const QueryH &qh,
+                                               int lane, int grp, int sub, unsigned lt) {
+  const unsigned full = 0xffffffffu;
+  int nn = 0;
+  for (int i0 = 0; i0 < nf; i0 += 8) {
+    if (nn > front_cap - 64) return -1;
+    const int ia = i0 + grp, ib = ia + 4;
+    const bool hasA = ia < nf, hasB = ib < nf;
+    const uint32_t nodeA = hasA ? src[ia] : 0u;
+    const uint2 *ra = lvl + (size_t)nodeA * kNodeRec + sub;
+    uint2 a0, a1, a2;
+    if (SMEM) {
+      a0 = ra[0]; a1 = ra[kFan]; a2 = ra[2 * kFan];
+    } else {
+      a0 = __ldg(ra); a1 = __ldg(ra + kFan); a2 = __ldg(ra + 2 * kFan);
+    }
+    if (i0 + 4 < nf) {  // a full step: two nodes per lane group
+      const uint32_t nodeB = hasB ? src[ib] : 0u;
+      const uint2 *rb = lvl + (size_t)nodeB * kNodeRec + sub;
+      uint2 b0, b1, b2;
+      if (SMEM) {
+        b0 = rb[0]; b1 = rb[kFan]; b2 = rb[2 * kFan];
+      } else {
+        b0 = __ldg(rb); b1 = __ldg(rb + kFan); b2 = __ldg(rb + 2 * kFan);
+      }
+      const float sa = box_d2_h(a0, a1, a2, qh), sb = box_d2_h(b0, b1, b2, qh);
+      const unsigned mA = __ballot_sync(full, hasA && sa <= qh.theta);
+      const unsigned mB = __ballot_sync(full, hasB && sb <= qh.theta);
+      const int nA = __popc(mA);
+      if ((mA >> lane) & 1u) dst[nn + __popc(mA & lt)] = nodeA * kFan + sub;
+      if ((mB >> lane) & 1u) dst[nn + nA + __popc(mB & lt)] = nodeB * kFan + sub;
+      nn += nA + __popc(mB);
+    } else {  // the level's tail: at most four nodes
+      const float sa = box_d2_h(a0, a1, a2, qh);
+      const unsigned mA = __ballot_sync(full, hasA && sa <= qh.theta);
+      if ((mA >> lane) & 1u) dst[nn + __popc(mA & lt)] = nodeA * kFan + sub;
+      nn += __popc(mA);
+    }
+  }
+  __syncwarp();
+  return nn;
+}
+
+// STAGE=false: hits become sort keys (entry|bucket|target|query) + d2 (never capped here: a
+// frontier of kFrontCap leaves holds fewer than 5 000 points).
+// STAGE=true : key = query_id << 32 | window index (parity hook, compared as sets).
+template <bool STAGE>
+__global__ void __launch_bounds__(kLeanWarps * 32, 1)
+k_search_lean(const __grid_constant__ IndexView ix, const __grid_constant__ SearchArgs a) {
+  extern __shared__ __align__(128) unsigned char s_dyn[];
+  __shared__ __align__(8) unsigned long long s_mbar;
+  __shared__ uint64_t s_bb_store[64];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int grp = lane >> 3, sub = lane & 7;
+  const unsigned full = 0xffffffffu;
+  const unsigned lt = (1u << lane) - 1u;
+  const uint2 *s_top = reinterpret_cast<const uint2 *>(s_dyn);
+  unsigned char *mine = s_dyn + lean_top_region(ix.smem_bytes) + (size_t)wid * kLeanWarpSmem;
+  uint64_t *st_key = reinterpret_cast<uint64_t *>(mine);
+  float *st_dist = reinterpret_cast<float *>(mine + (size_t)kLeanStage * 8);
+  uint32_t *fa = reinterpret_cast<uint32_t *>(mine + (size_t)kLeanStage * 12);
+  uint32_t *fb = fa + kFrontCap;
+  uint32_t *pcnt = fb + kFrontCap;
+
+  // ---- the top levels: one bulk copy per CTA, everybody waits on the mbarrier
+  if (threadIdx.x == 0) mbar_init(&s_mbar, 1);
+  __syncthreads();
+  if (threadIdx.x == 0 && ix.smem_bytes) {
+    mbar_expect_tx(&s_mbar, ix.smem_bytes);
+    bulk_g2s(s_dyn, ix.nodes, ix.smem_bytes, &s_mbar);
+  }
+  const bool bb_local = !STAGE && a.runs && a.n_buckets <= 64u;
+  if (bb_local && threadIdx.x < a.n_buckets) s_bb_store[threadIdx.x] = a.bucket_base[threadIdx.x];
+  const uint64_t *s_bb = bb_local ? s_bb_store : nullptr;
+  __syncthreads();
+  if (ix.smem_bytes) mbar_wait(&s_mbar, 0);
+
+  uint32_t nq = STAGE ? a.n_queries : a.q_off[a.B];
+  if (!STAGE && nq > a.nq_cap) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&a.ctr->error, 64u);
+    nq = a.nq_cap;
+  }
+  const float r2 = a.radius;
+  const int top_level = ix.n_levels - 1;
+  const int n_top = (int)ix.level_count[top_level];  // <= 8
+  const int front_cap = (int)a.front_cap;
+  const uint32_t grab = a.grab ? a.grab : (uint32_t)kLeanGrab;
+  const bool routed = !STAGE && a.runs;
+  int staged = 0;
+  uint32_t staged_entry = 0;
+  unsigned long long my_hits = 0;
+
+  for (;;) {
+    uint32_t q0 = 0;
+    if (lane == 0) q0 = atomicAdd(a.work, grab);
+    q0 = __shfl_sync(full, q0, 0);
+    if (q0 >= nq) break;
+    const uint32_t q1 = min(q0 + grab, nq);
+    for (uint32_t qi = q0; qi < q1; ++qi) {
+      // ---- the query
+      const uint32_t payload = a.order ? __ldg(a.order + qi) : qi;
+      float q[kDim];
+      uint64_t qk;
+      uint32_t entry = 0;
+      if (STAGE) {
+#pragma unroll
+        for (int d = 0; d < kDim; ++d) q[d] = __ldg(a.features + (size_t)payload * kDim + d);
+        qk = (uint64_t)payload << 32;
+      } else {
+        entry = payload >> kQueryBits;
+        const uint2 info = __ldg(a.entry_info + entry);
+        const uint32_t p = (uint32_t)a.step * ((payload & ((1u << kQueryBits) - 1u)) + 1u);
+        const float *f = a.features + (size_t)info.x * kFeatCap + p;
+#pragma unroll
+        for (int d = 0; d < kDim; ++d) q[d] = __ldg(f + d);
+        qk = a.key.pack(entry, 0u, 0u, p + info.y);
+        if (routed && staged && entry != staged_entry) {
+          flush_routed<kLeanStage>(a, st_key, st_dist, pcnt, s_bb, staged, staged_entry);
+          staged = 0;
+        }
+        staged_entry = entry;
+      }
+      const QueryH qh = make_query_h(q, r2);
+
+      // ---- node levels, top down
+      int nf = n_top;
+      if (lane < n_top) fa[lane] = (uint32_t)lane;
+      __syncwarp();
+      uint32_t *src = fa, *dst = fb;
+      for (int L = top_level; L >= 0 && nf > 0; --L) {
+        const uint32_t off = ix.level_off[L];
+        if (L >= ix.smem_from) nf = lean_node_level<true>(s_top + off, src, dst, nf, front_cap, qh, lane, grp, sub, lt);
+        else nf = lean_node_level<false>(ix.nodes + off, src, dst, nf, front_cap, qh, lane, grp, sub, lt);
+        uint32_t *t = src;
+        src = dst;
+        dst = t;
+      }
+      if (nf < 0) {  // frontier too large: the general kernel takes this query from scratch
+        if (lane == 0) a.ovf_list[atomicAdd(&a.ctr->n_overflow, 1u)] = payload;
+        continue;
+      }
+
+      // ---- leaves: eight per step, one point per lane and half step
+      for (int i0 = 0; i0 < nf; i0 += 8) {
+        const int ia = i0 + grp, ib = ia + 4;
+        const bool hasA = ia < nf, hasB = ib < nf;
+        const uint32_t leafA = hasA ? src[ia] : 0u, leafB = hasB ? src[ib] : 0u;
+        const uint2 *la = ix.leaves + (size_t)leafA * kLeafRec + sub;
+        const uint2 *lb = ix.leaves + (size_t)leafB * kLeafRec + sub;
+        const uint2 a01 = __ldg(la), a23 = __ldg(la + kLeaf), a45 = __ldg(la + 2 * kLeaf);
+        const uint2 b01 = __ldg(lb), b23 = __ldg(lb + kLeaf), b45 = __ldg(lb + 2 * kLeaf);
+        const float va[kDim] = {__uint_as_float(a01.x), __uint_as_float(a01.y), __uint_as_float(a23.x),
+                                __uint_as_float(a23.y), __uint_as_float(a45.x), __uint_as_float(a45.y)};
+        const float vb[kDim] = {__uint_as_float(b01.x), __uint_as_float(b01.y), __uint_as_float(b23.x),
+                                __uint_as_float(b23.y), __uint_as_float(b45.x), __uint_as_float(b45.y)};
+        const float d2a = exact_d2(q, va), d2b = exact_d2(q, vb);
+        const unsigned hitA = __ballot_sync(full, hasA && d2a < r2);
+        const unsigned hitB = __ballot_sync(full, hasB && d2b < r2);
+        if (hitA | hitB) {
+          const int nA = __popc(hitA), nh = nA + __popc(hitB);
+          if (staged + nh > kLeanStage) {
+            if (routed) flush_routed<kLeanStage>(a, st_key, st_dist, pcnt, s_bb, staged, staged_entry);
+            else flush_plain<kLeanStage>(a, st_key, st_dist, staged);
+            staged = 0;
+          }
+          if ((hitA >> lane) & 1u) {
+            const int at = staged + __popc(hitA & lt);
+            uint64_t key;
+            if (STAGE) {
+              key = qk | __ldg(ix.leaf_widx + (size_t)leafA * kLeaf + sub);
+            } else {
+              const uint2 tb = __ldg(la + 3 * kLeaf);
+              key = qk | ((uint64_t)tb.y << a.key.sh_b()) | ((uint64_t)tb.x << a.key.sh_t());
+            }
+            st_key[at] = key;
+            st_dist[at] = d2a;
+          }
+          if ((hitB >> lane) & 1u) {
+            const int at = staged + nA + __popc(hitB & lt);
+            uint64_t key;
+            if (STAGE) {
+              key = qk | __ldg(ix.leaf_widx + (size_t)leafB * kLeaf + sub);
+            } else {
+              const uint2 tb = __ldg(lb + 3 * kLeaf);
+              key = qk | ((uint64_t)tb.y << a.key.sh_b()) | ((uint64_t)tb.x << a.key.sh_t());
+            }
+            st_key[at] = key;
+            st_dist[at] = d2b;
+          }
+          __syncwarp();
+          staged += nh;
+          my_hits += (unsigned)nh;
+        }
+      }
+      __syncwarp();  // frontier reads are done before the next query refills it
+    }
+  }
+  if (staged) {
+    if (routed) flush_routed<kLeanStage>(a, st_key, st_dist, pcnt, s_bb, staged, staged_entry);
+    else flush_plain<kLeanStage>(a, st_key, st_dist, staged);
+  }
+  if (lane == 0 && my_hits) atomicAdd(&a.ctr->n_hits, my_hits);
+}
+
+// ---- the general kernel.
 // STAGE=false: hits become sort keys (entry|bucket|target|query) + d2, capped at 5000/query.
 // STAGE=true : key = query_id << 32 | window index, no cap (parity hook, compared as sets).
 //
-// Traversal: depth-first over LEVELS, eight nodes wide.  Every level has its own small stack;
-// the warp always works on the lowest non-empty level, pops up to eight of its nodes (two per
-// 8-lane group), tests their 64 child boxes with six independent 16-byte loads per lane in
-// flight, and pushes the survivors onto the (empty) stack of the level below -- so a level
-// never holds more than the 64 children of one step.  Surviving leaves queue up and are
-// evaluated eight at a time the same way.
-//
-// BFS = true changes the order only: the warp works on the HIGHEST level with waiting nodes as long
-// as the stack below has room for the 64 children of a step (else on the lowest one, whose child
-// stack is empty), so every level is consumed in full groups of eight nodes with at most one
-// partial group per level -- measured on the 4.6 Mbp index: 17.9 steps per query instead of 21.1.
-//
-// BOX16 = true (experimental, SMB_BOX=half): the box test itself runs in packed binary16 -- two
-// dimensions per instruction, no unpacking of the stored corners.  It stays conservative through a
-// per-query threshold: with qh = round16(q) (|qh - q| <= 2^-11 |q|) every per-dimension distance
-// computed in binary16 is at most (T_d + 2^-11 |q_d|)(1 + 2^-11) where T_d is the exact distance
-// to the stored box, so a box within r of q gives a sum of squares of at most
-// (r + 2^-11 |q|_2)^2 (1 + 2^-11)^8; anything above that is pruned.  Overflow gives +inf (pruned,
-// correctly: such a box is farther than 65504 - |q|), inf - inf gives NaN, which max() drops.
-template <bool STAGE, bool BFS = false, bool BOX16 = false>
+// Traversal: level-order over one small stack per level, eight nodes wide.  The warp works on the
+// HIGHEST level with waiting nodes as long as the stack below has room for the 64 children of a
+// step (else on the lowest one, whose child stack is empty), so every level is consumed in full
+// groups of eight nodes with at most one partial group per level; it pops up to eight nodes (two
+// per 8-lane group), tests their 64 child boxes with six independent loads per lane in flight,
+// and pushes the survivors onto the stack of the level below.  Surviving leaves queue up and are
+// evaluated eight at a time the same way.  Any frontier size works: a full stack just forces the
+// walk down to the leaves before the level above is continued.
+template <bool STAGE>
 __global__ void __launch_bounds__(kSearchWarps * 32, 4)
-k_radius_search(const IndexView ix, const SearchArgs a) {
+k_radius_search(const __grid_constant__ IndexView ix, const __grid_constant__ SearchArgs a) {
   extern __shared__ __align__(16) unsigned char s_dyn[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int grp = lane >> 3, sub = lane & 7;
@@ -284,113 +724,35 @@ k_radius_search(const IndexView ix, const SearchArgs a) {
   const unsigned lt = (1u << lane) - 1u;
   const int n_levels = ix.n_levels;
   unsigned char *mine = s_dyn + (size_t)wid * search_smem_per_warp(n_levels);
-  uint64_t *st_qk = reinterpret_cast<uint64_t *>(mine);
-  uint32_t *st_pid = reinterpret_cast<uint32_t *>(mine + kStageCap * 8);
-  float *st_dist = reinterpret_cast<float *>(mine + kStageCap * 12);
+  uint64_t *st_key = reinterpret_cast<uint64_t *>(mine);
+  float *st_dist = reinterpret_cast<float *>(mine + kStageCap * 8);
   uint32_t *leafq = reinterpret_cast<uint32_t *>(mine + kStageCap * 16);
   uint32_t *lcnt = leafq + kLeafQueueCap;          // [16] nodes waiting per level
   uint32_t *pcnt = lcnt + 16;                      // [kMaxParts] hits per part of the flush in progress
   uint32_t *lstk = pcnt + kMaxParts;               // [n_levels][kLevelCap]
-  const uint32_t nq = STAGE ? a.n_queries : a.q_off[a.B];
+  const uint32_t nq = a.qlist ? *a.qlist_n : (STAGE ? a.n_queries : a.q_off[a.B]);
   const float r2 = a.radius;
   const float r2_prune = r2 * 1.0001f + 1e-12f;
-  const uint32_t grab = a.grab ? a.grab : (uint32_t)kSearchGrab;
+  const uint32_t grab = a.qlist ? 1u : (a.grab ? a.grab : (uint32_t)kSearchGrab);
   const int top_level = n_levels - 1;
   const uint32_t n_top = ix.level_count[top_level];  // <= 8
+  const bool routed = !STAGE && a.runs;
   int staged = 0;
   unsigned long long my_hits = 0, my_capped = 0;
   // entry of the previous query and its query range (consecutive queries mostly share it)
   uint32_t entry = 0, e_q0 = 1, e_q1 = 0, slot = 0, ev_off = 0, frow = 0;
   uint32_t staged_entry = 0;  // the entry every staged hit belongs to (a run never mixes entries)
 
-  // staged hits -> global: one reservation, then target/bucket of every hit fetched with all
-  // loads of a pass in flight (they are off the traversal's critical path here)
   auto flush = [&]() {
     if (staged == 0) return;
-    if (STAGE || !a.runs) {
-      unsigned long long base = 0;
-      if (lane == 0) base = atomicAdd(&a.ctr->n_anchors, (unsigned long long)staged);
-      base = __shfl_sync(full, base, 0);
-#pragma unroll
-      for (int i0 = 0; i0 < kStageCap; i0 += 32) {
-        const int i = i0 + lane;
-        if (i < staged) {
-          const unsigned long long o = base + i;
-          const uint32_t pid = st_pid[i];
-          uint64_t key;
-          if (STAGE) {
-            key = st_qk[i] | __ldg(ix.leaf_widx + pid);
-          } else {
-            const uint2 tb = __ldg(ix.leaf_tb + pid);
-            key = st_qk[i] | ((uint64_t)tb.y << a.key.sh_b()) | ((uint64_t)tb.x << a.key.sh_t());
-          }
-          if (o < a.cap) {
-            a.out_key[o] = key;
-            a.out_dist[o] = st_dist[i];
-          }
-        }
-      }
-      __syncwarp();
-      staged = 0;
-      return;
-    }
-    // all staged hits belong to staged_entry; route them to its parts
-    pcnt[lane] = 0;
-    __syncwarp();
-    uint64_t key[kStageCap / 32];
-    uint32_t where[kStageCap / 32];  // part << 8 | rank inside the part (this flush)
-#pragma unroll
-    for (int u = 0; u < kStageCap / 32; ++u) {
-      const int i = u * 32 + lane;
-      key[u] = 0;
-      where[u] = 0;
-      if (i < staged) {
-        const uint2 tb = __ldg(ix.leaf_tb + st_pid[i]);
-        key[u] = st_qk[i] | ((uint64_t)tb.y << a.key.sh_b()) | ((uint64_t)tb.x << a.key.sh_t());
-        const uint32_t part = part_of(__ldg(a.bucket_base + tb.y) + tb.x, a.inv_span, a.n_parts);
-        where[u] = (part << 8) | atomicAdd(&pcnt[part], 1u);
-      }
-    }
-    __syncwarp();
-    const uint32_t mine = pcnt[lane];  // lane p: hits of part p
-    uint32_t incl = mine;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const uint32_t t = __shfl_up_sync(full, incl, d);
-      if (lane >= d) incl += t;
-    }
-    const uint32_t excl = incl - mine;
-    // both reservations are issued before either result is used: one round trip, not two
-    const size_t list = (size_t)staged_entry * a.n_parts + lane;
-    uint32_t r = 0;
-    if (mine) r = atomicAdd(&a.run_count[list], 1u);
-    unsigned long long base = 0;
-    if (lane == 0) base = atomicAdd(&a.ctr->n_anchors, (unsigned long long)staged);
-    base = __shfl_sync(full, base, 0);
-    if (mine) {
-      if (r < a.runs_cap) a.runs[list * a.runs_cap + r] = RunRec{(uint32_t)(base + excl), mine};
-      else atomicOr(&a.ctr->error, 8u);
-      atomicAdd(&a.entry_total[list], mine);
-    }
-#pragma unroll
-    for (int u = 0; u < kStageCap / 32; ++u) {
-      const int i = u * 32 + lane;
-      const uint32_t off = __shfl_sync(full, excl, (int)(where[u] >> 8));
-      if (i < staged) {
-        const unsigned long long o = base + off + (where[u] & 0xFFu);
-        if (o < a.cap) {
-          a.out_key[o] = key[u];
-          a.out_dist[o] = st_dist[i];
-        }
-      }
-    }
-    __syncwarp();
+    if (routed) flush_routed<kStageCap>(a, st_key, st_dist, pcnt, nullptr, staged, staged_entry);
+    else flush_plain<kStageCap>(a, st_key, st_dist, staged);
     staged = 0;
   };
 
   for (;;) {
     uint32_t q0 = 0;
-    if (lane == 0) q0 = atomicAdd(&a.ctr->work, grab);
+    if (lane == 0) q0 = atomicAdd(a.work, grab);
     q0 = __shfl_sync(full, q0, 0);
     if (q0 >= nq) break;
     const uint32_t q1 = min(q0 + grab, nq);
@@ -399,55 +761,58 @@ k_radius_search(const IndexView ix, const SearchArgs a) {
       float q[kDim];
       uint64_t qk;
       if (STAGE) {
+        const uint32_t id = a.qlist ? __ldg(a.qlist + qi) : qi;
 #pragma unroll
-        for (int d = 0; d < kDim; ++d) q[d] = __ldg(a.features + (size_t)qi * kDim + d);
-        qk = (uint64_t)qi << 32;
+        for (int d = 0; d < kDim; ++d) q[d] = __ldg(a.features + (size_t)id * kDim + d);
+        qk = (uint64_t)id << 32;
       } else {
-        if (qi < e_q0 || qi >= e_q1) {
-          flush();
-          entry = find_entry(a.q_off, a.B, qi, lane);
+        uint32_t p;
+        if (a.qlist) {
+          const uint32_t payload = __ldg(a.qlist + qi);
+          const uint32_t e = payload >> kQueryBits;
+          if (e != entry || e_q1 == 0) {
+            flush();
+            entry = e;
+            e_q1 = 1;  // marks `entry` valid
+            slot = __ldg(a.entry_slot + entry);
+            ev_off = a.slots[slot].num_events;
+            frow = __ldg(a.feat_row + entry);
+          }
           staged_entry = entry;
-          e_q0 = __ldg(a.q_off + entry);
-          e_q1 = __ldg(a.q_off + entry + 1);
-          slot = __ldg(a.entry_slot + entry);
-          ev_off = a.slots[slot].num_events;  // query_start_offset
-          frow = __ldg(a.feat_row + entry);
+          p = (uint32_t)a.step * ((payload & ((1u << kQueryBits) - 1u)) + 1u);
+        } else {
+          if (qi < e_q0 || qi >= e_q1) {
+            flush();
+            entry = find_entry(a.q_off, a.B, qi, lane);
+            staged_entry = entry;
+            e_q0 = __ldg(a.q_off + entry);
+            e_q1 = __ldg(a.q_off + entry + 1);
+            slot = __ldg(a.entry_slot + entry);
+            ev_off = a.slots[slot].num_events;  // query_start_offset
+            frow = __ldg(a.feat_row + entry);
+          }
+          p = (uint32_t)a.step * (qi - e_q0 + 1u);  // seeds at step, 2*step, ... (Q3)
         }
-        const uint32_t p = (uint32_t)a.step * (qi - e_q0 + 1u);  // seeds at step, 2*step, ... (Q3)
         const float *f = a.features + (size_t)frow * kFeatCap + p;
 #pragma unroll
         for (int d = 0; d < kDim; ++d) q[d] = __ldg(f + d);
         qk = a.key.pack(entry, 0u, 0u, p + ev_off);
       }
-      __half2 qh01, qh23, qh45;
-      float theta16 = 0.0f;
-      if (BOX16) {
-        qh01 = __floats2half2_rn(q[0], q[1]);
-        qh23 = __floats2half2_rn(q[2], q[3]);
-        qh45 = __floats2half2_rn(q[4], q[5]);
-        float qq = 0.0f;
-#pragma unroll
-        for (int d = 0; d < kDim; ++d) qq = __fmaf_rn(q[d], q[d], qq);
-        const float reach = sqrtf(r2) + 4.8828125e-4f * sqrtf(qq) * 1.001f;  // r + 2^-11 |q|_2
-        theta16 = reach * reach * 1.0045f;                                   // (1 + 2^-11)^8 < 1.004
-      }
       uint32_t qhits = 0;
       bool capped = false;
-      // L = lowest level with nodes waiting (n_levels when none), c = how many wait there
+      // L = level being worked on (n_levels when none), c = how many wait there
       int L = top_level, c = (int)n_top, nleaf = 0;
-      uint32_t waiting = 1u << top_level;  // BFS: levels with nodes on their stack
-      if (lane < 16) lcnt[lane] = (BFS && lane == top_level) ? n_top : 0u;
+      uint32_t waiting = 1u << top_level;  // levels with nodes on their stack
+      if (lane < 16) lcnt[lane] = (lane == top_level) ? n_top : 0u;
       if (lane < (int)n_top) lstk[top_level * kLevelCap + lane] = (uint32_t)lane;
       __syncwarp();
       for (;;) {
-        if (BFS) {
-          if (nleaf < 8 && waiting) {
-            L = 31 - __clz(waiting);
-            if (L > 0 && lcnt[L - 1] > (uint32_t)(kLevelCap - 64)) L = __ffs(waiting) - 1;
-            c = (int)lcnt[L];
-          } else {
-            L = waiting ? 0 : n_levels;
-          }
+        if (nleaf < 8 && waiting) {
+          L = 31 - __clz(waiting);
+          if (L > 0 && lcnt[L - 1] > (uint32_t)(kLevelCap - 64)) L = __ffs(waiting) - 1;
+          c = (int)lcnt[L];
+        } else {
+          L = waiting ? 0 : n_levels;
         }
         if (nleaf >= 8 || (L >= n_levels && nleaf > 0)) {
           // ---- leaf step: up to eight leaves, two per 8-lane group, one point each per lane
@@ -456,12 +821,14 @@ k_radius_search(const IndexView ix, const SearchArgs a) {
           const uint32_t leafA = hasA ? leafq[nleaf - 1 - grp] : 0u;
           const uint32_t leafB = hasB ? leafq[nleaf - 5 - grp] : 0u;
           nleaf -= take;
-          const float2 *la = ix.leaf_vals + (size_t)leafA * (3 * kLeaf) + sub;
-          const float2 *lb = ix.leaf_vals + (size_t)leafB * (3 * kLeaf) + sub;
-          const float2 a01 = __ldg(la), a23 = __ldg(la + kLeaf), a45 = __ldg(la + 2 * kLeaf);
-          const float2 b01 = __ldg(lb), b23 = __ldg(lb + kLeaf), b45 = __ldg(lb + 2 * kLeaf);
-          const float va[kDim] = {a01.x, a01.y, a23.x, a23.y, a45.x, a45.y};
-          const float vb[kDim] = {b01.x, b01.y, b23.x, b23.y, b45.x, b45.y};
+          const uint2 *la = ix.leaves + (size_t)leafA * kLeafRec + sub;
+          const uint2 *lb = ix.leaves + (size_t)leafB * kLeafRec + sub;
+          const uint2 a01 = __ldg(la), a23 = __ldg(la + kLeaf), a45 = __ldg(la + 2 * kLeaf);
+          const uint2 b01 = __ldg(lb), b23 = __ldg(lb + kLeaf), b45 = __ldg(lb + 2 * kLeaf);
+          const float va[kDim] = {__uint_as_float(a01.x), __uint_as_float(a01.y), __uint_as_float(a23.x),
+                                  __uint_as_float(a23.y), __uint_as_float(a45.x), __uint_as_float(a45.y)};
+          const float vb[kDim] = {__uint_as_float(b01.x), __uint_as_float(b01.y), __uint_as_float(b23.x),
+                                  __uint_as_float(b23.y), __uint_as_float(b45.x), __uint_as_float(b45.y)};
           const float d2a = exact_d2(q, va), d2b = exact_d2(q, vb);
           const uint32_t hitA = __ballot_sync(full, hasA && d2a < r2);
           const uint32_t hitB = __ballot_sync(full, hasB && d2b < r2);
@@ -488,9 +855,16 @@ k_radius_search(const IndexView ix, const SearchArgs a) {
             if (staged + nh > kStageCap) flush();
             if (hit & (1u << lane)) {
               const int at = staged + __popc(hit & lt);
-              st_pid[at] = (half ? leafB : leafA) * kLeaf + sub;
+              const uint32_t leaf = half ? leafB : leafA;
+              uint64_t key;
+              if (STAGE) {
+                key = qk | __ldg(ix.leaf_widx + (size_t)leaf * kLeaf + sub);
+              } else {
+                const uint2 tb = __ldg((half ? lb : la) + 3 * kLeaf);
+                key = qk | ((uint64_t)tb.y << a.key.sh_b()) | ((uint64_t)tb.x << a.key.sh_t());
+              }
+              st_key[at] = key;
               st_dist[at] = half ? d2b : d2a;
-              st_qk[at] = qk;
             }
             __syncwarp();
             staged += nh;
@@ -509,29 +883,15 @@ k_radius_search(const IndexView ix, const SearchArgs a) {
           const uint32_t nodeA = hasA ? stk[c - 1 - grp] : 0u;
           const uint32_t nodeB = hasB ? stk[c - 5 - grp] : 0u;
           c -= take;
-          const uint2 *base = ix.level_node[L] + sub;
-          const uint2 *ra = base + (size_t)nodeA * (3 * kFan);
-          const uint2 *rb = base + (size_t)nodeB * (3 * kFan);
+          const uint2 *base = ix.nodes + ix.level_off[L] + sub;
+          const uint2 *ra = base + (size_t)nodeA * kNodeRec;
+          const uint2 *rb = base + (size_t)nodeB * kNodeRec;
           const uint2 a0 = __ldg(ra), a1 = __ldg(ra + kFan), a2 = __ldg(ra + 2 * kFan);
           const uint2 b0 = __ldg(rb), b1 = __ldg(rb + kFan), b2 = __ldg(rb + 2 * kFan);
           // boxes only prune (stored rounded outwards, tested with slack), so this distance may
           // use FMA; the accept test may not
           float sa = 0.0f, sb = 0.0f;
-          if (BOX16) {
-            const __half2 zero = __float2half2_rn(0.0f);
-            auto as_h2 = [](uint32_t v) { return *reinterpret_cast<const __half2 *>(&v); };
-            auto box_d2 = [&](const uint2 r0, const uint2 r1, const uint2 r2_) -> float {
-              const __half2 t01 = __hmax2(__hmax2(__hsub2(as_h2(r0.x), qh01), __hsub2(qh01, as_h2(r1.y))), zero);
-              const __half2 t23 = __hmax2(__hmax2(__hsub2(as_h2(r0.y), qh23), __hsub2(qh23, as_h2(r2_.x))), zero);
-              const __half2 t45 = __hmax2(__hmax2(__hsub2(as_h2(r1.x), qh45), __hsub2(qh45, as_h2(r2_.y))), zero);
-              __half2 acc = __hmul2(t01, t01);
-              acc = __hfma2(t23, t23, acc);
-              acc = __hfma2(t45, t45, acc);
-              return __low2float(acc) + __high2float(acc);
-            };
-            sa = box_d2(a0, a1, a2);
-            sb = box_d2(b0, b1, b2);
-          } else {
+          {
             const float2 l01 = unpack_h2(a0.x), l23 = unpack_h2(a0.y), l45 = unpack_h2(a1.x);
             const float2 h01 = unpack_h2(a1.y), h23 = unpack_h2(a2.x), h45 = unpack_h2(a2.y);
             const float lo[kDim] = {l01.x, l01.y, l23.x, l23.y, l45.x, l45.y};
@@ -542,7 +902,7 @@ k_radius_search(const IndexView ix, const SearchArgs a) {
               sa = __fmaf_rn(t, t, sa);
             }
           }
-          if (!BOX16) {
+          {
             const float2 l01 = unpack_h2(b0.x), l23 = unpack_h2(b0.y), l45 = unpack_h2(b1.x);
             const float2 h01 = unpack_h2(b1.y), h23 = unpack_h2(b2.x), h45 = unpack_h2(b2.y);
             const float lo[kDim] = {l01.x, l01.y, l23.x, l23.y, l45.x, l45.y};
@@ -553,50 +913,29 @@ k_radius_search(const IndexView ix, const SearchArgs a) {
               sb = __fmaf_rn(t, t, sb);
             }
           }
-          const float prune_at = BOX16 ? theta16 : r2_prune;
-          const uint32_t mA = __ballot_sync(full, hasA && sa <= prune_at);
-          const uint32_t mB = __ballot_sync(full, hasB && sb <= prune_at);
+          const uint32_t mA = __ballot_sync(full, hasA && sa <= r2_prune);
+          const uint32_t mB = __ballot_sync(full, hasB && sb <= r2_prune);
           const int nA = __popc(mA), nB = __popc(mB);
-          if (BFS) {
-            if (L > 0) {
-              const uint32_t below = lcnt[L - 1];
-              uint32_t *dst = lstk + (L - 1) * kLevelCap + below;
-              if (mA & (1u << lane)) dst[__popc(mA & lt)] = nodeA * kFan + sub;
-              if (mB & (1u << lane)) dst[nA + __popc(mB & lt)] = nodeB * kFan + sub;
-              __syncwarp();  // every lane has read lcnt before lane 0 rewrites it
-              if (lane == 0) {
-                lcnt[L] = (uint32_t)c;
-                lcnt[L - 1] = below + (uint32_t)(nA + nB);
-              }
-              if (nA + nB) waiting |= 1u << (L - 1);
-            } else {
-              if (mA & (1u << lane)) leafq[nleaf + __popc(mA & lt)] = nodeA * kFan + sub;
-              if (mB & (1u << lane)) leafq[nleaf + nA + __popc(mB & lt)] = nodeB * kFan + sub;
-              nleaf += nA + nB;
-              __syncwarp();
-              if (lane == 0) lcnt[0] = (uint32_t)c;
-            }
-            if (c == 0) waiting &= ~(1u << L);
-            __syncwarp();
-            continue;
-          }
           if (L > 0) {
-            if (nA + nB) {
-              // descend: the level below is empty (it is always drained before this one)
-              uint32_t *dst = lstk + (L - 1) * kLevelCap;
-              if (mA & (1u << lane)) dst[__popc(mA & lt)] = nodeA * kFan + sub;
-              if (mB & (1u << lane)) dst[nA + __popc(mB & lt)] = nodeB * kFan + sub;
+            const uint32_t below = lcnt[L - 1];
+            uint32_t *dst = lstk + (L - 1) * kLevelCap + below;
+            if (mA & (1u << lane)) dst[__popc(mA & lt)] = nodeA * kFan + sub;
+            if (mB & (1u << lane)) dst[nA + __popc(mB & lt)] = nodeB * kFan + sub;
+            __syncwarp();  // every lane has read lcnt before lane 0 rewrites it
+            if (lane == 0) {
               lcnt[L] = (uint32_t)c;
-              --L;
-              c = nA + nB;
+              lcnt[L - 1] = below + (uint32_t)(nA + nB);
             }
+            if (nA + nB) waiting |= 1u << (L - 1);
           } else {
             if (mA & (1u << lane)) leafq[nleaf + __popc(mA & lt)] = nodeA * kFan + sub;
             if (mB & (1u << lane)) leafq[nleaf + nA + __popc(mB & lt)] = nodeB * kFan + sub;
             nleaf += nA + nB;
+            __syncwarp();
+            if (lane == 0) lcnt[0] = (uint32_t)c;
           }
+          if (c == 0) waiting &= ~(1u << L);
           __syncwarp();
-          while (c == 0 && ++L < n_levels) c = (int)lcnt[L];  // climb to the next waiting level
         } else {
           break;
         }

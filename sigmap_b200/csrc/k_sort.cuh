@@ -27,7 +27,8 @@
 
 namespace sb {
 
-constexpr int kRunsCap = 512;        // runs recorded per entry (a run = one flush of <= 128 hits)
+constexpr int kRunsCap = 512;        // run records a k_part_sort CTA holds in shared memory at a time (one tile of a
+                                     // list); the lists themselves hold runs_cap records, sized per step by the host
 // Two shapes of the kernel (template parameters CAP = anchors of one part held in shared memory,
 // THREADS, BINS = fine bins per part):
 //   <10240, 1024, 8192>  one 200 KB CTA per SM: fewest passes over an entry's runs
@@ -46,8 +47,9 @@ struct SegSortArgs {
   const float *dist_in;
   uint64_t *key_out;
   float *dist_out;
-  const RunRec *runs;           // [B * n_parts][kRunsCap]
+  const RunRec *runs;           // [B * n_parts][runs_cap]
   const uint32_t *run_count;    // [B * n_parts]
+  uint32_t runs_cap;            // run records per list
   uint32_t n_parts;             // run lists per entry (k_part_sort's partition; 1 = one list)
   uint32_t B;
   KeyLayout kl;
@@ -81,13 +83,14 @@ __global__ void __launch_bounds__(kSortThreads, kSortThreads == 1024 ? 1 : 2) k_
   const unsigned full = 0xffffffffu;
   const unsigned lt = (1u << lane) - 1u;
   // the entry's runs: the lists of its n_parts parts, addressed as one virtual list of
-  // n_parts * kRunsCap slots (slot v = list v / kRunsCap, run v % kRunsCap; unused slots skipped)
-  const RunRec *runs = a.runs + (size_t)entry * a.n_parts * kRunsCap;
+  // n_parts * runs_cap slots (slot v = list v / runs_cap, run v % runs_cap; unused slots skipped)
+  const uint32_t rcap = a.runs_cap;
+  const RunRec *runs = a.runs + (size_t)entry * a.n_parts * rcap;
   const uint32_t *rcount = a.run_count + (size_t)entry * a.n_parts;
-  const uint32_t nr = a.n_parts == 1 ? min(rcount[0], (uint32_t)kRunsCap) : a.n_parts * (uint32_t)kRunsCap;
+  const uint32_t nr = a.n_parts == 1 ? min(rcount[0], rcap) : a.n_parts * rcap;
   auto run_at = [&](uint32_t v) -> RunRec {
-    const uint32_t used = min(rcount[v / kRunsCap], (uint32_t)kRunsCap);
-    return (v % kRunsCap) < used ? runs[v] : RunRec{0u, 0u};
+    const uint32_t used = min(rcount[v / rcap], rcap);
+    return (v % rcap) < used ? runs[v] : RunRec{0u, 0u};
   };
   const KeyLayout kl = a.kl;
 
@@ -334,8 +337,9 @@ struct PartSortArgs {
   const float *dist_in;
   uint64_t *key_out;
   float *dist_out;
-  const RunRec *runs;           // [B * n_parts][kRunsCap]
+  const RunRec *runs;           // [B * n_parts][runs_cap]
   const uint32_t *run_count;    // [B * n_parts]
+  uint32_t runs_cap;            // run records per list
   const uint32_t *part_total;   // [B * n_parts] anchors of the part (<= CAP, checked by the host)
   const uint32_t *out_base;     // [B * n_parts] exclusive scan of part_total
   uint32_t n_parts;
@@ -348,7 +352,7 @@ struct PartSortArgs {
 };
 
 constexpr size_t part_sort_smem_bytes(int cap, int bins) {
-  return (size_t)cap * (8 + 4 + 2 + 2) + (size_t)bins * 4 + (size_t)kRunsCap * 8 + (size_t)kBigBinCap * 4 + 64 * 4;
+  return (size_t)cap * (8 + 4 + 2 + 2) + (size_t)bins * 4 + (size_t)(kRunsCap + 8) * 8 + (size_t)kBigBinCap * 4 + 64 * 4;
 }
 
 // largest anchor count of any (entry, part): the host picks the sort kernel with it
@@ -369,10 +373,10 @@ __global__ void __launch_bounds__(THREADS, THREADS >= 1024 ? 1 : (THREADS >= 512
   uint64_t *s_key = reinterpret_cast<uint64_t *>(s_raw);
   float *s_dist = reinterpret_cast<float *>(s_key + CAP);
   uint32_t *s_bins = reinterpret_cast<uint32_t *>(s_dist + CAP);
-  uint32_t *s_run_start = s_bins + BINS;          // [kRunsCap]
-  uint32_t *s_run_off = s_run_start + kRunsCap;   // [kRunsCap] exclusive scan of the run counts
-  uint32_t *s_big = s_run_off + kRunsCap;         // [kBigBinCap]
-  uint32_t *s_misc = s_big + kBigBinCap;          // [64]: 0..31 warp sums, 32 kept, 33 nbig
+  uint32_t *s_run_start = s_bins + BINS;            // [kRunsCap + 8] one tile of the run list
+  uint32_t *s_run_off = s_run_start + kRunsCap + 8;   // [kRunsCap + 8] exclusive scan of the run counts (+ end)
+  uint32_t *s_big = s_run_off + kRunsCap + 8;       // [kBigBinCap]
+  uint32_t *s_misc = s_big + kBigBinCap;            // [64]: 0..31 warp sums, 32 kept, 33 nbig, 34 tile base
   uint16_t *s_order = reinterpret_cast<uint16_t *>(s_misc + 64);
   uint16_t *s_order2 = s_order + CAP;
 
@@ -381,8 +385,8 @@ __global__ void __launch_bounds__(THREADS, THREADS >= 1024 ? 1 : (THREADS >= 512
   if (n_all == 0) return;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const unsigned full = 0xffffffffu;
-  const uint32_t nr = min(a.run_count[idx], (uint32_t)kRunsCap);
-  const RunRec *runs = a.runs + (size_t)idx * kRunsCap;
+  const uint32_t nr = min(a.run_count[idx], a.runs_cap);
+  const RunRec *runs = a.runs + (size_t)idx * a.runs_cap;
   const KeyLayout kl = a.kl;
   unsigned long long out = a.out_base[idx];
   const uint64_t g_part = (uint64_t)(idx % a.n_parts) * a.span;
@@ -403,38 +407,6 @@ __global__ void __launch_bounds__(THREADS, THREADS >= 1024 ? 1 : (THREADS >= 512
     return (bb_local ? s_bb[b] : __ldg(a.bucket_base + b)) + kl.target(k);
   };
 
-  // ---- run table -> shared memory, exclusive scan of the counts (kPer consecutive runs a thread)
-  {
-    constexpr int kPer = (kRunsCap + THREADS - 1) / THREADS;
-    uint32_t cnt[kPer], sum = 0;
-#pragma unroll
-    for (int j = 0; j < kPer; ++j) {
-      const uint32_t r = (uint32_t)tid * kPer + j;
-      RunRec rec = RunRec{0u, 0u};
-      if (r < nr) rec = runs[r];
-      if (r < (uint32_t)kRunsCap) s_run_start[r] = rec.start;
-      cnt[j] = rec.count;
-      sum += rec.count;
-    }
-    uint32_t incl = sum;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const uint32_t t = __shfl_up_sync(full, incl, d);
-      if (lane >= d) incl += t;
-    }
-    if (lane == 31) s_misc[wid] = incl;
-    __syncthreads();
-    uint32_t at = incl - sum;
-    for (int w = 0; w < wid; ++w) at += s_misc[w];
-    __syncthreads();
-#pragma unroll
-    for (int j = 0; j < kPer; ++j) {
-      const uint32_t r = (uint32_t)tid * kPer + j;
-      if (r < (uint32_t)kRunsCap) s_run_off[r] = at;
-      at += cnt[j];
-    }
-  }
-
   for (uint32_t sub = 0; sub < n_sub; ++sub) {
     const uint64_t g_lo = g_part + (uint64_t)sub * sub_span;
     // the first / last sub-range are open-ended: part boundaries are fuzzy (part_of)
@@ -444,6 +416,7 @@ __global__ void __launch_bounds__(THREADS, THREADS >= 1024 ? 1 : (THREADS >= 512
     if (tid == 0) {
       s_misc[32] = 0;
       s_misc[33] = 0;
+      s_misc[34] = 0;
     }
     __syncthreads();
 
@@ -461,34 +434,77 @@ __global__ void __launch_bounds__(THREADS, THREADS >= 1024 ? 1 : (THREADS >= 512
         atomicAdd(&s_bins[bin], 1u);
       }
     };
-    for (uint32_t r0 = (uint32_t)wid * 4u; r0 < nr; r0 += (THREADS / 32) * 4u) {
-      uint32_t st[4], of[4], cn[4];
-      uint64_t kq[4];
-      float dq[4];
+    // the run list goes through shared memory one tile of kRunsCap records at a time
+    for (uint32_t t0 = 0; t0 < nr; t0 += (uint32_t)kRunsCap) {
+      const uint32_t tn = min(nr - t0, (uint32_t)kRunsCap);
+      const uint32_t tile_base = s_misc[34];  // anchors of the tiles before this one
+      // ---- tile -> shared memory, exclusive scan of the counts (kPer consecutive runs a thread)
+      {
+        constexpr int kPer = (kRunsCap + THREADS - 1) / THREADS;
+        uint32_t cnt[kPer], sum = 0;
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const uint32_t r = r0 + u;
-        st[u] = 0;
-        of[u] = 0;
-        cn[u] = 0;
-        if (r < nr) {
-          st[u] = s_run_start[r];
-          of[u] = s_run_off[r];
-          cn[u] = (r + 1 < nr ? s_run_off[r + 1] : n_all) - of[u];
+        for (int j = 0; j < kPer; ++j) {
+          const uint32_t r = (uint32_t)tid * kPer + j;
+          RunRec rec = RunRec{0u, 0u};
+          if (r < tn) rec = runs[t0 + r];
+          if (r < (uint32_t)kRunsCap) s_run_start[r] = rec.start;
+          cnt[j] = rec.count;
+          sum += rec.count;
         }
-        kq[u] = ~0ull;
-        dq[u] = 0.0f;
-        if ((uint32_t)lane < cn[u]) {
-          kq[u] = a.key_in[st[u] + lane];
-          dq[u] = a.dist_in[st[u] + lane];
+        uint32_t incl = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const uint32_t t = __shfl_up_sync(full, incl, d);
+          if (lane >= d) incl += t;
+        }
+        if (lane == 31) s_misc[wid] = incl;
+        __syncthreads();
+        uint32_t at = tile_base + incl - sum;
+        for (int w = 0; w < wid; ++w) at += s_misc[w];
+#pragma unroll
+        for (int j = 0; j < kPer; ++j) {
+          const uint32_t r = (uint32_t)tid * kPer + j;
+          if (r < (uint32_t)kRunsCap) s_run_off[r] = at;
+          at += cnt[j];
+        }
+        if (tid == THREADS - 1) {
+          s_run_off[kRunsCap] = at;  // end of the tile = base of the next
+        }
+        __syncthreads();
+      }
+      const uint32_t tile_end = s_run_off[kRunsCap];
+      for (uint32_t r0 = (uint32_t)wid * 4u; r0 < tn; r0 += (THREADS / 32) * 4u) {
+        uint32_t st[4], of[4], cn[4];
+        uint64_t kq[4];
+        float dq[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const uint32_t r = r0 + u;
+          st[u] = 0;
+          of[u] = 0;
+          cn[u] = 0;
+          if (r < tn) {
+            st[u] = s_run_start[r];
+            of[u] = s_run_off[r];
+            cn[u] = (r + 1 < tn ? s_run_off[r + 1] : tile_end) - of[u];
+          }
+          kq[u] = ~0ull;
+          dq[u] = 0.0f;
+          if ((uint32_t)lane < cn[u]) {
+            kq[u] = a.key_in[st[u] + lane];
+            dq[u] = a.dist_in[st[u] + lane];
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if ((uint32_t)lane < cn[u]) place(of[u] + lane, kq[u], dq[u]);
+          for (uint32_t i = 32u + lane; i < cn[u]; i += 32u)  // runs longer than a warp
+            place(of[u] + i, a.key_in[st[u] + i], a.dist_in[st[u] + i]);
         }
       }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if ((uint32_t)lane < cn[u]) place(of[u] + lane, kq[u], dq[u]);
-        for (uint32_t i = 32u + lane; i < cn[u]; i += 32u)  // runs longer than a warp: rare
-          place(of[u] + i, a.key_in[st[u] + i], a.dist_in[st[u] + i]);
-      }
+      __syncthreads();  // the tile's records are not needed any more
+      if (tid == 0) s_misc[34] = tile_end;
+      __syncthreads();
     }
     __syncthreads();
     uint32_t n = n_all;

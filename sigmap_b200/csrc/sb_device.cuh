@@ -49,23 +49,32 @@ struct DevBuf {
 // ---- flat device index over the Morton-sorted window points (replaces nanoflann) ----
 // Leaves hold 8 consecutive points of the Morton order; a node holds the boxes of its 8
 // children (level 0: leaves 8n..8n+7, level l: nodes 8n..8n+7 of level l-1), pointer-free.
-// A warp works on FOUR nodes (or leaves) per step, one 8-lane group each, so records are laid
-// out for 8 lanes:
+// A warp works on FOUR nodes (or leaves) per half step, one 8-lane group each, so records are
+// laid out for 8 lanes:
 //   node  = [3][8 children] x four binary16: (lo0 lo1 lo2 lo3) (lo4 lo5 hi0 hi1) (hi2 hi3 hi4 hi5),
-//           box corners rounded outwards, 192 bytes, three coalesced 64-byte loads per lane
-//           group -- the search is bound by L2 bandwidth, and node records are most of it;
-//   leaf  = [3][8 points] float2: (v0 v1) (v2 v3) (v4 v5), 192 bytes.
+//           box corners rounded outwards, 192 bytes, three coalesced 64-byte loads per lane group;
+//   leaf  = [3][8 points] float2 (v0 v1) (v2 v3) (v4 v5), then [8] {target, bucket}: 256 bytes.
+//           The payload of a hit sits in the record the hit lane has just read (same 256-byte
+//           block), so emitting an anchor costs no dependent random load.
+// All node levels live in ONE buffer, top level first: the prefix that fits 64 KB (the levels
+// every query walks) is staged in shared memory by the search kernel with one TMA bulk copy.
+constexpr int kNodeRec = 3 * kFan;       // uint2 per node record
+constexpr int kLeafRec = 4 * kLeaf;      // uint2 per leaf record (24 values + 8 payload)
+constexpr uint32_t kTopSmemMax = 64u << 10;
 struct IndexView {
   uint64_t n_points;    // N (point cloud size); windows W = N - 5
   uint64_t n_windows;
   uint32_t n_leaves;    // ceil(W / 8)
   int n_levels;         // node levels; the top level has <= 8 nodes
   uint32_t level_count[kMaxLevels];  // nodes per level
-  const uint2 *level_node[kMaxLevels];
-  const float2 *leaf_vals;    // [n_leaves][3][8]
-  const uint2 *leaf_tb;       // [n_leaves*8] {target position (pos >> 1, low 32 bits),
-                              //               contig*2 + strand (0 = '+'), ~0u = padding}
-  const uint32_t *leaf_widx;  // [n_leaves*8] window index in the original cloud
+  uint32_t level_off[kMaxLevels];    // first uint2 of level L inside nodes[] (top level at 0)
+  const uint2 *nodes;         // every level, top-down
+  int smem_from;              // levels >= smem_from are staged in shared memory (n_levels: none)
+  uint32_t smem_bytes;        // size of those levels = prefix of nodes[], multiple of 16
+  const uint2 *leaves;        // [n_leaves][kLeafRec]: values, then {target position (pos >> 1, low
+                              // 32 bits), contig*2 + strand (0 = '+'), ~0u = padding}
+  const uint32_t *leaf_widx;  // [n_leaves*8] window index in the original cloud (parity hook only)
+  float vmin, inv_span;       // Morton quantisation of the build: cell = (v - vmin) * inv_span
 };
 
 // per-step packing of the 64-bit sort key: entry | bucket | target | query
@@ -128,7 +137,9 @@ struct Counters {
   unsigned long long sort_cursor;   // output position of the per-entry sort (k_seg_sort)
   unsigned long long n_cand;        // sharded: chain candidates this rank appended to its exchange list
   unsigned int n_segments;
-  unsigned int work;                // dynamic work counter for the search kernel
+  unsigned int work;                // dynamic work counter of the lean search kernel
+  unsigned int work2;               // ... and of the general search kernel
+  unsigned int n_overflow;          // queries the lean search kernel left to the general one
   unsigned int error;               // bit0 anchor overflow, bit1 carry overflow, bit2 chain scratch,
                                     // bit3 run table overflow, bit4 entry too dense for k_seg_sort,
                                     // bit5 candidate exchange list overflow

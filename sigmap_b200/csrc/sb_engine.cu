@@ -56,11 +56,13 @@ __global__ void k_reset_step(Counters *c) {
   c->n_linked = 0;
   c->n_segments = 0;
   c->work = 0;
+  c->work2 = 0;
+  c->n_overflow = 0;
   c->sort_cursor = 0;
   c->n_cand = 0;
   c->max_entry_anchors = 0;
   c->dp_cursor = 0;
-  c->error &= ~24u;  // per-step bits (run table overflow, dense entry); the others are per round
+  c->error &= ~(24u | 64u);  // per-step bits (run table overflow, dense entry, query buffers); the others are per round
 }
 
 // queries per entry (spatial_index.cc:349-409 with Q3: seeds at step, 2*step, ... while
@@ -182,6 +184,10 @@ struct SlotSpace {
 struct Workspace {
   // per-entry
   DevBuf<uint32_t> entry_slot, n_features, n_raw_events, n_queries, q_off, feat_row;
+  // queries in Morton order (lean search kernel) and the ones it leaves to the general kernel
+  DevBuf<uint32_t> qkey_a, qkey_b, qpay_a, qpay_b, ovf_list;
+  DevBuf<uint2> entry_info;
+  DevBuf<unsigned char> qsort_temp;
   // event lookahead block of the offline path: features of chunks [r0, r1) of the active reads
   // (two of them: the next block is computed on the event stream while this one is being mapped)
   DevBuf<float> feat_cache[2];
@@ -223,12 +229,15 @@ struct smb_ctx {
   // index
   bool has_index = false;
   IndexView ix{};
-  DevBuf<float2> leaf_vals;
-  DevBuf<uint2> level[kMaxLevels];
-  DevBuf<uint2> leaf_tb;
+  DevBuf<uint2> leaves;           // 256-byte leaf records (values + {target, bucket})
+  DevBuf<uint2> nodes;            // every node level, top level first
   DevBuf<uint32_t> leaf_widx;
   uint32_t max_tpos = 0, max_bucket = 0;
-  unsigned search_grid_main = 148 * 4;
+  unsigned search_grid_main = 148 * 4;   // general search kernel: every CTA that fits
+  unsigned n_sm = 148;
+  bool search_lean = true;        // SMB_SEARCH=general: every query through the general kernel
+  uint32_t front_cap = kFrontCap; // SMB_FRONT_CAP=n: frontier slots of the lean kernel (tests lower it)
+  uint32_t runs_cap_min = 0;      // SMB_RUNS_CAP=n: run records per (entry, part) list (0 = from the estimate)
   DevBuf<uint64_t> bucket_base;   // linear coordinate of every bucket's target 0 (k_sort.cuh)
   int gshift = 0;
   uint32_t n_coarse = 1;
@@ -241,8 +250,6 @@ struct smb_ctx {
   bool part_sort = true;          // SMB_SORT=entry: always the one-CTA-per-entry sort (k_seg_sort)
   bool seg_sort = true;           // per-entry shared-memory sort; SMB_SORT=global forces the radix sort
   uint32_t search_grab = 0;       // SMB_GRAB=n: queries per grab of the search work counter (0 = default)
-  bool search_box16 = false;      // SMB_BOX=half: experimental packed-binary16 box test (k_index.cuh), BFS only
-  bool search_bfs = true;         // level-order traversal (fuller 8-node steps); SMB_SEARCH=dfs: depth-first
   bool sort_small = false;        // SMB_SORT=small: two 100 KB sort CTAs per SM instead of one 200 KB CTA
   cudaStream_t stream_ev = nullptr;  // lookahead event blocks run here, next to the mapping rounds
   cudaEvent_t ev_blk_t0[2] = {}, ev_blk_t1[2] = {};
@@ -273,6 +280,7 @@ struct smb_ctx {
   uint64_t max_batch_anchors = 640ull << 20;  // x 32 B of sort/DP buffers = 20 GB of the 180 GB HBM
   uint64_t last_cap = 0;
   double est_anchors_per_chunk = 20000.0;
+  double est_queries_per_chunk = 260.0;
   // contig-sharded index: the exchange backend (null = this context holds every contig)
   std::unique_ptr<Exchange> ex;
   std::shared_ptr<LocalGroup> local_group;
@@ -324,18 +332,73 @@ static int fail(smb_ctx *ctx, int code, const std::string &msg) {
   return code;
 }
 
-// persistent grid of the search kernel: every CTA that fits on the device, no more
+// persistent grid of the general search kernel: every CTA that fits on the device, no more
 static size_t search_smem(const smb_ctx *ctx) { return kSearchWarps * search_smem_per_warp(ctx->ix.n_levels); }
 
-template <bool STAGE, bool BFS = false, bool BOX16 = false>
+template <bool STAGE>
 static unsigned search_grid(smb_ctx *ctx) {
   int n = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_radius_search<STAGE, BFS, BOX16>, kSearchWarps * 32,
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_radius_search<STAGE>, kSearchWarps * 32,
                                                     search_smem(ctx)) != cudaSuccess || n < 1)
     n = 4;
-  int n_sm = 148;
-  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device);
-  return (unsigned)(n_sm * n);
+  return ctx->n_sm * (unsigned)n;
+}
+
+// The whole radius search of one batch on stream s: Morton keys of the queries -> radix sort ->
+// lean kernel over the sorted queries -> general kernel over the queries the lean one left.
+// `sa` arrives with everything but the order / overflow fields filled in; nq_max bounds the
+// number of queries (the exact count is only known on the device in pipeline mode).
+template <bool STAGE>
+static int launch_search(smb_ctx *ctx, SearchArgs sa, uint32_t nq_max, cudaStream_t s) {
+  sa.nq_cap = nq_max;
+  Workspace &w = ctx->ws;
+  const size_t gsm = search_smem(ctx);
+  if (!ctx->search_lean || nq_max == 0) {
+    sa.work = &ctx->d_ctr->work;
+    k_radius_search<STAGE><<<STAGE ? search_grid<true>(ctx) : ctx->search_grid_main, kSearchWarps * 32, gsm, s>>>(ctx->ix, sa);
+    LAUNCH_CHECK();
+    return SMB_OK;
+  }
+  CK(w.qkey_a.ensure(nq_max));
+  CK(w.qkey_b.ensure(nq_max));
+  CK(w.qpay_a.ensure(nq_max));
+  CK(w.qpay_b.ensure(nq_max));
+  CK(w.ovf_list.ensure(nq_max));
+  if (STAGE) {
+    k_query_keys_stage<<<(nq_max + 255) / 256, 256, 0, s>>>(sa.features, nq_max, ctx->ix.vmin, ctx->ix.inv_span,
+                                                            w.qkey_a.p, w.qpay_a.p);
+  } else {
+    CK(w.entry_info.ensure(sa.B));
+    // entries without queries write nothing; the sort only looks at the first q_off[B] keys,
+    // but it is sized on the host: pad the tail with the largest key so it stays at the end
+    CK(cudaMemsetAsync(w.qkey_a.p, 0xFF, (size_t)nq_max * sizeof(uint32_t), s));
+    k_query_keys<<<sa.B, 128, 0, s>>>(sa.features, sa.feat_row, sa.q_off, sa.entry_slot, sa.slots, sa.B, sa.step,
+                                      ctx->ix.vmin, ctx->ix.inv_span, w.qkey_a.p, w.qpay_a.p, w.entry_info.p, nq_max);
+  }
+  LAUNCH_CHECK();
+  size_t tb = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tb, w.qkey_a.p, w.qkey_b.p, w.qpay_a.p, w.qpay_b.p, (int)nq_max, 0, 24, s);
+  CK(w.qsort_temp.ensure(tb));
+  CK(cub::DeviceRadixSort::SortPairs(w.qsort_temp.p, tb, w.qkey_a.p, w.qkey_b.p, w.qpay_a.p, w.qpay_b.p, (int)nq_max,
+                                     0, 24, s));
+  ctx->stats.launches += 5;
+  sa.order = w.qpay_b.p;
+  sa.entry_info = w.entry_info.p;
+  sa.front_cap = std::min<uint32_t>(std::max<uint32_t>(ctx->front_cap, 72u), (uint32_t)kFrontCap);
+  sa.ovf_list = w.ovf_list.p;
+  sa.work = &ctx->d_ctr->work;
+  sa.grab = ctx->search_grab;
+  k_search_lean<STAGE><<<ctx->n_sm, kLeanWarps * 32, lean_smem(ctx->ix.smem_bytes), s>>>(ctx->ix, sa);
+  LAUNCH_CHECK();
+  // the queries whose frontier outgrew the lean kernel's slots (none, mostly: the launch then
+  // finds an empty list and returns)
+  sa.qlist = w.ovf_list.p;
+  sa.qlist_n = &ctx->d_ctr->n_overflow;
+  sa.work = &ctx->d_ctr->work2;
+  sa.grab = 0;
+  k_radius_search<STAGE><<<STAGE ? search_grid<true>(ctx) : ctx->search_grid_main, kSearchWarps * 32, gsm, s>>>(ctx->ix, sa);
+  LAUNCH_CHECK();
+  return SMB_OK;
 }
 
 // ------------------------------------------------------------------ index build
@@ -425,38 +488,54 @@ static int build_index(smb_ctx *ctx, const uint64_t *pos, const float *val, size
   CK(tmp.ensure(tb));
   CK(cub::DeviceRadixSort::SortPairs(tmp.p, tb, code_a.p, code_b.p, w_a.p, w_b.p, (uint64_t)W, 0, 60, s));
   ctx->stats.launches += 8;
-  CK(ctx->leaf_vals.ensure((size_t)n_leaves * 3 * kLeaf));
-  CK(ctx->leaf_tb.ensure((size_t)n_leaves * kLeaf));
+  CK(ctx->leaves.ensure((size_t)n_leaves * kLeafRec));
   CK(ctx->leaf_widx.ensure((size_t)n_leaves * kLeaf));
   k_build_leaves<<<(unsigned)(((uint64_t)n_leaves * kLeaf + 255) / 256), 256, 0, s>>>(
-      d_val.p, d_pos.p, w_b.p, W, n_leaves, ctx->leaf_vals.p, ctx->leaf_tb.p, ctx->leaf_widx.p, d_wsrc.p, d_worig.p);
+      d_val.p, d_pos.p, w_b.p, W, n_leaves, ctx->leaves.p, ctx->leaf_widx.p, d_wsrc.p, d_worig.p);
   LAUNCH_CHECK();
   IndexView ix{};
   ix.n_points = n;
   ix.n_windows = W;
   ix.n_leaves = n_leaves;
-  uint32_t n_child = n_leaves;
+  ix.vmin = vmin;
+  ix.inv_span = 1.0f / span;
+  // level sizes bottom-up; storage top-down in one buffer, so the levels every query walks are a
+  // prefix of it (staged in shared memory by the lean search kernel)
   int L = 0;
-  for (;;) {
+  for (uint32_t n_child = n_leaves;;) {
     if (L >= kMaxLevels) return fail(ctx, SMB_ERR_CAPACITY, "index hierarchy deeper than kMaxLevels");
     const uint32_t n_nodes = (n_child + kFan - 1) / kFan;
     if (n_nodes >= (1u << 28)) return fail(ctx, SMB_ERR_CAPACITY, "index level exceeds 2^28 nodes");
-    CK(ctx->level[L].ensure((size_t)n_nodes * 3 * kFan));
-    const unsigned blocks = (unsigned)(((uint64_t)n_nodes * kFan + 255) / 256);
-    if (L == 0)
-      k_nodes_level0<<<blocks, 256, 0, s>>>(ctx->leaf_vals.p, ctx->leaf_tb.p, n_leaves, n_nodes, ctx->level[0].p);
-    else
-      k_nodes_up<<<blocks, 256, 0, s>>>(ctx->level[L - 1].p, n_child, n_nodes, ctx->level[L].p);
-    LAUNCH_CHECK();
-    ix.level_count[L] = n_nodes;
-    ix.level_node[L] = ctx->level[L].p;
-    ++L;
+    ix.level_count[L++] = n_nodes;
     if (n_nodes <= (uint32_t)kFan) break;  // the search starts from all nodes of the top level
     n_child = n_nodes;
   }
   ix.n_levels = L;
-  ix.leaf_vals = ctx->leaf_vals.p;
-  ix.leaf_tb = ctx->leaf_tb.p;
+  uint64_t total_rec = 0;
+  ix.smem_from = L;
+  ix.smem_bytes = 0;
+  for (int l = L - 1; l >= 0; --l) {
+    if (total_rec * kNodeRec > 0xFFFFFFF0ull) return fail(ctx, SMB_ERR_CAPACITY, "node levels exceed 2^32 records: shard the index");
+    ix.level_off[l] = (uint32_t)(total_rec * kNodeRec);
+    total_rec += ix.level_count[l];
+    if (ix.smem_from == l + 1 && total_rec * kNodeRec * sizeof(uint2) <= kTopSmemMax) {
+      ix.smem_from = l;
+      ix.smem_bytes = (uint32_t)(total_rec * kNodeRec * sizeof(uint2));
+    }
+  }
+  CK(ctx->nodes.ensure((size_t)total_rec * kNodeRec));
+  for (int l = 0; l < L; ++l) {
+    const uint32_t n_nodes = ix.level_count[l];
+    const unsigned blocks = (unsigned)(((uint64_t)n_nodes * kFan + 255) / 256);
+    if (l == 0)
+      k_nodes_level0<<<blocks, 256, 0, s>>>(ctx->leaves.p, n_leaves, n_nodes, ctx->nodes.p + ix.level_off[0]);
+    else
+      k_nodes_up<<<blocks, 256, 0, s>>>(ctx->nodes.p + ix.level_off[l - 1], ix.level_count[l - 1], n_nodes,
+                                        ctx->nodes.p + ix.level_off[l]);
+    LAUNCH_CHECK();
+  }
+  ix.nodes = ctx->nodes.p;
+  ix.leaves = ctx->leaves.p;
   ix.leaf_widx = ctx->leaf_widx.p;
   CK(cudaStreamSynchronize(s));
   d_val.release();
@@ -481,7 +560,7 @@ static int build_index(smb_ctx *ctx, const uint64_t *pos, const float *val, size
     ctx->n_coarse = (uint32_t)(base.back() >> ctx->gshift) + 1;
   }
   ctx->ix = ix;
-  ctx->search_grid_main = ctx->search_bfs ? search_grid<false, true>(ctx) : search_grid<false, false>(ctx);
+  ctx->search_grid_main = search_grid<false>(ctx);
   ctx->max_tpos = max_tpos;
   ctx->max_bucket = max_bucket;
   ctx->has_index = true;
@@ -670,8 +749,14 @@ static int run_step(smb_ctx *ctx, SlotSpace &sp, const StepEntries &en, StepSour
   }
   const float inv_span = 1.0f / (float)span;
   const size_t n_lists = (size_t)B * n_parts;
+  // run records per (entry, part) list: a query leaves at most one run per part and flush, so
+  // queries per chunk + the flushes forced by a full staging buffer, with room for dense chunks
+  uint32_t runs_cap = (uint32_t)(1.5 * ctx->est_queries_per_chunk +
+                                 3.0 * ctx->est_anchors_per_chunk / (double)kStageCap) + 128u;
+  runs_cap = std::max<uint32_t>((runs_cap + 63u) & ~63u, std::max<uint32_t>(ctx->runs_cap_min, 64u));
+  if (ctx->runs_cap_min) runs_cap = ctx->runs_cap_min;
   if (want_seg) {
-    CK(w.runs.ensure(n_lists * kRunsCap));
+    CK(w.runs.ensure(n_lists * runs_cap));
     CK(w.run_count.ensure(n_lists));
     CK(w.entry_total.ensure(n_lists));
     CK(w.part_base.ensure(n_lists + 1));
@@ -681,7 +766,7 @@ static int run_step(smb_ctx *ctx, SlotSpace &sp, const StepEntries &en, StepSour
   k_inject_carry<<<(B * 32 + kCarryThreads - 1) / kCarryThreads, kCarryThreads, 0, s>>>(
       w.entry_slot.p, w.n_queries.p, sp.slots.p, sp.pool_anchor[0].p, sp.pool_anchor[1].p, B, kl, w.key_a.p,
       w.dist_a.p, cap, ctx->d_ctr, want_seg ? w.runs.p : nullptr, w.run_count.p, w.entry_total.p,
-      (uint32_t)kRunsCap, n_parts, inv_span, ctx->bucket_base.p);
+      runs_cap, n_parts, inv_span, ctx->bucket_base.p);
   LAUNCH_CHECK();
   SearchArgs sa{};
   sa.features = src == SRC_CACHED ? w.feat_cache[w.cache_cur].p : w.features.p;
@@ -701,19 +786,21 @@ static int run_step(smb_ctx *ctx, SlotSpace &sp, const StepEntries &en, StepSour
   sa.runs = want_seg ? w.runs.p : nullptr;
   sa.run_count = w.run_count.p;
   sa.entry_total = w.entry_total.p;
-  sa.runs_cap = kRunsCap;
+  sa.runs_cap = runs_cap;
   sa.n_parts = n_parts;
   sa.inv_span = inv_span;
   sa.bucket_base = ctx->bucket_base.p;
   sa.grab = ctx->search_grab;
+  sa.n_buckets = ctx->max_bucket + 1u;
+  // query-order buffers are sized from a running estimate (the exact count is on the device)
+  const uint32_t q_per_chunk_max = (uint32_t)(kFeatCap - kDim) / (uint32_t)prm.step_size;
+  const uint32_t nq_max = (uint32_t)std::min<uint64_t>(
+      (uint64_t)Bpres * q_per_chunk_max, (uint64_t)(1.25 * ctx->est_queries_per_chunk * Bpres) + 4096u);
   CK(cudaEventRecord(ctx->ev[2], s));
-  if (ctx->search_bfs && ctx->search_box16)
-    k_radius_search<false, true, true><<<ctx->search_grid_main, kSearchWarps * 32, search_smem(ctx), s>>>(ctx->ix, sa);
-  else if (ctx->search_bfs)
-    k_radius_search<false, true><<<ctx->search_grid_main, kSearchWarps * 32, search_smem(ctx), s>>>(ctx->ix, sa);
-  else
-    k_radius_search<false, false><<<ctx->search_grid_main, kSearchWarps * 32, search_smem(ctx), s>>>(ctx->ix, sa);
-  LAUNCH_CHECK();
+  {
+    int rc = launch_search<false>(ctx, sa, nq_max, s);
+    if (rc) return rc;
+  }
   ctx->stats.search_launches++;
   CK(cudaEventRecord(ctx->ev[3], s));
   if (want_seg) {
@@ -751,10 +838,19 @@ static int run_step(smb_ctx *ctx, SlotSpace &sp, const StepEntries &en, StepSour
     ctx->stats.exchanges++;
   }
   if (overflow) return 1;  // nothing has been committed to the slots yet
+  if (ctx->h_ctr->error & 64u) {  // more queries than the order buffers were sized for: redo the step
+    ctx->est_queries_per_chunk = 1.1 * (double)ctx->h_ctr->n_queries / std::max(Bpres, 1u) + 8.0;
+    k_clear_error_bits<<<1, 1, 0, s>>>(ctx->d_ctr, 64u);
+    LAUNCH_CHECK();
+    return 2;
+  }
+  if (Bpres)
+    ctx->est_queries_per_chunk = std::max(0.9 * ctx->est_queries_per_chunk, (double)ctx->h_ctr->n_queries / Bpres);
   ctx->stats.queries += ctx->h_ctr->n_queries;
   ctx->stats.hits += ctx->h_ctr->n_hits;
   ctx->stats.anchors += n;
   ctx->stats.capped_queries += ctx->h_ctr->n_capped;
+  ctx->stats.overflow_queries += ctx->search_lean ? ctx->h_ctr->n_overflow : ctx->h_ctr->n_queries;
   ctx->stats.raw_events += ctx->h_ctr->n_events_raw;
   ctx->stats.events += ctx->h_ctr->n_events_kept;
   ctx->stats.chunks += Bpres;
@@ -782,6 +878,7 @@ static int run_step(smb_ctx *ctx, SlotSpace &sp, const StepEntries &en, StepSour
     ps.dist_out = w.dist_b.p;
     ps.runs = w.runs.p;
     ps.run_count = w.run_count.p;
+    ps.runs_cap = runs_cap;
     ps.part_total = w.entry_total.p;
     ps.out_base = w.part_base.p;
     ps.n_parts = n_parts;
@@ -819,6 +916,7 @@ static int run_step(smb_ctx *ctx, SlotSpace &sp, const StepEntries &en, StepSour
     ss.dist_out = w.dist_b.p;
     ss.runs = w.runs.p;
     ss.run_count = w.run_count.p;
+    ss.runs_cap = runs_cap;
     ss.n_parts = n_parts;
     ss.B = B;
     ss.kl = kl;
@@ -1072,6 +1170,7 @@ static int run_round(smb_ctx *ctx, SlotSpace &sp, const std::vector<uint32_t> &p
       if (!absent_done) en.slot.insert(en.slot.end(), absent.begin(), absent.end());
       en.B = (uint32_t)en.slot.size();
       rc = run_step(ctx, sp, en, src, prm, out_pool);
+      if (rc == 2) continue;  // query-order buffers were too small: the estimate has been raised
       if (rc == 1) {  // anchor buffer overflow: grow the buffers, or halve the step at the limit
         ctx->est_anchors_per_chunk *= 2.0;
         if (ctx->ex ? ctx->group_at_limit : ctx->last_cap >= ctx->max_batch_anchors) {
@@ -1166,6 +1265,42 @@ static void make_row(const smb_ctx *ctx, const SlotState &st, uint32_t read_len,
   }
 }
 
+// Run-time switches for A/B measurements and for tests that must reach the fallback paths.
+// Names are the SMB_<NAME> environment variables (read once by smb_create) without the prefix,
+// case-insensitive.  Returns false for an unknown name.
+static bool apply_option(smb_ctx *ctx, const char *name_in, const char *value) {
+  std::string name(name_in);
+  for (char &c : name) c = (char)toupper((unsigned char)c);
+  if (name == "SORT") {  // part (default) | entry | small | global
+    ctx->seg_sort = strcmp(value, "global") != 0;
+    ctx->sort_small = strcmp(value, "small") == 0;
+    ctx->part_sort = strcmp(value, "entry") != 0 && !ctx->sort_small && ctx->seg_sort;
+  } else if (name == "SEARCH") {  // lean (default) | general
+    ctx->search_lean = strcmp(value, "general") != 0;
+  } else if (name == "FRONT_CAP") {
+    ctx->front_cap = (uint32_t)std::max(atoi(value), 0);
+  } else if (name == "RUNS_CAP") {
+    ctx->runs_cap_min = (uint32_t)std::max(atoi(value), 0);
+  } else if (name == "GRAB") {
+    ctx->search_grab = (uint32_t)std::max(atoi(value), 0);
+  } else if (name == "PART_FILL") {
+    ctx->part_fill = atof(value);
+  } else if (name == "PART") {
+    ctx->part_small = strcmp(value, "small") == 0;
+  } else if (name == "DP") {
+    ctx->dp_dynamic = strcmp(value, "static") != 0;
+  } else if (name == "DP_PASSES") {
+    ctx->dp_passes = std::max(atoi(value), 0);
+  } else if (name == "EVENTS_OVERLAP") {
+    ctx->ev_overlap = strcmp(value, "0") != 0;
+  } else if (name == "EVENTS") {  // auto (default) | thread | warp
+    ctx->ev_warp_max = !strcmp(value, "thread") ? 0u : (!strcmp(value, "warp") ? 0xFFFFFFFFu : 2048u);
+  } else {
+    return false;
+  }
+  return true;
+}
+
 // ================================================================== C ABI
 extern "C" {
 
@@ -1229,35 +1364,30 @@ int smb_create(smb_ctx **out, int device) {
       (e = cudaFuncSetAttribute(k_seg_sort<kSortCapSmall, 512, 4096>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)sort_smem_bytes(kSortCapSmall, 4096))) != cudaSuccess)
     return bail("cudaFuncSetAttribute(k_seg_sort)", e);
-  // the search keeps one stack per index level in shared memory: from 7 levels on (> 16.7 M
-  // points, i.e. references beyond ~8 Mbp) a CTA needs more than the 48 KB a kernel gets by default
+  // the general search kernel keeps one stack per index level in shared memory: from 7 levels on
+  // (> 16.7 M points, i.e. references beyond ~8 Mbp) a CTA needs more than the default 48 KB; the
+  // lean one holds the top levels and its warps' frontiers in up to 208 KB
   {
     const int need = (int)(kSearchWarps * search_smem_per_warp(kMaxLevels));
-    if ((e = cudaFuncSetAttribute(k_radius_search<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, need)) != cudaSuccess ||
-        (e = cudaFuncSetAttribute(k_radius_search<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, need)) != cudaSuccess ||
-        (e = cudaFuncSetAttribute(k_radius_search<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, need)) != cudaSuccess ||
-        (e = cudaFuncSetAttribute(k_radius_search<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, need)) != cudaSuccess ||
-        (e = cudaFuncSetAttribute(k_radius_search<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, need)) != cudaSuccess ||
-        (e = cudaFuncSetAttribute(k_radius_search<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, need)) != cudaSuccess)
+    if ((e = cudaFuncSetAttribute(k_radius_search<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, need)) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(k_radius_search<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, need)) != cudaSuccess)
       return bail("cudaFuncSetAttribute(k_radius_search)", e);
+    const int lean = (int)lean_smem(kTopSmemMax);
+    if ((e = cudaFuncSetAttribute(k_search_lean<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lean)) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(k_search_lean<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lean)) != cudaSuccess)
+      return bail("cudaFuncSetAttribute(k_search_lean)", e);
+    int n_sm = 148;
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device);
+    ctx->n_sm = (unsigned)n_sm;
   }
   if ((e = cudaFuncSetAttribute(k_part_sort<kPartSortCap, 512, 4096>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)part_sort_smem_bytes(kPartSortCap, 4096))) != cudaSuccess ||
       (e = cudaFuncSetAttribute(k_part_sort<kPartSortCapSmall, 256, 2304>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)part_sort_smem_bytes(kPartSortCapSmall, 2304))) != cudaSuccess)
     return bail("cudaFuncSetAttribute(k_part_sort)", e);
-  if (const char *env = getenv("SMB_SORT")) {
-    ctx->seg_sort = strcmp(env, "global") != 0;
-    ctx->sort_small = strcmp(env, "small") == 0;
-    ctx->part_sort = strcmp(env, "entry") != 0 && !ctx->sort_small;
-  }
-  if (const char *env = getenv("SMB_SEARCH")) ctx->search_bfs = strcmp(env, "dfs") != 0;
-  if (const char *env = getenv("SMB_BOX")) ctx->search_box16 = strcmp(env, "half") == 0;
-  if (const char *env = getenv("SMB_GRAB")) ctx->search_grab = (uint32_t)std::max(atoi(env), 0);
-  if (const char *env = getenv("SMB_PART_FILL")) ctx->part_fill = atof(env);
-  if (const char *env = getenv("SMB_PART")) ctx->part_small = strcmp(env, "small") == 0;
-  if (const char *env = getenv("SMB_DP")) ctx->dp_dynamic = strcmp(env, "static") != 0;
-  if (const char *env = getenv("SMB_DP_PASSES")) ctx->dp_passes = std::max(atoi(env), 0);
+  for (const char *name : {"SORT", "SEARCH", "FRONT_CAP", "RUNS_CAP", "GRAB", "PART_FILL", "PART", "DP", "DP_PASSES",
+                           "EVENTS_OVERLAP", "EVENTS"})
+    if (const char *env = getenv((std::string("SMB_") + name).c_str())) apply_option(ctx, name, env);
   {
     int per_sm = 0, n_sm = 148;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_chain_dp, kDpThreads, 0) != cudaSuccess || per_sm < 1)
@@ -1275,11 +1405,6 @@ int smb_create(smb_ctx **out, int device) {
   for (int c = 0; c < 2; ++c)
     if ((e = cudaEventCreate(&ctx->ev_blk_t0[c])) != cudaSuccess || (e = cudaEventCreate(&ctx->ev_blk_t1[c])) != cudaSuccess)
       return bail("cudaEventCreate", e);
-  if (const char *env = getenv("SMB_EVENTS_OVERLAP")) ctx->ev_overlap = strcmp(env, "0") != 0;
-  if (const char *env = getenv("SMB_EVENTS")) {
-    if (!strcmp(env, "thread")) ctx->ev_warp_max = 0;
-    else if (!strcmp(env, "warp")) ctx->ev_warp_max = 0xFFFFFFFFu;
-  }
   *out = ctx;
   return SMB_OK;
 }
@@ -1303,8 +1428,9 @@ void smb_destroy(smb_ctx *ctx) {
   w.cand_counts.release(); w.ctl.release(); w.tags.release();
   ctx->ex.reset();
   ctx->local_group.reset();
-  ctx->leaf_vals.release(); ctx->leaf_tb.release(); ctx->leaf_widx.release(); ctx->bucket_base.release();
-  for (auto &l : ctx->level) l.release();
+  ctx->leaves.release(); ctx->nodes.release(); ctx->leaf_widx.release(); ctx->bucket_base.release();
+  w.qkey_a.release(); w.qkey_b.release(); w.qpay_a.release(); w.qpay_b.release(); w.ovf_list.release();
+  w.entry_info.release(); w.qsort_temp.release();
   ctx->raw.release(); ctx->kept.release(); ctx->d_read_off.release(); ctx->d_kept_off.release();
   ctx->d_dig.release(); ctx->d_range.release(); ctx->d_offset.release(); ctx->d_kept_len.release();
   for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
@@ -1350,6 +1476,12 @@ int smb_set_limits(smb_ctx *ctx, uint32_t max_batch_chunks, uint64_t max_batch_a
     if (max_batch_anchors >= (1ull << 30)) return fail(ctx, SMB_ERR_ARG, "max_batch_anchors must be < 2^30");
     ctx->max_batch_anchors = max_batch_anchors;
   }
+  return SMB_OK;
+}
+
+int smb_set_option(smb_ctx *ctx, const char *name, const char *value) {
+  if (!name || !value) return fail(ctx, SMB_ERR_ARG, "smb_set_option: null name or value");
+  if (!apply_option(ctx, name, value)) return fail(ctx, SMB_ERR_ARG, std::string("smb_set_option: unknown option ") + name);
   return SMB_OK;
 }
 
@@ -1831,13 +1963,10 @@ int smb_stage_radius(smb_ctx *ctx, const float *queries, size_t nq, float radius
   sa.out_dist = d_a.p;
   sa.cap = dcap;
   sa.ctr = ctx->d_ctr;
-  if (ctx->search_bfs && ctx->search_box16)
-    k_radius_search<true, true, true><<<search_grid<true, true, true>(ctx), kSearchWarps * 32, search_smem(ctx), s>>>(ctx->ix, sa);
-  else if (ctx->search_bfs)
-    k_radius_search<true, true><<<search_grid<true, true>(ctx), kSearchWarps * 32, search_smem(ctx), s>>>(ctx->ix, sa);
-  else
-    k_radius_search<true, false><<<search_grid<true, false>(ctx), kSearchWarps * 32, search_smem(ctx), s>>>(ctx->ix, sa);
-  LAUNCH_CHECK();
+  {
+    int rc = launch_search<true>(ctx, sa, (uint32_t)nq, s);
+    if (rc) return rc;
+  }
   CK(cudaMemcpyAsync(ctx->h_ctr, ctx->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
   const unsigned long long n = ctx->h_ctr->n_anchors;

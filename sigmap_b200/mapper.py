@@ -113,6 +113,12 @@ class Mapper:
         self._check(F.lib.smb_set_limits(self._ctx, max_batch_chunks, max_batch_anchors),
                     "smb_set_limits")
 
+    def set_option(self, name, value):
+        """Run-time switch (an SMB_<NAME> environment variable without the prefix): A/B
+        measurements, and tests that have to reach the fallback paths."""
+        self._check(F.lib.smb_set_option(self._ctx, str(name).encode(), str(value).encode()),
+                    "smb_set_option")
+
     def timer_start(self):
         self._check(F.lib.smb_timer_start(self._ctx), "smb_timer_start")
 
