@@ -281,6 +281,8 @@ int smbh_blow5_write(const char *path, const char *const *names, const int16_t *
                      const uint64_t *read_off, size_t n, double digitisation, double offset,
                      double range, double sampling_rate);
 int smbh_blow5_read(const char *path, smbh_reads *out); /* appends to *out (zero-init first) */
+/* message of the last failed smbh_* call on this thread (BLOW5 version / compression, ...) */
+const char *smbh_last_error(void);
 void smbh_reads_free(smbh_reads *r);
 /* Synthetic data: uniform ACGT reference, reads simulated from the
  * 6-mer model.  Deterministic in (seed, read index) so ranks can generate disjoint read

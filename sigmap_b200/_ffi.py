@@ -201,6 +201,7 @@ PROTOTYPES = {
                                    C.c_double, C.c_double, C.c_double]),
     "smbh_blow5_read": (C.c_int, [C.c_char_p, C.POINTER(Reads)]),
     "smbh_reads_free": (None, [C.POINTER(Reads)]),
+    "smbh_last_error": (C.c_char_p, []),
     "smbh_sim_reference": (C.c_int, [C.c_uint64, u32p, C.c_uint32, charpp]),
     "smbh_sim_reads": (C.c_int, [C.c_uint64, charpp, u32p, C.c_uint32, f32p, f32p, C.c_uint64,
                                  C.c_uint64, C.c_uint32, C.c_uint32, C.c_float, u64p, i16p, u32p]),

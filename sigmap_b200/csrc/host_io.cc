@@ -351,9 +351,16 @@ static bool inflate_all(const unsigned char *src, size_t n, std::vector<unsigned
 // length prefixes, and everything per record -- inflating zlib records, parsing the header,
 // copying the samples to their final place -- runs on all host cores.  The raw samples are
 // copied exactly once, into an array sized from the record headers.
+static thread_local std::string g_host_error;
+static int host_fail(int code, const std::string &msg) {
+  g_host_error = msg;
+  return code;
+}
+const char *smbh_last_error(void) { return g_host_error.c_str(); }
+
 int smbh_blow5_read(const char *path, smbh_reads *out) {
   const int fd = open(path, O_RDONLY);
-  if (fd < 0) return SMB_ERR_IO;
+  if (fd < 0) return host_fail(SMB_ERR_IO, std::string("cannot open ") + path);
   struct stat st;
   if (fstat(fd, &st) != 0 || st.st_size < 68) {
     close(fd);
@@ -369,11 +376,20 @@ int smbh_blow5_read(const char *path, smbh_reads *out) {
     size_t n;
     ~Unmap() { munmap(p, n); }
   } unmap{map, fsize};
-  if (memcmp(base, "BLOW5\1", 6) != 0) return SMB_ERR_IO;
+  if (memcmp(base, "BLOW5\1", 6) != 0) return host_fail(SMB_ERR_IO, std::string(path) + ": not a BLOW5 file");
+  // version triple, then: 0.1.0 (the reference's bundled slow5lib) {record compression u8,
+  // read groups u32}; from 0.2.0 on {record compression u8, SIGNAL compression u8, read groups u32}
+  const int vmaj = base[6], vmin = base[7], vpat = base[8];
+  const std::string ver = std::to_string(vmaj) + "." + std::to_string(vmin) + "." + std::to_string(vpat);
+  if (vmaj != 0 || (vmin != 1 && vmin != 2)) return host_fail(SMB_ERR_IO, std::string(path) + ": unsupported BLOW5 version " + ver);
   const int method = base[9];
+  if (vmin >= 2 && base[10] != 0)
+    return host_fail(SMB_ERR_IO, std::string(path) + ": unsupported BLOW5 signal compression (method " +
+                                     std::to_string((int)base[10]) + ", version " + ver + "); only uncompressed signals are read");
   uint32_t hl;
   memcpy(&hl, base + 64, 4);
-  if (method > 1 || (size_t)68 + hl > fsize) return SMB_ERR_IO;
+  if (method > 1) return host_fail(SMB_ERR_IO, std::string(path) + ": unsupported BLOW5 record compression (only none and zlib)");
+  if ((size_t)68 + hl > fsize) return host_fail(SMB_ERR_IO, std::string(path) + ": truncated BLOW5 header");
 
   // ---- record boundaries
   std::vector<size_t> rec_at;

@@ -17,9 +17,11 @@
 //   k_sel_trace      warp per segment: running max of the earlier buckets, traceback of the
 //                    segment's <= 3 end candidates with used-flags (spatial_index.cc:165-220)
 //   k_sel_scatter    contig-sharded runs: candidates gathered from the other ranks
-//   k_sel_final      warp per entry: primary chains, MAPQ (spatial_index.cc:222-274), then
-//                    StreamingMap's stop / output decision and tag sums (sigmap.cc:667-745);
-//                    survivors' anchors go to the carry pool for the next chunk.
+//   k_sel_pick       warp per entry: primary chains (spatial_index.cc:222-253) and the carry-pool
+//                    space they need; k_pool_check aborts the step if the pools are too small
+//   k_sel_commit     warp per entry: MAPQ (spatial_index.cc:255-274), then StreamingMap's stop /
+//                    output decision and tag sums (sigmap.cc:667-745); survivors' anchors go to
+//                    the carry pool for the next chunk.
 // All float arithmetic mirrors the reference expression by expression (no FMA).
 #ifndef SB_K_CHAIN_CUH
 #define SB_K_CHAIN_CUH
@@ -45,7 +47,7 @@ constexpr int kPrepTile = 1024;  // anchors per k_chain_prep block = per compact
 struct ChainArgs {
   const uint64_t *key;   // sorted
   const float *dist;     // sorted alongside
-  unsigned long long n;  // anchors this step
+  unsigned long long n_max;  // capacity of the anchor arrays; the count itself is ctr->n_anchors
   KeyLayout kl;
   float radius;
   float *score;
@@ -145,9 +147,11 @@ k_inject_carry(const uint32_t *__restrict__ entry_slot, const uint32_t *__restri
 // kernel finishes the reference's (target, query) order (spatial_index.h:22-25) by sorting
 // each such run in place; (target, query) pairs are unique inside a segment, so the result
 // is fully determined.  One thread per run head.
-__global__ void k_fix_ties(uint64_t *__restrict__ key, float *__restrict__ dist, uint32_t n, int lo_bits) {
+__global__ void k_fix_ties(uint64_t *__restrict__ key, float *__restrict__ dist, const Counters *__restrict__ ctr,
+                           int lo_bits) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  const uint32_t n = (uint32_t)ctr->n_anchors;
+  if (i >= n || ctr->abort) return;
   const uint64_t hi = key[i] >> lo_bits;
   if (i > 0 && (key[i - 1] >> lo_bits) == hi) return;  // inside a run: its head handles it
   uint32_t e = i + 1;
@@ -211,8 +215,10 @@ __global__ void __launch_bounds__(kPrepThreads, 8) k_chain_prep(ChainArgs a) {
   __shared__ int4 s_a[kPrepHalo + kPrepTile];
   constexpr int kSubTiles = kPrepTile / kPrepThreads;
   __shared__ uint32_t warp_cnt[kSubTiles][kPrepThreads / 32];  // linked anchors per (sub-tile, warp)
-  const uint32_t n = (uint32_t)a.n;  // < 2^30
+  if (a.ctr->abort) return;
+  const uint32_t n = (uint32_t)a.ctr->n_anchors;  // < 2^30
   const uint32_t tile0 = blockIdx.x * kPrepTile;
+  if (tile0 >= n) return;  // the grid is sized for the buffers, not for the count
   const KeyLayout kl = a.kl;
   for (int x = threadIdx.x; x < kPrepHalo + kPrepTile; x += kPrepThreads) {
     const long long g = (long long)tile0 - kPrepHalo + x;
@@ -524,6 +530,7 @@ __device__ __forceinline__ void dp_segment(const ChainArgs &a, const uint32_t sl
 // segments from a work cursor instead (dynamic = 0: warp w handles segment w).
 __global__ void __launch_bounds__(kDpThreads) k_chain_dp(ChainArgs a, int dynamic) {
   const int lane = threadIdx.x & 31;
+  if (a.ctr->abort) return;
   if (!dynamic) {
     const uint32_t slot = (blockIdx.x * kDpThreads + threadIdx.x) / 32;
     if (slot < a.n_slots) dp_segment(a, slot, lane);
@@ -553,10 +560,11 @@ __global__ void __launch_bounds__(kDpThreads) k_chain_dp(ChainArgs a, int dynami
 //                 to path[], so later copies are parallel gathers.
 //   k_sel_scatter (sharded only) candidates gathered from the other ranks join the per-entry
 //                 lists.
-//   k_sel_final   warp per entry: GeneratePrimaryChains + ComputeMAPQ (spatial_index.cc:222-274)
-//                 on lane 0, then all lanes copy the surviving chains' anchors to the carry
-//                 pool (only chains whose bucket this rank owns), the StreamingMap stop / output
-//                 decision and the tag sums (sigmap.cc:667-745).
+//   k_sel_pick    warp per entry: GeneratePrimaryChains (spatial_index.cc:222-253) on lane 0 and
+//                 the carry-pool space the survivors need (nothing committed yet)
+//   k_sel_commit  warp per entry: ComputeMAPQ (:255-274), all lanes copy the surviving chains'
+//                 anchors to the carry pool (only chains whose bucket this rank owns), the
+//                 StreamingMap stop / output decision and the tag sums (sigmap.cc:667-745).
 struct CandRec {  // an end candidate whose traceback produced a chain of >= 2 anchors
   float score;
   uint32_t entry, bucket, start, end, n;
@@ -612,12 +620,12 @@ __global__ void __launch_bounds__(kTraceThreads) k_sel_trace(SelectArgs a) {
   const int lane = threadIdx.x & 31;
   const unsigned full = 0xffffffffu;
   const uint32_t slot = (blockIdx.x * kTraceThreads + threadIdx.x) / 32;
-  if (slot >= a.c.n_slots) return;
+  if (slot >= a.c.n_slots || a.c.ctr->abort) return;
   const SegRec rec = a.c.seg[slot];
   if (rec.start == kSegEmpty || rec.ntop == 0u || rec.ntop > 3u) return;
   const KeyLayout kl = a.c.kl;
   const uint32_t bucket = slot & ((1u << kl.bbits) - 1u), entry = slot >> kl.bbits;
-  const uint32_t n = (uint32_t)a.c.n;
+  const uint32_t n = (uint32_t)a.c.ctr->n_anchors;
   uint32_t *pred = a.c.pred;
   const float *score = a.c.score;
 
@@ -700,7 +708,7 @@ __global__ void k_sel_scatter(SelectArgs a, const CandRec *__restrict__ all, con
                               uint32_t world, uint32_t per_rank) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t r = i / per_rank, k = i % per_rank;
-  if (r >= world || r == a.rank || k >= counts[r]) return;
+  if (r >= world || r == a.rank || k >= counts[r] || a.c.ctr->abort) return;
   add_candidate(a, all[(size_t)r * per_rank + k]);
 }
 
@@ -717,11 +725,80 @@ __device__ __forceinline__ bool chain_greater(const CandRec &x, const CandRec &y
 
 constexpr int kFinalThreads = 128;
 
-__global__ void __launch_bounds__(kFinalThreads) k_sel_final(SelectArgs a) {
+// what k_sel_pick decided for one entry
+struct PickRec {
+  uint32_t n_prim, prim_first, prim_second, total_anchors;
+};
+
+// warp per entry: GeneratePrimaryChains (spatial_index.cc:222-253) on the entry's candidate list,
+// and the carry-pool space the survivors will need.  Nothing is committed here: the pools are
+// checked against the step's total need (k_pool_check) before k_sel_commit writes anything, so a
+// step whose survivors do not fit can be redone with larger pools.
+__global__ void __launch_bounds__(kFinalThreads) k_sel_pick(SelectArgs a, PickRec *__restrict__ pick) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t b = (blockIdx.x * kFinalThreads + threadIdx.x) / 32;
+  if (b >= a.B || a.c.ctr->abort) return;
+  Counters *ctr = a.c.ctr;
+  if (a.n_queries[b] == 0) {  // chains unchanged: they move to the pool that survives the round
+    if (lane == 0) {
+      const SlotState &st = a.slots[a.entry_slot[b]];
+      if (st.n_chains > 0) {
+        atomicAdd(&ctr->need_chain, (unsigned long long)st.n_chains);
+        atomicAdd(&ctr->need_anchor, (unsigned long long)st.carry_n);
+      }
+    }
+    return;
+  }
+  if (lane != 0) return;
+  ChainTmp *ch = a.scratch + (size_t)b * a.max_chains;
+  const uint32_t nch = min(a.n_scratch[b], a.max_chains);
+  uint32_t n_prim = 0, prim_first = 0, prim_second = 0, total_anchors = 0;
+  float last_primary_score = 0.0f;
+  for (;;) {  // repeated extraction of the max = the reference's descending sort, lazily
+    int best = -1;
+    for (uint32_t c = 0; c < nch; ++c)
+      if (ch[c].state == 0 && (best < 0 || chain_greater(ch[c].c, ch[best].c))) best = (int)c;
+    if (best < 0) break;
+    const CandRec cb = ch[best].c;
+    if (n_prim > 0 && cb.score < __fdiv_rn(last_primary_score, 3.0f)) break;
+    bool ok = true;
+    for (uint32_t c = 0; c < nch && ok; ++c) {
+      if (ch[c].state != 1 || (ch[c].c.bucket >> 1) != (cb.bucket >> 1)) continue;
+      const uint32_t mx = max(cb.start, ch[c].c.start), mn = min(cb.end, ch[c].c.end);
+      if (!(mx > mn)) ok = false;
+    }
+    if (ok) {
+      ch[best].state = 1;
+      ch[best].rank = n_prim;
+      if (n_prim == 0) prim_first = (uint32_t)best;
+      if (n_prim == 1) prim_second = (uint32_t)best;
+      last_primary_score = cb.score;
+      if (cb.owner == a.rank) total_anchors += cb.n;
+      ++n_prim;
+    } else {
+      ch[best].state = 2;
+    }
+  }
+  pick[b] = PickRec{n_prim, prim_first, prim_second, total_anchors};
+  if (n_prim) {
+    atomicAdd(&ctr->need_chain, (unsigned long long)n_prim);
+    atomicAdd(&ctr->need_anchor, (unsigned long long)total_anchors);
+  }
+}
+
+__global__ void k_pool_check(Counters *ctr, uint32_t op, unsigned long long cap_chain, unsigned long long cap_anchor) {
+  if (ctr->carry_chain_used[op] + ctr->need_chain > cap_chain || ctr->carry_anchor_used[op] + ctr->need_anchor > cap_anchor)
+    ctr->abort |= kAbortPool;
+}
+
+// warp per entry: the survivors' records and anchors go to the carry pool, ComputeMAPQ
+// (spatial_index.cc:255-274), then StreamingMap's stop / output decision and the tag sums
+// (sigmap.cc:667-745) into the read slot.
+__global__ void __launch_bounds__(kFinalThreads) k_sel_commit(SelectArgs a, const PickRec *__restrict__ pick) {
   const int lane = threadIdx.x & 31;
   const unsigned full = 0xffffffffu;
   const uint32_t b = (blockIdx.x * kFinalThreads + threadIdx.x) / 32;
-  if (b >= a.B) return;
+  if (b >= a.B || a.c.ctr->abort) return;
   const uint32_t slot = a.entry_slot[b];
   SlotState st = a.slots[slot];
   const uint32_t op = a.out_pool;
@@ -738,14 +815,10 @@ __global__ void __launch_bounds__(kFinalThreads) k_sel_final(SelectArgs a) {
       }
       co = __shfl_sync(full, co, 0);
       ao = __shfl_sync(full, ao, 0);
-      if (co + st.n_chains > a.pool_chain_cap || ao + st.carry_n > a.pool_anchor_cap) {
-        if (lane == 0) atomicOr(&ctr->error, 2u);
-      } else {
-        const ChainRec *sc = a.pool_chain[st.pool] + st.chain_off;
-        const CarryAnchor *sa = a.pool_anchor[st.pool] + st.carry_off;
-        for (uint32_t i = lane; i < st.n_chains; i += 32) a.pool_chain[op][co + i] = sc[i];
-        for (uint32_t i = lane; i < st.carry_n; i += 32) a.pool_anchor[op][ao + i] = sa[i];
-      }
+      const ChainRec *sc = a.pool_chain[st.pool] + st.chain_off;
+      const CarryAnchor *sa = a.pool_anchor[st.pool] + st.carry_off;
+      for (uint32_t i = lane; i < st.n_chains; i += 32) a.pool_chain[op][co + i] = sc[i];
+      for (uint32_t i = lane; i < st.carry_n; i += 32) a.pool_anchor[op][ao + i] = sa[i];
       st.chain_off = co;
       st.carry_off = ao;
     }
@@ -757,48 +830,13 @@ __global__ void __launch_bounds__(kFinalThreads) k_sel_final(SelectArgs a) {
 
   const KeyLayout kl = a.c.kl;
   ChainTmp *ch = a.scratch + (size_t)b * a.max_chains;
-  const uint32_t nch = min(a.n_scratch[b], a.max_chains);
   if (a.n_scratch[b] > a.max_chains) st.flags |= 2u;
-
-  // ---- GeneratePrimaryChains (spatial_index.cc:222-253) by repeated extraction of the max
-  uint32_t n_prim = 0, prim_first = 0, prim_second = 0, total_anchors = 0;
-  if (lane == 0) {
-    float last_primary_score = 0.0f;
-    for (;;) {
-      int best = -1;
-      for (uint32_t c = 0; c < nch; ++c)
-        if (ch[c].state == 0 && (best < 0 || chain_greater(ch[c].c, ch[best].c))) best = (int)c;
-      if (best < 0) break;
-      const CandRec cb = ch[best].c;
-      if (n_prim > 0 && cb.score < __fdiv_rn(last_primary_score, 3.0f)) break;
-      bool ok = true;
-      for (uint32_t c = 0; c < nch && ok; ++c) {
-        if (ch[c].state != 1 || (ch[c].c.bucket >> 1) != (cb.bucket >> 1)) continue;
-        const uint32_t mx = max(cb.start, ch[c].c.start), mn = min(cb.end, ch[c].c.end);
-        if (!(mx > mn)) ok = false;
-      }
-      if (ok) {
-        ch[best].state = 1;
-        ch[best].rank = n_prim;
-        if (n_prim == 0) prim_first = (uint32_t)best;
-        if (n_prim == 1) prim_second = (uint32_t)best;
-        last_primary_score = cb.score;
-        if (cb.owner == a.rank) total_anchors += cb.n;
-        ++n_prim;
-      } else {
-        ch[best].state = 2;
-      }
-    }
-  }
-  __syncwarp(full);
-  n_prim = __shfl_sync(full, n_prim, 0);
-  prim_first = __shfl_sync(full, prim_first, 0);
-  prim_second = __shfl_sync(full, prim_second, 0);
-  total_anchors = __shfl_sync(full, total_anchors, 0);
+  const PickRec pk = pick[b];
+  const uint32_t n_prim = pk.n_prim, prim_first = pk.prim_first, prim_second = pk.prim_second;
+  const uint32_t total_anchors = pk.total_anchors;
 
   // ---- survivors to the carry pool, primary order, anchors end -> start
   unsigned long long co = 0, ao = 0;
-  bool pool_ok = true;
   if (n_prim > 0) {
     if (lane == 0) {
       co = atomicAdd(&ctr->carry_chain_used[op], (unsigned long long)n_prim);
@@ -806,10 +844,6 @@ __global__ void __launch_bounds__(kFinalThreads) k_sel_final(SelectArgs a) {
     }
     co = __shfl_sync(full, co, 0);
     ao = __shfl_sync(full, ao, 0);
-    if (co + n_prim > a.pool_chain_cap || ao + total_anchors > a.pool_anchor_cap) {
-      if (lane == 0) atomicOr(&ctr->error, 2u);
-      pool_ok = false;
-    }
   }
   float mean = 0.0f;
   uint32_t mapq0 = 0;
@@ -821,7 +855,7 @@ __global__ void __launch_bounds__(kFinalThreads) k_sel_final(SelectArgs a) {
     mq = mq > 60 ? 60 : (mq < 0 ? 0 : mq);
     mapq0 = (uint32_t)(uint8_t)mq;
   }
-  if (pool_ok && n_prim > 0) {
+  if (n_prim > 0) {
     uint32_t aoff = 0;
     for (uint32_t r = 0; r < n_prim; ++r) {  // ranks are 0..n_prim-1; emit in rank order
       uint32_t c = 0;
@@ -864,7 +898,7 @@ __global__ void __launch_bounds__(kFinalThreads) k_sel_final(SelectArgs a) {
   st.n_chains = n_prim;
   st.chain_off = co;
   st.carry_off = ao;
-  st.carry_n = pool_ok ? total_anchors : 0u;
+  st.carry_n = total_anchors;
   st.pool = op;
   st.num_events += a.n_features[b];  // sigmap.cc:666
   st.stop = 0;
@@ -873,7 +907,7 @@ __global__ void __launch_bounds__(kFinalThreads) k_sel_final(SelectArgs a) {
   st.owned0 = 0;
   st.s1 = st.s2 = st.sm = st.ad = st.at = st.aq = 0.0f;
   st.q_first = st.q_last = 0;
-  if (n_prim > 0 && pool_ok) {
+  if (n_prim > 0) {
     const CandRec c0 = ch[prim_first].c;
     const float s0 = c0.score;
     const float s1 = n_prim > 1 ? ch[prim_second].c.score : 0.0f;

@@ -79,6 +79,7 @@ __global__ void __launch_bounds__(kSortThreads, kSortThreads == 1024 ? 1 : 2) k_
   uint16_t *s_order2 = s_order + kSortCap;
 
   const uint32_t entry = blockIdx.x;
+  if (a.ctr->abort) return;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const unsigned full = 0xffffffffu;
   const unsigned lt = (1u << lane) - 1u;
@@ -148,7 +149,10 @@ __global__ void __launch_bounds__(kSortThreads, kSortThreads == 1024 ? 1 : 2) k_
       }
       s_part[++np] = a.n_coarse;
       s_misc[34] = dense ? 0u : np;
-      if (dense) atomicOr(&a.ctr->error, 16u);  // the caller falls back to the global sort
+      if (dense) {  // the host redoes the step with the global sort
+        atomicOr(&a.ctr->error, 16u);
+        atomicOr(&a.ctr->abort, kAbortSort);
+      }
     }
   } else if (tid == 0) {
     s_part[0] = 0;
@@ -382,7 +386,7 @@ __global__ void __launch_bounds__(THREADS, THREADS >= 1024 ? 1 : (THREADS >= 512
 
   const uint32_t idx = blockIdx.x;
   const uint32_t n_all = a.part_total[idx];
-  if (n_all == 0) return;
+  if (n_all == 0 || a.ctr->abort) return;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const unsigned full = 0xffffffffu;
   const uint32_t nr = min(a.run_count[idx], a.runs_cap);
@@ -511,7 +515,10 @@ __global__ void __launch_bounds__(THREADS, THREADS >= 1024 ? 1 : (THREADS >= 512
     if (n_sub > 1) {
       n = s_misc[32];
       if (n > (uint32_t)CAP) {
-        if (tid == 0) atomicOr(&a.ctr->error, 16u);
+        if (tid == 0) {
+          atomicOr(&a.ctr->error, 16u);
+          atomicOr(&a.ctr->abort, kAbortSort);
+        }
         n = CAP;
       }
     }

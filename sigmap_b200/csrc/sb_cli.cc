@@ -197,7 +197,7 @@ int map_reads(const Args &a) {
   smbh_reads reads;
   memset(&reads, 0, sizeof reads);
   for (const std::string &f : files)
-    if (smbh_blow5_read(f.c_str(), &reads)) die("Error in opening file " + f);
+    if (smbh_blow5_read(f.c_str(), &reads)) die("Error in opening file " + f + " (" + smbh_last_error() + ")");
   fprintf(stderr, "Loaded %zu reads in %fs.\n", reads.n, now() - t0);
   smbh_fasta fa;
   if (smbh_fasta_load(a.ref.c_str(), &fa)) die("Cannot find sequence file!");

@@ -145,7 +145,17 @@ struct Counters {
                                     // bit5 candidate exchange list overflow
   unsigned int max_entry_anchors;   // most anchors any one (entry, part) received this step
   unsigned int dp_cursor;           // next segment of the chaining DP's work queue
+  // The step runs without host round trips: what the host used to decide between kernels is
+  // decided on the device.  A non-zero `abort` makes every later kernel of the step return at
+  // once, so nothing is committed to the read slots and the host (which looks at the counters
+  // once, at the end of the step) can redo the step with larger buffers or another sort path.
+  unsigned int abort;               // kAbort* bits
+  unsigned long long need_chain, need_anchor;  // carry-pool records the step's surviving chains need
 };
+constexpr unsigned int kAbortAnchors = 1u;  // more anchors than the step's buffers hold
+constexpr unsigned int kAbortSort = 2u;     // the chosen sort path cannot take this step (run tables, dense part)
+constexpr unsigned int kAbortQueries = 4u;  // more queries than the order buffers hold
+constexpr unsigned int kAbortPool = 8u;     // carry pools too small for the surviving chains
 
 // Part of an entry that linear coordinate g = bucket_base[bucket] + target belongs to
 // (k_sort.cuh, k_part_sort).  Any function that is monotone in g gives contiguous parts; float

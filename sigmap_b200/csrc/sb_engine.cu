@@ -210,6 +210,7 @@ struct Workspace {
   DevBuf<uint32_t> run_count, entry_total, part_base;
   DevBuf<unsigned char> cub_temp;
   DevBuf<ChainTmp> chain_tmp;
+  DevBuf<PickRec> pick;
   DevBuf<float> seg_max;
   DevBuf<uint32_t> n_scratch;
   // contig-sharded runs (sb_exchange.cuh)
@@ -273,7 +274,7 @@ struct smb_ctx {
   SlotSpace map_slots;
   Counters *d_ctr = nullptr;
   Counters *h_ctr = nullptr;  // pinned
-  cudaEvent_t ev[6] = {};
+  cudaEvent_t ev[8] = {};
   cudaEvent_t timer[2] = {};
   smb_stats stats{};
   uint32_t max_batch_chunks = 32768;
@@ -281,6 +282,7 @@ struct smb_ctx {
   uint64_t last_cap = 0;
   double est_anchors_per_chunk = 20000.0;
   double est_queries_per_chunk = 260.0;
+  double runs_scale = 1.0;          // raised when a step overflowed its run tables
   // contig-sharded index: the exchange backend (null = this context holds every contig)
   std::unique_ptr<Exchange> ex;
   std::shared_ptr<LocalGroup> local_group;
@@ -646,14 +648,76 @@ static int run_events(smb_ctx *ctx, StepSource src, const void *samples, uint32_
   return SMB_OK;
 }
 
-// Returns SMB_OK, an error, or +1 when the anchor buffer overflowed (caller splits the batch).
+// How a step's anchors get sorted; a path that cannot take the step (run tables overflowed, a part
+// or an entry too dense for shared memory) aborts it on the device and the host redoes the step
+// one path down.
+enum SortMode { SORT_PART = 0, SORT_SEG = 1, SORT_GLOBAL = 2 };
+
+// what the end of a round wants read back together with the last step's counters
+struct RoundOut {
+  const std::vector<uint32_t> *ids = nullptr;  // slots whose (stop, events, chains) go to info
+  std::vector<RoundInfo> *info = nullptr;
+  std::vector<SlotState> *states = nullptr;    // all slots of the space, when asked for
+};
+
+static int host_sync(smb_ctx *ctx) {
+  ctx->stats.sync_points++;
+  CK(cudaStreamSynchronize(ctx->stream));
+  return SMB_OK;
+}
+
+namespace sb {
+// after the search: everything the host used to decide from the counters, decided here
+__global__ void k_step_check(Counters *c, unsigned long long cap, int sort_mode, unsigned int part_limit,
+                             unsigned long long seg_limit, uint32_t n_parts) {
+  unsigned int ab = 0;
+  if (c->n_anchors > cap) ab |= kAbortAnchors;
+  if (c->error & 64u) ab |= kAbortQueries;
+  if (sort_mode == 0 && ((c->error & 8u) || c->max_entry_anchors > part_limit)) ab |= kAbortSort;
+  if (sort_mode == 1 && ((c->error & 8u) || (unsigned long long)c->max_entry_anchors * n_parts > seg_limit)) ab |= kAbortSort;
+  c->abort |= ab;
+}
+// global-sort path: keys past the step's anchors must sort to the end (the radix sort is sized
+// for the buffers on the host)
+__global__ void k_pad_keys(uint64_t *__restrict__ key, const Counters *__restrict__ c, unsigned long long cap) {
+  const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < cap && i >= c->n_anchors) key[i] = ~0ull;
+}
+}  // namespace sb
+
+// grow a carry pool without losing what the earlier steps of the round put there
+template <class T>
+static cudaError_t grow_keep(DevBuf<T> &buf, size_t want, cudaStream_t s) {
+  if (want <= buf.cap) return cudaSuccess;
+  DevBuf<T> bigger;
+  cudaError_t e = bigger.ensure(want);
+  if (e != cudaSuccess) return e;
+  if (buf.p && buf.cap) {
+    e = cudaMemcpyAsync(bigger.p, buf.p, buf.cap * sizeof(T), cudaMemcpyDeviceToDevice, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) {
+      bigger.release();
+      return e;
+    }
+  }
+  buf.release();
+  buf = bigger;
+  return cudaSuccess;
+}
+
+// One pipeline step, enqueued without a host round trip; the host looks at the counters once, at
+// the end.  Returns SMB_OK, an error, +1 when the anchor buffers overflowed (the caller grows them
+// or splits the batch), +2 when the step was aborted for another reason that has been dealt with
+// (estimates raised, pools grown, *sort_mode moved one path down): the caller just runs it again.
+// Nothing is committed to the read slots by an aborted step.
 static int run_step(smb_ctx *ctx, SlotSpace &sp, const StepEntries &en, StepSource src,
-                    const smb_params &prm, uint32_t out_pool) {
+                    const smb_params &prm, uint32_t out_pool, int *sort_mode, const RoundOut *rout) {
   Workspace &w = ctx->ws;
   cudaStream_t s = ctx->stream;
   const uint32_t B = en.B, Bpres = en.B_present;
   if (B == 0) return SMB_OK;
   if (!ctx->has_index) return fail(ctx, SMB_ERR_STATE, "no index loaded");
+  const bool sharded = (bool)ctx->ex;
   // ---- key layout for this step
   uint32_t max_ev = 0;
   for (uint32_t b = 0; b < Bpres; ++b) max_ev = std::max(max_ev, sp.h_events[en.slot[b]]);
@@ -729,13 +793,14 @@ static int run_step(smb_ctx *ctx, SlotSpace &sp, const StepEntries &en, StepSour
   CK(w.score.ensure(cap));
   CK(w.coef.ensure(cap));
   CK(w.pred.ensure(cap));
-  const bool want_seg = ctx->seg_sort;
+  int mode = std::max(*sort_mode, !ctx->seg_sort ? (int)SORT_GLOBAL : (!ctx->part_sort ? (int)SORT_SEG : (int)SORT_PART));
+  const bool want_seg = mode != SORT_GLOBAL;
   // parts per entry (k_sort.cuh): equal coordinate ranges sized so that a part of an average
   // entry fills part_fill (70 %) of one k_part_sort CTA; more than kMaxParts -> one list, k_seg_sort
   uint32_t n_parts = 1;
   uint64_t span = std::max<uint64_t>(ctx->g_total, 1);
   const int part_cap = ctx->part_small ? kPartSortCapSmall : kPartSortCap;
-  if (want_seg && ctx->part_sort) {
+  if (mode == SORT_PART) {
     const double per_coord = std::max(ctx->est_anchors_per_chunk, 1.0) / (double)std::max<uint64_t>(ctx->g_total, 1);
     const double want = ctx->part_fill * (double)part_cap / per_coord;
     if (want < (double)ctx->g_total) {
@@ -751,9 +816,9 @@ static int run_step(smb_ctx *ctx, SlotSpace &sp, const StepEntries &en, StepSour
   const size_t n_lists = (size_t)B * n_parts;
   // run records per (entry, part) list: a query leaves at most one run per part and flush, so
   // queries per chunk + the flushes forced by a full staging buffer, with room for dense chunks
-  uint32_t runs_cap = (uint32_t)(1.5 * ctx->est_queries_per_chunk +
-                                 3.0 * ctx->est_anchors_per_chunk / (double)kStageCap) + 128u;
-  runs_cap = std::max<uint32_t>((runs_cap + 63u) & ~63u, std::max<uint32_t>(ctx->runs_cap_min, 64u));
+  uint32_t runs_cap = (uint32_t)(ctx->runs_scale * (1.5 * ctx->est_queries_per_chunk +
+                                                    3.0 * ctx->est_anchors_per_chunk / (double)kStageCap)) + 128u;
+  runs_cap = (runs_cap + 63u) & ~63u;
   if (ctx->runs_cap_min) runs_cap = ctx->runs_cap_min;
   if (want_seg) {
     CK(w.runs.ensure(n_lists * runs_cap));
@@ -807,65 +872,44 @@ static int run_step(smb_ctx *ctx, SlotSpace &sp, const StepEntries &en, StepSour
     k_max_u32<<<148, 256, 0, s>>>(w.entry_total.p, n_lists, &ctx->d_ctr->max_entry_anchors);
     LAUNCH_CHECK();
   }
-  CK(cudaMemcpyAsync(ctx->h_ctr, ctx->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
-  CK(cudaStreamSynchronize(s));
-  ctx->stats.d2h_bytes += sizeof(Counters);
-  const unsigned long long n = ctx->h_ctr->n_anchors;
-  float ms = 0;
-  cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
-  ctx->stats.ms_events += ms;
-  cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]);
-  ctx->stats.ms_search += ms;
-  bool overflow = n > cap;
-  unsigned long long n_est = n;  // what the batch-size estimate is updated with
-  if (ctx->ex) {
+  if (sharded) {
     // Sharded: every rank must take the same path through this step (the exchanges below are
-    // collective), so overflow and the estimate are agreed on first.
-    Workspace &wx = ctx->ws;
-    CK(wx.ctl.ensure(4));
-    ctx->h_ctl[0] = overflow ? 1.0 : 0.0;
-    ctx->h_ctl[1] = (overflow && ctx->last_cap >= ctx->max_batch_anchors) ? 1.0 : 0.0;
-    ctx->h_ctl[2] = (double)n;
-    ctx->h_ctl[3] = 0.0;
-    CK(cudaMemcpyAsync(wx.ctl.p, ctx->h_ctl, 4 * sizeof(double), cudaMemcpyHostToDevice, s));
-    int rc = ctx->ex->allreduce(wx.ctl.p, 4, EX_F64, EX_MAX, s, ctx->err);
+    // collective), so overflow and the estimate are agreed on first -- with a host round trip.
+    CK(cudaMemcpyAsync(ctx->h_ctr, ctx->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
+    int rc = host_sync(ctx);
     if (rc) return rc;
-    CK(cudaMemcpyAsync(ctx->h_ctl, wx.ctl.p, 4 * sizeof(double), cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    overflow = ctx->h_ctl[0] > 0.0;
-    ctx->group_at_limit = ctx->h_ctl[1] > 0.0;
-    n_est = (unsigned long long)ctx->h_ctl[2];
+    ctx->stats.d2h_bytes += sizeof(Counters);
+    const unsigned long long n_local = ctx->h_ctr->n_anchors;
+    const bool overflow_local = n_local > cap;
+    CK(w.ctl.ensure(4));
+    ctx->h_ctl[0] = overflow_local ? 1.0 : 0.0;
+    ctx->h_ctl[1] = (overflow_local && ctx->last_cap >= ctx->max_batch_anchors) ? 1.0 : 0.0;
+    ctx->h_ctl[2] = (double)n_local;
+    ctx->h_ctl[3] = (ctx->h_ctr->error & 64u) ? 1.0 : 0.0;
+    CK(cudaMemcpyAsync(w.ctl.p, ctx->h_ctl, 4 * sizeof(double), cudaMemcpyHostToDevice, s));
+    rc = ctx->ex->allreduce(w.ctl.p, 4, EX_F64, EX_MAX, s, ctx->err);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(ctx->h_ctl, w.ctl.p, 4 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    rc = host_sync(ctx);
+    if (rc) return rc;
     ctx->stats.exchanges++;
+    ctx->group_at_limit = ctx->h_ctl[1] > 0.0;
+    if (ctx->h_ctl[3] > 0.0) {  // some rank ran out of query-order slots: everybody redoes the step
+      ctx->est_queries_per_chunk = 1.1 * (double)q_per_chunk_max;
+      return 2;
+    }
+    if (ctx->h_ctl[0] > 0.0) return 1;  // nothing has been committed to the slots yet
   }
-  if (overflow) return 1;  // nothing has been committed to the slots yet
-  if (ctx->h_ctr->error & 64u) {  // more queries than the order buffers were sized for: redo the step
-    ctx->est_queries_per_chunk = 1.1 * (double)ctx->h_ctr->n_queries / std::max(Bpres, 1u) + 8.0;
-    k_clear_error_bits<<<1, 1, 0, s>>>(ctx->d_ctr, 64u);
-    LAUNCH_CHECK();
-    return 2;
-  }
-  if (Bpres)
-    ctx->est_queries_per_chunk = std::max(0.9 * ctx->est_queries_per_chunk, (double)ctx->h_ctr->n_queries / Bpres);
-  ctx->stats.queries += ctx->h_ctr->n_queries;
-  ctx->stats.hits += ctx->h_ctr->n_hits;
-  ctx->stats.anchors += n;
-  ctx->stats.capped_queries += ctx->h_ctr->n_capped;
-  ctx->stats.overflow_queries += ctx->search_lean ? ctx->h_ctr->n_overflow : ctx->h_ctr->n_queries;
-  ctx->stats.raw_events += ctx->h_ctr->n_events_raw;
-  ctx->stats.events += ctx->h_ctr->n_events_kept;
-  ctx->stats.chunks += Bpres;
-  ctx->stats.steps++;
+  k_step_check<<<1, 1, 0, s>>>(ctx->d_ctr, cap, mode, 8u * (unsigned)part_cap,
+                               8ull * (unsigned)(ctx->sort_small ? kSortCapSmall : kSortCapBig), n_parts);
+  LAUNCH_CHECK();
 
   // ---- sort by (entry, bucket, target, query)
-  CK(cudaEventRecord(ctx->ev[0], s));
-  const uint64_t *keys = w.key_a.p;
-  const float *dists = w.dist_a.p;
-  bool sorted = n <= 1;
-  // per-entry sort in shared memory (k_sort.cuh) when the run tables did not overflow:
-  // one CTA per (entry, part) if every part fits one CTA, else one CTA per entry working through
-  // the entry in several passes
-  const bool runs_ok = !sorted && want_seg && !(ctx->h_ctr->error & 8u);
-  if (runs_ok && ctx->part_sort && ctx->h_ctr->max_entry_anchors <= 8u * (unsigned)part_cap) {
+  CK(cudaEventRecord(ctx->ev[4], s));
+  const uint64_t *keys = w.key_b.p;
+  const float *dists = w.dist_b.p;
+  if (mode == SORT_PART) {
+    // one CTA per (entry, part) from the pre-routed runs; output offsets = scan of the part sizes
     size_t tb = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, tb, w.entry_total.p, w.part_base.p, (int)n_lists, s);
     CK(w.cub_temp.ensure(tb));
@@ -892,23 +936,8 @@ static int run_step(smb_ctx *ctx, SlotSpace &sp, const StepEntries &en, StepSour
     else
       k_part_sort<kPartSortCap, 512, 4096><<<(unsigned)n_lists, 512, part_sort_smem_bytes(kPartSortCap, 4096), s>>>(ps);
     LAUNCH_CHECK();
-    CK(cudaMemcpyAsync(ctx->h_ctr, ctx->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    ctx->stats.d2h_bytes += sizeof(Counters);
-    if (!(ctx->h_ctr->error & 16u)) {
-      sorted = true;
-      ctx->stats.seg_sort_steps++;
-      ctx->stats.part_sort_steps++;
-      keys = w.key_b.p;
-      dists = w.dist_b.p;
-    } else {
-      k_clear_error_bits<<<1, 1, 0, s>>>(ctx->d_ctr, 16u);  // the generic kernel reports through the same bit
-      LAUNCH_CHECK();
-      ctx->h_ctr->error &= ~16u;
-    }
-  }
-  if (!sorted && runs_ok &&
-      (uint64_t)ctx->h_ctr->max_entry_anchors * n_parts <= 8ull * (unsigned)(ctx->sort_small ? kSortCapSmall : kSortCapBig)) {
+  } else if (mode == SORT_SEG) {
+    // one CTA per entry working through the entry in several passes
     SegSortArgs ss{};
     ss.key_in = w.key_a.p;
     ss.dist_in = w.dist_a.p;
@@ -929,37 +958,29 @@ static int run_step(smb_ctx *ctx, SlotSpace &sp, const StepEntries &en, StepSour
     else
       k_seg_sort<kSortCapBig, 1024, 8192><<<B, 1024, sort_smem_bytes(kSortCapBig, 8192), s>>>(ss);
     LAUNCH_CHECK();
-    CK(cudaMemcpyAsync(ctx->h_ctr, ctx->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    ctx->stats.d2h_bytes += sizeof(Counters);
-    if (!(ctx->h_ctr->error & 16u)) {
-      sorted = true;
-      ctx->stats.seg_sort_steps++;
-      keys = w.key_b.p;
-      dists = w.dist_b.p;
-    }
-  }
-  if (!sorted) {
-    // radix sort on (entry, bucket, target) only; k_fix_ties orders equal-target runs by query
+  } else {
+    // radix sort on (entry, bucket, target) only; k_fix_ties orders equal-target runs by query.
+    // The sort is sized for the buffers (the count lives on the device): the slots past the
+    // step's anchors are filled with the largest key and stay at the end.
+    k_pad_keys<<<(unsigned)((cap + 255) / 256), 256, 0, s>>>(w.key_a.p, ctx->d_ctr, cap);
+    LAUNCH_CHECK();
     size_t tb = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, tb, w.key_a.p, w.key_b.p, w.dist_a.p, w.dist_b.p,
-                                    (uint64_t)n, kl.qbits, kl.total(), s);
+                                    (uint64_t)cap, kl.qbits, 64, s);
     CK(w.cub_temp.ensure(tb));
     CK(cub::DeviceRadixSort::SortPairs(w.cub_temp.p, tb, w.key_a.p, w.key_b.p, w.dist_a.p, w.dist_b.p,
-                                       (uint64_t)n, kl.qbits, kl.total(), s));
-    ctx->stats.launches += 2 + (kl.total() - kl.qbits + 7) / 8;
-    k_fix_ties<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(w.key_b.p, w.dist_b.p, (uint32_t)n, kl.qbits);
+                                       (uint64_t)cap, kl.qbits, 64, s));
+    ctx->stats.launches += 2 + (64 - kl.qbits + 7) / 8;
+    k_fix_ties<<<(unsigned)((cap + 255) / 256), 256, 0, s>>>(w.key_b.p, w.dist_b.p, ctx->d_ctr, kl.qbits);
     LAUNCH_CHECK();
-    keys = w.key_b.p;
-    dists = w.dist_b.p;
   }
-  CK(cudaEventRecord(ctx->ev[1], s));
+  CK(cudaEventRecord(ctx->ev[5], s));
 
   // ---- chaining
   ChainArgs ca{};
   ca.key = keys;
   ca.dist = dists;
-  ca.n = n;
+  ca.n_max = cap;
   ca.kl = kl;
   ca.radius = prm.search_radius;
   ca.score = w.score.p;
@@ -976,14 +997,14 @@ static int run_step(smb_ctx *ctx, SlotSpace &sp, const StepEntries &en, StepSour
   ca.dp_passes = ctx->dp_passes;
   CK(cudaMemsetAsync(w.seg.p, 0xFF, (size_t)ca.n_slots * sizeof(SegRec), s));
   CK(cudaMemsetAsync(w.seg_max.p, 0, (size_t)ca.n_slots * sizeof(float), s));
-  const unsigned n_tiles = (unsigned)((n + kPrepTile - 1) / kPrepTile);
+  const unsigned n_tiles = (unsigned)((cap + kPrepTile - 1) / kPrepTile);  // sized for the buffers
   CK(w.link_list.ensure((size_t)std::max(n_tiles, 1u) * kPrepTile));
   CK(w.link_count.ensure(std::max(n_tiles, 1u)));
   ca.link_list = w.link_list.p;
   ca.link_count = w.link_count.p;
-  if (n > 0) {
-    k_chain_prep<<<n_tiles, kPrepThreads, 0, s>>>(ca);
-    LAUNCH_CHECK();
+  k_chain_prep<<<n_tiles, kPrepThreads, 0, s>>>(ca);
+  LAUNCH_CHECK();
+  {
     const unsigned dp_blocks = (unsigned)(((uint64_t)ca.n_slots * 32 + kDpThreads - 1) / kDpThreads);
     if (ctx->dp_dynamic)
       k_chain_dp<<<std::min(dp_blocks, ctx->dp_grid), kDpThreads, 0, s>>>(ca, 1);
@@ -1001,10 +1022,11 @@ static int run_step(smb_ctx *ctx, SlotSpace &sp, const StepEntries &en, StepSour
   se.max_chains = std::min<uint32_t>(3u * (ctx->max_bucket + 1u), 4096u);
   CK(w.chain_tmp.ensure((size_t)B * se.max_chains));
   CK(w.n_scratch.ensure(B));
+  CK(w.pick.ensure(B));
   se.scratch = w.chain_tmp.p;
   se.n_scratch = w.n_scratch.p;
   se.path = w.link_list.p;  // the DP is done with its work lists: reuse them for the chain paths
-  se.rank = ctx->ex ? (uint32_t)ctx->ex->rank : 0u;
+  se.rank = sharded ? (uint32_t)ctx->ex->rank : 0u;
   se.out_pool = out_pool;
   for (int p = 0; p < 2; ++p) {
     se.pool_chain[p] = sp.pool_chain[p].p;
@@ -1014,21 +1036,19 @@ static int run_step(smb_ctx *ctx, SlotSpace &sp, const StepEntries &en, StepSour
   se.pool_anchor_cap = sp.pool_anchor[out_pool].cap;
   se.prm = prm;
   CK(cudaMemsetAsync(w.n_scratch.p, 0, B * sizeof(uint32_t), s));
-  if (ctx->ex) {
+  if (sharded) {
     // exchange 2: the per-bucket running max of every rank's own contigs
     int rc = ctx->ex->allreduce(w.seg_max.p, ca.n_slots, EX_F32, EX_MAX, s, ctx->err);
     if (rc) return rc;
     // a chain has >= 2 anchors of its own and a segment yields <= 3 of them
-    se.cand_cap = (uint32_t)std::min<uint64_t>(3ull * ca.n_slots, n / 2) + 1u;
+    se.cand_cap = (uint32_t)std::min<uint64_t>(3ull * ca.n_slots, cap / 2) + 1u;
     CK(w.cand_list.ensure(se.cand_cap));
     se.cand_list = w.cand_list.p;
     ctx->stats.exchanges++;
   }
-  if (n > 0) {
-    k_sel_trace<<<(unsigned)(((uint64_t)ca.n_slots * 32 + kTraceThreads - 1) / kTraceThreads), kTraceThreads, 0, s>>>(se);
-    LAUNCH_CHECK();
-  }
-  if (ctx->ex) {
+  k_sel_trace<<<(unsigned)(((uint64_t)ca.n_slots * 32 + kTraceThreads - 1) / kTraceThreads), kTraceThreads, 0, s>>>(se);
+  LAUNCH_CHECK();
+  if (sharded) {
     // exchange 3: candidate counts, then the candidate records padded to the largest count
     const uint32_t world = (uint32_t)ctx->ex->world;
     CK(w.cand_counts.ensure(world + 1));
@@ -1036,18 +1056,15 @@ static int run_step(smb_ctx *ctx, SlotSpace &sp, const StepEntries &en, StepSour
     if (rc) return rc;
     std::vector<unsigned long long> h_counts(world);
     CK(cudaMemcpyAsync(h_counts.data(), w.cand_counts.p, world * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
+    rc = host_sync(ctx);
+    if (rc) return rc;
     unsigned long long per_rank = 0;
     for (uint32_t r = 0; r < world; ++r) per_rank = std::max(per_rank, h_counts[r]);
     if (per_rank > 0) {
       // my own list must be able to serve a padded send of per_rank records
       if (w.cand_list.cap < per_rank) {
-        DevBuf<CandRec> grown;
-        CK(grown.ensure(per_rank));
-        CK(cudaMemcpyAsync(grown.p, w.cand_list.p, std::min<size_t>(w.cand_list.cap, h_counts[ctx->ex->rank]) * sizeof(CandRec), cudaMemcpyDeviceToDevice, s));
-        CK(cudaStreamSynchronize(s));
-        w.cand_list.release();
-        w.cand_list = grown;
+        cudaError_t ge = grow_keep(w.cand_list, (size_t)per_rank, s);
+        if (ge != cudaSuccess) return fail(ctx, SMB_ERR_CUDA, cudaGetErrorString(ge));
         se.cand_list = w.cand_list.p;
       }
       CK(w.cand_all.ensure((size_t)per_rank * world));
@@ -1059,21 +1076,105 @@ static int run_step(smb_ctx *ctx, SlotSpace &sp, const StepEntries &en, StepSour
     }
     ctx->stats.exchanges += 2;
   }
-  k_sel_final<<<(unsigned)(((uint64_t)B * 32 + kFinalThreads - 1) / kFinalThreads), kFinalThreads, 0, s>>>(se);
+  const unsigned final_blocks = (unsigned)(((uint64_t)B * 32 + kFinalThreads - 1) / kFinalThreads);
+  k_sel_pick<<<final_blocks, kFinalThreads, 0, s>>>(se, w.pick.p);
   LAUNCH_CHECK();
-  CK(cudaEventRecord(ctx->ev[2], s));
+  k_pool_check<<<1, 1, 0, s>>>(ctx->d_ctr, out_pool, se.pool_chain_cap, se.pool_anchor_cap);
+  LAUNCH_CHECK();
+  if (sharded) {
+    // a rank-local abort (sort path, carry pools) becomes everybody's: all ranks redo the step
+    int rc = ctx->ex->allreduce(&ctx->d_ctr->abort, 1, EX_U32, EX_MAX, s, ctx->err);
+    if (rc) return rc;
+    ctx->stats.exchanges++;
+  }
+  k_sel_commit<<<final_blocks, kFinalThreads, 0, s>>>(se, w.pick.p);
+  LAUNCH_CHECK();
+  CK(cudaEventRecord(ctx->ev[6], s));
+  // ---- the step's one look at the device: counters, and what the round wants read back
   CK(cudaMemcpyAsync(ctx->h_ctr, ctx->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
-  CK(cudaStreamSynchronize(s));
   ctx->stats.d2h_bytes += sizeof(Counters);
+  uint32_t n_ids = 0;
+  if (rout && rout->ids && rout->info) {
+    n_ids = (uint32_t)rout->ids->size();
+    rout->info->resize(n_ids);
+    if (n_ids) {
+      CK(w.ids.ensure(n_ids));
+      CK(w.round_info.ensure(n_ids));
+      CK(cudaMemcpyAsync(w.ids.p, rout->ids->data(), n_ids * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+      k_gather_round<<<(n_ids + 255) / 256, 256, 0, s>>>(sp.slots.p, w.ids.p, n_ids, w.round_info.p);
+      LAUNCH_CHECK();
+      CK(cudaMemcpyAsync(rout->info->data(), w.round_info.p, n_ids * sizeof(RoundInfo), cudaMemcpyDeviceToHost, s));
+      ctx->stats.h2d_bytes += n_ids * sizeof(uint32_t);
+      ctx->stats.d2h_bytes += n_ids * sizeof(RoundInfo);
+    }
+  }
+  if (rout && rout->states) {
+    rout->states->resize(std::max<size_t>(sp.n_slots, 1));
+    if (sp.n_slots) {
+      CK(cudaMemcpyAsync(rout->states->data(), sp.slots.p, sp.n_slots * sizeof(SlotState), cudaMemcpyDeviceToHost, s));
+      ctx->stats.d2h_bytes += sp.n_slots * sizeof(SlotState);
+    }
+  }
+  {
+    int rc = host_sync(ctx);
+    if (rc) return rc;
+  }
+  const Counters &hc = *ctx->h_ctr;
+  if (hc.abort) {
+    // nothing was committed; adjust what was too small and let the caller run the step again
+    if (hc.abort & kAbortAnchors) return 1;
+    if (hc.abort & kAbortQueries)
+      ctx->est_queries_per_chunk = 1.1 * (double)hc.n_queries / std::max(Bpres, 1u) + 8.0;
+    if (hc.abort & kAbortSort) {
+      if ((hc.error & 8u) && !ctx->runs_cap_min && ctx->runs_scale < 64.0) ctx->runs_scale *= 2.0;  // run tables overflowed
+      else *sort_mode = mode + 1;                                        // a part / an entry too dense
+      if (mode == SORT_GLOBAL) return fail(ctx, SMB_ERR_CAPACITY, "sort aborted on the radix path");
+    }
+    if (hc.abort & kAbortPool) {
+      const size_t want_c = (size_t)(hc.carry_chain_used[out_pool] + hc.need_chain) * 2 + 64;
+      const size_t want_a = (size_t)(hc.carry_anchor_used[out_pool] + hc.need_anchor) * 2 + 64;
+      cudaError_t ge = grow_keep(sp.pool_chain[out_pool], want_c, s);
+      if (ge == cudaSuccess) ge = grow_keep(sp.pool_anchor[out_pool], want_a, s);
+      if (ge != cudaSuccess) return fail(ctx, SMB_ERR_CUDA, std::string("growing the carry pools: ") + cudaGetErrorString(ge));
+    }
+    return 2;
+  }
+  const unsigned long long n = hc.n_anchors;
+  float ms = 0;
   cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+  ctx->stats.ms_events += ms;
+  cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]);
+  ctx->stats.ms_search += ms;
+  cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]);
   ctx->stats.ms_sort += ms;
-  cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]);
+  cudaEventElapsedTime(&ms, ctx->ev[5], ctx->ev[6]);
   ctx->stats.ms_chain += ms;
-  ctx->stats.linked += ctx->h_ctr->n_linked;
-  if (ctx->h_ctr->error & 2u) return fail(ctx, SMB_ERR_CAPACITY, "carry pool overflow");
-  if (ctx->h_ctr->error & 4u) return fail(ctx, SMB_ERR_CAPACITY, "per-read chain scratch overflow");
-  if (ctx->h_ctr->error & 32u) return fail(ctx, SMB_ERR_CAPACITY, "chain candidate exchange list overflow");
-  if (Bpres) ctx->est_anchors_per_chunk = 0.5 * ctx->est_anchors_per_chunk + 0.5 * ((double)n_est / Bpres);
+  ctx->stats.queries += hc.n_queries;
+  ctx->stats.hits += hc.n_hits;
+  ctx->stats.anchors += n;
+  ctx->stats.capped_queries += hc.n_capped;
+  ctx->stats.overflow_queries += ctx->search_lean ? hc.n_overflow : hc.n_queries;
+  ctx->stats.raw_events += hc.n_events_raw;
+  ctx->stats.events += hc.n_events_kept;
+  ctx->stats.chunks += Bpres;
+  ctx->stats.steps++;
+  ctx->stats.linked += hc.n_linked;
+  if (mode != SORT_GLOBAL) ctx->stats.seg_sort_steps++;
+  if (mode == SORT_PART) ctx->stats.part_sort_steps++;
+  if (hc.error & 4u) return fail(ctx, SMB_ERR_CAPACITY, "per-read chain scratch overflow");
+  if (hc.error & 32u) return fail(ctx, SMB_ERR_CAPACITY, "chain candidate exchange list overflow");
+  if (Bpres) {
+    double n_est = (double)n;
+    if (sharded) n_est = std::max(n_est, ctx->h_ctl[2]);
+    ctx->est_anchors_per_chunk = 0.5 * ctx->est_anchors_per_chunk + 0.5 * (n_est / Bpres);
+    ctx->est_queries_per_chunk = std::max(0.9 * ctx->est_queries_per_chunk, (double)hc.n_queries / Bpres);
+  }
+  // host mirror of the slots the round asked about
+  if (rout && rout->ids && rout->info)
+    for (uint32_t i = 0; i < n_ids; ++i) {
+      sp.h_events[(*rout->ids)[i]] = (*rout->info)[i].num_events;
+      sp.h_nchains[(*rout->ids)[i]] = (*rout->info)[i].n_chains;
+    }
   return SMB_OK;
 }
 
@@ -1117,34 +1218,13 @@ static int round_begin(smb_ctx *ctx, SlotSpace &sp, const std::vector<uint32_t> 
   return SMB_OK;
 }
 
-// refresh the host mirror (stop flag, kept events, chain count) of the given slots
-static int round_readback(smb_ctx *ctx, SlotSpace &sp, const std::vector<uint32_t> &slots,
-                          std::vector<RoundInfo> &out) {
-  const uint32_t n = (uint32_t)slots.size();
-  out.resize(n);
-  if (!n) return SMB_OK;
-  Workspace &w = ctx->ws;
-  CK(w.ids.ensure(n));
-  CK(w.round_info.ensure(n));
-  CK(cudaMemcpyAsync(w.ids.p, slots.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
-  k_gather_round<<<(n + 255) / 256, 256, 0, ctx->stream>>>(sp.slots.p, w.ids.p, n, w.round_info.p);
-  LAUNCH_CHECK();
-  CK(cudaMemcpyAsync(out.data(), w.round_info.p, n * sizeof(RoundInfo), cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
-  ctx->stats.h2d_bytes += n * sizeof(uint32_t);
-  ctx->stats.d2h_bytes += n * sizeof(RoundInfo);
-  for (uint32_t i = 0; i < n; ++i) {
-    sp.h_events[slots[i]] = out[i].num_events;
-    sp.h_nchains[slots[i]] = out[i].n_chains;
-  }
-  return SMB_OK;
-}
-
-// run one round over `present` (entries with a chunk) + `absent` slots, splitting into steps
+// run one round over `present` (entries with a chunk) + `absent` slots, splitting into steps;
+// what `rout` asks for is read back together with the counters of the round's last step
 template <class FillFn>
 static int run_round(smb_ctx *ctx, SlotSpace &sp, const std::vector<uint32_t> &present,
                      const std::vector<uint32_t> &absent, StepSource src, const smb_params &prm,
-                     FillFn fill /* (StepEntries&, first, count) for present entries */) {
+                     FillFn fill /* (StepEntries&, first, count) for present entries */,
+                     const RoundOut *rout = nullptr) {
   const uint32_t out_pool = sp.round & 1u;
   std::vector<uint32_t> all(present);
   all.insert(all.end(), absent.begin(), absent.end());
@@ -1160,17 +1240,21 @@ static int run_round(smb_ctx *ctx, SlotSpace &sp, const std::vector<uint32_t> &p
     const int ebits_max = 64 - kbits - bits_for((uint64_t)max_ev + kFeatCap);
     if (ebits_max < 1) return fail(ctx, SMB_ERR_CAPACITY, "sort key does not fit 64 bits");
     uint64_t Bmax = std::min<uint64_t>(ctx->max_batch_chunks, ebits_max >= 31 ? (1ull << 31) : (1ull << ebits_max));
+    Bmax = std::min<uint64_t>(Bmax, (1ull << (32 - kQueryBits)) - 1);  // the query payload holds the entry
     uint64_t by_anchors = (uint64_t)(0.6 * (double)ctx->max_batch_anchors / std::max(ctx->est_anchors_per_chunk, 1.0));
     uint32_t count = (uint32_t)std::min<uint64_t>(present.size() - at, std::max<uint64_t>(1, std::min(Bmax, by_anchors)));
-    for (;;) {
+    int sort_mode = SORT_PART;
+    for (int tries = 0;; ++tries) {
+      if (tries > 64) return fail(ctx, SMB_ERR_CAPACITY, "a pipeline step keeps aborting");
       StepEntries en;
       en.B_present = count;
       en.slot.assign(present.begin() + at, present.begin() + at + count);
       fill(en, at, count);
       if (!absent_done) en.slot.insert(en.slot.end(), absent.begin(), absent.end());
       en.B = (uint32_t)en.slot.size();
-      rc = run_step(ctx, sp, en, src, prm, out_pool);
-      if (rc == 2) continue;  // query-order buffers were too small: the estimate has been raised
+      const bool last = at + count >= present.size();
+      rc = run_step(ctx, sp, en, src, prm, out_pool, &sort_mode, last ? rout : nullptr);
+      if (rc == 2) continue;  // aborted on the device, cause dealt with: again
       if (rc == 1) {  // anchor buffer overflow: grow the buffers, or halve the step at the limit
         ctx->est_anchors_per_chunk *= 2.0;
         if (ctx->ex ? ctx->group_at_limit : ctx->last_cap >= ctx->max_batch_anchors) {
@@ -1816,9 +1900,10 @@ static int map_uploaded_impl(smb_ctx *ctx, const smb_params *prm_in, smb_mapping
       en.feat_row.resize(count);
       for (uint32_t i = 0; i < count; ++i) en.feat_row[i] = row_base[active[first + i]] + (round - ev_r0);
     };
-    rc = run_round(ctx, sp, active, none, SRC_CACHED, prm, fill);
-    if (rc) return rc;
-    rc = round_readback(ctx, sp, active, info);
+    RoundOut rout;
+    rout.ids = &active;
+    rout.info = &info;
+    rc = run_round(ctx, sp, active, none, SRC_CACHED, prm, fill, &rout);
     if (rc) return rc;
     ctx->stats.samples += (uint64_t)active.size() * kChunk;
     std::vector<uint32_t> next;
@@ -2050,13 +2135,13 @@ int smb_batch_generate_chains(smb_batch *b, const uint32_t *slots, uint32_t n, c
     en.d_features = d_feat.p;
     en.d_feat_off = d_off.p;
   };
-  int rc = run_round(ctx, b->sp, present, absent, SRC_FEATURES, *prm, fill);
-  if (rc == SMB_OK) {
-    std::vector<RoundInfo> info;
-    std::vector<uint32_t> all(present);
-    all.insert(all.end(), absent.begin(), absent.end());
-    rc = round_readback(ctx, b->sp, all, info);
-  }
+  std::vector<RoundInfo> info;
+  std::vector<uint32_t> all(present);
+  all.insert(all.end(), absent.begin(), absent.end());
+  RoundOut rout;
+  rout.ids = &all;
+  rout.info = &info;
+  int rc = run_round(ctx, b->sp, present, absent, SRC_FEATURES, *prm, fill, &rout);
   cudaStreamSynchronize(ctx->stream);
   d_feat.release();
   d_off.release();
@@ -2223,9 +2308,17 @@ int smb_stream_round(smb_ctx *ctx, const uint32_t *channels, uint32_t n, const i
   }
   std::vector<uint32_t> present;
   present.reserve(n);
+  {
+    // a channel named twice would put two chunks of one read into the same round
+    std::vector<uint8_t> named(sp.n_slots, 0);
+    for (uint32_t i = 0; i < n; ++i) {
+      if (channels[i] >= sp.n_slots) return fail(ctx, SMB_ERR_ARG, "bad channel");
+      if (named[channels[i]]) return fail(ctx, SMB_ERR_ARG, "channel named twice in one round");
+      named[channels[i]] = 1;
+    }
+  }
   for (uint32_t i = 0; i < n; ++i) {
     const uint32_t ch = channels[i];
-    if (ch >= sp.n_slots) return fail(ctx, SMB_ERR_ARG, "bad channel");
     std::vector<int16_t> &pend = ctx->stream_pending[ch];
     const int16_t *in = samples + sample_off[i];
     const size_t cnt = sample_off[i + 1] - sample_off[i];
@@ -2254,6 +2347,11 @@ int smb_stream_round(smb_ctx *ctx, const uint32_t *channels, uint32_t n, const i
       memcpy(ctx->h_stream_stage + present.size() * kChunk, pend.data(), kChunk * sizeof(int16_t));
       present.push_back(ch);
       pend.erase(pend.begin(), pend.begin() + kChunk);
+    } else if (ctx->stream_chunks[ch] >= (uint32_t)prm.max_num_chunks) {
+      // the read has used up its chunks (sigmap.cc:647): nothing more will be mapped, so the
+      // samples are only counted (read length of the row), not buffered
+      ctx->stream_kept[ch] += (uint32_t)pend.size();
+      pend.clear();
     }
   }
   // all other channels with live chains are carried forward
@@ -2262,6 +2360,11 @@ int smb_stream_round(smb_ctx *ctx, const uint32_t *channels, uint32_t n, const i
   std::vector<uint32_t> absent;
   for (uint32_t ch = 0; ch < sp.n_slots; ++ch)
     if (!seen[ch] && sp.h_nchains[ch] > 0) absent.push_back(ch);
+  // decisions + provisional rows for the channels named in this call come back with the round
+  std::vector<RoundInfo> info;
+  std::vector<uint32_t> everyone(present);
+  everyone.insert(everyone.end(), absent.begin(), absent.end());
+  std::vector<SlotState> st;
   if (!present.empty() || !absent.empty()) {
     const size_t n_stage = present.size() * kChunk;
     CK(ctx->d_stream_stage.ensure(std::max<size_t>(n_stage, 8)));
@@ -2281,25 +2384,24 @@ int smb_stream_round(smb_ctx *ctx, const uint32_t *channels, uint32_t n, const i
         en.scale[i] = ctx->stream_scale[ch];
       }
     };
-    int rc = run_round(ctx, sp, present, absent, SRC_RAW_KEPT, prm, fill);
+    RoundOut rout;
+    rout.ids = &everyone;
+    rout.info = &info;
+    rout.states = &st;
+    int rc = run_round(ctx, sp, present, absent, SRC_RAW_KEPT, prm, fill, &rout);
     if (rc) return rc;
     ctx->stats.samples += (uint64_t)present.size() * kChunk;
     for (uint32_t ch : present) {
       ctx->stream_chunks[ch]++;
       ctx->stream_kept[ch] += kChunk;
     }
+  } else {
+    // nothing to map this round: provisional rows from the slots as they are
+    st.resize(std::max<size_t>(sp.n_slots, 1));
+    if (sp.n_slots) CK(cudaMemcpy(st.data(), sp.slots.p, sp.n_slots * sizeof(SlotState), cudaMemcpyDeviceToHost));
+    ctx->stats.d2h_bytes += sp.n_slots * sizeof(SlotState);
   }
-  // decisions + provisional rows for the channels named in this call
-  std::vector<uint32_t> ids(channels, channels + n);
-  std::vector<RoundInfo> info;
-  std::vector<uint32_t> everyone(present);
-  everyone.insert(everyone.end(), absent.begin(), absent.end());
-  int rc = round_readback(ctx, sp, everyone, info);
-  if (rc) return rc;
-  std::vector<SlotState> st(sp.n_slots ? sp.n_slots : 1);
-  CK(cudaMemcpy(st.data(), sp.slots.p, sp.n_slots * sizeof(SlotState), cudaMemcpyDeviceToHost));
-  ctx->stats.d2h_bytes += sp.n_slots * sizeof(SlotState);
-  rc = merge_owner_tags(ctx, st, sp.n_slots);
+  int rc = merge_owner_tags(ctx, st, sp.n_slots);
   if (rc) return rc;
   for (uint32_t i = 0; i < n; ++i) {
     const uint32_t ch = channels[i];

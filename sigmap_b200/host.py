@@ -18,7 +18,8 @@ DIGITISATION, RANGE, OFFSET, SAMPLING_RATE = 8192.0, 1437.976685, 10.0, 4000.0
 
 def _check(rc, what):
     if rc != 0:
-        raise RuntimeError(f"{what} failed with code {rc}")
+        why = F.lib.smbh_last_error().decode()
+        raise RuntimeError(f"{what} failed with code {rc}" + (f": {why}" if why else ""))
 
 
 def load_pore_model(path=MODEL_PATH):

@@ -111,6 +111,41 @@ def test_blow5_round_trip_and_reference_reader(host, model, ref, tmp_path):
     assert np.array_equal(part.truth, reads.truth[3:])
 
 
+def test_blow5_version_and_signal_compression_are_checked(host, model, tmp_path):
+    """Files of slow5 >= 0.2.0 carry a signal-compression byte (svb-zd by default in current
+    slow5tools): anything this reader cannot decode is refused with a message that says why."""
+    g = host.sim_reference(4, [30000])
+    reads = host.sim_reads(13, g, 3, min_bases=300, max_bases=600, model=model)
+    plain = str(tmp_path / "v010.blow5")
+    reads.write_blow5(plain)
+    data = bytearray(open(plain, "rb").read())
+    assert tuple(data[6:9]) == (0, 1, 0)
+
+    def variant(name, **patch):
+        d = bytearray(data)
+        for off, val in patch.items():
+            d[int(off[1:])] = val
+        path = str(tmp_path / name)
+        open(path, "wb").write(d)
+        return path
+
+    # 0.2.0 with uncompressed signals: the read-group count moves by one byte, records are the same
+    d020 = bytearray(data)
+    d020[7] = 2
+    d020[11:15] = d020[10:14]
+    d020[10] = 0
+    p020 = str(tmp_path / "v020.blow5")
+    open(p020, "wb").write(d020)
+    back = host.ReadSet.read_blow5(p020)
+    assert back.names == reads.names and np.array_equal(back.raw, reads.raw)
+    for path, words in ((variant("svb.blow5", b7=2, b10=1), "signal compression"),
+                        (variant("v1.blow5", b6=1, b7=0), "unsupported BLOW5 version 1.0.0"),
+                        (variant("zstd.blow5", b9=2), "record compression")):
+        with pytest.raises(RuntimeError) as e:
+            host.ReadSet.read_blow5(path)
+        assert words in str(e.value), str(e.value)
+
+
 def test_blow5_zlib_records_truncation_and_append(host, model, tmp_path):
     """zlib-compressed records (slow5lib's default) read like plain ones; a truncated file is an
     error, not a short read set; reading a second file appends."""
