@@ -59,7 +59,7 @@ struct ChainArgs {
   uint32_t *link_list;   // [n_tiles * kPrepTile] indices of linked anchors, ascending per tile
   uint32_t *link_count;  // [n_tiles]
   Counters *ctr;
-  int dp_passes;         // thread-parallel passes of k_chain_dp before the in-order cooperative path
+  int dp_passes;         // k_dp_pass launches before the in-order kernel (host side)
 };
 
 constexpr int kCarryThreads = 256;
@@ -316,19 +316,103 @@ __global__ void __launch_bounds__(kPrepThreads, 8) k_chain_prep(ChainArgs a) {
 }
 
 constexpr int kDpThreads = 128;
-constexpr int kDpFreePasses = 1;  // thread-parallel passes before the in-order cooperative path (measured: 1 < 2 < 4)
+constexpr int kDpFreePasses = 2;  // k_dp_pass launches before the in-order kernel
 constexpr int kDpGroup = 4;       // predecessors fetched together in the thread-parallel lookback
+constexpr int kDpPassThreads = 256;
 
-// A warp owns a segment and takes its linked anchors 32 at a time, one per lane.
-//  * Thread-parallel passes: every lane runs the reference's lookback for its own anchor.  An
-//    anchor's score only depends on the scores of its gap-compatible predecessors; if one of
-//    them is still pending (a linked anchor earlier in the same 32) the lane defers, otherwise
-//    its result is final.  Background hits form chains of 2-3 anchors, so two passes settle
-//    almost everything.
-//  * What is still pending after that (true-locus clusters, where every anchor links to the
-//    previous one) is settled in order by the whole warp: lanes load 32 consecutive predecessors
-//    coalesced, score one each, and the sequential rules (continue/break, running best, +-1 skip
-//    counter with its > 25 break) are resolved with a prefix-max scan and ballots.
+// The DP in two kernels.
+//
+//  k_dp_pass   every linked anchor of the step at once, one THREAD each (block per k_chain_prep
+//              tile, lanes = consecutive linked anchors): the lane runs the reference's lookback
+//              for its anchor.  An anchor's score only depends on the scores of its gap-compatible
+//              predecessors; if the lookback meets one that is still pending the lane defers,
+//              otherwise its result is final -- whatever the other threads are doing meanwhile,
+//              so the result does not depend on timing.  Background hits form chains of 2-3
+//              anchors: two launches settle almost everything, at full occupancy and with no
+//              segment-sized serial work.  Scores of other threads' anchors are read past L1
+//              (ld.cg) after their pending bit was seen cleared; the writer orders score before
+//              bit with a fence.
+//  k_chain_dp  a warp owns a segment and walks its linked anchors 32 at a time, in order: what
+//              is still pending (true-locus clusters, where every anchor links to the previous
+//              one) is settled by the whole warp -- lanes load 32 consecutive predecessors
+//              coalesced, score one each, and the sequential rules (continue/break, running best,
+//              +-1 skip counter with its > 25 break) are resolved with a prefix-max scan and
+//              ballots -- then the running max and the end candidates of the batch are taken.
+__global__ void __launch_bounds__(kDpPassThreads) k_dp_pass(ChainArgs a) {
+  if (a.ctr->abort) return;
+  const uint32_t n = (uint32_t)a.ctr->n_anchors;
+  const uint32_t tile = blockIdx.x;
+  if ((unsigned long long)tile * kPrepTile >= n) return;
+  const uint32_t cnt = a.link_count[tile];
+  const uint32_t *list = a.link_list + (size_t)tile * kPrepTile;
+  const KeyLayout kl = a.kl;
+  const uint64_t *__restrict__ key = a.key;
+  float *score = a.score;
+  uint32_t *pred = a.pred;
+  for (uint32_t c = threadIdx.x; c < cnt; c += kDpPassThreads) {
+    const uint32_t i = list[c];
+    if (!(__ldcg(pred + i) & kPending)) continue;  // settled by an earlier pass
+    const uint64_t k = key[i];
+    const uint64_t sg = kl.seg(k);
+    const int32_t ti = (int32_t)kl.target(k), qi = (int32_t)kl.query(k);
+    const float ci = a.coef[i];
+    float M = __ldcg(score + i);  // 6 * coef from k_chain_prep = chaining_scores[anchor_index]
+    uint32_t best = i;
+    int S = 0;  // num_skips
+    bool defer = false, done = false;
+    const uint32_t lo = i > (uint32_t)kBand ? i - kBand : 0u;  // the segment start ends the walk earlier
+    // predecessors four at a time: the key loads of a group are independent, so the walk pays
+    // one memory round trip per group instead of one per predecessor
+    for (uint32_t jb = i; jb > lo && !done;) {
+      const uint32_t m = min(jb - lo, (uint32_t)kDpGroup);
+      uint64_t kk[kDpGroup];
+#pragma unroll
+      for (int u = 0; u < kDpGroup; ++u) kk[u] = (uint32_t)u < m ? key[jb - 1u - (uint32_t)u] : 0ull;
+#pragma unroll
+      for (int u = 0; u < kDpGroup; ++u) {
+        if (done || (uint32_t)u >= m) break;
+        const uint32_t j = jb - 1u - (uint32_t)u;
+        const uint64_t kj = kk[u];
+        if (kl.seg(kj) != sg) {  // first anchor of the segment passed
+          done = true;
+          break;
+        }
+        const int32_t pt = (int32_t)kl.target(kj), pq = (int32_t)kl.query(kj);
+        if (pq == qi || pt == ti) continue;
+        if (pt + kMaxTargetGap < ti) {
+          done = true;
+          break;
+        }
+        const int32_t dt = ti - pt, dq = qi - pq;
+        if (dq < 0) continue;
+        float cur = 0.0f;
+        if (gap_compatible(dt, dq)) {
+          if (__ldcg(pred + j) & kPending) {
+            defer = true;
+            done = true;
+            break;
+          }
+          cur = __fadd_rn(__ldcg(score + j), __fmul_rn((float)min(min(dt, dq), kDim), ci));
+        }
+        if (cur > M) {
+          M = cur;
+          best = j;
+          --S;
+        } else if (++S > kMaxSkips) {
+          done = true;
+          break;
+        }
+      }
+      jb -= m;
+    }
+    if (!defer) {
+      score[i] = M;
+      __threadfence();
+      pred[i] = best;  // clears kPending
+    }
+  }
+}
+
 __device__ __forceinline__ void dp_segment(const ChainArgs &a, const uint32_t slot, const int lane) {
   const unsigned full = 0xffffffffu;
   const unsigned le = (2u << lane) - 1u;  // lanes 0..lane
@@ -356,76 +440,24 @@ __device__ __forceinline__ void dp_segment(const ChainArgs &a, const uint32_t sl
       const bool valid = c < cnt && i >= s && i < e;
       if (!__ballot_sync(full, valid)) continue;
       int32_t ti = 0, qi = 0;
-      float ci = 0.0f, init = 0.0f, M = 0.0f;
+      float ci = 0.0f, M = 0.0f;
       uint32_t lo = 0;
+      bool todo = false;
       if (valid) {
-        const uint64_t k = key[i];
-        ti = (int32_t)kl.target(k);
-        qi = (int32_t)kl.query(k);
-        ci = a.coef[i];
-        init = score[i];  // 6 * coef from k_chain_prep = chaining_scores[anchor_index]
+        M = score[i];  // final, or 6 * coef from k_chain_prep while the anchor is pending
+        todo = (pred[i] & kPending) != 0u;
         lo = (i - s > (uint32_t)kBand) ? i - kBand : s;
       }
-      bool todo = valid;
-      // ---- thread-parallel passes
-      for (int pass = 0; pass < a.dp_passes; ++pass) {
-        if (todo) {
-          M = init;
-          uint32_t best = i;
-          int S = 0;  // num_skips
-          bool defer = false;
-          // predecessors four at a time: the key loads of a group are independent, so the walk
-          // pays one memory round trip per group instead of one per predecessor
-          bool done = false;
-          for (uint32_t jb = i; jb > lo && !done;) {
-            const uint32_t m = min(jb - lo, (uint32_t)kDpGroup);
-            uint64_t kk[kDpGroup];
-#pragma unroll
-            for (int u = 0; u < kDpGroup; ++u) kk[u] = (uint32_t)u < m ? key[jb - 1u - (uint32_t)u] : 0ull;
-#pragma unroll
-            for (int u = 0; u < kDpGroup; ++u) {
-              if (done || (uint32_t)u >= m) break;
-              const uint32_t j = jb - 1u - (uint32_t)u;
-              const uint64_t kj = kk[u];
-              const int32_t pt = (int32_t)kl.target(kj), pq = (int32_t)kl.query(kj);
-              if (pq == qi || pt == ti) continue;
-              if (pt + kMaxTargetGap < ti) {
-                done = true;
-                break;
-              }
-              const int32_t dt = ti - pt, dq = qi - pq;
-              if (dq < 0) continue;
-              float cur = 0.0f;
-              if (gap_compatible(dt, dq)) {
-                if (pred[j] & kPending) {
-                  defer = true;
-                  done = true;
-                  break;
-                }
-                cur = __fadd_rn(score[j], __fmul_rn((float)min(min(dt, dq), kDim), ci));
-              }
-              if (cur > M) {
-                M = cur;
-                best = j;
-                --S;
-              } else if (++S > kMaxSkips) {
-                done = true;
-                break;
-              }
-            }
-            jb -= m;
-          }
-          if (!defer) {
-            score[i] = M;
-            pred[i] = best;  // clears kPending
-            todo = false;
-          }
-        }
-        __syncwarp(full);  // settled scores are visible to the lanes that deferred
-        if (!__ballot_sync(full, todo)) break;
-      }
-      // ---- what is left, in order, by the whole warp
+      // ---- what the parallel passes left, in order, by the whole warp
       unsigned left = __ballot_sync(full, todo);
+      if (left) {
+        if (todo) {
+          const uint64_t k = key[i];
+          ti = (int32_t)kl.target(k);
+          qi = (int32_t)kl.query(k);
+          ci = a.coef[i];
+        }
+      }
       while (left) {
         const int src = __ffs(left) - 1;
         left &= left - 1;
@@ -433,7 +465,7 @@ __device__ __forceinline__ void dp_segment(const ChainArgs &a, const uint32_t sl
         const int32_t tii = __shfl_sync(full, ti, src), qii = __shfl_sync(full, qi, src);
         const float cii = __shfl_sync(full, ci, src);
         const uint32_t loi = __shfl_sync(full, lo, src);
-        float Mi = __shfl_sync(full, init, src);
+        float Mi = __shfl_sync(full, M, src);
         uint32_t best = ii;
         int S = 0;
         for (uint32_t jb = ii;; jb -= 32) {  // block of predecessors jb-1 .. jb-32

@@ -219,8 +219,8 @@ __host__ __device__ inline size_t search_smem_per_warp(int n_levels) {
   return (size_t)kStageCap * 16 + (size_t)kLeafQueueCap * 4 + 16 * 4 + kMaxParts * 4 +
          (size_t)n_levels * kLevelCap * 4;
 }
-// lean kernel, per warp: staged keys (8 B) and distances, two frontiers, per-part counts
-constexpr size_t kLeanWarpSmem = (size_t)kLeanStage * 12 + 2 * (size_t)kFrontCap * 4 + kMaxParts * 4;
+// lean kernel, per warp: staged keys (8 B), distances and part|rank (2 B), two frontiers, per-part counts
+constexpr size_t kLeanWarpSmem = (size_t)kLeanStage * 14 + 2 * (size_t)kFrontCap * 4 + kMaxParts * 4;
 __host__ __device__ inline size_t lean_top_region(uint32_t smem_bytes) { return ((size_t)smem_bytes + 127) & ~(size_t)127; }
 __host__ __device__ inline size_t lean_smem(uint32_t smem_bytes) {
   return lean_top_region(smem_bytes) + (size_t)kLeanWarps * kLeanWarpSmem;
@@ -349,28 +349,21 @@ __global__ void k_query_keys_stage(const float *__restrict__ queries, uint32_t n
 // ---- hits -> global memory.  `n` staged (key, d2) pairs of ONE batch entry: one reservation of
 // output space, the hits grouped by coordinate part inside it, one run record per part touched.
 // Not inlined: it is called from three places of two kernels and is off the traversal's path.
-template <int CAP>
 __device__ __noinline__ void flush_routed(const SearchArgs &a, const uint64_t *__restrict__ st_key,
-                                          const float *__restrict__ st_dist, uint32_t *__restrict__ pcnt,
-                                          const uint64_t *__restrict__ s_bb, int n, uint32_t entry) {
+                                          const float *__restrict__ st_dist, uint16_t *__restrict__ st_where,
+                                          uint32_t *__restrict__ pcnt, const uint64_t *__restrict__ s_bb, int n,
+                                          uint32_t entry) {
   const int lane = threadIdx.x & 31;
   const unsigned full = 0xffffffffu;
   pcnt[lane] = 0;
   __syncwarp();
-  uint64_t key[CAP / 32];
-  uint32_t where[CAP / 32];  // part << 8 | rank inside the part (this flush)
-#pragma unroll
-  for (int u = 0; u < CAP / 32; ++u) {
-    const int i = u * 32 + lane;
-    key[u] = 0;
-    where[u] = 0;
-    if (i < n) {
-      key[u] = st_key[i];
-      const uint32_t b = a.key.bucket(key[u]);
-      const uint64_t base = s_bb ? s_bb[b] : __ldg(a.bucket_base + b);
-      const uint32_t part = part_of(base + a.key.target(key[u]), a.inv_span, a.n_parts);
-      where[u] = (part << 8) | atomicAdd(&pcnt[part], 1u);
-    }
+  // pass 1: part of every hit and its rank inside the part (part << 8 | rank, kept in shared memory)
+  for (int i = lane; i < n; i += 32) {
+    const uint64_t key = st_key[i];
+    const uint32_t b = a.key.bucket(key);
+    const uint64_t base = s_bb ? s_bb[b] : __ldg(a.bucket_base + b);
+    const uint32_t part = part_of(base + a.key.target(key), a.inv_span, a.n_parts);
+    st_where[i] = (uint16_t)((part << 8) | atomicAdd(&pcnt[part], 1u));
   }
   __syncwarp();
   const uint32_t mine = pcnt[lane];  // lane p: hits of part p
@@ -393,16 +386,15 @@ __device__ __noinline__ void flush_routed(const SearchArgs &a, const uint64_t *_
     else atomicOr(&a.ctr->error, 8u);
     atomicAdd(&a.entry_total[list], mine);
   }
-#pragma unroll
-  for (int u = 0; u < CAP / 32; ++u) {
-    const int i = u * 32 + lane;
-    const uint32_t off = __shfl_sync(full, excl, (int)(where[u] >> 8));
-    if (i < n) {
-      const unsigned long long o = base + off + (where[u] & 0xFFu);
-      if (o < a.cap) {
-        a.out_key[o] = key[u];
-        a.out_dist[o] = st_dist[i];
-      }
+  pcnt[lane] = excl;  // offset of part p inside this flush
+  __syncwarp();
+  // pass 2: every hit to its place
+  for (int i = lane; i < n; i += 32) {
+    const uint32_t wh = st_where[i];
+    const unsigned long long o = base + pcnt[wh >> 8] + (wh & 0xFFu);
+    if (o < a.cap) {
+      a.out_key[o] = st_key[i];
+      a.out_dist[o] = st_dist[i];
     }
   }
   __syncwarp();
@@ -561,6 +553,7 @@ k_search_lean(const __grid_constant__ IndexView ix, const __grid_constant__ Sear
   uint32_t *fa = reinterpret_cast<uint32_t *>(mine + (size_t)kLeanStage * 12);
   uint32_t *fb = fa + kFrontCap;
   uint32_t *pcnt = fb + kFrontCap;
+  uint16_t *st_where = reinterpret_cast<uint16_t *>(pcnt + kMaxParts);
 
   // ---- the top levels: one bulk copy per CTA, everybody waits on the mbarrier
   if (threadIdx.x == 0) mbar_init(&s_mbar, 1);
@@ -615,7 +608,7 @@ k_search_lean(const __grid_constant__ IndexView ix, const __grid_constant__ Sear
         for (int d = 0; d < kDim; ++d) q[d] = __ldg(f + d);
         qk = a.key.pack(entry, 0u, 0u, p + info.y);
         if (routed && staged && entry != staged_entry) {
-          flush_routed<kLeanStage>(a, st_key, st_dist, pcnt, s_bb, staged, staged_entry);
+          flush_routed(a, st_key, st_dist, st_where, pcnt, s_bb, staged, staged_entry);
           staged = 0;
         }
         staged_entry = entry;
@@ -659,7 +652,7 @@ k_search_lean(const __grid_constant__ IndexView ix, const __grid_constant__ Sear
         if (hitA | hitB) {
           const int nA = __popc(hitA), nh = nA + __popc(hitB);
           if (staged + nh > kLeanStage) {
-            if (routed) flush_routed<kLeanStage>(a, st_key, st_dist, pcnt, s_bb, staged, staged_entry);
+            if (routed) flush_routed(a, st_key, st_dist, st_where, pcnt, s_bb, staged, staged_entry);
             else flush_plain<kLeanStage>(a, st_key, st_dist, staged);
             staged = 0;
           }
@@ -696,7 +689,7 @@ k_search_lean(const __grid_constant__ IndexView ix, const __grid_constant__ Sear
     }
   }
   if (staged) {
-    if (routed) flush_routed<kLeanStage>(a, st_key, st_dist, pcnt, s_bb, staged, staged_entry);
+    if (routed) flush_routed(a, st_key, st_dist, st_where, pcnt, s_bb, staged, staged_entry);
     else flush_plain<kLeanStage>(a, st_key, st_dist, staged);
   }
   if (lane == 0 && my_hits) atomicAdd(&a.ctr->n_hits, my_hits);
@@ -726,6 +719,7 @@ k_radius_search(const __grid_constant__ IndexView ix, const __grid_constant__ Se
   unsigned char *mine = s_dyn + (size_t)wid * search_smem_per_warp(n_levels);
   uint64_t *st_key = reinterpret_cast<uint64_t *>(mine);
   float *st_dist = reinterpret_cast<float *>(mine + kStageCap * 8);
+  uint16_t *st_where = reinterpret_cast<uint16_t *>(mine + kStageCap * 12);
   uint32_t *leafq = reinterpret_cast<uint32_t *>(mine + kStageCap * 16);
   uint32_t *lcnt = leafq + kLeafQueueCap;          // [16] nodes waiting per level
   uint32_t *pcnt = lcnt + 16;                      // [kMaxParts] hits per part of the flush in progress
@@ -745,7 +739,7 @@ k_radius_search(const __grid_constant__ IndexView ix, const __grid_constant__ Se
 
   auto flush = [&]() {
     if (staged == 0) return;
-    if (routed) flush_routed<kStageCap>(a, st_key, st_dist, pcnt, nullptr, staged, staged_entry);
+    if (routed) flush_routed(a, st_key, st_dist, st_where, pcnt, nullptr, staged, staged_entry);
     else flush_plain<kStageCap>(a, st_key, st_dist, staged);
     staged = 0;
   };

@@ -9,23 +9,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $O
 ( time timeout 1200 python -m pytest tests -m gpu -x -q ) > $OUT/pytest_gpu.log 2>&1
 echo "== pytest: $(grep -E 'passed|failed|error' $OUT/pytest_gpu.log | tail -1)"
 grep -E "^(FAILED|ERROR)|Error|assert " $OUT/pytest_gpu.log | head -20
-summ() {
-python - "$1" <<'PY'
-import json,sys
-for l in open(sys.argv[1]):
-    if l.startswith('{'):
-        d=json.loads(l)
-        def one(tag,d):
-            print(tag, round(d['value']/1e9,4),'G/s', round(d['ms_per_step'],1),'ms', {k:round(v,1) for k,v in d['pipeline']['kernel_ms_per_step'].items()},
-                  'e2e',round(d['e2e']['value']/1e9,4), 'roof',round(d['roofline']['frac'],3), 'mapped',d['mapped_reads'],'truth',d['truth_concordant_reads'])
-            c=d['pipeline']['counters_per_step']; print('   ', {k:c[k] for k in ('steps','capped_queries','overflow_queries','part_sort_steps','seg_sort_steps','sync_points')})
-            print('    conc', d.get('concordance'))
-        one('c2' if d['config']['baseline_config']=='configs[1]' else 'c3', d)
-        if d.get('latency'): print('    latency p50', round(d['latency']['p50'],3), 'p90', round(d['latency']['p90'],3))
-        if d.get('cpu_baseline'): print('    cpu', d['cpu_baseline']['value'], d['cpu_baseline']['cores'])
-        if d.get('config3'): one('c3@1', d['config3'])
-PY
-}
+source tools/summ.sh
 echo "== bench (default: c2 + c3 leg)"
 ( timeout 900 python bench.py --steps 4 --warmup 2 ) > $OUT/bench.json 2> $OUT/bench.err
 summ $OUT/bench.json; tail -3 $OUT/bench.err
