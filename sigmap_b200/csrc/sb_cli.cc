@@ -234,17 +234,31 @@ int map_reads(const Args &a) {
   } else {
     for (size_t g = 0; g < G; ++g) {
       if (smb_index_load(ctxs[g], a.ref_index.c_str())) die(std::string("smb_index_load: ") + smb_last_error(ctxs[g]));
-      smb_index_set_contigs(ctxs[g], fa.lengths, fa.n);
+      if (smb_index_set_contigs(ctxs[g], fa.lengths, fa.n)) die(std::string("smb_index_set_contigs: ") + smb_last_error(ctxs[g]));
     }
   }
   fprintf(stderr, "Loaded index successfully in %fs.\n", now() - t0);
   std::vector<smb_mapping> rows(reads.n ? reads.n : 1);
   t0 = now();
   uint64_t zero_off[1] = {0};
+  // A device holds the raw samples of a call twice (as read and filtered, 2 B each): map a signal
+  // directory larger than kMaxCallSamples per device in several calls -- reads are independent, so
+  // the rows are the same -- instead of failing in cudaMalloc (the reference only needs host RAM).
+  const uint64_t kMaxCallSamples = 12ull << 30;  // 48 GB of the 180 GB HBM
   if (G == 1) {
-    if (smb_map_reads(ctxs[0], reads.raw, reads.n ? reads.read_off : zero_off, reads.digitisation, reads.range,
-                      reads.offset, reads.n, &a.prm, rows.data()))
-      die(std::string("smb_map_reads: ") + smb_last_error(ctxs[0]));
+    for (size_t lo = 0; lo < reads.n || lo == 0;) {
+      size_t hi = lo;
+      while (hi < reads.n && (hi == lo || reads.read_off[hi + 1] - reads.read_off[lo] <= kMaxCallSamples)) ++hi;
+      const size_t cnt = hi - lo;
+      std::vector<uint64_t> off(cnt + 1, 0);
+      for (size_t r = 0; r <= cnt && reads.n; ++r) off[r] = reads.read_off[lo + r] - reads.read_off[lo];
+      const int16_t *raw = reads.n ? reads.raw + reads.read_off[lo] : reads.raw;
+      if (smb_map_reads(ctxs[0], raw, reads.n ? off.data() : zero_off, reads.digitisation + lo, reads.range + lo,
+                        reads.offset + lo, cnt, &a.prm, rows.data() + lo))
+        die(std::string("smb_map_reads: ") + smb_last_error(ctxs[0]));
+      if (hi >= reads.n) break;
+      lo = hi;
+    }
   } else {
     // reads: context g maps the g-th block of the reads; contigs: every context maps every read
     // (all calls identical, as the collectives require) and context 0's rows are the result
@@ -266,10 +280,22 @@ int map_reads(const Args &a) {
           all[g].resize(cnt ? cnt : 1);
           dst = all[g].data();
         }
-        const int16_t *raw = reads.n ? reads.raw + reads.read_off[lo] : reads.raw;
-        if (smb_map_reads(ctxs[g], raw, off.data(), reads.digitisation + lo, reads.range + lo, reads.offset + lo,
-                          cnt, &a.prm, dst))
-          err[g] = smb_last_error(ctxs[g]);
+        // (in several calls when the device's share is larger than kMaxCallSamples; contig shards
+        // must all make the same calls, which they do: the split depends on the reads only)
+        for (size_t b0 = 0; b0 < cnt || b0 == 0;) {
+          size_t b1 = b0;
+          while (b1 < cnt && (b1 == b0 || off[b1 + 1] - off[b0] <= kMaxCallSamples)) ++b1;
+          std::vector<uint64_t> boff(b1 - b0 + 1, 0);
+          for (size_t r = 0; r <= b1 - b0; ++r) boff[r] = off[b0 + r] - off[b0];
+          const int16_t *raw = reads.n ? reads.raw + reads.read_off[lo] + off[b0] : reads.raw;
+          if (smb_map_reads(ctxs[g], raw, boff.data(), reads.digitisation + lo + b0, reads.range + lo + b0,
+                            reads.offset + lo + b0, b1 - b0, &a.prm, dst + b0)) {
+            err[g] = smb_last_error(ctxs[g]);
+            break;
+          }
+          if (b1 >= cnt) break;
+          b0 = b1;
+        }
       });
     for (auto &t : th) t.join();
     for (size_t g = 0; g < G; ++g)
@@ -289,11 +315,14 @@ int map_reads(const Args &a) {
   if (!out) die("Cannot open output file!");
   const double mt = reads.n ? dt * 1000.0 / reads.n : 0.0;
   std::vector<char> line(4096);
+  std::vector<std::vector<uint32_t>> by_contig_rows(std::max(fa.n, 1u));
+  for (size_t r = 0; r < reads.n; ++r) {
+    const uint32_t bin = rows[r].mapped && rows[r].contig < fa.n ? rows[r].contig : 0;
+    by_contig_rows[bin].push_back((uint32_t)r);
+  }
   for (uint32_t c = 0; c < std::max(fa.n, 1u); ++c) {
-    for (size_t r = 0; r < reads.n; ++r) {
+    for (uint32_t r : by_contig_rows[c]) {
       const smb_mapping &m = rows[r];
-      const uint32_t bin = m.mapped ? m.contig : 0;
-      if (bin != c) continue;
       const char *cname = m.mapped && m.contig < fa.n ? fa.names[m.contig] : "*";
       const uint32_t clen = m.mapped && m.contig < fa.n ? fa.lengths[m.contig] : 0;
       smbh_format_paf(&m, reads.names[r], cname, clen, mt, line.data(), line.size());

@@ -58,6 +58,9 @@ __global__ void k_reset_step(Counters *c) {
   c->work = 0;
   c->work2 = 0;
   c->n_overflow = 0;
+  c->abort = 0;
+  c->need_chain = 0;
+  c->need_anchor = 0;
   c->sort_cursor = 0;
   c->n_cand = 0;
   c->max_entry_anchors = 0;
@@ -252,6 +255,11 @@ struct smb_ctx {
   bool seg_sort = true;           // per-entry shared-memory sort; SMB_SORT=global forces the radix sort
   uint32_t search_grab = 0;       // SMB_GRAB=n: queries per grab of the search work counter (0 = default)
   bool sort_small = false;        // SMB_SORT=small: two 100 KB sort CTAs per SM instead of one 200 KB CTA
+  cudaStream_t stream_cp = nullptr;  // smb_map_reads: upload slices (copy + K1 filter) run here, under the mapping
+  std::vector<cudaEvent_t> slice_events;
+  size_t upload_slice_bytes = 64u << 20;  // SMB_UPLOAD_SLICE_MB=n
+  uint32_t *h_kept_pinned = nullptr;      // kept length of every read, written by the device (pinned)
+  size_t h_kept_pinned_cap = 0;
   cudaStream_t stream_ev = nullptr;  // lookahead event blocks run here, next to the mapping rounds
   cudaEvent_t ev_blk_t0[2] = {}, ev_blk_t1[2] = {};
   bool ev_overlap = true;            // SMB_EVENTS_OVERLAP=0: compute every block when it is needed
@@ -1379,6 +1387,8 @@ static bool apply_option(smb_ctx *ctx, const char *name_in, const char *value) {
     ctx->dp_dynamic = strcmp(value, "static") != 0;
   } else if (name == "DP_PASSES") {
     ctx->dp_passes = std::max(atoi(value), 0);
+  } else if (name == "UPLOAD_SLICE_MB") {
+    ctx->upload_slice_bytes = (size_t)std::max(atoi(value), 1) << 20;
   } else if (name == "EVENTS_OVERLAP") {
     ctx->ev_overlap = strcmp(value, "0") != 0;
   } else if (name == "EVENTS") {  // auto (default) | thread | warp
@@ -1474,7 +1484,7 @@ int smb_create(smb_ctx **out, int device) {
                                 (int)part_sort_smem_bytes(kPartSortCapSmall, 2304))) != cudaSuccess)
     return bail("cudaFuncSetAttribute(k_part_sort)", e);
   for (const char *name : {"SORT", "SEARCH", "FRONT_CAP", "RUNS_CAP", "GRAB", "PART_FILL", "PART", "DP", "DP_PASSES",
-                           "EVENTS_OVERLAP", "EVENTS"})
+                           "EVENTS_OVERLAP", "EVENTS", "UPLOAD_SLICE_MB"})
     if (const char *env = getenv((std::string("SMB_") + name).c_str())) apply_option(ctx, name, env);
   {
     int per_sm = 0, n_sm = 148;
@@ -1488,7 +1498,8 @@ int smb_create(smb_ctx **out, int device) {
       (e = cudaFuncSetAttribute(k_ev_chunk_warp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)kEvWarpSmem)) != cudaSuccess)
     return bail("cudaFuncSetAttribute(k_ev_chunk_warp)", e);
-  if ((e = cudaStreamCreateWithFlags(&ctx->stream_ev, cudaStreamNonBlocking)) != cudaSuccess)
+  if ((e = cudaStreamCreateWithFlags(&ctx->stream_ev, cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = cudaStreamCreateWithFlags(&ctx->stream_cp, cudaStreamNonBlocking)) != cudaSuccess)
     return bail("cudaStreamCreate", e);
   for (int c = 0; c < 2; ++c)
     if ((e = cudaEventCreate(&ctx->ev_blk_t0[c])) != cudaSuccess || (e = cudaEventCreate(&ctx->ev_blk_t1[c])) != cudaSuccess)
@@ -1502,6 +1513,7 @@ void smb_destroy(smb_ctx *ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   if (ctx->stream_ev) cudaStreamSynchronize(ctx->stream_ev);
+  if (ctx->stream_cp) cudaStreamSynchronize(ctx->stream_cp);
   smb_stream_close(ctx);
   slots_release(ctx->map_slots);
   Workspace &w = ctx->ws;
@@ -1526,6 +1538,9 @@ void smb_destroy(smb_ctx *ctx) {
   for (auto &ev : ctx->ev_blk_t0) if (ev) cudaEventDestroy(ev);
   for (auto &ev : ctx->ev_blk_t1) if (ev) cudaEventDestroy(ev);
   if (ctx->stream_ev) cudaStreamDestroy(ctx->stream_ev);
+  if (ctx->stream_cp) cudaStreamDestroy(ctx->stream_cp);
+  for (auto &ev : ctx->slice_events) cudaEventDestroy(ev);
+  if (ctx->h_kept_pinned) cudaFreeHost(ctx->h_kept_pinned);
   if (ctx->d_ctr) cudaFree(ctx->d_ctr);
   if (ctx->h_ctr) cudaFreeHost(ctx->h_ctr);
   if (ctx->h_ctl) cudaFreeHost(ctx->h_ctl);
@@ -1695,10 +1710,11 @@ uint64_t smb_index_num_points(const smb_ctx *ctx) { return ctx->has_index ? ctx-
 uint32_t smb_index_num_contigs(const smb_ctx *ctx) { return (uint32_t)ctx->contig_len.size(); }
 
 // ------------------------------------------------------------ whole hot path
-int smb_reads_upload(smb_ctx *ctx, const int16_t *raw, const uint64_t *read_off, const float *dig,
-                     const float *range, const float *offset, size_t n_reads) {
-  CK(cudaSetDevice(ctx->device));
-  cudaStream_t s = ctx->stream;
+}  // extern "C"
+
+// device buffers and the per-read tables of a read set (everything but the samples), on stream s
+static int reads_prepare(smb_ctx *ctx, const uint64_t *read_off, const float *dig, const float *range,
+                         const float *offset, size_t n_reads, cudaStream_t s) {
   ctx->n_reads = n_reads;
   if (n_reads == 0) return SMB_OK;
   if (n_reads > 0xFFFFFFF0ull) return fail(ctx, SMB_ERR_ARG, "too many reads");
@@ -1720,46 +1736,88 @@ int smb_reads_upload(smb_ctx *ctx, const int16_t *raw, const uint64_t *read_off,
   CK(ctx->d_range.ensure(n_reads));
   CK(ctx->d_offset.ensure(n_reads));
   CK(ctx->d_kept_len.ensure(n_reads));
-  CK(cudaMemcpyAsync(ctx->raw.p, raw, total * sizeof(int16_t), cudaMemcpyHostToDevice, s));
+  if (n_reads > ctx->h_kept_pinned_cap) {
+    if (ctx->h_kept_pinned) cudaFreeHost(ctx->h_kept_pinned);
+    ctx->h_kept_pinned = nullptr;
+    ctx->h_kept_pinned_cap = 0;
+    CK(cudaMallocHost((void **)&ctx->h_kept_pinned, (n_reads + n_reads / 4 + 64) * sizeof(uint32_t)));
+    ctx->h_kept_pinned_cap = n_reads + n_reads / 4 + 64;
+  }
   CK(cudaMemcpyAsync(ctx->d_read_off.p, read_off, (n_reads + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
   CK(cudaMemcpyAsync(ctx->d_kept_off.p, ctx->h_kept_off.data(), n_reads * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
   CK(cudaMemcpyAsync(ctx->d_dig.p, dig, n_reads * sizeof(float), cudaMemcpyHostToDevice, s));
   CK(cudaMemcpyAsync(ctx->d_range.p, range, n_reads * sizeof(float), cudaMemcpyHostToDevice, s));
   CK(cudaMemcpyAsync(ctx->d_offset.p, offset, n_reads * sizeof(float), cudaMemcpyHostToDevice, s));
-  ctx->stats.h2d_bytes += total * 2 + n_reads * 28 + 8;
+  ctx->stats.h2d_bytes += n_reads * 28 + 8;
+  return SMB_OK;
+}
+
+extern "C" {
+
+int smb_reads_upload(smb_ctx *ctx, const int16_t *raw, const uint64_t *read_off, const float *dig,
+                     const float *range, const float *offset, size_t n_reads) {
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  int rc = reads_prepare(ctx, read_off, dig, range, offset, n_reads, s);
+  if (rc || n_reads == 0) return rc;
+  const uint64_t total = read_off[n_reads];
+  CK(cudaMemcpyAsync(ctx->raw.p, raw, total * sizeof(int16_t), cudaMemcpyHostToDevice, s));
+  ctx->stats.h2d_bytes += total * 2;
   CK(cudaStreamSynchronize(s));
   return SMB_OK;
 }
 
 }  // extern "C"
 
-// K1 over all uploaded reads: (30,200) pA filter + compaction, then kept lengths to the host
+// K1 over reads [r0, r1) on stream s: (30,200) pA filter + compaction, kept lengths to the
+// pinned host mirror (no wait here)
+static int filter_slice(smb_ctx *ctx, size_t r0, size_t r1, cudaStream_t s) {
+  if (r1 <= r0) return SMB_OK;
+  k_filter_compact<<<(unsigned)(r1 - r0), kFilterThreads, 0, s>>>(ctx->raw.p, ctx->d_read_off.p + r0, ctx->d_dig.p + r0,
+                                                                ctx->d_range.p + r0, ctx->d_offset.p + r0,
+                                                                ctx->d_kept_off.p + r0, ctx->kept.p,
+                                                                ctx->d_kept_len.p + r0, (uint32_t)(r1 - r0));
+  LAUNCH_CHECK();
+  CK(cudaMemcpyAsync(ctx->h_kept_pinned + r0, ctx->d_kept_len.p + r0, (r1 - r0) * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  ctx->stats.d2h_bytes += (r1 - r0) * 4;
+  return SMB_OK;
+}
+
+// K1 over all uploaded reads, then kept lengths to the host
 static int filter_reads(smb_ctx *ctx) {
   const size_t n_reads = ctx->n_reads;
   ctx->h_kept_len.resize(n_reads);
   if (!n_reads) return SMB_OK;
   cudaStream_t s = ctx->stream;
   CK(cudaEventRecord(ctx->ev[5], s));
-  k_filter_compact<<<(unsigned)n_reads, kFilterThreads, 0, s>>>(ctx->raw.p, ctx->d_read_off.p, ctx->d_dig.p,
-                                                              ctx->d_range.p, ctx->d_offset.p, ctx->d_kept_off.p,
-                                                              ctx->kept.p, ctx->d_kept_len.p, (uint32_t)n_reads);
-  LAUNCH_CHECK();
+  int rc = filter_slice(ctx, 0, n_reads, s);
+  if (rc) return rc;
   CK(cudaEventRecord(ctx->ev[4], s));
-  CK(cudaMemcpyAsync(ctx->h_kept_len.data(), ctx->d_kept_len.p, n_reads * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-  CK(cudaStreamSynchronize(s));
-  ctx->stats.d2h_bytes += n_reads * 4;
+  rc = host_sync(ctx);
+  if (rc) return rc;
+  memcpy(ctx->h_kept_len.data(), ctx->h_kept_pinned, n_reads * sizeof(uint32_t));
   float ms = 0;
   cudaEventElapsedTime(&ms, ctx->ev[5], ctx->ev[4]);
   ctx->stats.ms_filter += ms;
   return SMB_OK;
 }
 
+// smb_map_reads: the samples arrive in slices on the copy stream while earlier slices are being
+// mapped.  Slice k = reads [first_read[k], first_read[k+1]); done[k] fires once the slice has been
+// copied, filtered, and its kept lengths are in the pinned host mirror.
+struct UploadPlan {
+  std::vector<size_t> first_read;
+  std::vector<cudaEvent_t> done;
+  size_t admitted = 0;  // slices handed to the mapping loop so far
+  size_t n_slices() const { return done.size(); }
+};
+
 extern "C" {
 
-static int map_uploaded_impl(smb_ctx *ctx, const smb_params *prm_in, smb_mapping *out);
+static int map_uploaded_impl(smb_ctx *ctx, const smb_params *prm_in, smb_mapping *out, UploadPlan *plan);
 
 int smb_map_uploaded(smb_ctx *ctx, const smb_params *prm_in, smb_mapping *out) {
-  const int rc = map_uploaded_impl(ctx, prm_in, out);
+  const int rc = map_uploaded_impl(ctx, prm_in, out, nullptr);
   // a failed member must not leave its in-process peers waiting at a rendezvous
   if (rc && ctx->local_group) ctx->local_group->abort_all();
   return rc;
@@ -1767,7 +1825,7 @@ int smb_map_uploaded(smb_ctx *ctx, const smb_params *prm_in, smb_mapping *out) {
 
 }  // extern "C"
 
-static int map_uploaded_impl(smb_ctx *ctx, const smb_params *prm_in, smb_mapping *out) {
+static int map_uploaded_impl(smb_ctx *ctx, const smb_params *prm_in, smb_mapping *out, UploadPlan *plan) {
   CK(cudaSetDevice(ctx->device));
   if (!ctx->has_index) return fail(ctx, SMB_ERR_STATE, "no index loaded");
   smb_params prm = *prm_in;
@@ -1776,28 +1834,67 @@ static int map_uploaded_impl(smb_ctx *ctx, const smb_params *prm_in, smb_mapping
   SlotSpace &sp = ctx->map_slots;
   int rc = slots_init(ctx, sp, (uint32_t)R);
   if (rc) return rc;
-  rc = filter_reads(ctx);  // K1: part of the mapped path, redone on every call
-  if (rc) return rc;
-  std::vector<uint32_t> n_chunks(R), chunks_used(R, 1);
+  // The loop below advances in TICKS: tick t maps the next chunk of every active read.  Reads join
+  // ("are admitted") at a tick boundary -- all of them at tick 0 when the samples are already on
+  // the device, slice by slice as the copy stream delivers them otherwise -- so read r is at chunk
+  // t - t_admit[r]; which reads share a tick changes the composition of the batches, never a row.
+  std::vector<uint32_t> n_chunks(R, 0), chunks_used(R, 1), t_admit(R, 0);
   std::vector<uint32_t> active;
-  for (size_t r = 0; r < R; ++r) {
-    n_chunks[r] = ctx->h_kept_len[r] / kChunk;  // tail dropped, sigmap.cc:643
-    if (n_chunks[r] > 0 && prm.max_num_chunks > 0) active.push_back((uint32_t)r);
+  uint32_t round = 0;  // the tick
+  ctx->h_kept_len.resize(R);
+  auto chunk_limit = [&](uint32_t r) { return std::min<uint32_t>(n_chunks[r], (uint32_t)prm.max_num_chunks); };
+  auto admit = [&](size_t r0, size_t r1) {
+    for (size_t r = r0; r < r1; ++r) {
+      ctx->h_kept_len[r] = ctx->h_kept_pinned[r];
+      n_chunks[r] = ctx->h_kept_len[r] / kChunk;  // tail dropped, sigmap.cc:643
+      t_admit[r] = round;
+      if (n_chunks[r] > 0 && prm.max_num_chunks > 0) active.push_back((uint32_t)r);
+    }
+  };
+  // slices the copy stream has finished (wait = true: block for the next one)
+  auto admit_ready = [&](bool wait) -> int {
+    while (plan && plan->admitted < plan->n_slices()) {
+      const size_t k = plan->admitted;
+      cudaError_t q = cudaEventQuery(plan->done[k]);
+      if (q == cudaErrorNotReady) {
+        if (!wait) break;
+        ctx->stats.sync_points++;
+        CK(cudaEventSynchronize(plan->done[k]));
+      } else if (q != cudaSuccess) {
+        return fail(ctx, SMB_ERR_CUDA, std::string("upload slice: ") + cudaGetErrorString(q));
+      }
+      admit(plan->first_read[k], plan->first_read[k + 1]);
+      plan->admitted++;
+      wait = false;  // one is enough to go on; take whatever else is ready
+    }
+    return SMB_OK;
+  };
+  auto uploads_pending = [&]() { return plan && plan->admitted < plan->n_slices(); };
+  if (!plan) {
+    rc = filter_reads(ctx);  // K1: part of the mapped path, redone on every call
+    if (rc) return rc;
+    admit(0, R);
+  } else if (ctx->ex) {
+    // contig shards must run identical ticks on every rank: no timing-dependent admission
+    while (uploads_pending()) {
+      rc = admit_ready(true);
+      if (rc) return rc;
+    }
   }
   std::vector<RoundInfo> info;
   const std::vector<uint32_t> none;
-  uint32_t round = 0;
   // Event detection does not depend on the mapping state, only on the raw signal, and its
   // kernels are one-thread-per-chunk sequential scans that want as many chunks per launch as
-  // possible.  So events run in LOOKAHEAD BLOCKS: chunks [r0, r1) of every read active at r0 in
-  // one launch, cached as feature rows; the block is several rounds deep only while most reads
-  // survive from round to round (full-read mapping), one round deep when the stop rules retire
-  // most reads after their first chunk.  The kernels are latency-bound and leave the SMs almost
-  // idle, so the NEXT block is computed on the event stream while the rounds of the current one
-  // are being mapped (two feature caches); a block is handed over with a host wait on its event.
+  // possible.  So events run in LOOKAHEAD BLOCKS: the next `depth` chunks of every read active at
+  // tick r0 in one launch, cached as feature rows; the block is several ticks deep only while most
+  // reads survive from tick to tick (full-read mapping), one tick deep when the stop rules retire
+  // most reads after their first chunk or while reads are still being admitted.  The kernels are
+  // latency-bound and leave the SMs almost idle, so the NEXT block is computed on the event stream
+  // while the ticks of the current one are being mapped (two feature caches); a block is handed
+  // over with a host wait on its event.
   const uint32_t kEvRowCap = 96u << 10;
   struct EvBlock {
-    uint32_t r0 = 0, r1 = 0;
+    uint32_t r0 = 0, r1 = 0;            // ticks covered
     bool ready = false;                 // launched, not yet consumed
     std::vector<uint32_t> row_base;     // per read: first row of the read in the block's cache
     std::vector<uint64_t> cs;           // host chunk table (kept alive until the block is consumed)
@@ -1806,8 +1903,7 @@ static int map_uploaded_impl(smb_ctx *ctx, const smb_params *prm_in, smb_mapping
   int cur = 0;            // block being mapped (blk[cur].r0 <= round < blk[cur].r1 once consumed)
   bool have_next = false; // blk[1 - cur] holds a launched block for round == blk[cur].r1
   size_t prev_active = 0;
-  auto chunk_limit = [&](uint32_t r) { return std::min<uint32_t>(n_chunks[r], (uint32_t)prm.max_num_chunks); };
-  // enqueue the events of chunks [r0, r0 + depth) of `who` on the event stream, into cache `c`
+  // enqueue the events of ticks [r0, r0 + depth) of `who` on the event stream, into cache `c`
   auto launch_block = [&](int c, uint32_t r0, uint32_t depth, const std::vector<uint32_t> &who) -> int {
     EvBlock &b = blk[c];
     Workspace &w = ctx->ws;
@@ -1820,8 +1916,9 @@ static int map_uploaded_impl(smb_ctx *ctx, const smb_params *prm_in, smb_mapping
     b.csc.clear();
     for (uint32_t r : who) {
       b.row_base[r] = (uint32_t)b.cs.size();
-      const uint32_t lim = std::min(chunk_limit(r), b.r1);
-      for (uint32_t ch = r0; ch < lim; ++ch) {
+      const uint32_t c0 = r0 - t_admit[r];  // the read's chunk at tick r0
+      const uint32_t lim = std::min(chunk_limit(r), c0 + depth);
+      for (uint32_t ch = c0; ch < lim; ++ch) {
         b.cs.push_back(ctx->h_kept_off[r] + (uint64_t)kChunk * ch);
         b.co.push_back(ctx->h_offset[r]);
         b.csc.push_back(ctx->h_scale[r]);
@@ -1849,8 +1946,9 @@ static int map_uploaded_impl(smb_ctx *ctx, const smb_params *prm_in, smb_mapping
     b.ready = true;
     return SMB_OK;
   };
-  // wait for block `c` and make it the one the rounds read
+  // wait for block `c` and make it the one the ticks read
   auto consume_block = [&](int c) -> int {
+    ctx->stats.sync_points++;
     CK(cudaEventSynchronize(ctx->ev_blk_t1[c]));
     float ms = 0;
     cudaEventElapsedTime(&ms, ctx->ev_blk_t0[c], ctx->ev_blk_t1[c]);
@@ -1860,16 +1958,22 @@ static int map_uploaded_impl(smb_ctx *ctx, const smb_params *prm_in, smb_mapping
     ctx->ws.cache_cur = c;
     return SMB_OK;
   };
-  const uint32_t first_active = (uint32_t)active.size();
-  uint32_t after_first = first_active;
-  while (!active.empty()) {
+  uint64_t first_active = 0, after_first = 0;  // reads that had a first chunk / went past it
+  while (!active.empty() || uploads_pending()) {
     if (round >= blk[cur].r1) {
+      // a block boundary: the only place reads are admitted (every row of a block then belongs
+      // to a read that was there when the block was launched)
+      rc = admit_ready(active.empty());
+      if (rc) return rc;
+      if (active.empty()) continue;  // that slice held no read with a whole chunk
+      // (a prefetched block is only ever launched once every slice has been admitted, so it
+      // covers every read that is active now)
       if (have_next && blk[1 - cur].r0 == round) {
         rc = consume_block(1 - cur);
         if (rc) return rc;
       } else {
         uint32_t depth = 1;
-        if (round > 0 && active.size() * 2 > prev_active)
+        if (round > 0 && !uploads_pending() && active.size() * 2 > prev_active)
           depth = (uint32_t)std::min<size_t>(8, std::max<size_t>(1, kEvRowCap / active.size()));
         const int c = round == 0 ? 0 : 1 - cur;
         rc = launch_block(c, round, depth, active);
@@ -1880,15 +1984,16 @@ static int map_uploaded_impl(smb_ctx *ctx, const smb_params *prm_in, smb_mapping
       have_next = false;
     }
     // the block after this one, while this one is being mapped: worth it only while most reads
-    // go on from round to round (known from the previous round; for round 0 from the last call)
-    if (ctx->ev_overlap && !have_next) {
+    // go on from tick to tick (known from the previous tick; for tick 0 from the last call) and
+    // nobody is waiting to be admitted
+    if (ctx->ev_overlap && !have_next && !uploads_pending()) {
       const bool surviving = round > 0 ? active.size() * 2 > prev_active : ctx->ev_survival_hint > 0.5;
       if (surviving) {
         const uint32_t r0n = blk[cur].r1;
         std::vector<uint32_t> who;
         who.reserve(active.size());
         for (uint32_t r : active)
-          if (chunk_limit(r) > r0n) who.push_back(r);
+          if (chunk_limit(r) > r0n - t_admit[r]) who.push_back(r);
         if (!who.empty()) {
           const uint32_t depth = (uint32_t)std::min<size_t>(8, std::max<size_t>(1, kEvRowCap / who.size()));
           rc = launch_block(1 - cur, r0n, depth, who);
@@ -1914,22 +2019,27 @@ static int map_uploaded_impl(smb_ctx *ctx, const smb_params *prm_in, smb_mapping
     next.reserve(active.size());
     for (size_t i = 0; i < active.size(); ++i) {
       const uint32_t r = active[i];
-      chunks_used[r] = round + 1;
-      const bool more = round + 1 < n_chunks[r] && round + 1 < (uint32_t)prm.max_num_chunks;
+      const uint32_t done_chunks = round + 1 - t_admit[r];
+      chunks_used[r] = done_chunks;
+      const bool more = done_chunks < n_chunks[r] && done_chunks < (uint32_t)prm.max_num_chunks;
+      if (done_chunks == 1) {
+        ++first_active;
+        if (!info[i].stop && more) ++after_first;
+      }
       if (!info[i].stop && more) next.push_back(r);
     }
     active.swap(next);
-    if (round == 0) after_first = (uint32_t)active.size();
     ++round;
   }
-  // a block launched for rounds that never came (every read stopped) must not outlive the call
+  // a block launched for ticks that never came (every read stopped) must not outlive the call
   if (blk[0].ready || blk[1].ready) CK(cudaStreamSynchronize(ctx->stream_ev));
   if (first_active) ctx->ev_survival_hint = (double)after_first / (double)first_active;
   // final rows
   std::vector<SlotState> st(std::max<size_t>(R, 1));
   if (R) {
     CK(cudaMemcpyAsync(st.data(), sp.slots.p, R * sizeof(SlotState), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    rc = host_sync(ctx);
+    if (rc) return rc;
     ctx->stats.d2h_bytes += R * sizeof(SlotState);
     rc = merge_owner_tags(ctx, st, R);
     if (rc) return rc;
@@ -1943,9 +2053,52 @@ extern "C" {
 int smb_map_reads(smb_ctx *ctx, const int16_t *raw, const uint64_t *read_off, const float *dig,
                   const float *range, const float *offset, size_t n_reads, const smb_params *params,
                   smb_mapping *out) {
-  int rc = smb_reads_upload(ctx, raw, read_off, dig, range, offset, n_reads);
-  if (rc) return rc;
-  return smb_map_uploaded(ctx, params, out);
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t cs = ctx->stream_cp;
+  // the small per-read tables first, then the samples in slices of ~64 MB on the copy stream:
+  // copy -> K1 filter of the slice's reads -> kept lengths to the host -> event.  The mapping loop
+  // admits a slice's reads once its event has fired, so the rest of the upload hides behind the
+  // mapping of the reads that are already there (raw should be pinned host memory for that).
+  int rc = reads_prepare(ctx, read_off, dig, range, offset, n_reads, cs);
+  UploadPlan plan;
+  if (!rc && n_reads) {
+    const uint64_t slice_samples = ctx->upload_slice_bytes / sizeof(int16_t);
+    size_t r0 = 0;
+    while (r0 < n_reads && !rc) {
+      size_t r1 = r0 + 1;
+      while (r1 < n_reads && read_off[r1 + 1] - read_off[r0] <= slice_samples) ++r1;
+      const size_t k = plan.done.size();
+      if (k >= ctx->slice_events.size()) {
+        cudaEvent_t e;
+        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) {
+          rc = fail(ctx, SMB_ERR_CUDA, "cudaEventCreate (upload slice)");
+          break;
+        }
+        ctx->slice_events.push_back(e);
+      }
+      const uint64_t a = read_off[r0], b = read_off[r1];
+      cudaError_t ce = cudaMemcpyAsync(ctx->raw.p + a, raw + a, (b - a) * sizeof(int16_t), cudaMemcpyHostToDevice, cs);
+      if (ce != cudaSuccess) {
+        rc = fail(ctx, SMB_ERR_CUDA, std::string("upload slice: ") + cudaGetErrorString(ce));
+        break;
+      }
+      ctx->stats.h2d_bytes += (b - a) * 2;
+      rc = filter_slice(ctx, r0, r1, cs);
+      if (rc) break;
+      cudaEventRecord(ctx->slice_events[k], cs);
+      plan.first_read.push_back(r0);
+      plan.done.push_back(ctx->slice_events[k]);
+      r0 = r1;
+    }
+    plan.first_read.push_back(n_reads);
+  }
+  if (!rc) rc = map_uploaded_impl(ctx, params, out, n_reads ? &plan : nullptr);
+  if (rc) {
+    cudaStreamSynchronize(cs);  // nothing of this call may still be in flight when it returns
+    // a failed member must not leave its in-process peers waiting at a rendezvous
+    if (ctx->local_group) ctx->local_group->abort_all();
+  }
+  return rc;
 }
 
 // ------------------------------------------------------------- stage hooks

@@ -91,23 +91,46 @@ def test_radius_search_paths_agree_with_the_oracle(mapper, port, small):
 
 def test_hit_cap_5000(mapper, port, small):
     """spatial_index.cc:371-372 keeps the first 5 000 hits of a query in KD-tree traversal order
-    (H4: not reproducible by another index).  What is checked: a query over the cap contributes
-    exactly 5 000 anchors and is counted, reads with such a query are flagged, reads without one
-    still equal the oracle bit for bit at that radius, and the result is deterministic."""
+    (H4: not reproducible by another index).  What is checked: below the cap, queries with
+    thousands of hits still give the oracle's chains bit for bit; a query over the cap contributes
+    exactly 5 000 anchors and is counted, reads with such a query are flagged, and the result is
+    deterministic."""
+    from conftest import same_chains
     from sigmap_b200.mapper import default_params
-    radius = 0.55
-    n_reads = 10
-    feats, hq = [], []
+    n_reads = 8
+    feats = [port.generate_events(small.pa(port, r)[:4000]) for r in range(n_reads)]
+
+    def counts(radius):
+        out = []
+        for f in feats:
+            q = np.stack([f[p:p + 6] for p in range(2, 2 * ((len(f) - 6) // 2) + 1, 2)])
+            off, _, _ = mapper.radiusSearch(q, radius=radius, cap=1 << 26)
+            out.append(np.diff(off.astype(np.int64)))
+        return out
+
+    # radius 0.5: hundreds of hits per query (frontiers beyond the lean kernel's slots, the general
+    # kernel's big-query path), nothing at the cap: the oracle's chains, bit for bit
+    radius = 0.5
+    hq = counts(radius)
+    assert max(int(h.max()) for h in hq) < 5000 and sum(int(h.sum()) for h in hq) > 300000
+    batch = mapper.ChainBatch(n_reads)
+    mapper.stats_reset()
+    batch.GenerateChains(list(range(n_reads)), feats, default_params(search_radius=radius))
+    st = mapper.stats()
+    assert st["capped_queries"] == 0 and st["hits"] == sum(int(h.sum()) for h in hq)
+    assert st["overflow_queries"] > 0
     for r in range(n_reads):
-        f = port.generate_events(small.pa(port, r)[:4000])
-        feats.append(f)
-        q = np.stack([f[p:p + 6] for p in range(2, 2 * ((len(f) - 6) // 2) + 1, 2)])
-        off, _, _ = mapper.radiusSearch(q, radius=radius, cap=1 << 26)
-        hq.append(np.diff(off.astype(np.int64)))
+        cl = port.new_chain_list()
+        exp = port.generate_chains(small.pos, small.val, feats[r], 0, cl, radius=radius, n_targets=small.ref.n)
+        assert same_chains(batch.chains(r), exp), f"read {r} differs from the oracle at radius {radius}"
+        port.free_chain_list(cl)
+    # radius 1.2: a good share of the queries is over the cap
+    radius = 1.2
+    hq = counts(radius)
     over = [int((h >= 5000).sum()) for h in hq]
     assert sum(over) > 20, "radius too small to reach the cap"
     prm = default_params(search_radius=radius)
-    batch = mapper.ChainBatch(n_reads)
+    batch.reset()
     mapper.stats_reset()
     batch.GenerateChains(list(range(n_reads)), feats, prm)
     st = mapper.stats()
@@ -116,15 +139,8 @@ def test_hit_cap_5000(mapper, port, small):
     first = [batch.chains(r) for r in range(n_reads)]
     batch.reset()
     batch.GenerateChains(list(range(n_reads)), feats, prm)
-    from conftest import same_chains
     for r in range(n_reads):
         assert same_chains(batch.chains(r), first[r]), "capped result is not deterministic"
-        if over[r] == 0:  # no capped query: the oracle's chains, bit for bit
-            cl = port.new_chain_list()
-            exp = port.generate_chains(small.pos, small.val, feats[r], 0, cl, radius=radius,
-                                       n_targets=small.ref.n)
-            assert same_chains(first[r], exp), f"read {r} (uncapped) differs from the oracle"
-            port.free_chain_list(cl)
     batch.close()
     # whole path: flags bit 0 on exactly the reads that had a capped query in a consumed chunk
     sub = type(small.reads)(small.reads.names[:n_reads], small.reads.raw[:int(small.reads.read_off[n_reads])],
