@@ -169,12 +169,12 @@ def dist_setup(n_gpus):
     return rank, world, local, dist
 
 
-def build_workload(args, rank):
+def build_workload(args, rank, need_cloud=True):
     from sigmap_b200 import host as H
     model = H.load_pore_model()
     per = args.ref_bp // args.contigs
     ref = H.sim_reference(args.seed, [per] * args.contigs)
-    pos, val = H.build_point_cloud(ref, model[0])
+    pos, val = H.build_point_cloud(ref, model[0]) if need_cloud else (None, None)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.shard == "contigs":          # contig shards all see the same reads
         first, count = 0, args.reads
@@ -389,16 +389,31 @@ def measure(args, rank, world, local, dist, light=False):
     steps = args.c3_steps if light else args.steps
     warmup = min(args.warmup, 1) if light else args.warmup
     t_setup = time.time()
-    H, model, ref, pos, val, reads = build_workload(args, rank)
-    mapper = Mapper(local)  # raises if there is no CUDA device: no fallback
     by_contig = args.shard == "contigs" and world > 1
+    replicate = world > 1 and not by_contig
+    # read-sharded: only rank 0 builds the point cloud and the device index; the others receive the
+    # index over NVLink (one ncclBroadcast on the library's own communicator)
+    H, model, ref, pos, val, reads = build_workload(args, rank, need_cloud=by_contig or not replicate or rank == 0)
+    mapper = Mapper(local)  # raises if there is no CUDA device: no fallback
+    t_bcast = None
     if by_contig:
         from sigmap_b200 import shard
         shard.nccl_join(mapper, dist)  # the library's own NCCL communicator, on its own stream
         mapper.set_index_sharded(pos, val, shard.assign_contigs(ref.lengths, world))
+    elif replicate:
+        from sigmap_b200 import shard
+        shard.nccl_join(mapper, dist)
+        if rank == 0:
+            mapper.set_index(pos, val)
+            mapper.set_contigs(ref.lengths)
+        dist.barrier()
+        t_bcast = time.time()
+        mapper.broadcast_index(0)
+        t_bcast = time.time() - t_bcast
     else:
         mapper.set_index(pos, val)
     mapper.set_contigs(ref.lengths)
+    n_points = int(mapper.num_points)
     params = full_read_params() if args.mode == "full" else default_params()
     # pinned host staging of the raw reads (e2e leg copies from here every step)
     pinned = torch.empty(len(reads.raw), dtype=torch.int16, pin_memory=True)
@@ -506,11 +521,13 @@ def measure(args, rank, world, local, dist, light=False):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(args), "baseline_config": {"c2": "configs[1]", "c3": "configs[2]"}[args.workload],
                    "l2": "inputs larger than L2 (raw reads + index)",
-                   "index_points": int(len(pos)), "reads_this_rank": int(reads.n),
+                   "index_points": n_points, "reads_this_rank": int(reads.n),
+                   "index_broadcast_s": t_bcast,
                    "parallelism": (f"index sharded by contig x{world}, every rank maps every read, "
                                    f"{int(st['exchanges'])} NCCL collectives per rank in the timed region"
                                    if by_contig else
-                                   (f"the job's reads split over {world} rank(s), index replicated, no data-path collective"
+                                   (f"the job's reads split over {world} rank(s), index built on rank 0 and replicated with one "
+                                    f"ncclBroadcast, no data-path collective"
                                     if args.scaling == "strong" else f"read-sharded x{world}, index replicated"))},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "samples/s",

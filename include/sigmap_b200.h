@@ -171,7 +171,18 @@ int smb_shard_rank(const smb_ctx *ctx);
 int smb_shard_world(const smb_ctx *ctx);
 int smb_index_set_points_sharded(smb_ctx *ctx, const uint64_t *pos, const float *val, size_t n,
                                  const uint32_t *contig_owner, uint32_t n_contigs);
+/* The same from the rank's own part of the cloud (smbh_build_point_cloud_part with this context's
+ * shard rank): no rank ever needs the whole cloud in host memory. */
+struct smbh_cloud_part;
+int smb_index_set_points_part(smb_ctx *ctx, const struct smbh_cloud_part *part, uint32_t n_contigs);
 uint32_t smb_index_num_contigs(const smb_ctx *ctx);
+/* Read-sharded runs (reads split over the GPUs, index replicated; the taskloop of sigmap.cc:618-632
+ * spread over devices): the index is built once, on `root`, and copied to the other ranks of the
+ * group over NVLink (ncclBroadcast / peer copies) instead of being rebuilt by every rank.  Collective:
+ * every member of the group (smb_shard_nccl_init / smb_shard_local_group) calls it; only the root needs
+ * smb_index_load / smb_index_set_points + smb_index_set_contigs beforehand.  The mapping calls that
+ * follow are independent per rank (no collective on the data path). */
+int smb_index_broadcast(smb_ctx *ctx, int root);
 
 /* ------------------------------------------------------------ whole hot path */
 /* Replaces the per-read body of Sigmap::StreamingMap (sigmap.cc:630-866) for n_reads
@@ -263,6 +274,25 @@ size_t smbh_build_point_cloud(const char *const *seqs, const uint32_t *lengths, 
 /* The same in one pass: *pos / *val are allocated by the library (release with smbh_free). */
 int smbh_build_point_cloud_alloc(const char *const *seqs, const uint32_t *lengths, uint32_t n,
                                  const float *level_mean, uint64_t **pos, float **val, size_t *count);
+/* One rank's part of the point cloud for a contig-sharded index: the points of the contigs with
+ * owner[c] == rank and, after each stretch of them, the SMB_DIM-1 points that follow in the whole
+ * cloud (the last windows of the stretch straddle into them, Q2), as runs of consecutive cloud points.
+ * Run k = values [run_off[k], run_off[k+1]), its first point is point run_first[k] of the whole cloud;
+ * own[i] = 1 where point i belongs to the rank (only those start windows).  A rank of a genome-scale
+ * job holds its share of the cloud, never the whole (3.1 Gbp: 74 GB).  Free with smbh_cloud_part_free. */
+typedef struct smbh_cloud_part {
+  size_t n_values, n_runs;
+  uint64_t n_points_total; /* size of the whole cloud */
+  uint64_t *pos;
+  float *val;
+  uint8_t *own;
+  uint64_t *run_off;   /* n_runs + 1 */
+  uint64_t *run_first; /* n_runs */
+} smbh_cloud_part;
+int smbh_build_point_cloud_part(const char *const *seqs, const uint32_t *lengths, uint32_t n,
+                                const float *level_mean, const uint32_t *owner, uint32_t rank,
+                                smbh_cloud_part *out);
+void smbh_cloud_part_free(smbh_cloud_part *p);
 /* .pt file of SpatialIndex::Save (spatial_index.cc:105-123) */
 int smbh_pt_write(const char *prefix, const uint64_t *pos, const float *val, size_t n,
                   int dim, int max_leaf);

@@ -134,6 +134,19 @@ class Reads(C.Structure):
     ]
 
 
+class CloudPart(C.Structure):
+    _fields_ = [
+        ("n_values", C.c_size_t),
+        ("n_runs", C.c_size_t),
+        ("n_points_total", C.c_uint64),
+        ("pos", u64p),
+        ("val", f32p),
+        ("own", u8p),
+        ("run_off", u64p),
+        ("run_first", u64p),
+    ]
+
+
 # name -> (restype, argtypes); every symbol include/sigmap_b200.h declares
 PROTOTYPES = {
     "smb_default_params": (None, [C.POINTER(Params)]),
@@ -159,7 +172,12 @@ PROTOTYPES = {
     "smb_shard_world": (C.c_int, [C.c_void_p]),
     "smb_index_set_points_sharded": (C.c_int, [C.c_void_p, u64p, f32p, C.c_size_t, u32p,
                                                C.c_uint32]),
+    "smb_index_set_points_part": (C.c_int, [C.c_void_p, C.POINTER(CloudPart), C.c_uint32]),
+    "smbh_build_point_cloud_part": (C.c_int, [charpp, u32p, C.c_uint32, f32p, u32p, C.c_uint32,
+                                              C.POINTER(CloudPart)]),
+    "smbh_cloud_part_free": (None, [C.POINTER(CloudPart)]),
     "smb_index_num_contigs": (C.c_uint32, [C.c_void_p]),
+    "smb_index_broadcast": (C.c_int, [C.c_void_p, C.c_int]),
     "smb_map_reads": (C.c_int, [C.c_void_p, i16p, u64p, f32p, f32p, f32p, C.c_size_t,
                                 C.POINTER(Params), C.POINTER(Mapping)]),
     "smb_reads_upload": (C.c_int, [C.c_void_p, i16p, u64p, f32p, f32p, f32p, C.c_size_t]),

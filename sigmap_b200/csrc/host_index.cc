@@ -131,8 +131,40 @@ void walk_kmers(const StrandView &v, uint32_t a, uint32_t b, F fn, G fn_amb) {
   }
 }
 
+// Where the points go.  Whole cloud: pos/val (either may be null: count only).  One rank's part of a
+// contig-sharded index (part != nullptr): only the points of its own contigs plus, after each
+// stretch of them, the kDim-1 points that follow in the whole cloud (the windows at the end of
+// the stretch straddle into them, Q2) -- so a rank never holds more than its share of a genome-
+// scale cloud.
+struct PartSink {
+  const uint32_t *owner;
+  uint32_t rank;
+  std::vector<uint64_t> pos, run_off, run_first;
+  std::vector<float> val;
+  std::vector<unsigned char> own;
+  int trailing = 0;      // points after the last owned one still to be taken
+  bool open = false;     // a run is being written
+  void point(uint32_t contig, uint64_t P, float z, uint64_t index) {
+    const bool mine = owner[contig] == rank;
+    if (!mine && trailing == 0) {
+      open = false;
+      return;
+    }
+    if (!open) {
+      run_off.push_back(pos.size());
+      run_first.push_back(index);
+      open = true;
+    }
+    pos.push_back(P);
+    val.push_back(z);
+    own.push_back(mine ? 1 : 0);
+    trailing = mine ? SMB_DIM - 1 : trailing - 1;
+    if (!mine && trailing == 0) open = false;
+  }
+};
+
 size_t build_cloud(const char *const *seqs, const uint32_t *lengths, uint32_t n, const float *level_mean,
-                   uint64_t *pos, float *val) {
+                   uint64_t *pos, float *val, PartSink *sink = nullptr) {
   // k-mer census over the + strands (canonical, so the - strand adds nothing new)
   std::vector<uint32_t> hist((size_t)1 << (2 * kMaskK), 0);
   uint32_t *H = hist.data();
@@ -180,8 +212,11 @@ size_t build_cloud(const char *const *seqs, const uint32_t *lengths, uint32_t n,
       for (uint32_t p = 0; p < n_windows; ++p) {
         if (masked[p]) continue;
         if (p == 0 || !any || std::fabs((double)(z[p] - last)) > kMinDelta) {
-          if (pos) {
-            pos[count] = ((((uint64_t)s << 32) | p) << 1) | (uint64_t)strand;
+          const uint64_t P = ((((uint64_t)s << 32) | p) << 1) | (uint64_t)strand;
+          if (sink) {
+            sink->point(s, P, z[p], count);
+          } else if (pos) {
+            pos[count] = P;
             val[count] = z[p];
           }
           last = z[p];
@@ -224,4 +259,47 @@ extern "C" int smbh_build_point_cloud_alloc(const char *const *seqs, const uint3
   *val = V2 ? V2 : V;
   *count = c;
   return SMB_OK;
+}
+
+// One rank's part of the cloud (contig-sharded index, SURVEY.md 8e mode 2).  The census and the
+// `last kept value` chain still run over the whole genome -- they decide which points exist --
+// but only the rank's own points (and the five after each stretch) are kept in memory.
+extern "C" int smbh_build_point_cloud_part(const char *const *seqs, const uint32_t *lengths, uint32_t n,
+                                           const float *level_mean, const uint32_t *owner, uint32_t rank,
+                                           smbh_cloud_part *out) {
+  memset(out, 0, sizeof *out);
+  if (!owner) return SMB_ERR_ARG;
+  PartSink sink;
+  sink.owner = owner;
+  sink.rank = rank;
+  const size_t total = build_cloud(seqs, lengths, n, level_mean, nullptr, nullptr, &sink);
+  sink.run_off.push_back(sink.pos.size());
+  out->n_points_total = total;
+  out->n_values = sink.pos.size();
+  out->n_runs = sink.run_first.size();
+  auto dup = [](const void *src, size_t bytes) -> void * {
+    void *p = malloc(bytes ? bytes : 1);
+    if (p && bytes) memcpy(p, src, bytes);
+    return p;
+  };
+  out->pos = (uint64_t *)dup(sink.pos.data(), sink.pos.size() * sizeof(uint64_t));
+  out->val = (float *)dup(sink.val.data(), sink.val.size() * sizeof(float));
+  out->own = (uint8_t *)dup(sink.own.data(), sink.own.size());
+  out->run_off = (uint64_t *)dup(sink.run_off.data(), sink.run_off.size() * sizeof(uint64_t));
+  out->run_first = (uint64_t *)dup(sink.run_first.data(), sink.run_first.size() * sizeof(uint64_t));
+  if (!out->pos || !out->val || !out->own || !out->run_off || !out->run_first) {
+    smbh_cloud_part_free(out);
+    return SMB_ERR_IO;
+  }
+  return SMB_OK;
+}
+
+extern "C" void smbh_cloud_part_free(smbh_cloud_part *p) {
+  if (!p) return;
+  free(p->pos);
+  free(p->val);
+  free(p->own);
+  free(p->run_off);
+  free(p->run_first);
+  memset(p, 0, sizeof *p);
 }

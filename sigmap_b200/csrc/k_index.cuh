@@ -199,7 +199,7 @@ __global__ void k_nodes_up(const uint2 *__restrict__ child, uint32_t n_child, ui
 //                     outgrow its kFrontCap slots is handed, untouched, to
 //   k_radius_search   the general kernel (one small stack per level, any frontier size, the 5 000-hit
 //                     cap of spatial_index.cc:371-372), which works through the list of such queries.
-//                     A frontier of kFrontCap leaves holds 2 048 points, so a query that can reach the
+//                     A frontier of kFrontCap leaves holds 3 072 points, so a query that can reach the
 //                     cap always takes this path: the cap rule lives in one place.
 constexpr int kSearchWarps = 8;          // warps per CTA (general kernel)
 constexpr int kLevelCap = 128;           // entries per level stack: 64 waiting + the children of one 8-node step
@@ -208,8 +208,8 @@ constexpr int kStageCap = 128;           // staged hits per warp before one glob
 constexpr int kSearchGrab = 8;           // queries per grab of the dynamic work counter
 constexpr int kMaxParts = 32;            // parts per entry the flush can route to (k_part_sort)
 constexpr int kLeanWarps = 32;           // lean kernel: one 1024-thread CTA per SM
-constexpr int kFrontCap = 256;           // lean kernel: frontier slots (nodes of a level / leaves) per query
-constexpr int kLeanStage = 192;          // lean kernel: staged hits per warp
+constexpr int kFrontCap = 384;           // lean kernel: frontier slots (nodes of a level / leaves) per query
+constexpr int kLeanStage = 128;          // lean kernel: staged hits per warp
 constexpr int kLeanGrab = 4;             // lean kernel: sorted queries per grab
 constexpr int kQueryBits = 12;           // query payload = entry << kQueryBits | query number inside the entry
 
@@ -222,6 +222,8 @@ __host__ __device__ inline size_t search_smem_per_warp(int n_levels) {
 // lean kernel, per warp: staged keys (8 B), distances and part|rank (2 B), two frontiers, per-part counts
 constexpr size_t kLeanWarpSmem = (size_t)kLeanStage * 14 + 2 * (size_t)kFrontCap * 4 + kMaxParts * 4;
 __host__ __device__ inline size_t lean_top_region(uint32_t smem_bytes) { return ((size_t)smem_bytes + 127) & ~(size_t)127; }
+static_assert((size_t)kFrontCap * kLeaf < SMB_MAX_HITS, "the lean kernel must never be able to reach the hit cap");
+static_assert(kLeanStage >= 64 && kLeanStage <= 256, "a leaf step stages up to 64 hits; ranks are 8 bits");
 __host__ __device__ inline size_t lean_smem(uint32_t smem_bytes) {
   return lean_top_region(smem_bytes) + (size_t)kLeanWarps * kLeanWarpSmem;
 }
@@ -534,7 +536,7 @@ __device__ __forceinline__ int lean_node_level(const uint2 *__restrict__ lvl, co
 }
 
 // STAGE=false: hits become sort keys (entry|bucket|target|query) + d2 (never capped here: a
-// frontier of kFrontCap leaves holds fewer than 5 000 points).
+// frontier of kFrontCap = 384 leaves holds 3 072 points, fewer than the cap of 5 000).
 // STAGE=true : key = query_id << 32 | window index (parity hook, compared as sets).
 template <bool STAGE>
 __global__ void __launch_bounds__(kLeanWarps * 32, 1)

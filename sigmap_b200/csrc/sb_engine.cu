@@ -293,6 +293,7 @@ struct smb_ctx {
   double runs_scale = 1.0;          // raised when a step overflowed its run tables
   // contig-sharded index: the exchange backend (null = this context holds every contig)
   std::unique_ptr<Exchange> ex;
+  bool index_sharded = false;  // this context holds only its own contigs (smb_index_set_points_sharded)
   std::shared_ptr<LocalGroup> local_group;
   double *h_ctl = nullptr;  // pinned, 4 doubles
   bool group_at_limit = false;
@@ -416,15 +417,46 @@ static int launch_search(smb_ctx *ctx, SearchArgs sa, uint32_t nq_max, cudaStrea
 // windows whose first point lies on a contig with owner[contig] == rank; a window keeps its six
 // values even where it runs into the next contig / strand (Q2), so the shard holds exactly the
 // points the unsharded index holds for those contigs.
+// part != nullptr: the rank's own part of the cloud (smbh_build_point_cloud_part) instead of the
+// whole cloud + owner table; pos / val / n are then taken from it.
 static int build_index(smb_ctx *ctx, const uint64_t *pos, const float *val, size_t n,
-                       const uint32_t *owner = nullptr, uint32_t n_contigs = 0, uint32_t rank = 0) {
+                       const uint32_t *owner = nullptr, uint32_t n_contigs = 0, uint32_t rank = 0,
+                       const smbh_cloud_part *part = nullptr) {
+  if (part) {
+    pos = part->pos;
+    val = part->val;
+    n = (size_t)part->n_points_total;
+  }
   if (n < (size_t)kDim) return fail(ctx, SMB_ERR_ARG, "point cloud smaller than the index dimension");
   const uint64_t W_all = n - (kDim - 1);
   // ---- which windows, and where their values start in the uploaded value array
   std::vector<float> h_val;       // sharded: runs of owned values, each with 5 trailing values
   std::vector<uint64_t> h_pos;    // sharded: position of every owned window
   std::vector<uint32_t> h_wsrc, h_worig;
-  if (owner) {
+  if (part) {
+    // the runs are uploaded as they are; a window starts at every own point that has five more
+    // values after it in its run and is a window of the whole cloud (index < N - 5)
+    if (part->n_values > 0xFFFFFFF0ull)
+      return fail(ctx, SMB_ERR_CAPACITY, "more than 2^32 window points on one shard: use more ranks");
+    h_val.assign(part->val, part->val + part->n_values);
+    for (size_t k = 0; k < part->n_runs; ++k) {
+      const uint64_t a = part->run_off[k], b = part->run_off[k + 1];
+      for (uint64_t i = a; i < b; ++i) {
+        const uint64_t global = part->run_first[k] + (i - a);
+        if (!part->own[i] || i + (kDim - 1) >= b || global >= W_all) continue;
+        if ((part->pos[i] >> 33) >= n_contigs) return fail(ctx, SMB_ERR_ARG, "point cloud names a contig beyond n_contigs");
+        h_pos.push_back(part->pos[i]);
+        h_wsrc.push_back((uint32_t)i);
+        h_worig.push_back((uint32_t)global);
+      }
+    }
+    if (h_pos.empty()) {  // a rank may own nothing (more ranks than contigs): keep one padding leaf
+      h_val.assign(kDim, kPadValue);
+      h_pos.push_back(~0ull);
+      h_wsrc.push_back(0);
+      h_worig.push_back(0xFFFFFFFFu);
+    }
+  } else if (owner) {
     for (uint64_t w = 0; w < W_all;) {
       const uint64_t c = pos[w] >> 33;
       if (c >= n_contigs) return fail(ctx, SMB_ERR_ARG, "point cloud names a contig beyond n_contigs");
@@ -454,15 +486,22 @@ static int build_index(smb_ctx *ctx, const uint64_t *pos, const float *val, size
   } else if (W_all > 0xFFFFFFF0ull) {
     return fail(ctx, SMB_ERR_CAPACITY, "more than 2^32 window points: shard the index by contig");
   }
-  const uint64_t W = owner ? h_pos.size() : W_all;
-  const float *u_val = owner ? h_val.data() : val;
-  const uint64_t *u_pos = owner ? h_pos.data() : pos;
-  const size_t n_val = owner ? h_val.size() : n, n_pos = owner ? h_pos.size() : n;
+  const bool subset = owner || part;
+  const uint64_t W = subset ? h_pos.size() : W_all;
+  const float *u_val = subset ? h_val.data() : val;
+  const uint64_t *u_pos = subset ? h_pos.data() : pos;
+  const size_t n_val = subset ? h_val.size() : n, n_pos = subset ? h_pos.size() : n;
   const uint32_t n_leaves = (uint32_t)((W + kLeaf - 1) / kLeaf);
-  float vmin = val[0], vmax = val[0];
+  const size_t n_seen = part ? part->n_values : n;  // points this rank can look at
+  float vmin = n_seen ? val[0] : 0.0f, vmax = vmin;
   uint32_t max_tpos = 0, max_bucket = 0;
   std::vector<uint64_t> bucket_span;  // 1 + largest target seen per bucket
-  for (size_t i = 0; i < n; ++i) {
+  if (part && n_contigs) {
+    // every rank must agree on the bucket numbering (the exchanges are indexed by bucket)
+    max_bucket = 2u * n_contigs - 1u;
+    bucket_span.assign((size_t)max_bucket + 1, 0);
+  }
+  for (size_t i = 0; i < n_seen; ++i) {
     vmin = std::min(vmin, val[i]);
     vmax = std::max(vmax, val[i]);
     const uint32_t t = (uint32_t)(pos[i] >> 1), b = (uint32_t)(((pos[i] >> 33) << 1) | (pos[i] & 1));
@@ -485,7 +524,7 @@ static int build_index(smb_ctx *ctx, const uint64_t *pos, const float *val, size
   CK(w_b.ensure(W));
   CK(cudaMemcpyAsync(d_val.p, u_val, n_val * sizeof(float), cudaMemcpyHostToDevice, s));
   CK(cudaMemcpyAsync(d_pos.p, u_pos, n_pos * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
-  if (owner) {
+  if (subset) {
     CK(d_wsrc.ensure(W));
     CK(d_worig.ensure(W));
     CK(cudaMemcpyAsync(d_wsrc.p, h_wsrc.data(), W * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
@@ -725,7 +764,7 @@ static int run_step(smb_ctx *ctx, SlotSpace &sp, const StepEntries &en, StepSour
   const uint32_t B = en.B, Bpres = en.B_present;
   if (B == 0) return SMB_OK;
   if (!ctx->has_index) return fail(ctx, SMB_ERR_STATE, "no index loaded");
-  const bool sharded = (bool)ctx->ex;
+  const bool sharded = ctx->ex && ctx->index_sharded;
   // ---- key layout for this step
   uint32_t max_ev = 0;
   for (uint32_t b = 0; b < Bpres; ++b) max_ev = std::max(max_ev, sp.h_events[en.slot[b]]);
@@ -1269,7 +1308,7 @@ static int run_round(smb_ctx *ctx, SlotSpace &sp, const std::vector<uint32_t> &p
       if (rc == 2) continue;  // aborted on the device, cause dealt with: again
       if (rc == 1) {  // anchor buffer overflow: grow the buffers, or halve the step at the limit
         ctx->est_anchors_per_chunk *= 2.0;
-        if (ctx->ex ? ctx->group_at_limit : ctx->last_cap >= ctx->max_batch_anchors) {
+        if ((ctx->ex && ctx->index_sharded) ? ctx->group_at_limit : ctx->last_cap >= ctx->max_batch_anchors) {
           if (count <= 1) return fail(ctx, SMB_ERR_CAPACITY, "one chunk overflows max_batch_anchors");
           count = (count + 1) / 2;
         }
@@ -1289,7 +1328,7 @@ static int run_round(smb_ctx *ctx, SlotSpace &sp, const std::vector<uint32_t> &p
 // chain 0's anchors (SlotState::owned0); everybody else contributes zeros, so a SUM all-reduce
 // of the bit patterns hands every rank the owner's values.  flags bit0 (5000-hit cap) is OR-ed.
 static int merge_owner_tags(smb_ctx *ctx, std::vector<SlotState> &st, size_t n) {
-  if (!ctx->ex || n == 0) return SMB_OK;
+  if (!ctx->ex || !ctx->index_sharded || n == 0) return SMB_OK;
   std::vector<uint32_t> h(n * 6);
   auto bits = [](float f) { uint32_t u; memcpy(&u, &f, 4); return u; };
   for (size_t r = 0; r < n; ++r) {
@@ -1471,6 +1510,7 @@ int smb_create(smb_ctx **out, int device) {
         (e = cudaFuncSetAttribute(k_radius_search<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, need)) != cudaSuccess)
       return bail("cudaFuncSetAttribute(k_radius_search)", e);
     const int lean = (int)lean_smem(kTopSmemMax);
+    static_assert(kTopSmemMax + kLeanWarps * kLeanWarpSmem + 1024 <= 232448, "lean search kernel: 227 KB of shared memory per SM");
     if ((e = cudaFuncSetAttribute(k_search_lean<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lean)) != cudaSuccess ||
         (e = cudaFuncSetAttribute(k_search_lean<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lean)) != cudaSuccess)
       return bail("cudaFuncSetAttribute(k_search_lean)", e);
@@ -1591,6 +1631,7 @@ int smb_set_option(smb_ctx *ctx, const char *name, const char *value) {
 // -------------------------------------------------------------------- index
 int smb_index_set_points(smb_ctx *ctx, const uint64_t *pos, const float *val, size_t n) {
   CK(cudaSetDevice(ctx->device));
+  ctx->index_sharded = false;
   return build_index(ctx, pos, val, n);
 }
 
@@ -1623,7 +1664,99 @@ int smb_index_set_points_sharded(smb_ctx *ctx, const uint64_t *pos, const float 
   if (!ctx->ex) return fail(ctx, SMB_ERR_STATE, "join a shard group first (smb_shard_local_group / smb_shard_nccl_init)");
   for (uint32_t c = 0; c < n_contigs; ++c)
     if (contig_owner[c] >= (uint32_t)ctx->ex->world) return fail(ctx, SMB_ERR_ARG, "contig owner out of range");
-  return build_index(ctx, pos, val, n, contig_owner, n_contigs, (uint32_t)ctx->ex->rank);
+  const int rc = build_index(ctx, pos, val, n, contig_owner, n_contigs, (uint32_t)ctx->ex->rank);
+  ctx->index_sharded = rc == SMB_OK;
+  return rc;
+}
+
+int smb_index_set_points_part(smb_ctx *ctx, const smbh_cloud_part *part, uint32_t n_contigs) {
+  CK(cudaSetDevice(ctx->device));
+  if (!ctx->ex) return fail(ctx, SMB_ERR_STATE, "join a shard group first (smb_shard_local_group / smb_shard_nccl_init)");
+  if (!part || !n_contigs) return fail(ctx, SMB_ERR_ARG, "smb_index_set_points_part: no part / no contigs");
+  const int rc = build_index(ctx, nullptr, nullptr, 0, nullptr, n_contigs, (uint32_t)ctx->ex->rank, part);
+  ctx->index_sharded = rc == SMB_OK;
+  return rc;
+}
+
+// Read-sharded runs (SURVEY.md 8e mode 1): the index is built once, on `root`, and travels to
+// the other ranks of the group over NVLink (ncclBroadcast, or peer copies inside one process)
+// instead of being rebuilt from the point cloud by every rank.  Collective: every rank of the
+// group calls it; only the root needs an index (and contigs) beforehand.
+int smb_index_broadcast(smb_ctx *ctx, int root) {
+  CK(cudaSetDevice(ctx->device));
+  if (!ctx->ex) return fail(ctx, SMB_ERR_STATE, "join a group first (smb_shard_local_group / smb_shard_nccl_init)");
+  if (root < 0 || root >= ctx->ex->world) return fail(ctx, SMB_ERR_ARG, "bad root");
+  const bool is_root = ctx->ex->rank == root;
+  if (is_root && !ctx->has_index) return fail(ctx, SMB_ERR_STATE, "the root has no index to broadcast");
+  cudaStream_t s = ctx->stream;
+  // ---- header: the view (without pointers), bucket tables, contig lengths
+  struct Header {
+    IndexView ix;
+    uint32_t max_tpos, max_bucket, n_coarse, n_contigs;
+    int gshift;
+    uint64_t g_total, n_bucket_base, n_nodes_rec, n_leaf_rec, n_widx;
+  } h{};
+  if (is_root) {
+    h.ix = ctx->ix;
+    h.max_tpos = ctx->max_tpos;
+    h.max_bucket = ctx->max_bucket;
+    h.n_coarse = ctx->n_coarse;
+    h.gshift = ctx->gshift;
+    h.g_total = ctx->g_total;
+    h.n_contigs = (uint32_t)ctx->contig_len.size();
+    h.n_bucket_base = (uint64_t)ctx->max_bucket + 2;
+    uint64_t rec = 0;
+    for (int l = 0; l < ctx->ix.n_levels; ++l) rec += ctx->ix.level_count[l];
+    h.n_nodes_rec = rec * kNodeRec;
+    h.n_leaf_rec = (uint64_t)ctx->ix.n_leaves * kLeafRec;
+    h.n_widx = (uint64_t)ctx->ix.n_leaves * kLeaf;
+  }
+  DevBuf<unsigned char> d_h;
+  CK(d_h.ensure(sizeof(Header)));
+  if (is_root) CK(cudaMemcpyAsync(d_h.p, &h, sizeof(Header), cudaMemcpyHostToDevice, s));
+  int rc = ctx->ex->broadcast(d_h.p, sizeof(Header), root, s, ctx->err);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(&h, d_h.p, sizeof(Header), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  d_h.release();
+  // ---- the arrays, in place in the receivers' own buffers
+  if (!is_root) {
+    CK(ctx->nodes.ensure(h.n_nodes_rec));
+    CK(ctx->leaves.ensure(h.n_leaf_rec));
+    CK(ctx->leaf_widx.ensure(h.n_widx));
+    CK(ctx->bucket_base.ensure(h.n_bucket_base));
+  }
+  DevBuf<uint32_t> d_len;
+  CK(d_len.ensure(std::max<uint32_t>(h.n_contigs, 1)));
+  if (is_root && h.n_contigs)
+    CK(cudaMemcpyAsync(d_len.p, ctx->contig_len.data(), h.n_contigs * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+  if ((rc = ctx->ex->broadcast(ctx->nodes.p, h.n_nodes_rec * sizeof(uint2), root, s, ctx->err))) return rc;
+  if ((rc = ctx->ex->broadcast(ctx->leaves.p, h.n_leaf_rec * sizeof(uint2), root, s, ctx->err))) return rc;
+  if ((rc = ctx->ex->broadcast(ctx->leaf_widx.p, h.n_widx * sizeof(uint32_t), root, s, ctx->err))) return rc;
+  if ((rc = ctx->ex->broadcast(ctx->bucket_base.p, h.n_bucket_base * sizeof(uint64_t), root, s, ctx->err))) return rc;
+  if ((rc = ctx->ex->broadcast(d_len.p, std::max<uint32_t>(h.n_contigs, 1) * sizeof(uint32_t), root, s, ctx->err))) return rc;
+  ctx->stats.exchanges += 6;
+  if (!is_root) {
+    ctx->contig_len.resize(h.n_contigs);
+    if (h.n_contigs)
+      CK(cudaMemcpyAsync(ctx->contig_len.data(), d_len.p, h.n_contigs * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    IndexView ix = h.ix;
+    ix.nodes = ctx->nodes.p;
+    ix.leaves = ctx->leaves.p;
+    ix.leaf_widx = ctx->leaf_widx.p;
+    ctx->ix = ix;
+    ctx->max_tpos = h.max_tpos;
+    ctx->max_bucket = h.max_bucket;
+    ctx->n_coarse = h.n_coarse;
+    ctx->gshift = h.gshift;
+    ctx->g_total = h.g_total;
+    ctx->search_grid_main = search_grid<false>(ctx);
+    ctx->has_index = true;
+  }
+  CK(cudaStreamSynchronize(s));
+  d_len.release();
+  ctx->index_sharded = false;
+  return SMB_OK;
 }
 
 // ---------------------------------------------------------- contig-sharded runs
@@ -1874,7 +2007,7 @@ static int map_uploaded_impl(smb_ctx *ctx, const smb_params *prm_in, smb_mapping
     rc = filter_reads(ctx);  // K1: part of the mapped path, redone on every call
     if (rc) return rc;
     admit(0, R);
-  } else if (ctx->ex) {
+  } else if (ctx->ex && ctx->index_sharded) {
     // contig shards must run identical ticks on every rank: no timing-dependent admission
     while (uploads_pending()) {
       rc = admit_ready(true);

@@ -33,6 +33,8 @@
 #include <string>
 #include <vector>
 
+#include <algorithm>
+
 #include "sb_device.cuh"
 
 namespace sb {
@@ -62,6 +64,8 @@ struct Exchange {
   virtual int allreduce(void *d_buf, size_t n, ExDType t, ExOp op, cudaStream_t s, std::string &err) = 0;
   // d_recv receives world * bytes (rank-major); d_send may NOT alias d_recv
   virtual int allgather(const void *d_send, void *d_recv, size_t bytes, cudaStream_t s, std::string &err) = 0;
+  // root's d_buf -> everybody's d_buf (in place)
+  virtual int broadcast(void *d_buf, size_t bytes, int root, cudaStream_t s, std::string &err) = 0;
 };
 
 // ------------------------------------------------------------------ in-process group
@@ -127,6 +131,36 @@ struct LocalExchange : Exchange {
     return SMB_OK;
   }
 
+  int broadcast(void *d_buf, size_t bytes, int root, cudaStream_t s, std::string &err) override {
+    cudaError_t e = cudaStreamSynchronize(s);  // the root's buffer is complete
+    if (e != cudaSuccess) {
+      err = std::string("local exchange: ") + cudaGetErrorString(e);
+      g->abort_all();
+      return SMB_ERR_CUDA;
+    }
+    g->send[rank] = d_buf;
+    g->barrier();
+    if (g->broken) {
+      err = "local exchange: a group member failed";
+      return SMB_ERR_STATE;
+    }
+    if (rank != root && bytes) {
+      e = cudaMemcpyPeerAsync(d_buf, device, g->send[root], g->device[root], bytes, s);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+      if (e != cudaSuccess) {
+        err = std::string("local exchange: ") + cudaGetErrorString(e);
+        g->abort_all();
+        return SMB_ERR_CUDA;
+      }
+    }
+    g->barrier();  // the root does not touch its buffer before every peer has read it
+    if (g->broken) {
+      err = "local exchange: a group member failed";
+      return SMB_ERR_STATE;
+    }
+    return SMB_OK;
+  }
+
   int allreduce(void *d_buf, size_t n, ExDType t, ExOp op, cudaStream_t s, std::string &err) override {
     const size_t es = t == EX_F64 ? 8 : 4;
     if (tmp.ensure(n * es * (size_t)world) != cudaSuccess) {
@@ -158,6 +192,7 @@ struct NcclApi {
   const char *(*GetErrorString)(int) = nullptr;
   int (*AllReduce)(const void *, void *, size_t, int, int, comm_t, cudaStream_t) = nullptr;
   int (*AllGather)(const void *, void *, size_t, int, comm_t, cudaStream_t) = nullptr;
+  int (*Broadcast)(const void *, void *, size_t, int, int, comm_t, cudaStream_t) = nullptr;
   void *handle = nullptr;
   std::string error;
   bool load() {
@@ -182,7 +217,8 @@ struct NcclApi {
     GetErrorString = (decltype(GetErrorString))sym("ncclGetErrorString");
     AllReduce = (decltype(AllReduce))sym("ncclAllReduce");
     AllGather = (decltype(AllGather))sym("ncclAllGather");
-    if (!GetUniqueId || !CommInitRank || !CommDestroy || !GetErrorString || !AllReduce || !AllGather) {
+    Broadcast = (decltype(Broadcast))sym("ncclBroadcast");
+    if (!GetUniqueId || !CommInitRank || !CommDestroy || !GetErrorString || !AllReduce || !AllGather || !Broadcast) {
       dlclose(handle);
       handle = nullptr;
       return false;
@@ -212,6 +248,16 @@ struct NcclExchange : Exchange {
   }
   int allgather(const void *d_send, void *d_recv, size_t bytes, cudaStream_t s, std::string &err) override {
     return check(NcclApi::get().AllGather(d_send, d_recv, bytes, /*ncclUint8*/ 1, comm, s), "ncclAllGather", err);
+  }
+  int broadcast(void *d_buf, size_t bytes, int root, cudaStream_t s, std::string &err) override {
+    // in chunks below 2^31 bytes: one ncclBroadcast per GB keeps every count comfortably in range
+    for (size_t at = 0; at < bytes; at += (size_t)1 << 30) {
+      const size_t n = std::min<size_t>((size_t)1 << 30, bytes - at);
+      int rc = check(NcclApi::get().Broadcast((const unsigned char *)d_buf + at, (unsigned char *)d_buf + at, n,
+                                              /*ncclUint8*/ 1, root, comm, s), "ncclBroadcast", err);
+      if (rc) return rc;
+    }
+    return SMB_OK;
   }
 };
 

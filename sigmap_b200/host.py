@@ -149,6 +149,43 @@ def build_point_cloud(ref, level_mean):
     return pos, val
 
 
+class CloudPart:
+    """One rank's part of the point cloud (contig-sharded index): owns the C arrays."""
+
+    def __init__(self, c):
+        self.c = c
+
+    def arrays(self):
+        c = self.c
+        nv, nr = c.n_values, c.n_runs
+        take = lambda p, n, : np.ctypeslib.as_array(p, (max(n, 1),))[:n].copy()
+        return dict(pos=take(c.pos, nv), val=take(c.val, nv), own=take(c.own, nv),
+                    run_off=take(c.run_off, nr + 1), run_first=take(c.run_first, nr),
+                    n_points_total=int(c.n_points_total))
+
+    def close(self):
+        if self.c is not None:
+            F.lib.smbh_cloud_part_free(C.byref(self.c))
+            self.c = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def build_point_cloud_part(ref, level_mean, owner, rank):
+    """The part of the reference's point cloud that shard `rank` needs (its own contigs' points
+    and the five after each stretch): never the whole cloud in this process's memory."""
+    owner = np.ascontiguousarray(owner, np.uint32)
+    c = F.CloudPart()
+    _check(F.lib.smbh_build_point_cloud_part(ref.seq_ptrs, F.ptr(ref.lengths, F.u32p), ref.n,
+                                             F.ptr(level_mean, F.f32p), F.ptr(owner, F.u32p), rank,
+                                             C.byref(c)), "smbh_build_point_cloud_part")
+    return CloudPart(c)
+
+
 def write_pt(prefix, pos, val, dim=6, max_leaf=20):
     pos = np.ascontiguousarray(pos, np.uint64)
     val = np.ascontiguousarray(val, np.float32)

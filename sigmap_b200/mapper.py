@@ -91,6 +91,20 @@ class Mapper:
                                                        F.ptr(owner, F.u32p), len(owner)),
                     "smb_index_set_points_sharded")
 
+    def set_index_part(self, part, n_contigs):
+        """Contig-sharded index from this rank's own part of the cloud
+        (host.build_point_cloud_part with this context's shard rank)."""
+        self._check(F.lib.smb_index_set_points_part(self._ctx, C.byref(part.c), n_contigs),
+                    "smb_index_set_points_part")
+
+    def broadcast_index(self, root=0):
+        """Read-sharded runs: receive (or, on `root`, send) the device index over NVLink instead of
+        building it on every rank.  Collective over the joined group; contig lengths travel too."""
+        self._check(F.lib.smb_index_broadcast(self._ctx, root), "smb_index_broadcast")
+        n = F.lib.smb_index_num_contigs(self._ctx)
+        if self.contig_lengths is None or len(self.contig_lengths) != n:
+            self.contig_lengths = None  # the caller sets them with set_contigs() for PAF formatting
+
     @property
     def shard_rank(self):
         return F.lib.smb_shard_rank(self._ctx)

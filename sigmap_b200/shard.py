@@ -162,6 +162,30 @@ class ContigShardGroup:
             m.set_index_sharded(pos, val, self.owner)
             m.set_contigs(contig_lengths)
 
+    def set_index_from_reference(self, ref, level_mean, owner=None):
+        """Contig-sharded index where every member builds only ITS OWN part of the point cloud from
+        the reference sequences (host.build_point_cloud_part): the way a genome-scale reference is
+        indexed, since no member ever holds the whole cloud."""
+        from .host import build_point_cloud_part
+        owner = assign_contigs(ref.lengths, self.world) if owner is None else owner
+        self.owner = np.ascontiguousarray(owner, np.uint32)
+        for r, m in enumerate(self.mappers):
+            part = build_point_cloud_part(ref, level_mean, self.owner, r)
+            try:
+                m.set_index_part(part, ref.n)
+            finally:
+                part.close()
+            m.set_contigs(ref.lengths)
+
+    def replicate_index(self, pos, val, contig_lengths, root=0):
+        """Read-sharded mode: the index is built on `root` only and broadcast to the other members
+        over NVLink / peer copies (smb_index_broadcast); every member then maps its own reads."""
+        self.mappers[root].set_index(pos, val)
+        self.mappers[root].set_contigs(contig_lengths)
+        self._each(lambda m: m.broadcast_index(root))
+        for m in self.mappers:
+            m.set_contigs(contig_lengths)
+
     def map_reads(self, reads, params=None):
         """rows of every rank (list of lists); they are identical by construction."""
         return self._each(lambda m: m.map_reads(reads, params))

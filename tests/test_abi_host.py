@@ -212,3 +212,37 @@ def test_format_paf_rows(host):
     cols = host.format_paf(u, "short", "", 0, 0.0).rstrip("\n").split("\t")
     assert cols[:12] == ["short", "3999"] + ["*"] * 9 + ["61"]
     assert [c[:5] for c in cols[12:]] == ["mt:f:", "ci:i:", "sl:i:"]
+
+
+def test_point_cloud_parts_cover_the_whole_cloud(host, model):
+    """smbh_build_point_cloud_part: every rank's part holds exactly the windows of its own contigs,
+    with the values the whole cloud has there (including the windows that straddle into the next
+    contig / strand, Q2), and the parts of all ranks together are every window once."""
+    # short contigs too: one shorter than a window run, so trailing values cross several contigs
+    genome = host.sim_reference(31, [40000, 25, 30000, 14, 12, 22000, 9000])
+    level_mean = model[0]
+    pos, val = host.build_point_cloud(genome, level_mean)
+    n = len(pos)
+    for world in (2, 3):
+        from sigmap_b200 import shard
+        owner = shard.assign_contigs(genome.lengths, world)
+        seen = np.zeros(n - 5, np.int32)
+        for rank in range(world):
+            part = host.build_point_cloud_part(genome, level_mean, owner, rank)
+            a = part.arrays()
+            part.close()
+            assert a["n_points_total"] == n
+            ro = a["run_off"]
+            for k in range(len(a["run_first"])):
+                lo, hi, g0 = int(ro[k]), int(ro[k + 1]), int(a["run_first"][k])
+                # a run is a verbatim stretch of the whole cloud
+                assert np.array_equal(a["pos"][lo:hi], pos[g0:g0 + hi - lo])
+                assert np.array_equal(a["val"][lo:hi].view(np.uint32), val[g0:g0 + hi - lo].view(np.uint32))
+                own = a["own"][lo:hi].astype(bool)
+                assert np.array_equal(own, owner[(a["pos"][lo:hi] >> np.uint64(33)).astype(np.int64)] == rank)
+                # every own point that is a window of the whole cloud has its six values in the run
+                idx = g0 + np.nonzero(own)[0]
+                idx = idx[idx < n - 5]
+                assert np.all(idx - g0 + 5 < hi - lo)
+                seen[idx] += 1
+        assert np.all(seen == 1)

@@ -126,3 +126,43 @@ def test_nccl_two_ranks_when_two_gpus():
                        capture_output=True, text=True, timeout=600, env=dict(os.environ, CHECK_READS="120"))
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "PASS" in r.stdout
+
+
+def test_broadcast_index_replicas_map_like_the_root(multi, whole):
+    """Read-sharded mode: the index built on rank 0 is broadcast to the other members of the group
+    (smb_index_broadcast: NCCL across processes, peer copies here); each member then maps its own
+    slice of the reads, with no collective on the data path, and the rows are the unsharded run's."""
+    from sigmap_b200 import shard
+    from sigmap_b200.mapper import default_params
+    g = shard.ContigShardGroup([0, 0, 0])
+    try:
+        g.replicate_index(multi.pos, multi.val, multi.ref.lengths)
+        assert all(m.num_points == whole.num_points for m in g.mappers)
+        exp = whole.map_reads(multi.reads, default_params())
+        for m in g.mappers:
+            m.stats_reset()
+        parts = [shard.shard_reads(multi.reads, g.world, r) for r in range(g.world)]
+        got = g._each(lambda m: m.map_reads(parts[g.mappers.index(m)], default_params()))
+        rows = [r for part in got for r in part]
+        assert row_bytes(rows) == row_bytes(exp)
+        assert all(m.stats()["exchanges"] == 0 for m in g.mappers)  # nothing collective while mapping
+    finally:
+        g.close()
+
+
+def test_sharded_index_from_own_cloud_parts(multi, whole, model):
+    """The way a genome-scale reference is indexed: every member of the group builds only ITS OWN
+    part of the point cloud from the sequences (smbh_build_point_cloud_part) and its device index
+    from that (smb_index_set_points_part).  Rows must equal the unsharded run's."""
+    from sigmap_b200 import shard
+    from sigmap_b200.mapper import default_params, full_read_params
+    g = shard.ContigShardGroup([0, 0, 0])
+    try:
+        g.set_index_from_reference(multi.ref, model[0])
+        assert sum(m.stats()["launches"] > 0 for m in g.mappers) == 3
+        for prm in (default_params(), full_read_params()):
+            exp = whole.map_reads(multi.reads, prm)
+            for rank_rows in g.map_reads(multi.reads, prm):
+                assert row_bytes(rank_rows) == row_bytes(exp)
+    finally:
+        g.close()

@@ -40,7 +40,7 @@ PATHS = [
     ("events_overlap", "0", lambda st: True),
     ("part", "small", lambda st: st["part_sort_steps"] > 0),
 ]
-RESET = {"sort": "part", "runs_cap": "0", "search": "lean", "front_cap": "256", "grab": "0", "dp": "dynamic",
+RESET = {"sort": "part", "runs_cap": "0", "search": "lean", "front_cap": "384", "grab": "0", "dp": "dynamic",
          "dp_passes": "1", "events": "auto", "events_overlap": "1", "part": "big"}
 
 
