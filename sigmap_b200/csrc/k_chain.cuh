@@ -327,11 +327,11 @@ constexpr int kDpPassThreads = 256;
 //              for its anchor.  An anchor's score only depends on the scores of its gap-compatible
 //              predecessors; if the lookback meets one that is still pending the lane defers,
 //              otherwise its result is final -- whatever the other threads are doing meanwhile,
-//              so the result does not depend on timing.  The tile's keys (and the 256 before it)
-//              are staged unpacked in shared memory, so a step of the walk is two shared-memory
-//              loads and a handful of integer compares; lanes that had to defer try again, up to
-//              three rounds inside the block.  Background hits form chains of 2-3 anchors: this
-//              settles almost everything, at full occupancy and with no segment-sized serial work.  Scores of other threads' anchors are read past L1
+//              so the result does not depend on timing.  Lanes that had to defer try again, up
+//              to three times inside their warp (a warp walks its tiles in order, so most of what
+//              an anchor waits for was settled by the same warp a moment earlier).  Background
+//              hits form chains of 2-3 anchors: this settles almost everything, at full occupancy
+//              and with no segment-sized serial work.  Scores of other threads' anchors are read past L1
 //              (ld.cg) after their pending bit was seen cleared; the writer orders score before
 //              bit with a fence.
 //  k_chain_dp  a warp owns a segment and walks its linked anchors 32 at a time, in order: what
@@ -340,108 +340,103 @@ constexpr int kDpPassThreads = 256;
 //              coalesced, score one each, and the sequential rules (continue/break, running best,
 //              +-1 skip counter with its > 25 break) are resolved with a prefix-max scan and
 //              ballots -- then the running max and the end candidates of the batch are taken.
-constexpr int kDpHalo = 256;    // predecessors of the tile staged in shared memory
-constexpr int kDpIters = 3;      // in-block rounds over the anchors that had to defer
+constexpr int kDpIters = 3;      // tries per anchor inside its warp before it is left to the in-order kernel
 
-__global__ void __launch_bounds__(kDpPassThreads) k_dp_pass(ChainArgs a) {
-  // the tile's anchors and the kDpHalo before it, unpacked: {segment id, target, query}
-  __shared__ int s_seg[kDpHalo + kPrepTile];
-  __shared__ int2 s_tq[kDpHalo + kPrepTile];
-  __shared__ int s_again;
+// Persistent warps; warp w takes the k_chain_prep tiles w, w + W, ... and walks each tile's linked
+// anchors 32 at a time, in order, one per lane.  (One block per tile was measured first: a block's
+// life is a chain of dependent loads -- count, list, keys, scores -- and 590 000 blocks of that
+// made the kernel latency-bound on block turnover: 6-8 ms where this takes a third.)
+__global__ void __launch_bounds__(kDpPassThreads, 6) k_dp_pass(ChainArgs a) {
   if (a.ctr->abort) return;
   const uint32_t n = (uint32_t)a.ctr->n_anchors;
-  const uint32_t tile = blockIdx.x;
-  const uint32_t tile0 = tile * kPrepTile;
-  if (tile0 >= n) return;
-  const uint32_t cnt = a.link_count[tile];
-  if (cnt == 0) return;
-  const uint32_t *list = a.link_list + (size_t)tile * kPrepTile;
+  const uint32_t n_tiles = (n + kPrepTile - 1) / kPrepTile;
+  const int lane = threadIdx.x & 31;
+  const uint32_t warp = (blockIdx.x * kDpPassThreads + threadIdx.x) >> 5;
+  const uint32_t n_warps = (gridDim.x * kDpPassThreads) >> 5;
+  const unsigned full = 0xffffffffu;
   const KeyLayout kl = a.kl;
   const uint64_t *__restrict__ key = a.key;
   float *score = a.score;
   uint32_t *pred = a.pred;
-  const uint32_t first = list[0];  // nothing before the first linked anchor's lookback is needed
-  const long long lo_stage = (long long)first - kDpHalo;
-  const int n_stage = (int)min((long long)(tile0 + kPrepTile), (long long)n) - (int)max(lo_stage, 0ll);
-  const uint32_t g0 = (uint32_t)max(lo_stage, 0ll);  // global index of s_*[0]
-  for (int x = threadIdx.x; x < n_stage && x < kDpHalo + kPrepTile; x += kDpPassThreads) {
-    const uint64_t k = key[g0 + x];
-    s_seg[x] = (int)(uint32_t)kl.seg(k);
-    s_tq[x] = make_int2((int)kl.target(k), (int)kl.query(k));
-  }
-  __syncthreads();
-  for (uint32_t c0 = 0; c0 < cnt; c0 += kDpPassThreads) {  // one trip unless > 256 of the 1024 are linked
-    const uint32_t c = c0 + threadIdx.x;
-    const bool have = c < cnt;
-    const uint32_t i = have ? list[c] : 0u;
-    bool todo = have && (__ldcg(pred + i) & kPending);  // a second launch finds most anchors settled
-    int sg = 0, ti = 0, qi = 0;
-    float ci = 0.0f, init = 0.0f;
-    if (todo) {
-      const int me = (int)(i - g0);
-      sg = s_seg[me];
-      ti = s_tq[me].x;
-      qi = s_tq[me].y;
-      ci = a.coef[i];
-      init = __ldcg(score + i);  // 6 * coef from k_chain_prep = chaining_scores[anchor_index]
-    }
-    for (int iter = 0; iter < kDpIters; ++iter) {
+  for (uint32_t tile = warp; tile < n_tiles; tile += n_warps) {
+    const uint32_t cnt = a.link_count[tile];
+    const uint32_t *list = a.link_list + (size_t)tile * kPrepTile;
+    for (uint32_t c0 = 0; c0 < cnt; c0 += 32) {
+      const uint32_t c = c0 + lane;
+      const bool have = c < cnt;
+      const uint32_t i = have ? list[c] : 0u;
+      bool todo = have && (__ldcg(pred + i) & kPending);
+      uint64_t sg = 0;
+      int32_t ti = 0, qi = 0;
+      float ci = 0.0f, init = 0.0f;
       if (todo) {
-        float M = init;
-        uint32_t best = i;
-        int S = 0;  // num_skips
-        bool defer = false;
-        const uint32_t lo = i > (uint32_t)kBand ? i - kBand : 0u;  // the segment start ends the walk earlier
-        for (uint32_t j = i; j > lo;) {
-          --j;
-          int pseg, pt, pq;
-          if (j >= g0) {
-            const int x = (int)(j - g0);
-            pseg = s_seg[x];
-            pt = s_tq[x].x;
-            pq = s_tq[x].y;
-          } else {  // deeper than what is staged: rare
-            const uint64_t kj = key[j];
-            pseg = (int)(uint32_t)kl.seg(kj);
-            pt = (int)kl.target(kj);
-            pq = (int)kl.query(kj);
-          }
-          if (pseg != sg) break;  // first anchor of the segment passed
-          if (pq == qi || pt == ti) continue;
-          if (pt + kMaxTargetGap < ti) break;
-          const int32_t dt = ti - pt, dq = qi - pq;
-          if (dq < 0) continue;
-          float cur = 0.0f;
-          if (gap_compatible(dt, dq)) {
-            if (__ldcg(pred + j) & kPending) {
-              defer = true;
-              break;
-            }
-            cur = __fadd_rn(__ldcg(score + j), __fmul_rn((float)min(min(dt, dq), kDim), ci));
-          }
-          if (cur > M) {
-            M = cur;
-            best = j;
-            --S;
-          } else if (++S > kMaxSkips) {
-            break;
-          }
-        }
-        if (!defer) {
-          score[i] = M;
-          __threadfence();
-          pred[i] = best;  // clears kPending
-          todo = false;
-        }
+        const uint64_t k = key[i];
+        sg = kl.seg(k);
+        ti = (int32_t)kl.target(k);
+        qi = (int32_t)kl.query(k);
+        ci = a.coef[i];
+        init = __ldcg(score + i);  // 6 * coef from k_chain_prep = chaining_scores[anchor_index]
       }
-      // another round only if somebody deferred (its predecessor may have been settled meanwhile)
-      if (threadIdx.x == 0) s_again = 0;
-      __syncthreads();
-      if (todo) s_again = 1;
-      __syncthreads();
-      const int again = s_again;
-      __syncthreads();  // everybody has read the flag before anybody clears it again
-      if (!again) break;
+      for (int iter = 0; iter < kDpIters && __any_sync(full, todo); ++iter) {
+        if (todo) {
+          float M = init;
+          uint32_t best = i;
+          int S = 0;  // num_skips
+          bool defer = false, done = false;
+          const uint32_t lo = i > (uint32_t)kBand ? i - kBand : 0u;  // the segment start ends the walk earlier
+          // predecessors four at a time: the key loads of a group are independent, so the walk
+          // pays one memory round trip per group instead of one per predecessor
+          for (uint32_t jb = i; jb > lo && !done;) {
+            const uint32_t m = min(jb - lo, (uint32_t)kDpGroup);
+            uint64_t kk[kDpGroup];
+#pragma unroll
+            for (int u = 0; u < kDpGroup; ++u) kk[u] = (uint32_t)u < m ? key[jb - 1u - (uint32_t)u] : 0ull;
+#pragma unroll
+            for (int u = 0; u < kDpGroup; ++u) {
+              if (done || (uint32_t)u >= m) break;
+              const uint32_t j = jb - 1u - (uint32_t)u;
+              const uint64_t kj = kk[u];
+              if (kl.seg(kj) != sg) {  // first anchor of the segment passed
+                done = true;
+                break;
+              }
+              const int32_t pt = (int32_t)kl.target(kj), pq = (int32_t)kl.query(kj);
+              if (pq == qi || pt == ti) continue;
+              if (pt + kMaxTargetGap < ti) {
+                done = true;
+                break;
+              }
+              const int32_t dt = ti - pt, dq = qi - pq;
+              if (dq < 0) continue;
+              float cur = 0.0f;
+              if (gap_compatible(dt, dq)) {
+                if (__ldcg(pred + j) & kPending) {
+                  defer = true;
+                  done = true;
+                  break;
+                }
+                cur = __fadd_rn(__ldcg(score + j), __fmul_rn((float)min(min(dt, dq), kDim), ci));
+              }
+              if (cur > M) {
+                M = cur;
+                best = j;
+                --S;
+              } else if (++S > kMaxSkips) {
+                done = true;
+                break;
+              }
+            }
+            jb -= m;
+          }
+          if (!defer) {
+            score[i] = M;
+            __threadfence();
+            pred[i] = best;  // clears kPending
+            todo = false;
+          }
+        }
+        __syncwarp(full);
+      }
     }
   }
 }

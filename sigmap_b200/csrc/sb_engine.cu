@@ -776,9 +776,10 @@ static int run_step(smb_ctx *ctx, SlotSpace &sp, const StepEntries &en, StepSour
   if (kl.total() > 64) return fail(ctx, SMB_ERR_CAPACITY, "sort key exceeds 64 bits: lower max_batch_chunks");
   if (ctx->max_batch_anchors >= (1ull << 30)) return fail(ctx, SMB_ERR_ARG, "max_batch_anchors must stay below 2^30");
   // anchor buffers sized from the running estimate (they grow on overflow, up to the limit)
+  // (the step's capacity follows the estimate, not the buffers' high-water mark: grids that are
+  // sized for it -- k_chain_prep -- would otherwise launch mostly empty blocks on small steps)
   const uint64_t cap = std::min<uint64_t>(
-      ctx->max_batch_anchors,
-      std::max<uint64_t>((uint64_t)(1.5 * ctx->est_anchors_per_chunk * std::max(Bpres, 1u)) + (1u << 20), w.key_a.cap));
+      ctx->max_batch_anchors, (uint64_t)(1.5 * ctx->est_anchors_per_chunk * std::max(Bpres, 1u)) + (1u << 20));
   ctx->last_cap = cap;
 
   // ---- per-entry arrays
@@ -1052,7 +1053,7 @@ static int run_step(smb_ctx *ctx, SlotSpace &sp, const StepEntries &en, StepSour
   k_chain_prep<<<n_tiles, kPrepThreads, 0, s>>>(ca);
   LAUNCH_CHECK();
   for (int pass = 0; pass < ctx->dp_passes; ++pass) {
-    k_dp_pass<<<n_tiles, kDpPassThreads, 0, s>>>(ca);
+    k_dp_pass<<<ctx->n_sm * 6u, kDpPassThreads, 0, s>>>(ca);
     LAUNCH_CHECK();
   }
   {

@@ -49,6 +49,38 @@ def main():
         print(f"rank {rank}/{world} {name}: {diff} of {len(exp)} rows differ from the unsharded run; "
               f"{sum(r.mapped for r in got)} mapped; {st['exchanges']} collectives, {st['hits']} local hits, "
               f"{dt * 1e3:.0f} ms", flush=True)
+    # the same with every rank building only its own part of the point cloud (genome-scale path)
+    part2 = Mapper(local)
+    shard.nccl_join(part2, dist)
+    cp = H.build_point_cloud_part(ref, model[0], owner, rank)
+    part2.set_index_part(cp, ref.n)
+    cp.close()
+    part2.set_contigs(ref.lengths)
+    exp = whole.map_reads(reads, default_params())
+    dist.barrier()
+    got = part2.map_reads(reads, default_params())
+    diff = sum(bytes(a) != bytes(b) for a, b in zip(exp, got))
+    bad += diff
+    print(f"rank {rank}/{world} own-part index ({part2.num_points} points in the whole cloud): {diff} rows differ", flush=True)
+    part2.close()
+    # read-sharded: index built on rank 0, broadcast over NCCL, every rank maps its own reads
+    rep = Mapper(local)
+    shard.nccl_join(rep, dist)
+    if rank == 0:
+        rep.set_index(pos, val)
+        rep.set_contigs(ref.lengths)
+    dist.barrier()
+    t0 = time.time()
+    rep.broadcast_index(0)
+    dt = time.time() - t0
+    rep.set_contigs(ref.lengths)
+    mine = shard.shard_reads(reads, world, rank)
+    lo, hi = shard.block_range(reads.n, world, rank)
+    got = rep.map_reads(mine, default_params())
+    diff = sum(bytes(a) != bytes(b) for a, b in zip(exp[lo:hi], got))
+    bad += diff
+    print(f"rank {rank}/{world} broadcast index: {dt * 1e3:.1f} ms, {diff} of {len(got)} rows differ", flush=True)
+    rep.close()
     t = torch.tensor([bad], device=f"cuda:{local}")
     dist.all_reduce(t)
     whole.close()
