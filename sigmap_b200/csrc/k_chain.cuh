@@ -341,11 +341,19 @@ constexpr int kDpPassThreads = 256;
 //              +-1 skip counter with its > 25 break) are resolved with a prefix-max scan and
 //              ballots -- then the running max and the end candidates of the batch are taken.
 constexpr int kDpIters = 3;      // tries per anchor inside its warp before it is left to the in-order kernel
+constexpr int kDpShort = 16;     // predecessors a lane walks on its own before the warp takes the walk over
 
 // Persistent warps; warp w takes the k_chain_prep tiles w, w + W, ... and walks each tile's linked
 // anchors 32 at a time, in order, one per lane.  (One block per tile was measured first: a block's
 // life is a chain of dependent loads -- count, list, keys, scores -- and 590 000 blocks of that
-// made the kernel latency-bound on block turnover: 6-8 ms where this takes a third.)
+// made the kernel latency-bound on block turnover.)
+//
+// Walk lengths are very uneven: a background anchor sees ~10 predecessors inside the 5 000-position
+// window, an anchor in a true-locus cluster hundreds (most of them "continue" cases that do not
+// count as skips) -- and a warp waits for its slowest lane.  So a lane walks at most kDpShort
+// predecessors on its own; a walk that is not over by then is finished by the WHOLE warp, 32
+// predecessors per step (one each, coalesced), the sequential rules resolved with a prefix-max scan
+// and ballots exactly as in the in-order kernel.
 __global__ void __launch_bounds__(kDpPassThreads, 6) k_dp_pass(ChainArgs a) {
   if (a.ctr->abort) return;
   const uint32_t n = (uint32_t)a.ctr->n_anchors;
@@ -354,6 +362,7 @@ __global__ void __launch_bounds__(kDpPassThreads, 6) k_dp_pass(ChainArgs a) {
   const uint32_t warp = (blockIdx.x * kDpPassThreads + threadIdx.x) >> 5;
   const uint32_t n_warps = (gridDim.x * kDpPassThreads) >> 5;
   const unsigned full = 0xffffffffu;
+  const unsigned le = (2u << lane) - 1u;  // lanes 0..lane
   const KeyLayout kl = a.kl;
   const uint64_t *__restrict__ key = a.key;
   float *score = a.score;
@@ -377,63 +386,143 @@ __global__ void __launch_bounds__(kDpPassThreads, 6) k_dp_pass(ChainArgs a) {
         ci = a.coef[i];
         init = __ldcg(score + i);  // 6 * coef from k_chain_prep = chaining_scores[anchor_index]
       }
+      const uint32_t lo = i > (uint32_t)kBand ? i - kBand : 0u;  // the segment start ends the walk earlier
       for (int iter = 0; iter < kDpIters && __any_sync(full, todo); ++iter) {
-        if (todo) {
-          float M = init;
-          uint32_t best = i;
-          int S = 0;  // num_skips
-          bool defer = false, done = false;
-          const uint32_t lo = i > (uint32_t)kBand ? i - kBand : 0u;  // the segment start ends the walk earlier
-          // predecessors four at a time: the key loads of a group are independent, so the walk
-          // pays one memory round trip per group instead of one per predecessor
-          for (uint32_t jb = i; jb > lo && !done;) {
-            const uint32_t m = min(jb - lo, (uint32_t)kDpGroup);
-            uint64_t kk[kDpGroup];
+        // ---- every lane on its own, at most kDpShort predecessors
+        float M = init;
+        uint32_t best = i, jb = i;
+        int S = 0;  // num_skips
+        bool defer = false, done = !todo;
+        for (int g = 0; g < kDpShort / kDpGroup && !done; ++g) {
+          // four at a time: the key loads of a group are independent, so the walk pays one
+          // memory round trip per group instead of one per predecessor
+          const uint32_t m = min(jb - lo, (uint32_t)kDpGroup);
+          if (m == 0) {
+            done = true;
+            break;
+          }
+          uint64_t kk[kDpGroup];
 #pragma unroll
-            for (int u = 0; u < kDpGroup; ++u) kk[u] = (uint32_t)u < m ? key[jb - 1u - (uint32_t)u] : 0ull;
+          for (int u = 0; u < kDpGroup; ++u) kk[u] = (uint32_t)u < m ? key[jb - 1u - (uint32_t)u] : 0ull;
 #pragma unroll
-            for (int u = 0; u < kDpGroup; ++u) {
-              if (done || (uint32_t)u >= m) break;
-              const uint32_t j = jb - 1u - (uint32_t)u;
-              const uint64_t kj = kk[u];
-              if (kl.seg(kj) != sg) {  // first anchor of the segment passed
-                done = true;
-                break;
-              }
-              const int32_t pt = (int32_t)kl.target(kj), pq = (int32_t)kl.query(kj);
-              if (pq == qi || pt == ti) continue;
-              if (pt + kMaxTargetGap < ti) {
-                done = true;
-                break;
-              }
-              const int32_t dt = ti - pt, dq = qi - pq;
-              if (dq < 0) continue;
-              float cur = 0.0f;
-              if (gap_compatible(dt, dq)) {
-                if (__ldcg(pred + j) & kPending) {
-                  defer = true;
-                  done = true;
-                  break;
-                }
-                cur = __fadd_rn(__ldcg(score + j), __fmul_rn((float)min(min(dt, dq), kDim), ci));
-              }
-              if (cur > M) {
-                M = cur;
-                best = j;
-                --S;
-              } else if (++S > kMaxSkips) {
-                done = true;
-                break;
-              }
+          for (int u = 0; u < kDpGroup; ++u) {
+            if (done || (uint32_t)u >= m) break;
+            const uint32_t j = jb - 1u - (uint32_t)u;
+            const uint64_t kj = kk[u];
+            if (kl.seg(kj) != sg) {  // first anchor of the segment passed
+              done = true;
+              break;
             }
-            jb -= m;
+            const int32_t pt = (int32_t)kl.target(kj), pq = (int32_t)kl.query(kj);
+            if (pq == qi || pt == ti) continue;
+            if (pt + kMaxTargetGap < ti) {
+              done = true;
+              break;
+            }
+            const int32_t dt = ti - pt, dq = qi - pq;
+            if (dq < 0) continue;
+            float cur = 0.0f;
+            if (gap_compatible(dt, dq)) {
+              if (__ldcg(pred + j) & kPending) {
+                defer = true;
+                done = true;
+                break;
+              }
+              cur = __fadd_rn(__ldcg(score + j), __fmul_rn((float)min(min(dt, dq), kDim), ci));
+            }
+            if (cur > M) {
+              M = cur;
+              best = j;
+              --S;
+            } else if (++S > kMaxSkips) {
+              done = true;
+              break;
+            }
           }
-          if (!defer) {
-            score[i] = M;
-            __threadfence();
-            pred[i] = best;  // clears kPending
-            todo = false;
+          jb -= m;
+          if (jb <= lo) done = true;
+        }
+        // ---- walks that are not over yet: the whole warp, 32 predecessors per step
+        unsigned longm = __ballot_sync(full, todo && !done);
+        while (longm) {
+          const int src = __ffs(longm) - 1;
+          longm &= longm - 1;
+          const uint32_t ii = __shfl_sync(full, i, src), loi = __shfl_sync(full, lo, src);
+          const int32_t tii = __shfl_sync(full, ti, src), qii = __shfl_sync(full, qi, src);
+          const float cii = __shfl_sync(full, ci, src);
+          const uint32_t sgl = __shfl_sync(full, (uint32_t)sg, src), sgh = __shfl_sync(full, (uint32_t)(sg >> 32), src);
+          const uint64_t sgi = ((uint64_t)sgh << 32) | sgl;
+          float Mi = __shfl_sync(full, M, src);
+          uint32_t bi = __shfl_sync(full, best, src);
+          int Si = __shfl_sync(full, S, src);
+          bool dfr = false;
+          for (uint32_t jc = __shfl_sync(full, jb, src);; jc -= 32) {  // predecessors jc-1 .. jc-32
+            // my predecessor: >= 0 candidate score (counted), -1 continue, -2 lookback ends,
+            // -3 gap-compatible but still pending
+            float cd = -2.0f;
+            if (jc >= loi + 1u + (uint32_t)lane) {
+              const uint32_t j = jc - 1u - (uint32_t)lane;
+              const uint64_t kj = key[j];
+              const int32_t pt = (int32_t)kl.target(kj), pq = (int32_t)kl.query(kj);
+              const int32_t dt = tii - pt, dq = qii - pq;
+              if (kl.seg(kj) != sgi) cd = -2.0f;
+              else if (pq == qii || pt == tii) cd = -1.0f;
+              else if (pt + kMaxTargetGap < tii) cd = -2.0f;
+              else if (dq < 0) cd = -1.0f;
+              else if (gap_compatible(dt, dq)) {
+                if (__ldcg(pred + j) & kPending) cd = -3.0f;
+                else cd = __fadd_rn(__ldcg(score + j), __fmul_rn((float)min(min(dt, dq), kDim), cii));
+              } else cd = 0.0f;
+            }
+            // a pending predecessor ends the block like the end of the lookback would; whether the
+            // walk really reaches it is decided below
+            const unsigned pendm = __ballot_sync(full, cd == -3.0f);
+            const int first_pend = pendm ? __ffs(pendm) - 1 : 32;
+            if (lane >= first_pend) cd = -2.0f;
+            // resolve the 32 predecessors in order (lane 0 = most recent)
+            const bool counted = cd >= 0.0f;
+            const unsigned cntm = __ballot_sync(full, counted);
+            unsigned impm = 0u;
+            if (__ballot_sync(full, cd > Mi)) {
+              float pm = counted ? cd : 0.0f;  // inclusive prefix max of the candidate scores
+#pragma unroll
+              for (int d = 1; d < 32; d <<= 1) {
+                const float t = __shfl_up_sync(full, pm, d);
+                if (lane >= d) pm = fmaxf(pm, t);
+              }
+              float ex = __shfl_up_sync(full, pm, 1);
+              ex = fmaxf(lane == 0 ? 0.0f : ex, Mi);
+              impm = __ballot_sync(full, counted && cd > ex);
+            }
+            const int Sl = Si + __popc(cntm & ~impm & le) - __popc(impm & le);
+            const bool stop_here = (counted && !((impm >> lane) & 1u) && Sl > kMaxSkips) || cd == -2.0f;
+            const unsigned stopm = __ballot_sync(full, stop_here);
+            const unsigned below = stopm ? ((stopm & (0u - stopm)) - 1u) : full;
+            const unsigned imp_b = impm & below;
+            if (imp_b) {
+              const int L = 31 - __clz(imp_b);
+              Mi = __shfl_sync(full, cd, L);
+              bi = jc - 1u - (uint32_t)L;
+            }
+            if (stopm) {
+              // stopped AT the first pending predecessor: the walk reaches it, so the anchor waits
+              dfr = first_pend < 32 && (__ffs(stopm) - 1) == first_pend;
+              break;
+            }
+            Si += __popc(cntm & ~impm) - __popc(impm);
           }
+          if (lane == src) {
+            M = Mi;
+            best = bi;
+            defer = dfr;
+            done = true;
+          }
+        }
+        if (todo && !defer) {
+          score[i] = M;
+          __threadfence();
+          pred[i] = best;  // clears kPending
+          todo = false;
         }
         __syncwarp(full);
       }

@@ -434,16 +434,18 @@ struct QueryH {
   __half2 q01, q23, q45;
   float theta;
 };
-__device__ __forceinline__ QueryH make_query_h(const float q[kDim], float r2) {
+// r = sqrt(r2) is computed once per kernel; |q|_2 is bounded by sqrt(6) max|q_d| (no square root
+// per query: the bound only has to be an upper one)
+__device__ __forceinline__ QueryH make_query_h(const float q[kDim], float r) {
   QueryH h;
   h.q01 = __floats2half2_rn(q[0], q[1]);
   h.q23 = __floats2half2_rn(q[2], q[3]);
   h.q45 = __floats2half2_rn(q[4], q[5]);
-  float qq = 0.0f;
+  float qmax = 0.0f;
 #pragma unroll
-  for (int d = 0; d < kDim; ++d) qq = __fmaf_rn(q[d], q[d], qq);
-  const float reach = sqrtf(r2) + 4.8828125e-4f * sqrtf(qq) * 1.001f;  // r + 2^-11 |q|_2
-  h.theta = reach * reach * 1.0045f + 1e-6f;                            // (1 + 2^-11)^8 < 1.004; + underflow slack
+  for (int d = 0; d < kDim; ++d) qmax = fmaxf(qmax, fabsf(q[d]));
+  const float reach = r + 4.8828125e-4f * 2.4495f * qmax * 1.001f;  // r + 2^-11 sqrt(6) max|q_d| >= r + 2^-11 |q|_2
+  h.theta = reach * reach * 1.0045f + 1e-6f;                          // (1 + 2^-11)^8 < 1.004; + underflow slack
   return h;
 }
 __device__ __forceinline__ float box_d2_h(const uint2 r0, const uint2 r1, const uint2 r2, const QueryH &h) {
@@ -489,34 +491,52 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t pari
 
 // One level of the lean traversal: the nf frontier nodes in src[] -> the surviving children in
 // dst[]; returns their number, or -1 when dst would outgrow front_cap.  SMEM: the level's records
-// are in shared memory.
+// are in shared memory.  Sixteen nodes per step while the level has that many left (four per
+// 8-lane group: twelve independent loads per lane in flight, the loop's fixed cost shared by 128
+// box tests), then eight, then the tail of at most four.
+template <bool SMEM>
+__device__ __forceinline__ uint2 node_ld(const uint2 *p) {
+  return SMEM ? *p : __ldg(p);
+}
 template <bool SMEM>
 __device__ __forceinline__ int lean_node_level(const uint2 *__restrict__ lvl, const uint32_t *__restrict__ src,
                                                uint32_t *__restrict__ dst, int nf, int front_cap, const QueryH &qh,
                                                int lane, int grp, int sub, unsigned lt) {
   const unsigned full = 0xffffffffu;
-  int nn = 0;
-  for (int i0 = 0; i0 < nf; i0 += 8) {
+  int nn = 0, i0 = 0;
+  for (; i0 + 8 < nf; i0 += 16) {  // more than eight left: a 16-node step
+    if (nn > front_cap - 128) return -1;
+    uint32_t node[4];
+    uint2 r0[4], r1[4], r2[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int ia = i0 + grp + 4 * u;
+      node[u] = ia < nf ? src[ia] : 0u;
+      const uint2 *ra = lvl + (size_t)node[u] * kNodeRec + sub;
+      r0[u] = node_ld<SMEM>(ra);
+      r1[u] = node_ld<SMEM>(ra + kFan);
+      r2[u] = node_ld<SMEM>(ra + 2 * kFan);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int ia = i0 + grp + 4 * u;
+      const float sd = box_d2_h(r0[u], r1[u], r2[u], qh);
+      const unsigned m = __ballot_sync(full, ia < nf && sd <= qh.theta);
+      if ((m >> lane) & 1u) dst[nn + __popc(m & lt)] = node[u] * kFan + sub;
+      nn += __popc(m);
+    }
+  }
+  for (; i0 < nf; i0 += 8) {
     if (nn > front_cap - 64) return -1;
     const int ia = i0 + grp, ib = ia + 4;
     const bool hasA = ia < nf, hasB = ib < nf;
     const uint32_t nodeA = hasA ? src[ia] : 0u;
     const uint2 *ra = lvl + (size_t)nodeA * kNodeRec + sub;
-    uint2 a0, a1, a2;
-    if (SMEM) {
-      a0 = ra[0]; a1 = ra[kFan]; a2 = ra[2 * kFan];
-    } else {
-      a0 = __ldg(ra); a1 = __ldg(ra + kFan); a2 = __ldg(ra + 2 * kFan);
-    }
+    const uint2 a0 = node_ld<SMEM>(ra), a1 = node_ld<SMEM>(ra + kFan), a2 = node_ld<SMEM>(ra + 2 * kFan);
     if (i0 + 4 < nf) {  // a full step: two nodes per lane group
       const uint32_t nodeB = hasB ? src[ib] : 0u;
       const uint2 *rb = lvl + (size_t)nodeB * kNodeRec + sub;
-      uint2 b0, b1, b2;
-      if (SMEM) {
-        b0 = rb[0]; b1 = rb[kFan]; b2 = rb[2 * kFan];
-      } else {
-        b0 = __ldg(rb); b1 = __ldg(rb + kFan); b2 = __ldg(rb + 2 * kFan);
-      }
+      const uint2 b0 = node_ld<SMEM>(rb), b1 = node_ld<SMEM>(rb + kFan), b2 = node_ld<SMEM>(rb + 2 * kFan);
       const float sa = box_d2_h(a0, a1, a2, qh), sb = box_d2_h(b0, b1, b2, qh);
       const unsigned mA = __ballot_sync(full, hasA && sa <= qh.theta);
       const unsigned mB = __ballot_sync(full, hasB && sb <= qh.theta);
@@ -576,6 +596,7 @@ k_search_lean(const __grid_constant__ IndexView ix, const __grid_constant__ Sear
     nq = a.nq_cap;
   }
   const float r2 = a.radius;
+  const float r_up = sqrtf(r2) * 1.000001f;  // an upper bound of the radius itself
   const int top_level = ix.n_levels - 1;
   const int n_top = (int)ix.level_count[top_level];  // <= 8
   const int front_cap = (int)a.front_cap;
@@ -615,7 +636,10 @@ k_search_lean(const __grid_constant__ IndexView ix, const __grid_constant__ Sear
         }
         staged_entry = entry;
       }
-      const QueryH qh = make_query_h(q, r2);
+      // a NaN coordinate (a chunk whose event means are all equal: 0/0 in the z-score) matches
+      // nothing in the reference (nanoflann: NaN < radius is false) -- and would pass every box test here
+      if (!(fabsf(q[0] + q[1] + q[2] + q[3] + q[4] + q[5]) <= 3.0e38f)) continue;
+      const QueryH qh = make_query_h(q, r_up);
 
       // ---- node levels, top down
       int nf = n_top;
@@ -794,6 +818,7 @@ k_radius_search(const __grid_constant__ IndexView ix, const __grid_constant__ Se
         for (int d = 0; d < kDim; ++d) q[d] = __ldg(f + d);
         qk = a.key.pack(entry, 0u, 0u, p + ev_off);
       }
+      if (!(fabsf(q[0] + q[1] + q[2] + q[3] + q[4] + q[5]) <= 3.0e38f)) continue;  // NaN: no hits (see k_search_lean)
       uint32_t qhits = 0;
       bool capped = false;
       // L = level being worked on (n_levels when none), c = how many wait there

@@ -10,6 +10,7 @@
 #include <stdint.h>
 
 #include <string>
+#include <vector>
 
 #include "../../include/sigmap_b200.h"
 
@@ -24,6 +25,23 @@ constexpr int kLeaf = 8;                // points per leaf = one 8-lane group (3
 constexpr int kFan = 8;                 // children per node; a warp tests 4 nodes per step
 constexpr int kMaxLevels = 12;          // 8^12 leaves: never reached below 2^32 points
 
+// cudaFree waits for the whole device -- including an upload still queued on the copy stream,
+// which would serialise the upload and the mapping it is supposed to hide behind.  While
+// defer_frees() is on (smb_map_reads), buffers that have to grow park their old allocation here;
+// it is released when the call is over and every stream is idle.
+struct FreeLater {
+  static inline thread_local bool on = false;
+  static inline thread_local std::vector<void *> parked;
+  static void drain() {
+    for (void *q : parked) cudaFree(q);
+    parked.clear();
+  }
+};
+inline void dev_free(void *q) {
+  if (FreeLater::on) FreeLater::parked.push_back(q);
+  else cudaFree(q);
+}
+
 // growable device buffer (contents are NOT preserved across growth)
 template <class T>
 struct DevBuf {
@@ -31,7 +49,7 @@ struct DevBuf {
   size_t cap = 0;
   cudaError_t ensure(size_t n) {
     if (n <= cap) return cudaSuccess;
-    if (p) cudaFree(p);
+    if (p) dev_free(p);
     p = nullptr;
     cap = 0;
     size_t want = n + n / 4 + 64;
@@ -40,7 +58,7 @@ struct DevBuf {
     return e;
   }
   void release() {
-    if (p) cudaFree(p);
+    if (p) dev_free(p);
     p = nullptr;
     cap = 0;
   }

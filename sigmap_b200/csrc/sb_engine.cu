@@ -2194,6 +2194,14 @@ int smb_map_reads(smb_ctx *ctx, const int16_t *raw, const uint64_t *read_off, co
   // admits a slice's reads once its event has fired, so the rest of the upload hides behind the
   // mapping of the reads that are already there (raw should be pinned host memory for that).
   int rc = reads_prepare(ctx, read_off, dig, range, offset, n_reads, cs);
+  // from here to the end of the call no cudaFree: a buffer that grows parks its old allocation
+  struct DeferFrees {
+    DeferFrees() { FreeLater::on = true; }
+    ~DeferFrees() {
+      FreeLater::on = false;
+      FreeLater::drain();
+    }
+  } defer_frees;
   UploadPlan plan;
   if (!rc && n_reads) {
     const uint64_t slice_samples = ctx->upload_slice_bytes / sizeof(int16_t);
@@ -2227,8 +2235,8 @@ int smb_map_reads(smb_ctx *ctx, const int16_t *raw, const uint64_t *read_off, co
     plan.first_read.push_back(n_reads);
   }
   if (!rc) rc = map_uploaded_impl(ctx, params, out, n_reads ? &plan : nullptr);
+  cudaStreamSynchronize(cs);  // nothing of this call may still be in flight when it returns (or when buffers are freed)
   if (rc) {
-    cudaStreamSynchronize(cs);  // nothing of this call may still be in flight when it returns
     // a failed member must not leave its in-process peers waiting at a rendezvous
     if (ctx->local_group) ctx->local_group->abort_all();
   }

@@ -132,6 +132,20 @@ def test_radius_search_edge_queries(mapper, port, small):
         assert np.array_equal(idx[off[k]:off[k + 1]], ei)
         assert np.array_equal(bits(d2[off[k]:off[k + 1]]), bits(ed))
     assert 1000 in idx[off[1]:off[2]]
+    # NaN / infinite coordinates (a chunk whose event means are all equal gives 0/0 z-scores):
+    # no hits, like nanoflann (NaN < radius is false), and no walk through the whole index
+    weird = np.zeros((4, 6), np.float32)
+    weird[0, 2] = np.nan
+    weird[1, :] = np.nan
+    weird[2, 0] = np.inf
+    weird[3, 5] = -np.inf
+    for name, value in (("search", "lean"), ("search", "general")):
+        mapper.set_option(name, value)
+        try:
+            off, idx, d2 = mapper.radiusSearch(np.concatenate([weird, on_point]), radius=0.08)
+        finally:
+            mapper.set_option("search", "lean")
+        assert list(off[:5]) == [0, 0, 0, 0, 0] and 1000 in idx[off[4]:off[5]]
 
 
 def test_generate_chains_multi_chunk_state(mapper, port, small):
