@@ -59,7 +59,7 @@ struct ChainArgs {
   uint32_t *link_list;   // [n_tiles * kPrepTile] indices of linked anchors, ascending per tile
   uint32_t *link_count;  // [n_tiles]
   Counters *ctr;
-  int dp_passes;         // k_dp_pass launches before the in-order kernel (host side)
+  int dp_passes;         // thread-parallel passes of k_chain_dp before the in-order cooperative path
 };
 
 constexpr int kCarryThreads = 256;
@@ -207,6 +207,7 @@ __device__ __forceinline__ float distance_coefficient(float dist, double radius)
 }
 
 constexpr int kPrepHalo = 128;     // predecessors staged in shared memory ahead of the tile
+constexpr int kPrepShort = 12;     // predecessors a lane checks itself before the warp takes the range over
 constexpr int kPrepThreads = 256;  // kPrepTile / kPrepThreads anchors per thread
 constexpr uint32_t kPending = 0x40000000u;  // pred[] bit: linked anchor not yet settled by the DP
 
@@ -238,9 +239,10 @@ __global__ void __launch_bounds__(kPrepThreads, 8) k_chain_prep(ChainArgs a) {
   for (int sub = 0; sub < kSubTiles; ++sub) {
     const int local = sub * kPrepThreads + threadIdx.x;
     const uint32_t i = tile0 + local;
-    bool linked = false;
+    bool linked = false, open = false;
+    int d_next = 0;
+    const int me = kPrepHalo + local;
     if (i < n) {
-      const int me = kPrepHalo + local;
       const int4 mine = s_a[me];
       const uint32_t sg = (uint32_t)mine.x;
       const int32_t ti = mine.y, qi = mine.z;
@@ -252,12 +254,15 @@ __global__ void __launch_bounds__(kPrepThreads, 8) k_chain_prep(ChainArgs a) {
         }
         if (i == n - 1) a.seg[sg].end = n;
       }
-      // position-only link test over the maximal lookback range
+      // position-only link test over the maximal lookback range: the lane looks at the nearest
+      // kPrepShort predecessors itself; a range that goes on beyond them is finished by the whole
+      // warp below (ranges are very uneven -- ~10 anchors for a background hit, hundreds next to a
+      // true-locus cluster -- and a warp waits for its slowest lane)
       const int depth = (int)min(i, (uint32_t)kBand);
-      const int in_smem = min(depth, me);
+      const int lim = min(min(depth, me), kPrepShort);
       int d = 1;
-      bool open = true;  // the range continues past what has been looked at
-      for (; d <= in_smem; ++d) {
+      open = true;  // the range continues past what has been looked at
+      for (; d <= lim; ++d) {
         const int4 p = s_a[me - d];
         if (p.x != mine.x || p.y + kMaxTargetGap < ti) {
           open = false;
@@ -269,17 +274,41 @@ __global__ void __launch_bounds__(kPrepThreads, 8) k_chain_prep(ChainArgs a) {
           break;
         }
       }
-      if (open) {  // rare: deeper than what is staged
-        for (; d <= depth; ++d) {
-          const uint64_t kj = a.key[i - d];
-          const int32_t pt = (int32_t)kl.target(kj);
-          if ((uint32_t)kl.seg(kj) != sg || pt + kMaxTargetGap < ti) break;
-          if (gap_compatible(ti - pt, qi - (int32_t)kl.query(kj))) {
-            linked = true;
-            break;
+      if (d > depth) open = false;
+      d_next = d;
+    }
+    // ---- ranges still open: the warp walks them 32 predecessors per step (shared memory while
+    // the staged halo lasts, global memory beyond it)
+    for (unsigned openm = __ballot_sync(0xffffffffu, open); openm; openm &= openm - 1) {
+      const int src = __ffs(openm) - 1;
+      const int me_s = __shfl_sync(0xffffffffu, me, src);
+      const uint32_t i_s = __shfl_sync(0xffffffffu, i, src);
+      const int4 m_s = s_a[me_s];
+      const int depth_s = (int)min(i_s, (uint32_t)kBand);
+      bool res = false;
+      for (int d0 = __shfl_sync(0xffffffffu, d_next, src); d0 <= depth_s; d0 += 32) {
+        const int dd = d0 + lane;
+        bool endf = dd > depth_s, comp = false;
+        if (!endf) {
+          int4 p;
+          if (dd <= me_s) {
+            p = s_a[me_s - dd];
+          } else {
+            const uint64_t kj = a.key[i_s - (uint32_t)dd];
+            p = make_int4((int)(uint32_t)kl.seg(kj), (int32_t)kl.target(kj), (int32_t)kl.query(kj), 0);
           }
+          endf = p.x != m_s.x || p.y + kMaxTargetGap < m_s.y;
+          comp = !endf && gap_compatible(m_s.y - p.y, m_s.z - p.z);
+        }
+        const unsigned cm = __ballot_sync(0xffffffffu, comp), em = __ballot_sync(0xffffffffu, endf);
+        if (cm | em) {  // whichever comes first, going backwards
+          res = cm && (!em || __ffs(cm) < __ffs(em));
+          break;
         }
       }
+      if (lane == src) linked = res;
+    }
+    if (i < n) {
       const float ci = distance_coefficient(a.dist[i], (double)a.radius);
       a.coef[i] = ci;
       a.score[i] = __fmul_rn(ci, (float)kDim);
@@ -316,220 +345,19 @@ __global__ void __launch_bounds__(kPrepThreads, 8) k_chain_prep(ChainArgs a) {
 }
 
 constexpr int kDpThreads = 128;
-constexpr int kDpFreePasses = 1;  // k_dp_pass launches before the in-order kernel (it iterates inside a block)
+constexpr int kDpFreePasses = 1;  // thread-parallel passes before the in-order cooperative path (measured: 1 < 2 < 4)
 constexpr int kDpGroup = 4;       // predecessors fetched together in the thread-parallel lookback
-constexpr int kDpPassThreads = 256;
 
-// The DP in two kernels.
-//
-//  k_dp_pass   every linked anchor of the step at once, one THREAD each (block per k_chain_prep
-//              tile, lanes = consecutive linked anchors): the lane runs the reference's lookback
-//              for its anchor.  An anchor's score only depends on the scores of its gap-compatible
-//              predecessors; if the lookback meets one that is still pending the lane defers,
-//              otherwise its result is final -- whatever the other threads are doing meanwhile,
-//              so the result does not depend on timing.  Lanes that had to defer try again, up
-//              to three times inside their warp (a warp walks its tiles in order, so most of what
-//              an anchor waits for was settled by the same warp a moment earlier).  Background
-//              hits form chains of 2-3 anchors: this settles almost everything, at full occupancy
-//              and with no segment-sized serial work.  Scores of other threads' anchors are read past L1
-//              (ld.cg) after their pending bit was seen cleared; the writer orders score before
-//              bit with a fence.
-//  k_chain_dp  a warp owns a segment and walks its linked anchors 32 at a time, in order: what
-//              is still pending (true-locus clusters, where every anchor links to the previous
-//              one) is settled by the whole warp -- lanes load 32 consecutive predecessors
-//              coalesced, score one each, and the sequential rules (continue/break, running best,
-//              +-1 skip counter with its > 25 break) are resolved with a prefix-max scan and
-//              ballots -- then the running max and the end candidates of the batch are taken.
-constexpr int kDpIters = 3;      // tries per anchor inside its warp before it is left to the in-order kernel
-constexpr int kDpShort = 16;     // predecessors a lane walks on its own before the warp takes the walk over
-
-// Persistent warps; warp w takes the k_chain_prep tiles w, w + W, ... and walks each tile's linked
-// anchors 32 at a time, in order, one per lane.  (One block per tile was measured first: a block's
-// life is a chain of dependent loads -- count, list, keys, scores -- and 590 000 blocks of that
-// made the kernel latency-bound on block turnover.)
-//
-// Walk lengths are very uneven: a background anchor sees ~10 predecessors inside the 5 000-position
-// window, an anchor in a true-locus cluster hundreds (most of them "continue" cases that do not
-// count as skips) -- and a warp waits for its slowest lane.  So a lane walks at most kDpShort
-// predecessors on its own; a walk that is not over by then is finished by the WHOLE warp, 32
-// predecessors per step (one each, coalesced), the sequential rules resolved with a prefix-max scan
-// and ballots exactly as in the in-order kernel.
-__global__ void __launch_bounds__(kDpPassThreads, 6) k_dp_pass(ChainArgs a) {
-  if (a.ctr->abort) return;
-  const uint32_t n = (uint32_t)a.ctr->n_anchors;
-  const uint32_t n_tiles = (n + kPrepTile - 1) / kPrepTile;
-  const int lane = threadIdx.x & 31;
-  const uint32_t warp = (blockIdx.x * kDpPassThreads + threadIdx.x) >> 5;
-  const uint32_t n_warps = (gridDim.x * kDpPassThreads) >> 5;
-  const unsigned full = 0xffffffffu;
-  const unsigned le = (2u << lane) - 1u;  // lanes 0..lane
-  const KeyLayout kl = a.kl;
-  const uint64_t *__restrict__ key = a.key;
-  float *score = a.score;
-  uint32_t *pred = a.pred;
-  for (uint32_t tile = warp; tile < n_tiles; tile += n_warps) {
-    const uint32_t cnt = a.link_count[tile];
-    const uint32_t *list = a.link_list + (size_t)tile * kPrepTile;
-    for (uint32_t c0 = 0; c0 < cnt; c0 += 32) {
-      const uint32_t c = c0 + lane;
-      const bool have = c < cnt;
-      const uint32_t i = have ? list[c] : 0u;
-      bool todo = have && (__ldcg(pred + i) & kPending);
-      uint64_t sg = 0;
-      int32_t ti = 0, qi = 0;
-      float ci = 0.0f, init = 0.0f;
-      if (todo) {
-        const uint64_t k = key[i];
-        sg = kl.seg(k);
-        ti = (int32_t)kl.target(k);
-        qi = (int32_t)kl.query(k);
-        ci = a.coef[i];
-        init = __ldcg(score + i);  // 6 * coef from k_chain_prep = chaining_scores[anchor_index]
-      }
-      const uint32_t lo = i > (uint32_t)kBand ? i - kBand : 0u;  // the segment start ends the walk earlier
-      for (int iter = 0; iter < kDpIters && __any_sync(full, todo); ++iter) {
-        // ---- every lane on its own, at most kDpShort predecessors
-        float M = init;
-        uint32_t best = i, jb = i;
-        int S = 0;  // num_skips
-        bool defer = false, done = !todo;
-        for (int g = 0; g < kDpShort / kDpGroup && !done; ++g) {
-          // four at a time: the key loads of a group are independent, so the walk pays one
-          // memory round trip per group instead of one per predecessor
-          const uint32_t m = min(jb - lo, (uint32_t)kDpGroup);
-          if (m == 0) {
-            done = true;
-            break;
-          }
-          uint64_t kk[kDpGroup];
-#pragma unroll
-          for (int u = 0; u < kDpGroup; ++u) kk[u] = (uint32_t)u < m ? key[jb - 1u - (uint32_t)u] : 0ull;
-#pragma unroll
-          for (int u = 0; u < kDpGroup; ++u) {
-            if (done || (uint32_t)u >= m) break;
-            const uint32_t j = jb - 1u - (uint32_t)u;
-            const uint64_t kj = kk[u];
-            if (kl.seg(kj) != sg) {  // first anchor of the segment passed
-              done = true;
-              break;
-            }
-            const int32_t pt = (int32_t)kl.target(kj), pq = (int32_t)kl.query(kj);
-            if (pq == qi || pt == ti) continue;
-            if (pt + kMaxTargetGap < ti) {
-              done = true;
-              break;
-            }
-            const int32_t dt = ti - pt, dq = qi - pq;
-            if (dq < 0) continue;
-            float cur = 0.0f;
-            if (gap_compatible(dt, dq)) {
-              if (__ldcg(pred + j) & kPending) {
-                defer = true;
-                done = true;
-                break;
-              }
-              cur = __fadd_rn(__ldcg(score + j), __fmul_rn((float)min(min(dt, dq), kDim), ci));
-            }
-            if (cur > M) {
-              M = cur;
-              best = j;
-              --S;
-            } else if (++S > kMaxSkips) {
-              done = true;
-              break;
-            }
-          }
-          jb -= m;
-          if (jb <= lo) done = true;
-        }
-        // ---- walks that are not over yet: the whole warp, 32 predecessors per step
-        unsigned longm = __ballot_sync(full, todo && !done);
-        while (longm) {
-          const int src = __ffs(longm) - 1;
-          longm &= longm - 1;
-          const uint32_t ii = __shfl_sync(full, i, src), loi = __shfl_sync(full, lo, src);
-          const int32_t tii = __shfl_sync(full, ti, src), qii = __shfl_sync(full, qi, src);
-          const float cii = __shfl_sync(full, ci, src);
-          const uint32_t sgl = __shfl_sync(full, (uint32_t)sg, src), sgh = __shfl_sync(full, (uint32_t)(sg >> 32), src);
-          const uint64_t sgi = ((uint64_t)sgh << 32) | sgl;
-          float Mi = __shfl_sync(full, M, src);
-          uint32_t bi = __shfl_sync(full, best, src);
-          int Si = __shfl_sync(full, S, src);
-          bool dfr = false;
-          for (uint32_t jc = __shfl_sync(full, jb, src);; jc -= 32) {  // predecessors jc-1 .. jc-32
-            // my predecessor: >= 0 candidate score (counted), -1 continue, -2 lookback ends,
-            // -3 gap-compatible but still pending
-            float cd = -2.0f;
-            if (jc >= loi + 1u + (uint32_t)lane) {
-              const uint32_t j = jc - 1u - (uint32_t)lane;
-              const uint64_t kj = key[j];
-              const int32_t pt = (int32_t)kl.target(kj), pq = (int32_t)kl.query(kj);
-              const int32_t dt = tii - pt, dq = qii - pq;
-              if (kl.seg(kj) != sgi) cd = -2.0f;
-              else if (pq == qii || pt == tii) cd = -1.0f;
-              else if (pt + kMaxTargetGap < tii) cd = -2.0f;
-              else if (dq < 0) cd = -1.0f;
-              else if (gap_compatible(dt, dq)) {
-                if (__ldcg(pred + j) & kPending) cd = -3.0f;
-                else cd = __fadd_rn(__ldcg(score + j), __fmul_rn((float)min(min(dt, dq), kDim), cii));
-              } else cd = 0.0f;
-            }
-            // a pending predecessor ends the block like the end of the lookback would; whether the
-            // walk really reaches it is decided below
-            const unsigned pendm = __ballot_sync(full, cd == -3.0f);
-            const int first_pend = pendm ? __ffs(pendm) - 1 : 32;
-            if (lane >= first_pend) cd = -2.0f;
-            // resolve the 32 predecessors in order (lane 0 = most recent)
-            const bool counted = cd >= 0.0f;
-            const unsigned cntm = __ballot_sync(full, counted);
-            unsigned impm = 0u;
-            if (__ballot_sync(full, cd > Mi)) {
-              float pm = counted ? cd : 0.0f;  // inclusive prefix max of the candidate scores
-#pragma unroll
-              for (int d = 1; d < 32; d <<= 1) {
-                const float t = __shfl_up_sync(full, pm, d);
-                if (lane >= d) pm = fmaxf(pm, t);
-              }
-              float ex = __shfl_up_sync(full, pm, 1);
-              ex = fmaxf(lane == 0 ? 0.0f : ex, Mi);
-              impm = __ballot_sync(full, counted && cd > ex);
-            }
-            const int Sl = Si + __popc(cntm & ~impm & le) - __popc(impm & le);
-            const bool stop_here = (counted && !((impm >> lane) & 1u) && Sl > kMaxSkips) || cd == -2.0f;
-            const unsigned stopm = __ballot_sync(full, stop_here);
-            const unsigned below = stopm ? ((stopm & (0u - stopm)) - 1u) : full;
-            const unsigned imp_b = impm & below;
-            if (imp_b) {
-              const int L = 31 - __clz(imp_b);
-              Mi = __shfl_sync(full, cd, L);
-              bi = jc - 1u - (uint32_t)L;
-            }
-            if (stopm) {
-              // stopped AT the first pending predecessor: the walk reaches it, so the anchor waits
-              dfr = first_pend < 32 && (__ffs(stopm) - 1) == first_pend;
-              break;
-            }
-            Si += __popc(cntm & ~impm) - __popc(impm);
-          }
-          if (lane == src) {
-            M = Mi;
-            best = bi;
-            defer = dfr;
-            done = true;
-          }
-        }
-        if (todo && !defer) {
-          score[i] = M;
-          __threadfence();
-          pred[i] = best;  // clears kPending
-          todo = false;
-        }
-        __syncwarp(full);
-      }
-    }
-  }
-}
-
+// A warp owns a segment and takes its linked anchors 32 at a time, one per lane.
+//  * Thread-parallel passes: every lane runs the reference's lookback for its own anchor.  An
+//    anchor's score only depends on the scores of its gap-compatible predecessors; if one of
+//    them is still pending (a linked anchor earlier in the same 32) the lane defers, otherwise
+//    its result is final.  Background hits form chains of 2-3 anchors, so two passes settle
+//    almost everything.
+//  * What is still pending after that (true-locus clusters, where every anchor links to the
+//    previous one) is settled in order by the whole warp: lanes load 32 consecutive predecessors
+//    coalesced, score one each, and the sequential rules (continue/break, running best, +-1 skip
+//    counter with its > 25 break) are resolved with a prefix-max scan and ballots.
 __device__ __forceinline__ void dp_segment(const ChainArgs &a, const uint32_t slot, const int lane) {
   const unsigned full = 0xffffffffu;
   const unsigned le = (2u << lane) - 1u;  // lanes 0..lane
@@ -557,24 +385,76 @@ __device__ __forceinline__ void dp_segment(const ChainArgs &a, const uint32_t sl
       const bool valid = c < cnt && i >= s && i < e;
       if (!__ballot_sync(full, valid)) continue;
       int32_t ti = 0, qi = 0;
-      float ci = 0.0f, M = 0.0f;
+      float ci = 0.0f, init = 0.0f, M = 0.0f;
       uint32_t lo = 0;
-      bool todo = false;
       if (valid) {
-        M = score[i];  // final, or 6 * coef from k_chain_prep while the anchor is pending
-        todo = (pred[i] & kPending) != 0u;
+        const uint64_t k = key[i];
+        ti = (int32_t)kl.target(k);
+        qi = (int32_t)kl.query(k);
+        ci = a.coef[i];
+        init = score[i];  // 6 * coef from k_chain_prep = chaining_scores[anchor_index]
         lo = (i - s > (uint32_t)kBand) ? i - kBand : s;
       }
-      // ---- what the parallel passes left, in order, by the whole warp
-      unsigned left = __ballot_sync(full, todo);
-      if (left) {
+      bool todo = valid;
+      // ---- thread-parallel passes
+      for (int pass = 0; pass < a.dp_passes; ++pass) {
         if (todo) {
-          const uint64_t k = key[i];
-          ti = (int32_t)kl.target(k);
-          qi = (int32_t)kl.query(k);
-          ci = a.coef[i];
+          M = init;
+          uint32_t best = i;
+          int S = 0;  // num_skips
+          bool defer = false;
+          // predecessors four at a time: the key loads of a group are independent, so the walk
+          // pays one memory round trip per group instead of one per predecessor
+          bool done = false;
+          for (uint32_t jb = i; jb > lo && !done;) {
+            const uint32_t m = min(jb - lo, (uint32_t)kDpGroup);
+            uint64_t kk[kDpGroup];
+#pragma unroll
+            for (int u = 0; u < kDpGroup; ++u) kk[u] = (uint32_t)u < m ? key[jb - 1u - (uint32_t)u] : 0ull;
+#pragma unroll
+            for (int u = 0; u < kDpGroup; ++u) {
+              if (done || (uint32_t)u >= m) break;
+              const uint32_t j = jb - 1u - (uint32_t)u;
+              const uint64_t kj = kk[u];
+              const int32_t pt = (int32_t)kl.target(kj), pq = (int32_t)kl.query(kj);
+              if (pq == qi || pt == ti) continue;
+              if (pt + kMaxTargetGap < ti) {
+                done = true;
+                break;
+              }
+              const int32_t dt = ti - pt, dq = qi - pq;
+              if (dq < 0) continue;
+              float cur = 0.0f;
+              if (gap_compatible(dt, dq)) {
+                if (pred[j] & kPending) {
+                  defer = true;
+                  done = true;
+                  break;
+                }
+                cur = __fadd_rn(score[j], __fmul_rn((float)min(min(dt, dq), kDim), ci));
+              }
+              if (cur > M) {
+                M = cur;
+                best = j;
+                --S;
+              } else if (++S > kMaxSkips) {
+                done = true;
+                break;
+              }
+            }
+            jb -= m;
+          }
+          if (!defer) {
+            score[i] = M;
+            pred[i] = best;  // clears kPending
+            todo = false;
+          }
         }
+        __syncwarp(full);  // settled scores are visible to the lanes that deferred
+        if (!__ballot_sync(full, todo)) break;
       }
+      // ---- what is left, in order, by the whole warp
+      unsigned left = __ballot_sync(full, todo);
       while (left) {
         const int src = __ffs(left) - 1;
         left &= left - 1;
@@ -582,7 +462,7 @@ __device__ __forceinline__ void dp_segment(const ChainArgs &a, const uint32_t sl
         const int32_t tii = __shfl_sync(full, ti, src), qii = __shfl_sync(full, qi, src);
         const float cii = __shfl_sync(full, ci, src);
         const uint32_t loi = __shfl_sync(full, lo, src);
-        float Mi = __shfl_sync(full, M, src);
+        float Mi = __shfl_sync(full, init, src);
         uint32_t best = ii;
         int S = 0;
         for (uint32_t jb = ii;; jb -= 32) {  // block of predecessors jb-1 .. jb-32

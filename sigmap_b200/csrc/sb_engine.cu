@@ -1052,10 +1052,6 @@ static int run_step(smb_ctx *ctx, SlotSpace &sp, const StepEntries &en, StepSour
   ca.link_count = w.link_count.p;
   k_chain_prep<<<n_tiles, kPrepThreads, 0, s>>>(ca);
   LAUNCH_CHECK();
-  for (int pass = 0; pass < ctx->dp_passes; ++pass) {
-    k_dp_pass<<<ctx->n_sm * 6u, kDpPassThreads, 0, s>>>(ca);
-    LAUNCH_CHECK();
-  }
   {
     const unsigned dp_blocks = (unsigned)(((uint64_t)ca.n_slots * 32 + kDpThreads - 1) / kDpThreads);
     if (ctx->dp_dynamic)
