@@ -298,6 +298,10 @@ int smbh_pt_write(const char *prefix, const uint64_t *pos, const float *val, siz
                   int dim, int max_leaf);
 int smbh_pt_read(const char *prefix, uint64_t **pos, float **val, size_t *n, int *dim,
                  int *max_leaf);
+/* <prefix>.si: a KD-tree over the window points in the layout of nanoflann's saveIndex_
+ * (nanoflann.hpp:1051-1058), so that the reference's own `sigmap -m` (SpatialIndex::Load,
+ * spatial_index.cc:132-163) can load an index written by this program.  This library never reads it. */
+int smbh_si_write(const char *prefix, const float *val, size_t n_points, int dim, int max_leaf);
 void smbh_free(void *p);
 /* BLOW5 (slow5lib 0.2.0 binary layout, uncompressed or zlib records) */
 typedef struct smbh_reads {

@@ -214,6 +214,7 @@ PROTOTYPES = {
     "smbh_pt_write": (C.c_int, [C.c_char_p, u64p, f32p, C.c_size_t, C.c_int, C.c_int]),
     "smbh_pt_read": (C.c_int, [C.c_char_p, C.POINTER(u64p), C.POINTER(f32p),
                                C.POINTER(C.c_size_t), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "smbh_si_write": (C.c_int, [C.c_char_p, f32p, C.c_size_t, C.c_int, C.c_int]),
     "smbh_free": (None, [C.c_void_p]),
     "smbh_blow5_write": (C.c_int, [C.c_char_p, charpp, i16p, u64p, C.c_size_t, C.c_double,
                                    C.c_double, C.c_double, C.c_double]),

@@ -303,3 +303,125 @@ extern "C" void smbh_cloud_part_free(smbh_cloud_part *p) {
   free(p->run_first);
   memset(p, 0, sizeof *p);
 }
+
+// ---------------------------------------------------------------------------------------------
+// <prefix>.si: a KD-tree over the window points in the on-disk layout of nanoflann 1.3.2's
+// saveIndex_ (nanoflann.hpp:1051-1058, written by SpatialIndex::Save, spatial_index.cc:105-130), so
+// that an index built by this program can be loaded by the reference's `sigmap -m`:
+//   size_t m_size (= points - dim + 1), int dim, vector<{float low, high}> root_bbox,
+//   size_t leaf_max_size, vector<size_t> vind, then the nodes in pre-order, 32 bytes each:
+//   union {leaf: size_t left, right | inner: int divfeat; float divlow, divhigh}, two child pointers
+//   (only tested for NULL by load_tree, nanoflann.hpp:1035-1044).
+// The tree is this program's own (balanced median splits on the widest dimension; nanoflann splits
+// at the middle value): searchLevel (nanoflann.hpp:1347-1410) only needs every point of child1 to
+// be <= divlow and every point of child2 >= divhigh in dimension divfeat, and the exact radius
+// search returns the same set from any valid tree.  (The order of the hits, which the 5 000-hit cap
+// of spatial_index.cc:371-372 depends on, is the tree's -- as it is for any other builder.)
+namespace {
+
+struct SiNode {  // sizeof == 32, as nanoflann's Node on LP64
+  union {
+    struct { uint64_t left, right; } lr;
+    struct { int32_t divfeat; float divlow, divhigh; } sub;
+  } u;
+  uint64_t child1, child2;
+};
+static_assert(sizeof(SiNode) == 32, "nanoflann node layout");
+
+struct SiBuilder {
+  const float *val;
+  int dim;
+  size_t leaf_max;
+  std::vector<uint64_t> vind;
+  // nodes of a subtree in pre-order; subtrees are built independently and spliced
+  void build(size_t l, size_t r, std::vector<SiNode> &out) {
+    SiNode nd;
+    memset(&nd, 0, sizeof nd);
+    if (r - l <= leaf_max) {
+      nd.u.lr.left = l;
+      nd.u.lr.right = r;
+      out.push_back(nd);
+      return;
+    }
+    // widest dimension of the points' own bounding box
+    float lo[16], hi[16];
+    for (int d = 0; d < dim; ++d) {
+      lo[d] = 3.0e38f;
+      hi[d] = -3.0e38f;
+    }
+    for (size_t i = l; i < r; ++i) {
+      const float *v = val + vind[i];
+      for (int d = 0; d < dim; ++d) {
+        lo[d] = std::min(lo[d], v[d]);
+        hi[d] = std::max(hi[d], v[d]);
+      }
+    }
+    int cut = 0;
+    for (int d = 1; d < dim; ++d)
+      if (hi[d] - lo[d] > hi[cut] - lo[cut]) cut = d;
+    const size_t mid = l + (r - l) / 2;
+    std::nth_element(vind.begin() + l, vind.begin() + mid, vind.begin() + r,
+                     [&](uint64_t a, uint64_t b) { return val[a + cut] < val[b + cut]; });
+    float divlow = -3.0e38f;
+    for (size_t i = l; i < mid; ++i) divlow = std::max(divlow, val[vind[i] + cut]);
+    nd.u.sub.divfeat = cut;
+    nd.u.sub.divlow = divlow;                 // max of child1
+    nd.u.sub.divhigh = val[vind[mid] + cut];  // min of child2 (the nth element)
+    nd.child1 = nd.child2 = 1;                // non-NULL
+    const size_t at = out.size();
+    out.push_back(nd);
+    if (r - l >= (size_t)1 << 16) {
+      // big subtrees: the two halves in parallel, spliced in pre-order
+      std::vector<SiNode> left, right;
+#pragma omp task shared(left) if (r - l >= (size_t)1 << 18)
+      build(l, mid, left);
+      build(mid, r, right);
+#pragma omp taskwait
+      out.insert(out.end(), left.begin(), left.end());
+      out.insert(out.end(), right.begin(), right.end());
+    } else {
+      build(l, mid, out);
+      build(mid, r, out);
+    }
+    (void)at;
+  }
+};
+
+}  // namespace
+
+extern "C" int smbh_si_write(const char *prefix, const float *val, size_t n_points, int dim, int max_leaf) {
+  if (dim < 1 || dim > 16 || max_leaf < 1 || n_points < (size_t)dim) return SMB_ERR_ARG;
+  const size_t m = n_points - (size_t)dim + 1;  // window points (sigmap_adaptor.h:89-91)
+  SiBuilder b;
+  b.val = val;
+  b.dim = dim;
+  b.leaf_max = (size_t)max_leaf;
+  b.vind.resize(m);
+  for (size_t i = 0; i < m; ++i) b.vind[i] = i;
+  std::vector<SiNode> nodes;
+#pragma omp parallel
+#pragma omp single
+  b.build(0, m, nodes);
+  // root bounding box: exact, over all window points (computeInitialDistances uses it)
+  std::vector<float> box(2 * (size_t)dim);
+  for (int d = 0; d < dim; ++d) {
+    float lo = 3.0e38f, hi = -3.0e38f;
+    for (size_t i = 0; i < m; ++i) {
+      lo = std::min(lo, val[i + d]);
+      hi = std::max(hi, val[i + d]);
+    }
+    box[2 * d] = lo;
+    box[2 * d + 1] = hi;
+  }
+  const std::string path = std::string(prefix) + ".si";
+  FILE *f = fopen(path.c_str(), "wb");
+  if (!f) return SMB_ERR_IO;
+  const uint64_t m64 = m, dim64 = (uint64_t)dim, leaf64 = (uint64_t)max_leaf;
+  const int32_t dim32 = dim;
+  bool ok = fwrite(&m64, 8, 1, f) == 1 && fwrite(&dim32, 4, 1, f) == 1 && fwrite(&dim64, 8, 1, f) == 1 &&
+            fwrite(box.data(), sizeof(float), box.size(), f) == box.size() && fwrite(&leaf64, 8, 1, f) == 1 &&
+            fwrite(&m64, 8, 1, f) == 1 && fwrite(b.vind.data(), 8, m, f) == m &&
+            fwrite(nodes.data(), sizeof(SiNode), nodes.size(), f) == nodes.size();
+  ok = (fclose(f) == 0) && ok;
+  return ok ? SMB_OK : SMB_ERR_IO;
+}

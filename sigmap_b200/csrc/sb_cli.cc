@@ -174,6 +174,10 @@ int build_index(const Args &a) {
   fprintf(stderr, "Collected %zu points.\n", n);
   if (smbh_pt_write(a.output.c_str(), pos, val, n, a.dimension, a.max_leaf))
     die("Cannot write index file!");
+  // <prefix>.si: not read by this program (the flat device index is built from .pt); written so
+  // that the reference's own `sigmap -m` can use the index
+  if (smbh_si_write(a.output.c_str(), val, n, a.dimension, a.max_leaf))
+    die("Cannot write index file!");
   smbh_free(pos);
   smbh_free(val);
   smbh_fasta_free(&fa);

@@ -193,6 +193,12 @@ def write_pt(prefix, pos, val, dim=6, max_leaf=20):
                                dim, max_leaf), "smbh_pt_write")
 
 
+def write_si(prefix, val, dim=6, max_leaf=20):
+    """<prefix>.si in nanoflann's layout, for the reference's own `sigmap -m` (we never read it)."""
+    val = np.ascontiguousarray(val, np.float32)
+    _check(F.lib.smbh_si_write(prefix.encode(), F.ptr(val, F.f32p), len(val), dim, max_leaf), "smbh_si_write")
+
+
 def read_pt(prefix):
     pp, vp = F.u64p(), F.f32p()
     n, dim, ml = C.c_size_t(), C.c_int(), C.c_int()

@@ -62,3 +62,43 @@ def test_restatement_rows_equal_live_reference_rows(port, ref, host, noisy, tmp_
     assert mapped >= ds.reads.n // 2
     if mode == "default":
         assert chunks > ds.reads.n  # the noise makes some reads need more than one chunk
+
+
+def test_reference_loads_and_uses_our_si(host, model, ref, port, tmp_path):
+    """`sigmap -i` of this repo writes <prefix>.pt and <prefix>.si; the UNMODIFIED reference must be
+    able to load them (SpatialIndex::Load, spatial_index.cc:132-163) and map with them exactly as
+    with an index it built itself: same radius-search hit sets, same PAF."""
+    if ref is None:
+        pytest.skip("oracle/_ref not built")
+    from conftest import Dataset, paf_cols
+    from sigmap_b200.host import MODEL_PATH
+    ds = Dataset(host, model, tmp_path, [180000, 90000], 40, seed=17)
+    host.write_si(ds.prefix, ds.val)                      # next to the .pt the fixture wrote
+    own = str(tmp_path / "own")
+    r = ref.cli(["-i", "-r", ds.fasta, "-p", MODEL_PATH, "-o", own])
+    assert r.returncode == 0, r.stderr[-300:]
+    assert open(own + ".pt", "rb").read() == open(ds.prefix + ".pt", "rb").read()
+    # stage level: the reference's radiusSearch over OUR tree = brute force
+    h = ref.index_load(ds.prefix)
+    n_hits = 0
+    for rd in range(3):
+        f = port.generate_events(ds.pa(port, rd)[:4000])
+        for p in range(2, len(f) - 5, 16):
+            q = f[p:p + 6]
+            ri, rdist = ref.radius_search(h, q)
+            ei, ed = port.radius_search(ds.val, q)
+            o = np.argsort(ri)
+            keep = np.abs(ed - np.float32(0.08)) > 1e-5
+            rkeep = np.abs(rdist[o] - np.float32(0.08)) > 1e-5
+            assert np.array_equal(ri[o][rkeep], ei[keep])
+            n_hits += len(ei)
+    ref.index_free(h)
+    assert n_hits > 100
+    # whole path: the reference CLI with our index files vs with its own
+    outs = []
+    for prefix in (ds.prefix, own):
+        out = str(tmp_path / (os.path.basename(prefix) + ".paf"))
+        r = ref.cli(["-m", "-r", ds.fasta, "-p", MODEL_PATH, "-x", prefix, "-s", ds.sigdir, "-o", out, "-t", "4"])
+        assert r.returncode == 0, r.stderr[-300:]
+        outs.append({l.split("\t")[0]: paf_cols(l) for l in open(out)})
+    assert len(outs[0]) == ds.reads.n and outs[0] == outs[1]
