@@ -207,7 +207,6 @@ __device__ __forceinline__ float distance_coefficient(float dist, double radius)
 }
 
 constexpr int kPrepHalo = 128;     // predecessors staged in shared memory ahead of the tile
-constexpr int kPrepShort = 12;     // predecessors a lane checks itself before the warp takes the range over
 constexpr int kPrepThreads = 256;  // kPrepTile / kPrepThreads anchors per thread
 constexpr uint32_t kPending = 0x40000000u;  // pred[] bit: linked anchor not yet settled by the DP
 
@@ -239,10 +238,9 @@ __global__ void __launch_bounds__(kPrepThreads, 8) k_chain_prep(ChainArgs a) {
   for (int sub = 0; sub < kSubTiles; ++sub) {
     const int local = sub * kPrepThreads + threadIdx.x;
     const uint32_t i = tile0 + local;
-    bool linked = false, open = false;
-    int d_next = 0;
-    const int me = kPrepHalo + local;
+    bool linked = false;
     if (i < n) {
+      const int me = kPrepHalo + local;
       const int4 mine = s_a[me];
       const uint32_t sg = (uint32_t)mine.x;
       const int32_t ti = mine.y, qi = mine.z;
@@ -254,15 +252,12 @@ __global__ void __launch_bounds__(kPrepThreads, 8) k_chain_prep(ChainArgs a) {
         }
         if (i == n - 1) a.seg[sg].end = n;
       }
-      // position-only link test over the maximal lookback range: the lane looks at the nearest
-      // kPrepShort predecessors itself; a range that goes on beyond them is finished by the whole
-      // warp below (ranges are very uneven -- ~10 anchors for a background hit, hundreds next to a
-      // true-locus cluster -- and a warp waits for its slowest lane)
+      // position-only link test over the maximal lookback range
       const int depth = (int)min(i, (uint32_t)kBand);
-      const int lim = min(min(depth, me), kPrepShort);
+      const int in_smem = min(depth, me);
       int d = 1;
-      open = true;  // the range continues past what has been looked at
-      for (; d <= lim; ++d) {
+      bool open = true;  // the range continues past what has been looked at
+      for (; d <= in_smem; ++d) {
         const int4 p = s_a[me - d];
         if (p.x != mine.x || p.y + kMaxTargetGap < ti) {
           open = false;
@@ -274,41 +269,17 @@ __global__ void __launch_bounds__(kPrepThreads, 8) k_chain_prep(ChainArgs a) {
           break;
         }
       }
-      if (d > depth) open = false;
-      d_next = d;
-    }
-    // ---- ranges still open: the warp walks them 32 predecessors per step (shared memory while
-    // the staged halo lasts, global memory beyond it)
-    for (unsigned openm = __ballot_sync(0xffffffffu, open); openm; openm &= openm - 1) {
-      const int src = __ffs(openm) - 1;
-      const int me_s = __shfl_sync(0xffffffffu, me, src);
-      const uint32_t i_s = __shfl_sync(0xffffffffu, i, src);
-      const int4 m_s = s_a[me_s];
-      const int depth_s = (int)min(i_s, (uint32_t)kBand);
-      bool res = false;
-      for (int d0 = __shfl_sync(0xffffffffu, d_next, src); d0 <= depth_s; d0 += 32) {
-        const int dd = d0 + lane;
-        bool endf = dd > depth_s, comp = false;
-        if (!endf) {
-          int4 p;
-          if (dd <= me_s) {
-            p = s_a[me_s - dd];
-          } else {
-            const uint64_t kj = a.key[i_s - (uint32_t)dd];
-            p = make_int4((int)(uint32_t)kl.seg(kj), (int32_t)kl.target(kj), (int32_t)kl.query(kj), 0);
+      if (open) {  // rare: deeper than what is staged
+        for (; d <= depth; ++d) {
+          const uint64_t kj = a.key[i - d];
+          const int32_t pt = (int32_t)kl.target(kj);
+          if ((uint32_t)kl.seg(kj) != sg || pt + kMaxTargetGap < ti) break;
+          if (gap_compatible(ti - pt, qi - (int32_t)kl.query(kj))) {
+            linked = true;
+            break;
           }
-          endf = p.x != m_s.x || p.y + kMaxTargetGap < m_s.y;
-          comp = !endf && gap_compatible(m_s.y - p.y, m_s.z - p.z);
-        }
-        const unsigned cm = __ballot_sync(0xffffffffu, comp), em = __ballot_sync(0xffffffffu, endf);
-        if (cm | em) {  // whichever comes first, going backwards
-          res = cm && (!em || __ffs(cm) < __ffs(em));
-          break;
         }
       }
-      if (lane == src) linked = res;
-    }
-    if (i < n) {
       const float ci = distance_coefficient(a.dist[i], (double)a.radius);
       a.coef[i] = ci;
       a.score[i] = __fmul_rn(ci, (float)kDim);
@@ -553,6 +524,118 @@ __device__ __forceinline__ void dp_segment(const ChainArgs &a, const uint32_t sl
     a.seg_max[slot] = runmax;
   }
 }
+
+// ---- small batches (read-until rounds): the same lookback for every linked anchor of the step at
+// once.  With a few hundred chunks there are only a few hundred segments, and a warp walking a
+// segment's ~1 500 linked anchors 32 at a time is a 50-step serial chain: the round's latency.
+// Here persistent warps take k_chain_prep TILES instead, so the anchors of one segment are walked
+// by many warps at once.  An anchor's score only depends on the scores of its gap-compatible
+// predecessors; if the lookback meets one that is still pending the lane defers (<= 3 tries, then
+// it is left to the in-order kernel), otherwise its result is final whatever other warps are doing,
+// so results do not depend on timing.  Scores of other warps' anchors are read past L1 (ld.cg)
+// after their pending bit was seen cleared; the writer orders score before bit with a fence.  On
+// large batches this loses to the in-segment pass (every cross-warp score is an L2 round trip in
+// the middle of a walk; measured 7 ms against 5.5 ms on 360 M anchors), so the host only launches
+// it below kDpPassMaxSlots segments.
+constexpr int kDpPassThreads = 256;
+constexpr uint32_t kDpPassMaxSlots = 8192;
+constexpr int kDpIters = 3;      // tries per anchor inside its warp before it is left to the in-order kernel
+
+__global__ void __launch_bounds__(kDpPassThreads, 6) k_dp_pass(ChainArgs a) {
+  if (a.ctr->abort) return;
+  const uint32_t n = (uint32_t)a.ctr->n_anchors;
+  const uint32_t n_tiles = (n + kPrepTile - 1) / kPrepTile;
+  const int lane = threadIdx.x & 31;
+  const uint32_t warp = (blockIdx.x * kDpPassThreads + threadIdx.x) >> 5;
+  const uint32_t n_warps = (gridDim.x * kDpPassThreads) >> 5;
+  const unsigned full = 0xffffffffu;
+  const KeyLayout kl = a.kl;
+  const uint64_t *__restrict__ key = a.key;
+  float *score = a.score;
+  uint32_t *pred = a.pred;
+  for (uint32_t tile = warp; tile < n_tiles; tile += n_warps) {
+    const uint32_t cnt = a.link_count[tile];
+    const uint32_t *list = a.link_list + (size_t)tile * kPrepTile;
+    for (uint32_t c0 = 0; c0 < cnt; c0 += 32) {
+      const uint32_t c = c0 + lane;
+      const bool have = c < cnt;
+      const uint32_t i = have ? list[c] : 0u;
+      bool todo = have && (__ldcg(pred + i) & kPending);
+      uint64_t sg = 0;
+      int32_t ti = 0, qi = 0;
+      float ci = 0.0f, init = 0.0f;
+      if (todo) {
+        const uint64_t k = key[i];
+        sg = kl.seg(k);
+        ti = (int32_t)kl.target(k);
+        qi = (int32_t)kl.query(k);
+        ci = a.coef[i];
+        init = __ldcg(score + i);  // 6 * coef from k_chain_prep = chaining_scores[anchor_index]
+      }
+      for (int iter = 0; iter < kDpIters && __any_sync(full, todo); ++iter) {
+        if (todo) {
+          float M = init;
+          uint32_t best = i;
+          int S = 0;  // num_skips
+          bool defer = false, done = false;
+          const uint32_t lo = i > (uint32_t)kBand ? i - kBand : 0u;  // the segment start ends the walk earlier
+          // predecessors four at a time: the key loads of a group are independent, so the walk
+          // pays one memory round trip per group instead of one per predecessor
+          for (uint32_t jb = i; jb > lo && !done;) {
+            const uint32_t m = min(jb - lo, (uint32_t)kDpGroup);
+            uint64_t kk[kDpGroup];
+#pragma unroll
+            for (int u = 0; u < kDpGroup; ++u) kk[u] = (uint32_t)u < m ? key[jb - 1u - (uint32_t)u] : 0ull;
+#pragma unroll
+            for (int u = 0; u < kDpGroup; ++u) {
+              if (done || (uint32_t)u >= m) break;
+              const uint32_t j = jb - 1u - (uint32_t)u;
+              const uint64_t kj = kk[u];
+              if (kl.seg(kj) != sg) {  // first anchor of the segment passed
+                done = true;
+                break;
+              }
+              const int32_t pt = (int32_t)kl.target(kj), pq = (int32_t)kl.query(kj);
+              if (pq == qi || pt == ti) continue;
+              if (pt + kMaxTargetGap < ti) {
+                done = true;
+                break;
+              }
+              const int32_t dt = ti - pt, dq = qi - pq;
+              if (dq < 0) continue;
+              float cur = 0.0f;
+              if (gap_compatible(dt, dq)) {
+                if (__ldcg(pred + j) & kPending) {
+                  defer = true;
+                  done = true;
+                  break;
+                }
+                cur = __fadd_rn(__ldcg(score + j), __fmul_rn((float)min(min(dt, dq), kDim), ci));
+              }
+              if (cur > M) {
+                M = cur;
+                best = j;
+                --S;
+              } else if (++S > kMaxSkips) {
+                done = true;
+                break;
+              }
+            }
+            jb -= m;
+          }
+          if (!defer) {
+            score[i] = M;
+            __threadfence();
+            pred[i] = best;  // clears kPending
+            todo = false;
+          }
+        }
+        __syncwarp(full);
+      }
+    }
+  }
+}
+
 
 // Segments differ a lot in how many linked anchors they hold, so a fixed warp <-> segment
 // assignment leaves most warps of a block idle behind its slowest one: persistent warps take

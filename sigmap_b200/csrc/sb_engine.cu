@@ -248,6 +248,8 @@ struct smb_ctx {
   uint64_t g_total = 1;           // linear coordinates of the whole index (sum of the bucket spans)
   double part_fill = 0.70;        // share of a k_part_sort CTA's capacity an average part should fill
   int dp_passes = kDpFreePasses;  // SMB_DP_PASSES=n
+  uint32_t dp_pass_max_slots = kDpPassMaxSlots;  // SMB_DP_TILES=n: per-tile DP pass below n segments (0 = never)
+  uint32_t sort_queries_min = 200000;  // SMB_SORT_QUERIES_MIN=n: batches with fewer queries keep their natural order
   bool dp_dynamic = true;         // SMB_DP=static: warp w of the DP grid handles segment w
   unsigned dp_grid = 148 * 8;     // persistent DP grid: every block that fits on the device
   bool part_small = false;        // SMB_PART=small: four 52 KB k_part_sort CTAs per SM instead of two 105 KB ones
@@ -370,11 +372,37 @@ static int launch_search(smb_ctx *ctx, SearchArgs sa, uint32_t nq_max, cudaStrea
     LAUNCH_CHECK();
     return SMB_OK;
   }
+  CK(w.ovf_list.ensure(nq_max));
+  if (nq_max < ctx->sort_queries_min) {
+    // a small batch (a read-until round) fits the caches whatever the order: the queries keep their
+    // natural order (consecutive queries share an entry, so a flush serves several of them) and the
+    // round saves the key kernel and the five launches of the radix sort
+    if (!STAGE) {
+      CK(w.entry_info.ensure(sa.B));
+      k_entry_info<<<(sa.B + 255) / 256, 256, 0, s>>>(sa.feat_row, sa.entry_slot, sa.slots, sa.B, w.entry_info.p);
+      LAUNCH_CHECK();
+    }
+    sa.order = nullptr;
+    sa.nq_cap = 0xFFFFFFFFu;
+    sa.entry_info = w.entry_info.p;
+    sa.front_cap = std::min<uint32_t>(std::max<uint32_t>(ctx->front_cap, 72u), (uint32_t)kFrontCap);
+    sa.ovf_list = w.ovf_list.p;
+    sa.work = &ctx->d_ctr->work;
+    sa.grab = ctx->search_grab;
+    k_search_lean<STAGE><<<ctx->n_sm, kLeanWarps * 32, lean_smem(ctx->ix.smem_bytes), s>>>(ctx->ix, sa);
+    LAUNCH_CHECK();
+    sa.qlist = w.ovf_list.p;
+    sa.qlist_n = &ctx->d_ctr->n_overflow;
+    sa.work = &ctx->d_ctr->work2;
+    sa.grab = 0;
+    k_radius_search<STAGE><<<STAGE ? search_grid<true>(ctx) : ctx->search_grid_main, kSearchWarps * 32, gsm, s>>>(ctx->ix, sa);
+    LAUNCH_CHECK();
+    return SMB_OK;
+  }
   CK(w.qkey_a.ensure(nq_max));
   CK(w.qkey_b.ensure(nq_max));
   CK(w.qpay_a.ensure(nq_max));
   CK(w.qpay_b.ensure(nq_max));
-  CK(w.ovf_list.ensure(nq_max));
   if (STAGE) {
     k_query_keys_stage<<<(nq_max + 255) / 256, 256, 0, s>>>(sa.features, nq_max, ctx->ix.vmin, ctx->ix.inv_span,
                                                             w.qkey_a.p, w.qpay_a.p);
@@ -1052,6 +1080,10 @@ static int run_step(smb_ctx *ctx, SlotSpace &sp, const StepEntries &en, StepSour
   ca.link_count = w.link_count.p;
   k_chain_prep<<<n_tiles, kPrepThreads, 0, s>>>(ca);
   LAUNCH_CHECK();
+  if (ca.n_slots <= ctx->dp_pass_max_slots) {  // small batch: per-tile parallel pass first (latency)
+    k_dp_pass<<<ctx->n_sm * 6u, kDpPassThreads, 0, s>>>(ca);
+    LAUNCH_CHECK();
+  }
   {
     const unsigned dp_blocks = (unsigned)(((uint64_t)ca.n_slots * 32 + kDpThreads - 1) / kDpThreads);
     if (ctx->dp_dynamic)
@@ -1421,6 +1453,10 @@ static bool apply_option(smb_ctx *ctx, const char *name_in, const char *value) {
     ctx->part_small = strcmp(value, "small") == 0;
   } else if (name == "DP") {
     ctx->dp_dynamic = strcmp(value, "static") != 0;
+  } else if (name == "DP_TILES") {
+    ctx->dp_pass_max_slots = (uint32_t)std::max(atoi(value), 0);
+  } else if (name == "SORT_QUERIES_MIN") {
+    ctx->sort_queries_min = (uint32_t)std::max(atoi(value), 0);
   } else if (name == "DP_PASSES") {
     ctx->dp_passes = std::max(atoi(value), 0);
   } else if (name == "UPLOAD_SLICE_MB") {
@@ -1521,7 +1557,7 @@ int smb_create(smb_ctx **out, int device) {
                                 (int)part_sort_smem_bytes(kPartSortCapSmall, 2304))) != cudaSuccess)
     return bail("cudaFuncSetAttribute(k_part_sort)", e);
   for (const char *name : {"SORT", "SEARCH", "FRONT_CAP", "RUNS_CAP", "GRAB", "PART_FILL", "PART", "DP", "DP_PASSES",
-                           "EVENTS_OVERLAP", "EVENTS", "UPLOAD_SLICE_MB"})
+                           "DP_TILES", "SORT_QUERIES_MIN", "EVENTS_OVERLAP", "EVENTS", "UPLOAD_SLICE_MB"})
     if (const char *env = getenv((std::string("SMB_") + name).c_str())) apply_option(ctx, name, env);
   {
     int per_sm = 0, n_sm = 148;

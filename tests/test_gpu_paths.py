@@ -31,6 +31,10 @@ PATHS = [
     ("runs_cap", "8", lambda st: st["part_sort_steps"] < st["steps"]),   # run tables overflow -> radix sort
     ("search", "general", lambda st: st["overflow_queries"] == st["queries"]),
     ("front_cap", "72", lambda st: 0 < st["overflow_queries"] < st["queries"]),
+    ("sort_queries_min", "0", lambda st: True),    # Morton-ordered queries even on this small batch
+    ("sort_queries_min", "4000000000", lambda st: True),  # ... and never
+    ("dp_tiles", "0", lambda st: True),            # no per-tile DP pass (the large-batch configuration)
+    ("dp_tiles", "100000000", lambda st: True),    # ... and always
     ("grab", "1", lambda st: True),
     ("dp", "static", lambda st: True),
     ("dp_passes", "0", lambda st: True),   # the cooperative in-order DP path settles everything
@@ -40,7 +44,7 @@ PATHS = [
     ("events_overlap", "0", lambda st: True),
     ("part", "small", lambda st: st["part_sort_steps"] > 0),
 ]
-RESET = {"sort": "part", "runs_cap": "0", "search": "lean", "front_cap": "384", "grab": "0", "dp": "dynamic",
+RESET = {"sort_queries_min": "200000", "dp_tiles": "8192", "sort": "part", "runs_cap": "0", "search": "lean", "front_cap": "384", "grab": "0", "dp": "dynamic",
          "dp_passes": "1", "events": "auto", "events_overlap": "1", "part": "big"}
 
 
@@ -76,7 +80,8 @@ def test_radius_search_paths_agree_with_the_oracle(mapper, port, small):
     q = q[rng.permutation(len(q))]
     for radius in (0.08, 0.3):
         exp = [port.radius_search(small.val, x, radius=radius) for x in q[:160]]
-        for name, value in (("search", "lean"), ("search", "general"), ("front_cap", "72")):
+        for name, value in (("search", "lean"), ("search", "general"), ("front_cap", "72"),
+                            ("sort_queries_min", "0")):
             mapper.set_option(name, value)
             try:
                 off, idx, d2 = mapper.radiusSearch(q[:160], radius=radius, cap=1 << 24)
