@@ -393,13 +393,16 @@ def measure(args, rank, world, local, dist, light=False):
     replicate = world > 1 and not by_contig
     # read-sharded: only rank 0 builds the point cloud and the device index; the others receive the
     # index over NVLink (one ncclBroadcast on the library's own communicator)
-    H, model, ref, pos, val, reads = build_workload(args, rank, need_cloud=by_contig or not replicate or rank == 0)
+    # contig-sharded: a rank only ever builds its own part of the cloud (the genome-scale path)
+    H, model, ref, pos, val, reads = build_workload(args, rank, need_cloud=not by_contig and (not replicate or rank == 0))
     mapper = Mapper(local)  # raises if there is no CUDA device: no fallback
     t_bcast = None
     if by_contig:
         from sigmap_b200 import shard
         shard.nccl_join(mapper, dist)  # the library's own NCCL communicator, on its own stream
-        mapper.set_index_sharded(pos, val, shard.assign_contigs(ref.lengths, world))
+        part = H.build_point_cloud_part(ref, model[0], shard.assign_contigs(ref.lengths, world), rank)
+        mapper.set_index_part(part, ref.n)
+        part.close()
     elif replicate:
         from sigmap_b200 import shard
         shard.nccl_join(mapper, dist)
@@ -510,7 +513,7 @@ def measure(args, rank, world, local, dist, light=False):
     pipe_gbps = sum_over_ranks(pipeline_bytes) / (ms / 1000.0) / 1e9 / max(world, 1) if not by_contig else \
         pipeline_bytes / (ms / 1000.0) / 1e9
     counters = {k: int(sum_over_ranks(float(st[k])) // max(steps, 1)) for k in
-                ("samples", "events", "queries", "hits", "anchors", "capped_queries", "chunks", "steps", "linked",
+                ("samples", "events", "queries", "hits", "anchors", "capped_queries", "chunks", "steps", "linked", "pending",
                  "seg_sort_steps", "part_sort_steps", "overflow_queries", "sync_points")}
 
     out = {

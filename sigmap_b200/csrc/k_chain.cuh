@@ -58,8 +58,11 @@ struct ChainArgs {
   uint32_t n_slots;      // B << bbits
   uint32_t *link_list;   // [n_tiles * kPrepTile] indices of linked anchors, ascending per tile
   uint32_t *link_count;  // [n_tiles]
+  uint16_t *pend_list;   // [n_tiles * kPrepTile] of those, the ones k_chain_prep could not settle itself
+  uint32_t *pend_count;  //   (index inside the tile, ascending); [n_tiles]
   Counters *ctr;
   int dp_passes;         // thread-parallel passes of k_chain_dp before the in-order cooperative path
+  int prep_rounds;       // settle rounds inside k_chain_prep (0: every linked anchor is left to the DP kernels)
 };
 
 constexpr int kCarryThreads = 256;
@@ -209,12 +212,26 @@ __device__ __forceinline__ float distance_coefficient(float dist, double radius)
 constexpr int kPrepHalo = 128;     // predecessors staged in shared memory ahead of the tile
 constexpr int kPrepThreads = 256;  // kPrepTile / kPrepThreads anchors per thread
 constexpr uint32_t kPending = 0x40000000u;  // pred[] bit: linked anchor not yet settled by the DP
+constexpr int kPrepRounds = 2;     // settle rounds inside k_chain_prep
 
+// Phase 2 of k_chain_prep: the lookback itself for the linked anchors it can finish on its own.
+// 80-90 % of the linked anchors are background pairs and triples: their gap-compatible predecessors
+// are unlinked anchors (score final = 6 * coef) a few places back, all inside the tile that is
+// already unpacked in shared memory.  The tile's linked anchors, compacted, are taken one per
+// thread; a thread runs the reference's lookback (continue/break rules, running best, +-1 skip
+// counter with its > 25 break) over shared memory and settles its anchor iff every gap-compatible
+// predecessor it meets is final -- unlinked, or settled in an EARLIER round (rounds are separated
+// by barriers, so what a thread reads never depends on timing).  A predecessor in the halo (state
+// unknown), a pending one, or a walk that runs off the staged range defers the anchor: it stays
+// pending and goes to the tile's pending list for k_chain_dp, which then only walks the true-locus
+// chains.
 __global__ void __launch_bounds__(kPrepThreads, 8) k_chain_prep(ChainArgs a) {
-  // the tile's anchors and the kPrepHalo before it, unpacked: {segment id, target, query, -}
+  // the tile's anchors and the kPrepHalo before it, unpacked: {segment id, target, query, score bits}
   __shared__ int4 s_a[kPrepHalo + kPrepTile];
   constexpr int kSubTiles = kPrepTile / kPrepThreads;
   __shared__ uint32_t warp_cnt[kSubTiles][kPrepThreads / 32];  // linked anchors per (sub-tile, warp)
+  __shared__ uint16_t s_list[kPrepTile];  // the tile's linked anchors (index inside the tile), ascending
+  __shared__ uint8_t s_state[kPrepTile];  // 0 final (no predecessor), 0xFF pending, r settled in round r
   if (a.ctr->abort) return;
   const uint32_t n = (uint32_t)a.ctr->n_anchors;  // < 2^30
   const uint32_t tile0 = blockIdx.x * kPrepTile;
@@ -281,10 +298,13 @@ __global__ void __launch_bounds__(kPrepThreads, 8) k_chain_prep(ChainArgs a) {
         }
       }
       const float ci = distance_coefficient(a.dist[i], (double)a.radius);
+      const float init = __fmul_rn(ci, (float)kDim);
       a.coef[i] = ci;
-      a.score[i] = __fmul_rn(ci, (float)kDim);
+      a.score[i] = init;
       a.pred[i] = linked ? (i | kPending) : i;
+      s_a[me].w = __float_as_int(init);  // phase 1 readers only look at x, y, z
     }
+    s_state[local] = linked ? (uint8_t)0xFF : (uint8_t)0;
     link_mask[sub] = __ballot_sync(0xffffffffu, linked);
     if (lane == 0) warp_cnt[sub][wid] = __popc(link_mask[sub]);
   }
@@ -303,8 +323,10 @@ __global__ void __launch_bounds__(kPrepThreads, 8) k_chain_prep(ChainArgs a) {
     }
     const unsigned m = link_mask[sub];
     if (m & (1u << lane)) {
-      const uint32_t i = tile0 + sub * kPrepThreads + threadIdx.x;
-      a.link_list[(size_t)blockIdx.x * kPrepTile + at + before + __popc(m & ((1u << lane) - 1u))] = i;
+      const uint32_t local = sub * kPrepThreads + threadIdx.x;
+      const uint32_t at_list = at + before + __popc(m & ((1u << lane) - 1u));
+      a.link_list[(size_t)blockIdx.x * kPrepTile + at_list] = tile0 + local;
+      s_list[at_list] = (uint16_t)local;
     }
     at += sub_total;
     total += sub_total;
@@ -312,6 +334,86 @@ __global__ void __launch_bounds__(kPrepThreads, 8) k_chain_prep(ChainArgs a) {
   if (threadIdx.x == 0) {
     a.link_count[blockIdx.x] = total;
     if (total) atomicAdd(&a.ctr->n_linked, (unsigned long long)total);
+  }
+  if (total == 0) {
+    if (threadIdx.x == 0) a.pend_count[blockIdx.x] = 0;
+    return;
+  }
+  __syncthreads();  // s_list, s_state and the scores are complete
+
+  // ---- phase 2: settle rounds
+  for (int round = 1; round <= a.prep_rounds; ++round) {
+    for (uint32_t c = threadIdx.x; c < total; c += kPrepThreads) {
+      const int local = s_list[c];
+      if (s_state[local] != 0xFF) continue;
+      const int me = kPrepHalo + local;
+      const int4 mine = s_a[me];
+      const int32_t ti = mine.y, qi = mine.z;
+      const uint32_t i = tile0 + (uint32_t)local;
+      const float ci = a.coef[i];
+      float M = __int_as_float(mine.w);  // 6 * coef = chaining_scores[anchor_index]
+      uint32_t best = i;
+      int S = 0;  // num_skips
+      bool defer = false;
+      int x = me - 1;
+      for (; x >= 0; --x) {
+        const int4 p = s_a[x];
+        if (p.x != mine.x) break;  // the first anchor of the segment has been passed
+        if (p.z == qi || p.y == ti) continue;
+        if (p.y + kMaxTargetGap < ti) break;
+        const int32_t dt = ti - p.y, dq = qi - p.z;
+        if (dq < 0) continue;
+        float cur = 0.0f;
+        if (gap_compatible(dt, dq)) {
+          const int pl = x - kPrepHalo;
+          if (pl < 0 || s_state[pl] >= (uint32_t)round) {  // halo / pending / being settled right now
+            defer = true;
+            break;
+          }
+          cur = __fadd_rn(__int_as_float(p.w), __fmul_rn((float)min(min(dt, dq), kDim), ci));
+        }
+        if (cur > M) {
+          M = cur;
+          best = tile0 + (uint32_t)(x - kPrepHalo);
+          --S;
+        } else if (++S > kMaxSkips) {
+          break;
+        }
+      }
+      if (x < 0) defer = true;  // the range goes on before the staged halo
+      if (!defer) {
+        s_a[me].w = __float_as_int(M);
+        s_state[local] = (uint8_t)round;
+        a.score[i] = M;
+        a.pred[i] = best;  // clears kPending
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- what is still pending, compacted in order, for k_chain_dp / k_dp_pass
+  uint32_t pbase = 0;
+  for (uint32_t c0 = 0; c0 < total; c0 += kPrepThreads) {
+    const uint32_t c = c0 + threadIdx.x;
+    const uint32_t local = c < total ? s_list[c] : 0u;
+    const bool pend = c < total && s_state[local] == 0xFF;
+    const unsigned m = __ballot_sync(0xffffffffu, pend);
+    if (lane == 0) warp_cnt[0][wid] = __popc(m);
+    __syncthreads();
+    uint32_t before = 0, chunk_total = 0;
+#pragma unroll
+    for (int w = 0; w < kPrepThreads / 32; ++w) {
+      const uint32_t t = warp_cnt[0][w];
+      if (w < wid) before += t;
+      chunk_total += t;
+    }
+    if (pend) a.pend_list[(size_t)blockIdx.x * kPrepTile + pbase + before + __popc(m & ((1u << lane) - 1u))] = (uint16_t)local;
+    pbase += chunk_total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    a.pend_count[blockIdx.x] = pbase;
+    if (pbase) atomicAdd(&a.ctr->n_pending, (unsigned long long)pbase);
   }
 }
 
@@ -348,12 +450,13 @@ __device__ __forceinline__ void dp_segment(const ChainArgs &a, const uint32_t sl
   int ntop = 0;
 
   for (uint32_t tile = s / kPrepTile; tile * kPrepTile < e; ++tile) {
-    const uint32_t cnt = a.link_count[tile];
-    const uint32_t *list = a.link_list + (size_t)tile * kPrepTile;
-    for (uint32_t c0 = 0; c0 < cnt; c0 += 32) {
+    // ---- phase A: the lookback for the anchors k_chain_prep (and k_dp_pass) left pending
+    const uint32_t pcnt = a.pend_count[tile];
+    const uint16_t *plist = a.pend_list + (size_t)tile * kPrepTile;
+    for (uint32_t c0 = 0; c0 < pcnt; c0 += 32) {
       const uint32_t c = c0 + lane;
-      uint32_t i = c < cnt ? list[c] : 0xFFFFFFFFu;
-      const bool valid = c < cnt && i >= s && i < e;
+      uint32_t i = c < pcnt ? tile * kPrepTile + (uint32_t)plist[c] : 0xFFFFFFFFu;
+      const bool valid = c < pcnt && i >= s && i < e && (pred[i] & kPending);
       if (!__ballot_sync(full, valid)) continue;
       int32_t ti = 0, qi = 0;
       float ci = 0.0f, init = 0.0f, M = 0.0f;
@@ -363,7 +466,7 @@ __device__ __forceinline__ void dp_segment(const ChainArgs &a, const uint32_t sl
         ti = (int32_t)kl.target(k);
         qi = (int32_t)kl.query(k);
         ci = a.coef[i];
-        init = score[i];  // 6 * coef from k_chain_prep = chaining_scores[anchor_index]
+        init = score[i];  // still 6 * coef from k_chain_prep = chaining_scores[anchor_index]
         lo = (i - s > (uint32_t)kBand) ? i - kBand : s;
       }
       bool todo = valid;
@@ -485,10 +588,21 @@ __device__ __forceinline__ void dp_segment(const ChainArgs &a, const uint32_t sl
         }
         __syncwarp(full);  // visible to the later anchors of this batch
       }
-      // ---- running max and local end candidates (spatial_index.cc:542-549), lanes in order;
-      // the caller applies the max of the earlier buckets, which only shortens this list.
-      // Order: score desc, index desc (compare(), :11-20); a tie puts the later anchor first.
-      float pm = valid ? M : 0.0f;
+    }
+    // ---- phase B: running max and local end candidates (spatial_index.cc:542-549) over ALL linked
+    // anchors of the tile, lanes in order; the caller applies the max of the earlier buckets, which
+    // only shortens this list.  Order: score desc, index desc (compare(), :11-20); a tie puts the
+    // later anchor first.
+    __syncwarp(full);
+    const uint32_t cnt = a.link_count[tile];
+    const uint32_t *list = a.link_list + (size_t)tile * kPrepTile;
+    for (uint32_t c0 = 0; c0 < cnt; c0 += 32) {
+      const uint32_t c = c0 + lane;
+      const uint32_t i = c < cnt ? list[c] : 0xFFFFFFFFu;
+      const bool valid = c < cnt && i >= s && i < e;
+      if (!__ballot_sync(full, valid)) continue;
+      const float M = valid ? score[i] : 0.0f;
+      float pm = M;
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
         const float t = __shfl_up_sync(full, pm, d);
@@ -554,12 +668,12 @@ __global__ void __launch_bounds__(kDpPassThreads, 6) k_dp_pass(ChainArgs a) {
   float *score = a.score;
   uint32_t *pred = a.pred;
   for (uint32_t tile = warp; tile < n_tiles; tile += n_warps) {
-    const uint32_t cnt = a.link_count[tile];
-    const uint32_t *list = a.link_list + (size_t)tile * kPrepTile;
+    const uint32_t cnt = a.pend_count[tile];
+    const uint16_t *list = a.pend_list + (size_t)tile * kPrepTile;
     for (uint32_t c0 = 0; c0 < cnt; c0 += 32) {
       const uint32_t c = c0 + lane;
       const bool have = c < cnt;
-      const uint32_t i = have ? list[c] : 0u;
+      const uint32_t i = have ? tile * kPrepTile + (uint32_t)list[c] : 0u;
       bool todo = have && (__ldcg(pred + i) & kPending);
       uint64_t sg = 0;
       int32_t ti = 0, qi = 0;

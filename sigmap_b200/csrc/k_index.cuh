@@ -56,6 +56,105 @@ __global__ void k_morton(const float *__restrict__ val, uint64_t n_windows, floa
   widx[w] = (uint32_t)w;
 }
 
+// ---- aligned KD order (the default point order).  The pointer-free hierarchy puts node k of level
+// l over the points [k * 8^(l+1), (k+1) * 8^(l+1)) of the order, so any order works; what the search
+// pays for is how tight those groups are.  Morton order cuts space at fixed midpoints and a group of
+// 8^k consecutive codes can straddle a large cell boundary; here every power-of-two-aligned group
+// is a KD cell instead: for s = 2^k >= W down to 16, every aligned segment of s positions is sorted
+// along the dimension in which its points spread most, so its lower half (the next level's left
+// segment) is a half-space cut of it.  Measured on config 2 (tools/emulate_kd.py): 334 box tests per
+// query instead of 679, 28.6 leaves instead of 31.7.
+//   k_kd_extent  per-segment min / max of the six coordinates (order-preserving u32 images)
+//   k_kd_keys    key = segment << 32 | image of the coordinate along the segment's widest dimension
+//   (one stable radix sort of (key, window) per level in between)
+__device__ __forceinline__ uint32_t f2ord(float f) {
+  const uint32_t u = __float_as_uint(f);
+  return u ^ ((u >> 31) ? 0xFFFFFFFFu : 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(uint32_t o) {
+  return __uint_as_float(o ^ ((o >> 31) ? 0x80000000u : 0xFFFFFFFFu));
+}
+
+constexpr int kKdThreads = 256;
+
+// idx == nullptr: the identity order (first level)
+__global__ void __launch_bounds__(kKdThreads)
+k_kd_extent(const float *__restrict__ val, const uint32_t *__restrict__ idx, const uint32_t *__restrict__ wsrc,
+            uint64_t W, int log2s, uint32_t *__restrict__ ext_min, uint32_t *__restrict__ ext_max) {
+  __shared__ uint32_t s_red[kKdThreads / 32][2 * kDim];
+  const uint64_t i = (uint64_t)blockIdx.x * kKdThreads + threadIdx.x;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  uint32_t mn[kDim], mx[kDim];
+#pragma unroll
+  for (int d = 0; d < kDim; ++d) {
+    mn[d] = 0xFFFFFFFFu;
+    mx[d] = 0u;
+  }
+  if (i < W) {
+    const uint32_t w = idx ? idx[i] : (uint32_t)i;
+    const uint64_t v0 = wsrc ? (uint64_t)wsrc[w] : (uint64_t)w;
+#pragma unroll
+    for (int d = 0; d < kDim; ++d) mn[d] = mx[d] = f2ord(val[v0 + d]);
+  }
+  // lanes that share a segment: the whole warp (log2s >= 5) or each half of it (log2s == 4)
+  const unsigned m = log2s >= 5 ? 0xFFFFFFFFu : (lane < 16 ? 0x0000FFFFu : 0xFFFF0000u);
+#pragma unroll
+  for (int d = 0; d < kDim; ++d) {
+    mn[d] = __reduce_min_sync(m, mn[d]);
+    mx[d] = __reduce_max_sync(m, mx[d]);
+  }
+  if (log2s >= 8) {  // the whole block lies in one segment: one set of atomics per block
+    if (lane == 0) {
+#pragma unroll
+      for (int d = 0; d < kDim; ++d) {
+        s_red[wid][d] = mn[d];
+        s_red[wid][kDim + d] = mx[d];
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 * kDim) {
+      const bool is_max = threadIdx.x >= kDim;
+      uint32_t r = s_red[0][threadIdx.x];
+      for (int w = 1; w < kKdThreads / 32; ++w) r = is_max ? max(r, s_red[w][threadIdx.x]) : min(r, s_red[w][threadIdx.x]);
+      const uint64_t seg = ((uint64_t)blockIdx.x * kKdThreads) >> log2s;
+      if ((uint64_t)blockIdx.x * kKdThreads < W) {
+        if (is_max) atomicMax(&ext_max[seg * kDim + (threadIdx.x - kDim)], r);
+        else atomicMin(&ext_min[seg * kDim + threadIdx.x], r);
+      }
+    }
+  } else if (i < W && (lane == 0 || (log2s == 4 && lane == 16))) {
+    const uint64_t seg = i >> log2s;
+#pragma unroll
+    for (int d = 0; d < kDim; ++d) {
+      atomicMin(&ext_min[seg * kDim + d], mn[d]);
+      atomicMax(&ext_max[seg * kDim + d], mx[d]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kKdThreads)
+k_kd_keys(const float *__restrict__ val, const uint32_t *__restrict__ idx, const uint32_t *__restrict__ wsrc,
+          uint64_t W, int log2s, const uint32_t *__restrict__ ext_min, const uint32_t *__restrict__ ext_max,
+          uint64_t *__restrict__ key, uint32_t *__restrict__ idx_out) {
+  const uint64_t i = (uint64_t)blockIdx.x * kKdThreads + threadIdx.x;
+  if (i >= W) return;
+  const uint64_t seg = i >> log2s;
+  int dim = 0;
+  float widest = -1.0f;
+#pragma unroll
+  for (int d = 0; d < kDim; ++d) {
+    const float e = ord2f(ext_max[seg * kDim + d]) - ord2f(ext_min[seg * kDim + d]);
+    if (e > widest) {  // ties: the lowest dimension
+      widest = e;
+      dim = d;
+    }
+  }
+  const uint32_t w = idx ? idx[i] : (uint32_t)i;
+  const uint64_t v0 = wsrc ? (uint64_t)wsrc[w] : (uint64_t)w;
+  key[i] = (seg << 32) | (uint64_t)f2ord(val[v0 + dim]);
+  if (!idx) idx_out[i] = w;
+}
+
 // sorted rank i -> leaf records; one thread per slot of the padded leaf array
 __global__ void k_build_leaves(const float *__restrict__ val, const uint64_t *__restrict__ pos,
                                const uint32_t *__restrict__ order, uint64_t n_windows,

@@ -150,6 +150,7 @@ struct Counters {
   unsigned long long n_events_raw;
   unsigned long long n_events_kept;
   unsigned long long n_linked;      // anchors with a gap-compatible predecessor (k_chain_prep)
+  unsigned long long n_pending;     // of those, the ones k_chain_prep left to the DP kernels
   unsigned long long carry_anchor_used[2];
   unsigned long long carry_chain_used[2];
   unsigned long long sort_cursor;   // output position of the per-entry sort (k_seg_sort)

@@ -54,6 +54,7 @@ __global__ void k_reset_step(Counters *c) {
   c->n_events_raw = 0;
   c->n_events_kept = 0;
   c->n_linked = 0;
+  c->n_pending = 0;
   c->n_segments = 0;
   c->work = 0;
   c->work2 = 0;
@@ -207,7 +208,8 @@ struct Workspace {
   // anchors
   DevBuf<uint64_t> key_a, key_b;
   DevBuf<float> dist_a, dist_b, score, coef;
-  DevBuf<uint32_t> pred, link_list, link_count;
+  DevBuf<uint32_t> pred, link_list, link_count, pend_count;
+  DevBuf<uint16_t> pend_list;
   DevBuf<SegRec> seg;
   DevBuf<RunRec> runs;
   DevBuf<uint32_t> run_count, entry_total, part_base;
@@ -248,7 +250,9 @@ struct smb_ctx {
   uint64_t g_total = 1;           // linear coordinates of the whole index (sum of the bucket spans)
   double part_fill = 0.70;        // share of a k_part_sort CTA's capacity an average part should fill
   int dp_passes = kDpFreePasses;  // SMB_DP_PASSES=n
+  int prep_rounds = kPrepRounds;  // SMB_PREP_ROUNDS=n: settle rounds inside k_chain_prep (0 = none)
   uint32_t dp_pass_max_slots = kDpPassMaxSlots;  // SMB_DP_TILES=n: per-tile DP pass below n segments (0 = never)
+  bool index_kd = true;           // SMB_INDEX=morton: points in Morton order instead of the aligned KD order
   uint32_t sort_queries_min = 200000;  // SMB_SORT_QUERIES_MIN=n: batches with fewer queries keep their natural order
   bool dp_dynamic = true;         // SMB_DP=static: warp w of the DP grid handles segment w
   unsigned dp_grid = 148 * 8;     // persistent DP grid: every block that fits on the device
@@ -558,17 +562,52 @@ static int build_index(smb_ctx *ctx, const uint64_t *pos, const float *val, size
     CK(cudaMemcpyAsync(d_wsrc.p, h_wsrc.data(), W * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(d_worig.p, h_worig.data(), W * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
   }
-  k_morton<<<(unsigned)((W + 255) / 256), 256, 0, s>>>(d_val.p, W, vmin, 1.0f / span, code_a.p, w_a.p, d_wsrc.p);
-  LAUNCH_CHECK();
-  size_t tb = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, tb, code_a.p, code_b.p, w_a.p, w_b.p, (uint64_t)W, 0, 60, s);
-  CK(tmp.ensure(tb));
-  CK(cub::DeviceRadixSort::SortPairs(tmp.p, tb, code_a.p, code_b.p, w_a.p, w_b.p, (uint64_t)W, 0, 60, s));
-  ctx->stats.launches += 8;
+  DevBuf<uint32_t> ext_min, ext_max;
+  const uint32_t *d_order = nullptr;
+  if (ctx->index_kd && W > (uint64_t)kLeaf) {
+    // aligned KD order (k_index.cuh): one pass per power-of-two segment size, top down
+    int log2s = 4;
+    while ((1ull << log2s) < W) ++log2s;
+    const unsigned blocks = (unsigned)((W + kKdThreads - 1) / kKdThreads);
+    const size_t n_ext = (size_t)((W + 15) / 16) * kDim;
+    CK(ext_min.ensure(n_ext));
+    CK(ext_max.ensure(n_ext));
+    size_t tb = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tb, code_a.p, code_b.p, w_a.p, w_b.p, (uint64_t)W, 0, 64, s);
+    CK(tmp.ensure(tb));
+    uint32_t *ia = w_a.p, *ib = w_b.p;
+    bool first = true;
+    for (; log2s >= 4; --log2s) {
+      const uint64_t n_seg = (W + (1ull << log2s) - 1) >> log2s;
+      CK(cudaMemsetAsync(ext_min.p, 0xFF, n_seg * kDim * sizeof(uint32_t), s));
+      CK(cudaMemsetAsync(ext_max.p, 0x00, n_seg * kDim * sizeof(uint32_t), s));
+      k_kd_extent<<<blocks, kKdThreads, 0, s>>>(d_val.p, first ? nullptr : ia, d_wsrc.p, W, log2s, ext_min.p, ext_max.p);
+      LAUNCH_CHECK();
+      k_kd_keys<<<blocks, kKdThreads, 0, s>>>(d_val.p, first ? nullptr : ia, d_wsrc.p, W, log2s, ext_min.p, ext_max.p,
+                                              code_a.p, ia);
+      LAUNCH_CHECK();
+      int seg_bits = 0;
+      while ((1ull << seg_bits) < n_seg) ++seg_bits;
+      CK(cub::DeviceRadixSort::SortPairs(tmp.p, tb, code_a.p, code_b.p, ia, ib, (uint64_t)W, 0, 32 + seg_bits, s));
+      std::swap(ia, ib);
+      first = false;
+      ctx->stats.launches += 9;
+    }
+    d_order = ia;
+  } else {
+    k_morton<<<(unsigned)((W + 255) / 256), 256, 0, s>>>(d_val.p, W, vmin, 1.0f / span, code_a.p, w_a.p, d_wsrc.p);
+    LAUNCH_CHECK();
+    size_t tb = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tb, code_a.p, code_b.p, w_a.p, w_b.p, (uint64_t)W, 0, 60, s);
+    CK(tmp.ensure(tb));
+    CK(cub::DeviceRadixSort::SortPairs(tmp.p, tb, code_a.p, code_b.p, w_a.p, w_b.p, (uint64_t)W, 0, 60, s));
+    ctx->stats.launches += 8;
+    d_order = w_b.p;
+  }
   CK(ctx->leaves.ensure((size_t)n_leaves * kLeafRec));
   CK(ctx->leaf_widx.ensure((size_t)n_leaves * kLeaf));
   k_build_leaves<<<(unsigned)(((uint64_t)n_leaves * kLeaf + 255) / 256), 256, 0, s>>>(
-      d_val.p, d_pos.p, w_b.p, W, n_leaves, ctx->leaves.p, ctx->leaf_widx.p, d_wsrc.p, d_worig.p);
+      d_val.p, d_pos.p, d_order, W, n_leaves, ctx->leaves.p, ctx->leaf_widx.p, d_wsrc.p, d_worig.p);
   LAUNCH_CHECK();
   IndexView ix{};
   ix.n_points = n;
@@ -624,6 +663,8 @@ static int build_index(smb_ctx *ctx, const uint64_t *pos, const float *val, size
   d_wsrc.release();
   d_worig.release();
   tmp.release();
+  ext_min.release();
+  ext_max.release();
   {
     // linear coordinate g = bucket_base[bucket] + target: monotone in the sort order, dense
     // enough to be cut into equal-width bins by the per-entry sort
@@ -1076,8 +1117,13 @@ static int run_step(smb_ctx *ctx, SlotSpace &sp, const StepEntries &en, StepSour
   const unsigned n_tiles = (unsigned)((cap + kPrepTile - 1) / kPrepTile);  // sized for the buffers
   CK(w.link_list.ensure((size_t)std::max(n_tiles, 1u) * kPrepTile));
   CK(w.link_count.ensure(std::max(n_tiles, 1u)));
+  CK(w.pend_list.ensure((size_t)std::max(n_tiles, 1u) * kPrepTile));
+  CK(w.pend_count.ensure(std::max(n_tiles, 1u)));
   ca.link_list = w.link_list.p;
   ca.link_count = w.link_count.p;
+  ca.pend_list = w.pend_list.p;
+  ca.pend_count = w.pend_count.p;
+  ca.prep_rounds = ctx->prep_rounds;
   k_chain_prep<<<n_tiles, kPrepThreads, 0, s>>>(ca);
   LAUNCH_CHECK();
   if (ca.n_slots <= ctx->dp_pass_max_slots) {  // small batch: per-tile parallel pass first (latency)
@@ -1239,6 +1285,7 @@ static int run_step(smb_ctx *ctx, SlotSpace &sp, const StepEntries &en, StepSour
   ctx->stats.chunks += Bpres;
   ctx->stats.steps++;
   ctx->stats.linked += hc.n_linked;
+  ctx->stats.pending += hc.n_pending;
   if (mode != SORT_GLOBAL) ctx->stats.seg_sort_steps++;
   if (mode == SORT_PART) ctx->stats.part_sort_steps++;
   if (hc.error & 4u) return fail(ctx, SMB_ERR_CAPACITY, "per-read chain scratch overflow");
@@ -1453,10 +1500,14 @@ static bool apply_option(smb_ctx *ctx, const char *name_in, const char *value) {
     ctx->part_small = strcmp(value, "small") == 0;
   } else if (name == "DP") {
     ctx->dp_dynamic = strcmp(value, "static") != 0;
+  } else if (name == "INDEX") {  // kd (default) | morton; takes effect at the next index build
+    ctx->index_kd = strcmp(value, "morton") != 0;
   } else if (name == "DP_TILES") {
     ctx->dp_pass_max_slots = (uint32_t)std::max(atoi(value), 0);
   } else if (name == "SORT_QUERIES_MIN") {
     ctx->sort_queries_min = (uint32_t)std::max(atoi(value), 0);
+  } else if (name == "PREP_ROUNDS") {
+    ctx->prep_rounds = std::min(std::max(atoi(value), 0), 200);
   } else if (name == "DP_PASSES") {
     ctx->dp_passes = std::max(atoi(value), 0);
   } else if (name == "UPLOAD_SLICE_MB") {
@@ -1557,7 +1608,7 @@ int smb_create(smb_ctx **out, int device) {
                                 (int)part_sort_smem_bytes(kPartSortCapSmall, 2304))) != cudaSuccess)
     return bail("cudaFuncSetAttribute(k_part_sort)", e);
   for (const char *name : {"SORT", "SEARCH", "FRONT_CAP", "RUNS_CAP", "GRAB", "PART_FILL", "PART", "DP", "DP_PASSES",
-                           "DP_TILES", "SORT_QUERIES_MIN", "EVENTS_OVERLAP", "EVENTS", "UPLOAD_SLICE_MB"})
+                           "DP_TILES", "SORT_QUERIES_MIN", "INDEX", "PREP_ROUNDS", "EVENTS_OVERLAP", "EVENTS", "UPLOAD_SLICE_MB"})
     if (const char *env = getenv((std::string("SMB_") + name).c_str())) apply_option(ctx, name, env);
   {
     int per_sm = 0, n_sm = 148;
@@ -1595,7 +1646,7 @@ void smb_destroy(smb_ctx *ctx) {
   w.blk_chunk_start.release(); w.blk_chunk_offset.release(); w.blk_chunk_scale.release(); w.absent.release(); w.chunk_start.release(); w.chunk_offset.release();
   w.chunk_scale.release(); w.ps.release(); w.pss.release(); w.t1.release(); w.t2.release();
   w.means.release(); w.features.release(); w.key_a.release(); w.key_b.release(); w.dist_a.release();
-  w.dist_b.release(); w.score.release(); w.coef.release(); w.pred.release(); w.seg.release(); w.runs.release(); w.run_count.release(); w.entry_total.release(); w.part_base.release(); w.link_list.release(); w.link_count.release(); w.cub_temp.release();
+  w.dist_b.release(); w.score.release(); w.coef.release(); w.pred.release(); w.seg.release(); w.runs.release(); w.run_count.release(); w.entry_total.release(); w.part_base.release(); w.link_list.release(); w.link_count.release(); w.pend_list.release(); w.pend_count.release(); w.cub_temp.release();
   w.chain_tmp.release(); w.ids.release(); w.round_info.release();
   w.seg_max.release(); w.n_scratch.release(); w.cand_list.release(); w.cand_all.release();
   w.cand_counts.release(); w.ctl.release(); w.tags.release();

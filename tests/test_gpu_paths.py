@@ -35,6 +35,9 @@ PATHS = [
     ("sort_queries_min", "4000000000", lambda st: True),  # ... and never
     ("dp_tiles", "0", lambda st: True),            # no per-tile DP pass (the large-batch configuration)
     ("dp_tiles", "100000000", lambda st: True),    # ... and always
+    ("prep_rounds", "0", lambda st: st["pending"] == st["linked"] > 0),   # every linked anchor walked by k_chain_dp
+    ("prep_rounds", "1", lambda st: 0 < st["pending"] < st["linked"]),
+    ("prep_rounds", "5", lambda st: 0 < st["pending"] < st["linked"]),
     ("grab", "1", lambda st: True),
     ("dp", "static", lambda st: True),
     ("dp_passes", "0", lambda st: True),   # the cooperative in-order DP path settles everything
@@ -44,7 +47,7 @@ PATHS = [
     ("events_overlap", "0", lambda st: True),
     ("part", "small", lambda st: st["part_sort_steps"] > 0),
 ]
-RESET = {"sort_queries_min": "200000", "dp_tiles": "8192", "sort": "part", "runs_cap": "0", "search": "lean", "front_cap": "384", "grab": "0", "dp": "dynamic",
+RESET = {"prep_rounds": "2", "sort_queries_min": "200000", "dp_tiles": "8192", "sort": "part", "runs_cap": "0", "search": "lean", "front_cap": "384", "grab": "0", "dp": "dynamic",
          "dp_passes": "1", "events": "auto", "events_overlap": "1", "part": "big"}
 
 
@@ -92,6 +95,31 @@ def test_radius_search_paths_agree_with_the_oracle(mapper, port, small):
                 assert np.array_equal(gi, ei), f"{name}={value} r={radius} query {k}: hit set differs"
                 assert np.array_equal(bits(gd), bits(ed))
     assert sum(len(e[0]) for e in exp) > 10000  # radius 0.3: dense enough to matter
+
+
+def test_point_order_of_the_index_changes_nothing(mapper, port, small):
+    """The index keeps its points in the aligned KD order by default and in Morton order with
+    option index=morton (read when the index is built): same hit sets and d2 bits against the
+    oracle, same PAF rows."""
+    from sigmap_b200.mapper import Mapper
+    f = port.generate_events(small.pa(port, 3)[:4000])
+    q = np.stack([f[p:p + 6] for p in range(2, len(f) - 5, 2)])[:120]
+    exp = [port.radius_search(small.val, x, radius=0.08) for x in q]
+    base = _lines(mapper, small)
+    m = Mapper(0)
+    try:
+        m.set_option("index", "morton")
+        m.set_index(small.pos, small.val)
+        m.set_contigs(small.ref.lengths)
+        for mm in (mapper, m):
+            off, idx, d2 = mm.radiusSearch(q, radius=0.08, cap=1 << 24)
+            for k, (ei, ed) in enumerate(exp):
+                gi, gd = idx[off[k]:off[k + 1]], d2[off[k]:off[k + 1]]
+                assert np.array_equal(gi, ei), f"query {k}: hit set differs"
+                assert np.array_equal(bits(gd), bits(ed))
+        assert _lines(m, small) == base
+    finally:
+        m.close()
 
 
 def test_hit_cap_5000(mapper, port, small):
