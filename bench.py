@@ -361,7 +361,7 @@ def stream_latency(mapper, reads, n_channels, rounds, warm=3):
             after = mapper.stats()
             detail.append({"round": rd - warm, "ms": round(dt * 1000.0, 3),
                            **{k: round(after[k] - before[k], 3) for k in
-                              ("ms_events", "ms_search", "ms_sort", "ms_chain", "steps", "chunks", "anchors")}})
+                              ("ms_events", "ms_search", "ms_sort", "ms_chain", "ms_stream_stage", "steps", "chunks", "anchors")}})
         for ch in range(n_channels):
             at[ch] += chunk
             r = cur[ch]

@@ -108,6 +108,7 @@ typedef struct smb_stats {
   uint64_t overflow_queries; /* queries whose frontier outgrew the lean search kernel's slots and went
                                 through the general one (every query does with option search=general) */
   uint64_t sync_points;     /* host waits on the device inside the mapping calls */
+  double ms_stream_stage;   /* host milliseconds smb_stream_round spent filtering / cutting / staging chunks */
   uint64_t pending;         /* of `linked`, the anchors left to the DP kernels (the chain-prep kernel
                                settles the rest itself) */
 } smb_stats;

@@ -115,6 +115,7 @@ class Stats(C.Structure):
         ("part_sort_steps", C.c_uint64),
         ("overflow_queries", C.c_uint64),
         ("sync_points", C.c_uint64),
+        ("ms_stream_stage", C.c_double),
         ("pending", C.c_uint64),
     ]
 

@@ -56,6 +56,7 @@ struct ChainArgs {
   SegRec *seg;           // [n_slots], memset to 0xFF before k_chain_prep
   float *seg_max;        // [n_slots], zeroed: SegRec::max of every segment (0 when empty)
   uint32_t n_slots;      // B << bbits
+  const uint32_t *seg_qmin;  // [n_slots] lower bound of the query positions in the segment (k_seg_qmin_init, k_inject_carry)
   uint32_t *link_list;   // [n_tiles * kPrepTile] indices of linked anchors, ascending per tile
   uint32_t *link_count;  // [n_tiles]
   uint16_t *pend_list;   // [n_tiles * kPrepTile] of those, the ones k_chain_prep could not settle itself
@@ -64,6 +65,16 @@ struct ChainArgs {
   int dp_passes;         // thread-parallel passes of k_chain_dp before the in-order cooperative path
   int prep_rounds;       // settle rounds inside k_chain_prep (0: every linked anchor is left to the DP kernels)
 };
+
+// Every query of this step's chunk of an entry lies above the entry's event offset; carried anchors
+// (older chunks) lower the bound of their own segment in k_inject_carry.  k_chain_prep's link test
+// stops where no predecessor can be gap-compatible any more: 0.75 < dq/dt needs 3 dt < 4 dq, and
+// dq <= q_i - seg_qmin.
+__global__ void k_seg_qmin_init(const uint32_t *__restrict__ entry_slot, const SlotState *__restrict__ slots,
+                                uint32_t n_slots, int bbits, uint32_t *__restrict__ seg_qmin) {
+  const uint32_t sg = blockIdx.x * blockDim.x + threadIdx.x;
+  if (sg < n_slots) seg_qmin[sg] = slots[entry_slot[sg >> bbits]].num_events;
+}
 
 constexpr int kCarryThreads = 256;
 constexpr int kCarryMaxParts = 32;  // = kMaxParts of k_index.cuh
@@ -78,7 +89,8 @@ k_inject_carry(const uint32_t *__restrict__ entry_slot, const uint32_t *__restri
                uint64_t *__restrict__ out_key, float *__restrict__ out_dist,
                unsigned long long cap, Counters *__restrict__ ctr, RunRec *__restrict__ runs,
                uint32_t *__restrict__ run_count, uint32_t *__restrict__ entry_total,
-               uint32_t runs_cap, uint32_t n_parts, float inv_span, const uint64_t *__restrict__ bucket_base) {
+               uint32_t runs_cap, uint32_t n_parts, float inv_span, const uint64_t *__restrict__ bucket_base,
+               uint32_t *__restrict__ seg_qmin) {
   __shared__ uint32_t s_cnt[kCarryThreads / 32][kCarryMaxParts];
   const uint32_t b = (blockIdx.x * blockDim.x + threadIdx.x) / 32, lane = threadIdx.x & 31;
   const unsigned full = 0xffffffffu;
@@ -93,6 +105,7 @@ k_inject_carry(const uint32_t *__restrict__ entry_slot, const uint32_t *__restri
     base = __shfl_sync(full, base, 0);
     for (uint32_t i = lane; i < st.carry_n; i += 32) {
       const CarryAnchor c = src[i];
+      atomicMin(&seg_qmin[(b << kl.bbits) | c.bucket], c.query);
       if (base + i < cap) {
         out_key[base + i] = kl.pack(b, c.bucket, c.target, c.query);
         out_dist[base + i] = c.dist;
@@ -111,6 +124,7 @@ k_inject_carry(const uint32_t *__restrict__ entry_slot, const uint32_t *__restri
     uint32_t part = 0, rank = 0;
     if (valid) {
       c = src[i];
+      atomicMin(&seg_qmin[(b << kl.bbits) | c.bucket], c.query);
       part = part_of(bucket_base[c.bucket] + c.target, inv_span, n_parts);
       rank = atomicAdd(&pcnt[part], 1u);
     }
@@ -269,14 +283,16 @@ __global__ void __launch_bounds__(kPrepThreads, 8) k_chain_prep(ChainArgs a) {
         }
         if (i == n - 1) a.seg[sg].end = n;
       }
-      // position-only link test over the maximal lookback range
+      // position-only link test over the maximal lookback range, cut where the target gap alone
+      // rules every further predecessor out: 3 dt >= 4 (q_i - qmin) >= 4 dq
+      const int32_t qlim = (a.seg_qmin && sg < a.n_slots) ? 4 * (qi - (int32_t)a.seg_qmin[sg]) : 0x7FFFFFFF;
       const int depth = (int)min(i, (uint32_t)kBand);
       const int in_smem = min(depth, me);
       int d = 1;
       bool open = true;  // the range continues past what has been looked at
       for (; d <= in_smem; ++d) {
         const int4 p = s_a[me - d];
-        if (p.x != mine.x || p.y + kMaxTargetGap < ti) {
+        if (p.x != mine.x || p.y + kMaxTargetGap < ti || 3 * (ti - p.y) >= qlim) {
           open = false;
           break;
         }
@@ -290,7 +306,7 @@ __global__ void __launch_bounds__(kPrepThreads, 8) k_chain_prep(ChainArgs a) {
         for (; d <= depth; ++d) {
           const uint64_t kj = a.key[i - d];
           const int32_t pt = (int32_t)kl.target(kj);
-          if ((uint32_t)kl.seg(kj) != sg || pt + kMaxTargetGap < ti) break;
+          if ((uint32_t)kl.seg(kj) != sg || pt + kMaxTargetGap < ti || 3 * (ti - pt) >= qlim) break;
           if (gap_compatible(ti - pt, qi - (int32_t)kl.query(kj))) {
             linked = true;
             break;

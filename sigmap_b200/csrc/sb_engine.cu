@@ -13,6 +13,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -208,7 +209,7 @@ struct Workspace {
   // anchors
   DevBuf<uint64_t> key_a, key_b;
   DevBuf<float> dist_a, dist_b, score, coef;
-  DevBuf<uint32_t> pred, link_list, link_count, pend_count;
+  DevBuf<uint32_t> pred, link_list, link_count, pend_count, seg_qmin;
   DevBuf<uint16_t> pend_list;
   DevBuf<SegRec> seg;
   DevBuf<RunRec> runs;
@@ -250,6 +251,7 @@ struct smb_ctx {
   uint64_t g_total = 1;           // linear coordinates of the whole index (sum of the bucket spans)
   double part_fill = 0.70;        // share of a k_part_sort CTA's capacity an average part should fill
   int dp_passes = kDpFreePasses;  // SMB_DP_PASSES=n
+  bool prep_bound = true;         // SMB_PREP_BOUND=0: link test over the whole 5 000-position range
   int prep_rounds = kPrepRounds;  // SMB_PREP_ROUNDS=n: settle rounds inside k_chain_prep (0 = none)
   uint32_t dp_pass_max_slots = kDpPassMaxSlots;  // SMB_DP_TILES=n: per-tile DP pass below n segments (0 = never)
   bool index_kd = true;           // SMB_INDEX=morton: points in Morton order instead of the aligned KD order
@@ -945,10 +947,16 @@ static int run_step(smb_ctx *ctx, SlotSpace &sp, const StepEntries &en, StepSour
     CK(cudaMemsetAsync(w.run_count.p, 0, n_lists * sizeof(uint32_t), s));
     CK(cudaMemsetAsync(w.entry_total.p, 0, n_lists * sizeof(uint32_t), s));
   }
+  const uint64_t n_slots64 = (uint64_t)B << kl.bbits;
+  if (n_slots64 >= (1ull << 31)) return fail(ctx, SMB_ERR_CAPACITY, "segment table too large: lower max_batch_chunks");
+  CK(w.seg_qmin.ensure((size_t)n_slots64));
+  k_seg_qmin_init<<<(unsigned)((n_slots64 + 255) / 256), 256, 0, s>>>(w.entry_slot.p, sp.slots.p, (uint32_t)n_slots64,
+                                                                       kl.bbits, w.seg_qmin.p);
+  LAUNCH_CHECK();
   k_inject_carry<<<(B * 32 + kCarryThreads - 1) / kCarryThreads, kCarryThreads, 0, s>>>(
       w.entry_slot.p, w.n_queries.p, sp.slots.p, sp.pool_anchor[0].p, sp.pool_anchor[1].p, B, kl, w.key_a.p,
       w.dist_a.p, cap, ctx->d_ctr, want_seg ? w.runs.p : nullptr, w.run_count.p, w.entry_total.p,
-      runs_cap, n_parts, inv_span, ctx->bucket_base.p);
+      runs_cap, n_parts, inv_span, ctx->bucket_base.p, w.seg_qmin.p);
   LAUNCH_CHECK();
   SearchArgs sa{};
   sa.features = src == SRC_CACHED ? w.feat_cache[w.cache_cur].p : w.features.p;
@@ -1103,9 +1111,8 @@ static int run_step(smb_ctx *ctx, SlotSpace &sp, const StepEntries &en, StepSour
   ca.score = w.score.p;
   ca.coef = w.coef.p;
   ca.pred = w.pred.p;
-  const uint64_t n_slots64 = (uint64_t)B << kl.bbits;
-  if (n_slots64 >= (1ull << 31)) return fail(ctx, SMB_ERR_CAPACITY, "segment table too large: lower max_batch_chunks");
   ca.n_slots = (uint32_t)n_slots64;
+  ca.seg_qmin = ctx->prep_bound ? w.seg_qmin.p : nullptr;
   CK(w.seg.ensure(ca.n_slots));
   CK(w.seg_max.ensure(ca.n_slots));
   ca.seg = w.seg.p;
@@ -1506,6 +1513,8 @@ static bool apply_option(smb_ctx *ctx, const char *name_in, const char *value) {
     ctx->dp_pass_max_slots = (uint32_t)std::max(atoi(value), 0);
   } else if (name == "SORT_QUERIES_MIN") {
     ctx->sort_queries_min = (uint32_t)std::max(atoi(value), 0);
+  } else if (name == "PREP_BOUND") {
+    ctx->prep_bound = atoi(value) != 0;
   } else if (name == "PREP_ROUNDS") {
     ctx->prep_rounds = std::min(std::max(atoi(value), 0), 200);
   } else if (name == "DP_PASSES") {
@@ -1608,7 +1617,7 @@ int smb_create(smb_ctx **out, int device) {
                                 (int)part_sort_smem_bytes(kPartSortCapSmall, 2304))) != cudaSuccess)
     return bail("cudaFuncSetAttribute(k_part_sort)", e);
   for (const char *name : {"SORT", "SEARCH", "FRONT_CAP", "RUNS_CAP", "GRAB", "PART_FILL", "PART", "DP", "DP_PASSES",
-                           "DP_TILES", "SORT_QUERIES_MIN", "INDEX", "PREP_ROUNDS", "EVENTS_OVERLAP", "EVENTS", "UPLOAD_SLICE_MB"})
+                           "DP_TILES", "SORT_QUERIES_MIN", "INDEX", "PREP_ROUNDS", "PREP_BOUND", "EVENTS_OVERLAP", "EVENTS", "UPLOAD_SLICE_MB"})
     if (const char *env = getenv((std::string("SMB_") + name).c_str())) apply_option(ctx, name, env);
   {
     int per_sm = 0, n_sm = 148;
@@ -1646,7 +1655,7 @@ void smb_destroy(smb_ctx *ctx) {
   w.blk_chunk_start.release(); w.blk_chunk_offset.release(); w.blk_chunk_scale.release(); w.absent.release(); w.chunk_start.release(); w.chunk_offset.release();
   w.chunk_scale.release(); w.ps.release(); w.pss.release(); w.t1.release(); w.t2.release();
   w.means.release(); w.features.release(); w.key_a.release(); w.key_b.release(); w.dist_a.release();
-  w.dist_b.release(); w.score.release(); w.coef.release(); w.pred.release(); w.seg.release(); w.runs.release(); w.run_count.release(); w.entry_total.release(); w.part_base.release(); w.link_list.release(); w.link_count.release(); w.pend_list.release(); w.pend_count.release(); w.cub_temp.release();
+  w.dist_b.release(); w.score.release(); w.coef.release(); w.pred.release(); w.seg.release(); w.runs.release(); w.run_count.release(); w.entry_total.release(); w.part_base.release(); w.link_list.release(); w.link_count.release(); w.pend_list.release(); w.pend_count.release(); w.seg_qmin.release(); w.cub_temp.release();
   w.chain_tmp.release(); w.ids.release(); w.round_info.release();
   w.seg_max.release(); w.n_scratch.release(); w.cand_list.release(); w.cand_all.release();
   w.cand_counts.release(); w.ctl.release(); w.tags.release();
@@ -2688,6 +2697,7 @@ int smb_stream_round(smb_ctx *ctx, const uint32_t *channels, uint32_t n, const i
     CK(cudaMallocHost((void **)&ctx->h_stream_stage, want * sizeof(int16_t)));
     ctx->h_stream_stage_cap = want;
   }
+  const auto t_stage0 = std::chrono::steady_clock::now();
   std::vector<uint32_t> present;
   present.reserve(n);
   {
@@ -2699,43 +2709,69 @@ int smb_stream_round(smb_ctx *ctx, const uint32_t *channels, uint32_t n, const i
       named[channels[i]] = 1;
     }
   }
-  for (uint32_t i = 0; i < n; ++i) {
+  // Channels are independent (each named once), so filtering and chunk cutting run on all host
+  // cores; channel i's chunk goes to staging slot i and the slots of the channels that completed
+  // a chunk are closed up afterwards (nothing moves when every channel did: the usual round).
+  std::vector<uint8_t> ready(n, 0);
+#pragma omp parallel for schedule(static) if (n >= 64)
+  for (int64_t ii = 0; ii < (int64_t)n; ++ii) {
+    const uint32_t i = (uint32_t)ii;
     const uint32_t ch = channels[i];
     std::vector<int16_t> &pend = ctx->stream_pending[ch];
     const int16_t *in = samples + sample_off[i];
     const size_t cnt = sample_off[i + 1] - sample_off[i];
+    int16_t *slot = ctx->h_stream_stage + (size_t)i * kChunk;
+    const bool wants = ctx->stream_chunks[ch] < (uint32_t)prm.max_num_chunks;
+    bool clean = false;
+    if (!ctx->stream_generic[ch]) {
+      const int lo = ctx->stream_lo[ch], hi = ctx->stream_hi[ch];
+      int outside = 0;
+      for (size_t k = 0; k < cnt; ++k) outside |= (in[k] < lo) | (in[k] > hi);
+      clean = !outside;
+    }
+    if (clean && wants && pend.empty() && cnt >= (size_t)kChunk) {
+      // nothing filtered, nothing left over: the chunk goes straight from the caller's buffer
+      memcpy(slot, in, kChunk * sizeof(int16_t));
+      pend.assign(in + kChunk, in + cnt);
+      ready[i] = 1;
+      continue;
+    }
     if (ctx->stream_generic[ch]) {
       const float off = ctx->stream_offset[ch], scale = ctx->stream_scale[ch];
       for (size_t k = 0; k < cnt; ++k)
         if (host_keep(in[k], off, scale)) pend.push_back(in[k]);
+    } else if (clean) {
+      pend.insert(pend.end(), in, in + cnt);
     } else {
       const int lo = ctx->stream_lo[ch], hi = ctx->stream_hi[ch];
-      int outside = 0;
-      for (size_t k = 0; k < cnt; ++k) outside |= (in[k] < lo) | (in[k] > hi);
-      if (!outside) {
-        pend.insert(pend.end(), in, in + cnt);
-      } else {
-        const size_t old = pend.size();
-        pend.resize(old + cnt);
-        int16_t *w = pend.data() + old;
-        for (size_t k = 0; k < cnt; ++k) {
-          *w = in[k];
-          w += (in[k] >= lo) & (in[k] <= hi);
-        }
-        pend.resize((size_t)(w - pend.data()));
+      const size_t old = pend.size();
+      pend.resize(old + cnt);
+      int16_t *w = pend.data() + old;
+      for (size_t k = 0; k < cnt; ++k) {
+        *w = in[k];
+        w += (in[k] >= lo) & (in[k] <= hi);
       }
+      pend.resize((size_t)(w - pend.data()));
     }
-    if (pend.size() >= (size_t)kChunk && ctx->stream_chunks[ch] < (uint32_t)prm.max_num_chunks) {
-      memcpy(ctx->h_stream_stage + present.size() * kChunk, pend.data(), kChunk * sizeof(int16_t));
-      present.push_back(ch);
+    if (pend.size() >= (size_t)kChunk && wants) {
+      memcpy(slot, pend.data(), kChunk * sizeof(int16_t));
       pend.erase(pend.begin(), pend.begin() + kChunk);
-    } else if (ctx->stream_chunks[ch] >= (uint32_t)prm.max_num_chunks) {
+      ready[i] = 1;
+    } else if (!wants) {
       // the read has used up its chunks (sigmap.cc:647): nothing more will be mapped, so the
       // samples are only counted (read length of the row), not buffered
       ctx->stream_kept[ch] += (uint32_t)pend.size();
       pend.clear();
     }
   }
+  for (uint32_t i = 0; i < n; ++i) {
+    if (!ready[i]) continue;
+    if (present.size() != i)
+      memmove(ctx->h_stream_stage + present.size() * kChunk, ctx->h_stream_stage + (size_t)i * kChunk, kChunk * sizeof(int16_t));
+    present.push_back(channels[i]);
+  }
+  ctx->stats.ms_stream_stage +=
+      std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_stage0).count();
   // all other channels with live chains are carried forward
   std::vector<uint8_t> seen(sp.n_slots, 0);
   for (uint32_t ch : present) seen[ch] = 1;

@@ -38,6 +38,7 @@ PATHS = [
     ("prep_rounds", "0", lambda st: st["pending"] == st["linked"] > 0),   # every linked anchor walked by k_chain_dp
     ("prep_rounds", "1", lambda st: 0 < st["pending"] < st["linked"]),
     ("prep_rounds", "5", lambda st: 0 < st["pending"] < st["linked"]),
+    ("prep_bound", "0", lambda st: True),          # link test over the whole 5 000-position range
     ("grab", "1", lambda st: True),
     ("dp", "static", lambda st: True),
     ("dp_passes", "0", lambda st: True),   # the cooperative in-order DP path settles everything
@@ -47,13 +48,17 @@ PATHS = [
     ("events_overlap", "0", lambda st: True),
     ("part", "small", lambda st: st["part_sort_steps"] > 0),
 ]
-RESET = {"prep_rounds": "2", "sort_queries_min": "200000", "dp_tiles": "8192", "sort": "part", "runs_cap": "0", "search": "lean", "front_cap": "384", "grab": "0", "dp": "dynamic",
+RESET = {"prep_bound": "1", "prep_rounds": "2", "sort_queries_min": "200000", "dp_tiles": "8192", "sort": "part", "runs_cap": "0", "search": "lean", "front_cap": "384", "grab": "0", "dp": "dynamic",
          "dp_passes": "1", "events": "auto", "events_overlap": "1", "part": "big"}
 
 
 def test_every_shipped_path_gives_the_default_rows(mapper, small):
     from sigmap_b200.mapper import full_read_params
-    base = {"default": _lines(mapper, small), "full": _lines(mapper, small, full_read_params())}
+    base, linked = {}, {}
+    for mode, prm in (("default", None), ("full", full_read_params())):
+        mapper.stats_reset()
+        base[mode] = _lines(mapper, small, prm)
+        linked[mode] = mapper.stats()["linked"]
     for name, value, seen in PATHS:
         mapper.set_option(name, value)
         try:
@@ -63,6 +68,8 @@ def test_every_shipped_path_gives_the_default_rows(mapper, small):
                 st = mapper.stats()
                 assert got == base[mode], f"{name}={value} ({mode}) changes PAF rows"
                 assert seen(st), f"{name}={value} ({mode}): the path did not run: {st}"
+                # the set of anchors with a gap-compatible predecessor does not depend on the path
+                assert st["linked"] == linked[mode], f"{name}={value} ({mode}): linked anchors differ"
         finally:
             mapper.set_option(name, RESET[name])
     with pytest.raises(Exception):
