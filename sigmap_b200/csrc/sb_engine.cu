@@ -18,6 +18,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 #include <string>
@@ -254,6 +255,7 @@ struct smb_ctx {
   bool prep_bound = true;         // SMB_PREP_BOUND=0: link test over the whole 5 000-position range
   int prep_rounds = kPrepRounds;  // SMB_PREP_ROUNDS=n: settle rounds inside k_chain_prep (0 = none)
   uint32_t dp_pass_max_slots = kDpPassMaxSlots;  // SMB_DP_TILES=n: per-tile DP pass below n segments (0 = never)
+  int pipeline_mode = 0;          // SMB_PIPELINE=auto|on|off: wave-pipelined ticks (see map_uploaded_impl)
   bool index_kd = true;           // SMB_INDEX=morton: points in Morton order instead of the aligned KD order
   uint32_t sort_queries_min = 200000;  // SMB_SORT_QUERIES_MIN=n: batches with fewer queries keep their natural order
   bool dp_dynamic = true;         // SMB_DP=static: warp w of the DP grid handles segment w
@@ -270,6 +272,7 @@ struct smb_ctx {
   size_t h_kept_pinned_cap = 0;
   cudaStream_t stream_ev = nullptr;  // lookahead event blocks run here, next to the mapping rounds
   cudaEvent_t ev_blk_t0[2] = {}, ev_blk_t1[2] = {};
+  cudaEvent_t ev_cp[2] = {};         // first / last filter-only slice of a wave-pipelined call (copy stream)
   bool ev_overlap = true;            // SMB_EVENTS_OVERLAP=0: compute every block when it is needed
   double ev_survival_hint = 0.0;     // share of reads that went past their first chunk in the last call
   uint32_t ev_warp_max = 2048;    // event batches up to this many chunks run warp-per-chunk in shared memory
@@ -1513,6 +1516,8 @@ static bool apply_option(smb_ctx *ctx, const char *name_in, const char *value) {
     ctx->dp_pass_max_slots = (uint32_t)std::max(atoi(value), 0);
   } else if (name == "SORT_QUERIES_MIN") {
     ctx->sort_queries_min = (uint32_t)std::max(atoi(value), 0);
+  } else if (name == "PIPELINE") {
+    ctx->pipeline_mode = strcmp(value, "on") == 0 ? 1 : (strcmp(value, "off") == 0 ? 2 : 0);
   } else if (name == "PREP_BOUND") {
     ctx->prep_bound = atoi(value) != 0;
   } else if (name == "PREP_ROUNDS") {
@@ -1617,7 +1622,7 @@ int smb_create(smb_ctx **out, int device) {
                                 (int)part_sort_smem_bytes(kPartSortCapSmall, 2304))) != cudaSuccess)
     return bail("cudaFuncSetAttribute(k_part_sort)", e);
   for (const char *name : {"SORT", "SEARCH", "FRONT_CAP", "RUNS_CAP", "GRAB", "PART_FILL", "PART", "DP", "DP_PASSES",
-                           "DP_TILES", "SORT_QUERIES_MIN", "INDEX", "PREP_ROUNDS", "PREP_BOUND", "EVENTS_OVERLAP", "EVENTS", "UPLOAD_SLICE_MB"})
+                           "DP_TILES", "SORT_QUERIES_MIN", "INDEX", "PREP_ROUNDS", "PREP_BOUND", "PIPELINE", "EVENTS_OVERLAP", "EVENTS", "UPLOAD_SLICE_MB"})
     if (const char *env = getenv((std::string("SMB_") + name).c_str())) apply_option(ctx, name, env);
   {
     int per_sm = 0, n_sm = 148;
@@ -1635,7 +1640,8 @@ int smb_create(smb_ctx **out, int device) {
       (e = cudaStreamCreateWithFlags(&ctx->stream_cp, cudaStreamNonBlocking)) != cudaSuccess)
     return bail("cudaStreamCreate", e);
   for (int c = 0; c < 2; ++c)
-    if ((e = cudaEventCreate(&ctx->ev_blk_t0[c])) != cudaSuccess || (e = cudaEventCreate(&ctx->ev_blk_t1[c])) != cudaSuccess)
+    if ((e = cudaEventCreate(&ctx->ev_blk_t0[c])) != cudaSuccess || (e = cudaEventCreate(&ctx->ev_blk_t1[c])) != cudaSuccess ||
+        (e = cudaEventCreate(&ctx->ev_cp[c])) != cudaSuccess)
       return bail("cudaEventCreate", e);
   *out = ctx;
   return SMB_OK;
@@ -1669,6 +1675,7 @@ void smb_destroy(smb_ctx *ctx) {
   for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
   for (auto &ev : ctx->timer) if (ev) cudaEventDestroy(ev);
   for (auto &ev : ctx->ev_blk_t0) if (ev) cudaEventDestroy(ev);
+  for (auto &ev : ctx->ev_cp) if (ev) cudaEventDestroy(ev);
   for (auto &ev : ctx->ev_blk_t1) if (ev) cudaEventDestroy(ev);
   if (ctx->stream_ev) cudaStreamDestroy(ctx->stream_ev);
   if (ctx->stream_cp) cudaStreamDestroy(ctx->stream_cp);
@@ -2038,12 +2045,34 @@ struct UploadPlan {
   size_t n_slices() const { return done.size(); }
 };
 
+// from construction to destruction no cudaFree (it waits for the whole device, i.e. for the queued
+// slices): a buffer that grows parks its old allocation
+struct DeferFrees {
+  DeferFrees() { FreeLater::on = true; }
+  ~DeferFrees() {
+    FreeLater::on = false;
+    FreeLater::drain();
+  }
+};
+
+static int slice_event(smb_ctx *ctx, size_t k, cudaEvent_t *out) {
+  while (k >= ctx->slice_events.size()) {
+    cudaEvent_t e;
+    if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess)
+      return fail(ctx, SMB_ERR_CUDA, "cudaEventCreate (upload slice)");
+    ctx->slice_events.push_back(e);
+  }
+  *out = ctx->slice_events[k];
+  return SMB_OK;
+}
+
 extern "C" {
 
 static int map_uploaded_impl(smb_ctx *ctx, const smb_params *prm_in, smb_mapping *out, UploadPlan *plan);
 
 int smb_map_uploaded(smb_ctx *ctx, const smb_params *prm_in, smb_mapping *out) {
   const int rc = map_uploaded_impl(ctx, prm_in, out, nullptr);
+  if (rc) cudaStreamSynchronize(ctx->stream_cp);  // filter-only slices of a failed wave-pipelined call
   // a failed member must not leave its in-process peers waiting at a rendezvous
   if (rc && ctx->local_group) ctx->local_group->abort_all();
   return rc;
@@ -2096,11 +2125,49 @@ static int map_uploaded_impl(smb_ctx *ctx, const smb_params *prm_in, smb_mapping
     return SMB_OK;
   };
   auto uploads_pending = [&]() { return plan && plan->admitted < plan->n_slices(); };
+  // Wave-pipelined ticks (below) when the stop rules retire most reads after their first chunk
+  // (known from the previous call; a fresh context starts this way): K1 and the events of the next
+  // wave run while the current one is being mapped (option pipeline=on: also with resident samples,
+  // which then join in waves of filter-only slices).  Contig shards must run identical ticks on every
+  // rank: no timing-dependent admission there.
+  const bool sharded_index = ctx->ex && ctx->index_sharded;
+  // auto: only when the samples arrive from the host during the call.  With resident samples the
+  // GPU is busy mapping from the first tick on and the overlap only adds contention and steps
+  // (measured on config 3: 437 ms pipelined against 403 ms; with host buffers on two GPUs e2e
+  // 1.65 against 1.58 G samples/s).
+  const bool pipeline = !sharded_index && R > 0 && prm.max_num_chunks > 0 &&
+                        (ctx->pipeline_mode == 1 ||
+                         (ctx->pipeline_mode == 0 && plan != nullptr && ctx->ev_survival_hint <= 0.5));
+  UploadPlan local_plan;
+  std::unique_ptr<DeferFrees> local_defer;
+  if (!plan && pipeline) {
+    // samples resident: slices that only filter (K1 on the copy stream, kept lengths to the host)
+    local_defer.reset(new DeferFrees());
+    const uint64_t slice_samples = std::max<uint64_t>(ctx->upload_slice_bytes / sizeof(int16_t), 1);
+    CK(cudaEventRecord(ctx->ev_cp[0], ctx->stream_cp));
+    size_t r0 = 0;
+    while (r0 < R) {
+      size_t r1 = r0 + 1;
+      while (r1 < R && ctx->h_kept_off[r1] - ctx->h_kept_off[r0] <= slice_samples) ++r1;
+      cudaEvent_t done_ev;
+      rc = slice_event(ctx, local_plan.done.size(), &done_ev);
+      if (rc) return rc;
+      rc = filter_slice(ctx, r0, r1, ctx->stream_cp);
+      if (rc) return rc;
+      CK(cudaEventRecord(done_ev, ctx->stream_cp));
+      local_plan.first_read.push_back(r0);
+      local_plan.done.push_back(done_ev);
+      r0 = r1;
+    }
+    CK(cudaEventRecord(ctx->ev_cp[1], ctx->stream_cp));
+    local_plan.first_read.push_back(R);
+    plan = &local_plan;
+  }
   if (!plan) {
     rc = filter_reads(ctx);  // K1: part of the mapped path, redone on every call
     if (rc) return rc;
     admit(0, R);
-  } else if (ctx->ex && ctx->index_sharded) {
+  } else if (sharded_index) {
     // contig shards must run identical ticks on every rank: no timing-dependent admission
     while (uploads_pending()) {
       rc = admit_ready(true);
@@ -2185,7 +2252,126 @@ static int map_uploaded_impl(smb_ctx *ctx, const smb_params *prm_in, smb_mapping
     return SMB_OK;
   };
   uint64_t first_active = 0, after_first = 0;  // reads that had a first chunk / went past it
-  while (!active.empty() || uploads_pending()) {
+  if (pipeline) {
+    // ---- wave-pipelined ticks.  Every tick maps the reads of ONE event block (one tick deep); while
+    // it is being mapped, the block of the next tick is computed on the event stream for the reads
+    // that are known by then: the survivors of the PREVIOUS tick (they wait one tick, carried forward
+    // as absent slots) and the reads whose slices have arrived since -- at most one step's worth.  So
+    // neither K1 nor event detection is ever waited for after the first wave, however the reads
+    // arrive.  A read's chunk at tick T is T - t_admit[r]; t_admit is (re)set whenever the read is
+    // put into a block, which is all that "waiting a tick" takes.  Which reads share a tick changes
+    // the composition of batches, never a row.
+    std::vector<uint32_t> done_chunks(R, 0), members[2], waiting, absent;
+    auto want_reads = [&]() -> size_t {
+      const uint64_t by_anchors = (uint64_t)(0.6 * (double)ctx->max_batch_anchors / std::max(ctx->est_anchors_per_chunk, 1.0));
+      return (size_t)std::max<uint64_t>(1, std::min<uint64_t>(by_anchors, ctx->max_batch_chunks));
+    };
+    // reads of the slices that have arrived, in order, at most `cap` of them; wait = true: block
+    // until at least `min_new` reads have joined or no slice is left
+    auto gather_new = [&](std::vector<uint32_t> &into, size_t min_new, size_t cap, bool wait) -> int {
+      size_t got = 0;
+      while (plan->admitted < plan->n_slices() && got < cap) {
+        const size_t k = plan->admitted;
+        cudaError_t q = cudaEventQuery(plan->done[k]);
+        if (q == cudaErrorNotReady) {
+          if (!wait || got >= min_new) break;
+          ctx->stats.sync_points++;
+          CK(cudaEventSynchronize(plan->done[k]));
+        } else if (q != cudaSuccess) {
+          return fail(ctx, SMB_ERR_CUDA, std::string("upload slice: ") + cudaGetErrorString(q));
+        }
+        for (size_t r = plan->first_read[k]; r < plan->first_read[k + 1]; ++r) {
+          ctx->h_kept_len[r] = ctx->h_kept_pinned[r];
+          n_chunks[r] = ctx->h_kept_len[r] / kChunk;  // tail dropped, sigmap.cc:643
+          if (n_chunks[r] > 0) {
+            into.push_back((uint32_t)r);
+            ++got;
+          }
+        }
+        plan->admitted++;
+      }
+      return SMB_OK;
+    };
+    auto launch_for = [&](int c, uint32_t tick) -> int {
+      for (uint32_t r : members[c]) t_admit[r] = tick - done_chunks[r];
+      return launch_block(c, tick, 1, members[c]);
+    };
+    int c = 0;
+    bool have_blk = false;  // blk[c] has been launched for tick `round` with members[c]
+    for (;;) {
+      if (!have_blk) {
+        // nothing was prefetched for this tick: whoever is waiting, plus new reads (a batch, or
+        // what is left of the input)
+        members[c].swap(waiting);
+        waiting.clear();
+        const size_t want = want_reads();
+        if (members[c].size() < want && uploads_pending()) {
+          const size_t room = want - members[c].size();
+          rc = gather_new(members[c], (room + 1) / 2, room, true);
+          if (rc) return rc;
+        }
+        if (members[c].empty()) {
+          if (!uploads_pending()) break;
+          continue;  // slices without a single whole chunk
+        }
+        rc = launch_for(c, round);
+        if (rc) return rc;
+      }
+      rc = consume_block(c);
+      if (rc) return rc;
+      have_blk = false;
+      const std::vector<uint32_t> &act = members[c];
+      // the next tick's block while this one is mapped
+      absent.clear();
+      for (uint32_t r : waiting)
+        if (sp.h_nchains[r] > 0) absent.push_back(r);
+      if (ctx->ev_overlap) {
+        std::vector<uint32_t> &nx = members[1 - c];
+        nx.swap(waiting);
+        waiting.clear();
+        const size_t want = want_reads();
+        if (nx.size() < want && uploads_pending()) {
+          rc = gather_new(nx, 0, want - nx.size(), false);
+          if (rc) return rc;
+        }
+        if (!nx.empty()) {
+          rc = launch_for(1 - c, round + 1);
+          if (rc) return rc;
+          have_blk = true;
+        }
+      }
+      const std::vector<uint32_t> &row_base = blk[c].row_base;
+      auto fill = [&](StepEntries &en, size_t first, uint32_t count) {
+        en.feat_row.resize(count);
+        for (uint32_t i = 0; i < count; ++i) en.feat_row[i] = row_base[act[first + i]];
+      };
+      RoundOut rout;
+      rout.ids = &act;
+      rout.info = &info;
+      rc = run_round(ctx, sp, act, absent, SRC_CACHED, prm, fill, &rout);
+      if (rc) return rc;
+      ctx->stats.samples += (uint64_t)act.size() * kChunk;
+      for (size_t i = 0; i < act.size(); ++i) {
+        const uint32_t r = act[i];
+        const uint32_t dc = round + 1 - t_admit[r];
+        chunks_used[r] = dc;
+        done_chunks[r] = dc;
+        const bool more = dc < n_chunks[r] && dc < (uint32_t)prm.max_num_chunks;
+        if (dc == 1) {
+          ++first_active;
+          if (!info[i].stop && more) ++after_first;
+        }
+        if (!info[i].stop && more) waiting.push_back(r);
+      }
+      ++round;
+      if (have_blk) c = 1 - c;
+    }
+    if (plan == &local_plan) {  // K1 time of the call: first to last filter-only slice on the copy stream
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, ctx->ev_cp[0], ctx->ev_cp[1]) == cudaSuccess) ctx->stats.ms_filter += ms;
+    }
+  }
+  while (!pipeline && (!active.empty() || uploads_pending())) {
     if (round >= blk[cur].r1) {
       // a block boundary: the only place reads are admitted (every row of a block then belongs
       // to a read that was there when the block was launched)
@@ -2286,14 +2472,7 @@ int smb_map_reads(smb_ctx *ctx, const int16_t *raw, const uint64_t *read_off, co
   // admits a slice's reads once its event has fired, so the rest of the upload hides behind the
   // mapping of the reads that are already there (raw should be pinned host memory for that).
   int rc = reads_prepare(ctx, read_off, dig, range, offset, n_reads, cs);
-  // from here to the end of the call no cudaFree: a buffer that grows parks its old allocation
-  struct DeferFrees {
-    DeferFrees() { FreeLater::on = true; }
-    ~DeferFrees() {
-      FreeLater::on = false;
-      FreeLater::drain();
-    }
-  } defer_frees;
+  DeferFrees defer_frees;
   UploadPlan plan;
   if (!rc && n_reads) {
     const uint64_t slice_samples = ctx->upload_slice_bytes / sizeof(int16_t);
@@ -2301,15 +2480,9 @@ int smb_map_reads(smb_ctx *ctx, const int16_t *raw, const uint64_t *read_off, co
     while (r0 < n_reads && !rc) {
       size_t r1 = r0 + 1;
       while (r1 < n_reads && read_off[r1 + 1] - read_off[r0] <= slice_samples) ++r1;
-      const size_t k = plan.done.size();
-      if (k >= ctx->slice_events.size()) {
-        cudaEvent_t e;
-        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) {
-          rc = fail(ctx, SMB_ERR_CUDA, "cudaEventCreate (upload slice)");
-          break;
-        }
-        ctx->slice_events.push_back(e);
-      }
+      cudaEvent_t done_ev;
+      rc = slice_event(ctx, plan.done.size(), &done_ev);
+      if (rc) break;
       const uint64_t a = read_off[r0], b = read_off[r1];
       cudaError_t ce = cudaMemcpyAsync(ctx->raw.p + a, raw + a, (b - a) * sizeof(int16_t), cudaMemcpyHostToDevice, cs);
       if (ce != cudaSuccess) {
@@ -2319,9 +2492,9 @@ int smb_map_reads(smb_ctx *ctx, const int16_t *raw, const uint64_t *read_off, co
       ctx->stats.h2d_bytes += (b - a) * 2;
       rc = filter_slice(ctx, r0, r1, cs);
       if (rc) break;
-      cudaEventRecord(ctx->slice_events[k], cs);
+      cudaEventRecord(done_ev, cs);
       plan.first_read.push_back(r0);
-      plan.done.push_back(ctx->slice_events[k]);
+      plan.done.push_back(done_ev);
       r0 = r1;
     }
     plan.first_read.push_back(n_reads);

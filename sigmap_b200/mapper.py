@@ -10,6 +10,7 @@ Reference interface mirrored (names kept so parity tests read like the reference
 All compute happens in libsigmap_b200.so on the GPU; this module only marshals numpy arrays.
 There is no CPU fallback: constructing a Mapper without a CUDA device raises.
 """
+import collections.abc
 import ctypes as C
 
 import numpy as np
@@ -41,6 +42,28 @@ def full_read_params(**overrides):
               min_num_anchors=2000000000)
     kw.update(overrides)
     return default_params(**kw)
+
+
+class Rows(collections.abc.Sequence):
+    """The smb_mapping rows of a mapping call: a read-only sequence over the ctypes array the
+    library filled (no per-row Python work inside the call: 100 000 rows cost 45 ms as a list)."""
+
+    __slots__ = ("_arr", "_n")
+
+    def __init__(self, arr, n):
+        self._arr, self._n = arr, n
+
+    def __len__(self):
+        return self._n
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self._arr[k] for k in range(*i.indices(self._n))]
+        if i < 0:
+            i += self._n
+        if not 0 <= i < self._n:
+            raise IndexError(i)
+        return self._arr[i]
 
 
 class Mapper:
@@ -163,7 +186,7 @@ class Mapper:
         params = params or default_params()
         out = (F.Mapping * max(self._n_uploaded, 1))()
         self._check(F.lib.smb_map_uploaded(self._ctx, C.byref(params), out), "smb_map_uploaded")
-        return [out[i] for i in range(self._n_uploaded)]
+        return Rows(out, self._n_uploaded)
 
     def map_reads(self, reads, params=None):
         """Raw host reads in, PAF rows out (host<->device copies included)."""
@@ -174,7 +197,7 @@ class Mapper:
                                         F.ptr(reads.digitisation, F.f32p), F.ptr(reads.range, F.f32p),
                                         F.ptr(reads.offset, F.f32p), reads.n, C.byref(params), out),
                     "smb_map_reads")
-        return [out[i] for i in range(reads.n)]
+        return Rows(out, reads.n)
 
     StreamingMap = map_reads
 

@@ -39,6 +39,8 @@ PATHS = [
     ("prep_rounds", "1", lambda st: 0 < st["pending"] < st["linked"]),
     ("prep_rounds", "5", lambda st: 0 < st["pending"] < st["linked"]),
     ("prep_bound", "0", lambda st: True),          # link test over the whole 5 000-position range
+    ("pipeline", "on", lambda st: True),           # wave-pipelined ticks (one wave on this small input)
+    ("pipeline", "off", lambda st: True),
     ("grab", "1", lambda st: True),
     ("dp", "static", lambda st: True),
     ("dp_passes", "0", lambda st: True),   # the cooperative in-order DP path settles everything
@@ -48,7 +50,7 @@ PATHS = [
     ("events_overlap", "0", lambda st: True),
     ("part", "small", lambda st: st["part_sort_steps"] > 0),
 ]
-RESET = {"prep_bound": "1", "prep_rounds": "2", "sort_queries_min": "200000", "dp_tiles": "8192", "sort": "part", "runs_cap": "0", "search": "lean", "front_cap": "384", "grab": "0", "dp": "dynamic",
+RESET = {"pipeline": "auto", "prep_bound": "1", "prep_rounds": "2", "sort_queries_min": "200000", "dp_tiles": "8192", "sort": "part", "runs_cap": "0", "search": "lean", "front_cap": "384", "grab": "0", "dp": "dynamic",
          "dp_passes": "1", "events": "auto", "events_overlap": "1", "part": "big"}
 
 
@@ -74,6 +76,37 @@ def test_every_shipped_path_gives_the_default_rows(mapper, small):
             mapper.set_option(name, RESET[name])
     with pytest.raises(Exception):
         mapper.set_option("no_such_option", "1")
+    assert _lines(mapper, small) == base["default"]
+
+
+def test_wave_pipelined_ticks_give_identical_rows(mapper, small):
+    """Reads joining in waves (1 MB slices, seven reads per tick: survivors wait a tick and are carried
+    forward as absent slots while the next wave's events run) give the rows of the one-batch run, with
+    host buffers and with resident samples, default and full-read rules, with and without event overlap."""
+    from sigmap_b200.mapper import full_read_params
+    modes = (("default", None), ("full", full_read_params()))
+    base = {mode: _lines(mapper, small, prm) for mode, prm in modes}
+    names = small.ref.names
+    try:
+        mapper.set_option("upload_slice_mb", "1")
+        mapper.set_limits(max_batch_chunks=7)
+        for pipe, overlap in (("on", "1"), ("on", "0"), ("off", "1")):
+            mapper.set_option("pipeline", pipe)
+            mapper.set_option("events_overlap", overlap)
+            for mode, prm in modes:
+                mapper.stats_reset()
+                assert _lines(mapper, small, prm) == base[mode], f"pipeline={pipe} overlap={overlap} {mode}: host buffers"
+                if pipe == "on":
+                    assert mapper.stats()["steps"] >= small.reads.n // 7
+                mapper.upload_reads(small.reads)
+                rows = mapper.map_uploaded(prm)
+                got = [paf_cols(l) for l in mapper.paf_lines(small.reads, rows, names)]
+                assert got == base[mode], f"pipeline={pipe} overlap={overlap} {mode}: resident samples"
+    finally:
+        mapper.set_option("pipeline", "auto")
+        mapper.set_option("events_overlap", "1")
+        mapper.set_option("upload_slice_mb", "64")
+        mapper.set_limits(max_batch_chunks=32768)
     assert _lines(mapper, small) == base["default"]
 
 
