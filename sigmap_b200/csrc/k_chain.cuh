@@ -226,7 +226,7 @@ __device__ __forceinline__ float distance_coefficient(float dist, double radius)
 constexpr int kPrepHalo = 128;     // predecessors staged in shared memory ahead of the tile
 constexpr int kPrepThreads = 256;  // kPrepTile / kPrepThreads anchors per thread
 constexpr uint32_t kPending = 0x40000000u;  // pred[] bit: linked anchor not yet settled by the DP
-constexpr int kPrepRounds = 2;     // settle rounds inside k_chain_prep
+constexpr int kPrepRounds = 1;     // settle rounds inside k_chain_prep
 
 // Phase 2 of k_chain_prep: the lookback itself for the linked anchors it can finish on its own.
 // 80-90 % of the linked anchors are background pairs and triples: their gap-compatible predecessors
@@ -272,6 +272,7 @@ __global__ void __launch_bounds__(kPrepThreads, 8) k_chain_prep(ChainArgs a) {
     bool linked = false;
     if (i < n) {
       const int me = kPrepHalo + local;
+      const float di = a.dist[i];  // needed after the walk: in flight during it
       const int4 mine = s_a[me];
       const uint32_t sg = (uint32_t)mine.x;
       const int32_t ti = mine.y, qi = mine.z;
@@ -313,7 +314,7 @@ __global__ void __launch_bounds__(kPrepThreads, 8) k_chain_prep(ChainArgs a) {
           }
         }
       }
-      const float ci = distance_coefficient(a.dist[i], (double)a.radius);
+      const float ci = distance_coefficient(di, (double)a.radius);
       const float init = __fmul_rn(ci, (float)kDim);
       a.coef[i] = ci;
       a.score[i] = init;
@@ -367,6 +368,9 @@ __global__ void __launch_bounds__(kPrepThreads, 8) k_chain_prep(ChainArgs a) {
       const int32_t ti = mine.y, qi = mine.z;
       const uint32_t i = tile0 + (uint32_t)local;
       const float ci = a.coef[i];
+      // no predecessor at or beyond 3 dt >= 4 (q_i - qmin) can be gap-compatible: whatever the
+      // reference's loop still does there (count skips, break) leaves score and predecessor as they are
+      const int32_t qlim = (a.seg_qmin && (uint32_t)mine.x < a.n_slots) ? 4 * (qi - (int32_t)a.seg_qmin[mine.x]) : 0x7FFFFFFF;
       float M = __int_as_float(mine.w);  // 6 * coef = chaining_scores[anchor_index]
       uint32_t best = i;
       int S = 0;  // num_skips
@@ -375,6 +379,7 @@ __global__ void __launch_bounds__(kPrepThreads, 8) k_chain_prep(ChainArgs a) {
       for (; x >= 0; --x) {
         const int4 p = s_a[x];
         if (p.x != mine.x) break;  // the first anchor of the segment has been passed
+        if (3 * (ti - p.y) >= qlim) break;
         if (p.z == qi || p.y == ti) continue;
         if (p.y + kMaxTargetGap < ti) break;
         const int32_t dt = ti - p.y, dq = qi - p.z;
@@ -612,35 +617,50 @@ __device__ __forceinline__ void dp_segment(const ChainArgs &a, const uint32_t sl
     __syncwarp(full);
     const uint32_t cnt = a.link_count[tile];
     const uint32_t *list = a.link_list + (size_t)tile * kPrepTile;
-    for (uint32_t c0 = 0; c0 < cnt; c0 += 32) {
-      const uint32_t c = c0 + lane;
-      const uint32_t i = c < cnt ? list[c] : 0xFFFFFFFFu;
-      const bool valid = c < cnt && i >= s && i < e;
-      if (!__ballot_sync(full, valid)) continue;
-      const float M = valid ? score[i] : 0.0f;
-      float pm = M;
+    // four batches of 32 per round trip: the list entries, then their scores, are loaded together
+    for (uint32_t c0 = 0; c0 < cnt; c0 += 128) {
+      uint32_t iv[4];
+      float Mv[4];
 #pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const float t = __shfl_up_sync(full, pm, d);
-        if (lane >= d) pm = fmaxf(pm, t);
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t c = c0 + 32u * (uint32_t)u + lane;
+        iv[u] = c < cnt ? list[c] : 0xFFFFFFFFu;
       }
-      pm = fmaxf(pm, runmax);
-      unsigned candm = __ballot_sync(full, valid && M >= 10.0f && M > __fdiv_rn(pm, 2.0f));
-      runmax = __shfl_sync(full, pm, 31);
-      while (candm) {
-        const int l = __ffs(candm) - 1;
-        candm &= candm - 1;
-        const float Ml = __shfl_sync(full, M, l);
-        const uint32_t il = __shfl_sync(full, i, l);
-        if (ntop < 1 || Ml >= ts0) {
-          ts2 = ts1; ti2 = ti1; ts1 = ts0; ti1 = ti0; ts0 = Ml; ti0 = il;
-          if (ntop < 3) ++ntop;
-        } else if (ntop < 2 || Ml >= ts1) {
-          ts2 = ts1; ti2 = ti1; ts1 = Ml; ti1 = il;
-          if (ntop < 3) ++ntop;
-        } else if (ntop < 3 || Ml >= ts2) {
-          ts2 = Ml; ti2 = il;
-          if (ntop < 3) ++ntop;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (iv[u] < s || iv[u] >= e) iv[u] = 0xFFFFFFFFu;  // another segment's anchor
+        Mv[u] = iv[u] != 0xFFFFFFFFu ? score[iv[u]] : 0.0f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const bool valid = iv[u] != 0xFFFFFFFFu;
+        if (!__ballot_sync(full, valid)) continue;
+        const uint32_t i = iv[u];
+        const float M = Mv[u];
+        float pm = M;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const float t = __shfl_up_sync(full, pm, d);
+          if (lane >= d) pm = fmaxf(pm, t);
+        }
+        pm = fmaxf(pm, runmax);
+        unsigned candm = __ballot_sync(full, valid && M >= 10.0f && M > __fdiv_rn(pm, 2.0f));
+        runmax = __shfl_sync(full, pm, 31);
+        while (candm) {
+          const int l = __ffs(candm) - 1;
+          candm &= candm - 1;
+          const float Ml = __shfl_sync(full, M, l);
+          const uint32_t il = __shfl_sync(full, i, l);
+          if (ntop < 1 || Ml >= ts0) {
+            ts2 = ts1; ti2 = ti1; ts1 = ts0; ti1 = ti0; ts0 = Ml; ti0 = il;
+            if (ntop < 3) ++ntop;
+          } else if (ntop < 2 || Ml >= ts1) {
+            ts2 = ts1; ti2 = ti1; ts1 = Ml; ti1 = il;
+            if (ntop < 3) ++ntop;
+          } else if (ntop < 3 || Ml >= ts2) {
+            ts2 = Ml; ti2 = il;
+            if (ntop < 3) ++ntop;
+          }
         }
       }
     }

@@ -477,34 +477,49 @@ __global__ void __launch_bounds__(THREADS, THREADS >= 1024 ? 1 : (THREADS >= 512
         __syncthreads();
       }
       const uint32_t tile_end = s_run_off[kRunsCap];
-      for (uint32_t r0 = (uint32_t)wid * 4u; r0 < tn; r0 += (THREADS / 32) * 4u) {
-        uint32_t st[4], of[4], cn[4];
+      // the tile's anchors as one flat range: a warp takes four windows of 32 consecutive slots at
+      // a time; the run holding a window's first slot by binary search (uniform), a lane's own run
+      // a few steps further (runs are ~16 anchors: a query's hits of one part), so every lane has an
+      // anchor whatever the run lengths are and eight loads per lane are in flight
+      const uint32_t tile_total = tile_end - tile_base;
+      for (uint32_t w0 = (uint32_t)wid * 128u; w0 < tile_total; w0 += (THREADS / 32) * 128u) {
+        uint32_t hh[4], src[4];
         uint64_t kq[4];
         float dq[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          const uint32_t r = r0 + u;
-          st[u] = 0;
-          of[u] = 0;
-          cn[u] = 0;
-          if (r < tn) {
-            st[u] = s_run_start[r];
-            of[u] = s_run_off[r];
-            cn[u] = (r + 1 < tn ? s_run_off[r + 1] : tile_end) - of[u];
-          }
-          kq[u] = ~0ull;
-          dq[u] = 0.0f;
-          if ((uint32_t)lane < cn[u]) {
-            kq[u] = a.key_in[st[u] + lane];
-            dq[u] = a.dist_in[st[u] + lane];
+          const uint32_t f0 = w0 + 32u * (uint32_t)u;  // warp-uniform
+          hh[u] = 0xFFFFFFFFu;
+          src[u] = 0u;
+          if (f0 < tile_total) {
+            const uint32_t h0 = tile_base + f0;
+            uint32_t lo = 0u, hi = tn;
+            while (hi - lo > 1u) {
+              const uint32_t mid = (lo + hi) >> 1;
+              if (s_run_off[mid] <= h0) lo = mid;
+              else hi = mid;
+            }
+            const uint32_t h = h0 + (uint32_t)lane;
+            if (h < tile_end) {
+              uint32_t r = lo;
+              while (r + 1u < tn && s_run_off[r + 1u] <= h) ++r;
+              hh[u] = h;
+              src[u] = s_run_start[r] + (h - s_run_off[r]);
+            }
           }
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          if ((uint32_t)lane < cn[u]) place(of[u] + lane, kq[u], dq[u]);
-          for (uint32_t i = 32u + lane; i < cn[u]; i += 32u)  // runs longer than a warp
-            place(of[u] + i, a.key_in[st[u] + i], a.dist_in[st[u] + i]);
+          kq[u] = ~0ull;
+          dq[u] = 0.0f;
+          if (hh[u] != 0xFFFFFFFFu) {
+            kq[u] = a.key_in[src[u]];
+            dq[u] = a.dist_in[src[u]];
+          }
         }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (hh[u] != 0xFFFFFFFFu) place(hh[u], kq[u], dq[u]);
       }
       __syncthreads();  // the tile's records are not needed any more
       if (tid == 0) s_misc[34] = tile_end;
@@ -555,54 +570,41 @@ __global__ void __launch_bounds__(THREADS, THREADS >= 1024 ? 1 : (THREADS >= 512
       s_order[atomicAdd(&s_bins[s_order2[slot]], 1u)] = (uint16_t)slot;
     __syncthreads();
 
-    // ---- order every bin by the full key (bucket | target | query)
-    for (int b = tid; b < BINS; b += THREADS) {
-      const uint32_t lo = b ? s_bins[b - 1] : 0u, hi = s_bins[b];
-      const uint32_t m = hi - lo;
-      if (m < 2) continue;
-      bool by_thread = m <= (uint32_t)kSmallBin;
-      if (!by_thread) {
-        const uint32_t at = atomicAdd(&s_misc[33], 1u);
-        if (at < (uint32_t)kBigBinCap) s_big[at] = (uint32_t)b;
-        else by_thread = true;  // queue full: slow but correct
-      }
-      if (by_thread) {
-        for (uint32_t x = lo + 1; x < hi; ++x) {
-          const uint16_t ox = s_order[x];
-          const uint64_t kx = s_key[ox];
-          uint32_t y = x;
-          while (y > lo && s_key[s_order[y - 1]] > kx) {
-            s_order[y] = s_order[y - 1];
-            --y;
+    // ---- order every bin by the full key (bucket | target | query): every anchor counts the
+    // mates of its bin with a smaller key (keys are unique), one anchor per thread and pass, so
+    // all lanes work whatever the bin sizes are (58 % of the anchors share their bin with another
+    // one at the usual fill; a thread-per-bin insertion sort left most lanes idle and the block
+    // waiting for its densest bin).  The final order replaces the bin numbers in s_order2 once
+    // every thread has read what it needs.
+    {
+      constexpr int kPer = (CAP + THREADS - 1) / THREADS;
+      uint32_t placed[kPer];  // final position << 16 | slot
+#pragma unroll
+      for (int j = 0; j < kPer; ++j) {
+        const uint32_t pos = (uint32_t)tid + (uint32_t)j * THREADS;
+        placed[j] = 0xFFFFFFFFu;
+        if (pos < n) {
+          const uint32_t slot = s_order[pos];
+          const uint32_t b = s_order2[slot];
+          const uint32_t lo = b ? s_bins[b - 1] : 0u, hi = s_bins[b];
+          uint32_t rank = 0;
+          if (hi - lo > 1u) {
+            const uint64_t kx = s_key[slot];
+            for (uint32_t y = lo; y < hi; ++y) rank += s_key[s_order[y]] < kx ? 1u : 0u;
           }
-          s_order[y] = ox;
+          placed[j] = ((lo + rank) << 16) | slot;
         }
       }
-    }
-    __syncthreads();
-    const uint32_t nbig = min(s_misc[33], (uint32_t)kBigBinCap);
-    for (uint32_t bi = wid; bi < nbig; bi += THREADS / 32) {
-      const uint32_t b = s_big[bi];
-      const uint32_t lo = b ? s_bins[b - 1] : 0u, hi = s_bins[b];
-      const uint32_t m = hi - lo;
-      for (uint32_t x = lane; x < m; x += 32) {
-        const uint16_t ox = s_order[lo + x];
-        const uint64_t kx = s_key[ox];
-        uint32_t rank = 0;
-        for (uint32_t y = 0; y < m; ++y) {
-          const uint64_t ky = s_key[s_order[lo + y]];
-          rank += (ky < kx || (ky == kx && y < x)) ? 1u : 0u;
-        }
-        s_order2[lo + rank] = ox;
-      }
-      __syncwarp();
-      for (uint32_t x = lane; x < m; x += 32) s_order[lo + x] = s_order2[lo + x];
+      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < kPer; ++j)
+        if (placed[j] != 0xFFFFFFFFu) s_order2[placed[j] >> 16] = (uint16_t)(placed[j] & 0xFFFFu);
     }
     __syncthreads();
 
     // ---- write the sub-range back, sorted
     for (uint32_t pos = tid; pos < n; pos += THREADS) {
-      const uint32_t slot = s_order[pos];
+      const uint32_t slot = s_order2[pos];
       a.key_out[out + pos] = s_key[slot];
       a.dist_out[out + pos] = s_dist[slot];
     }

@@ -36,7 +36,7 @@ PATHS = [
     ("dp_tiles", "0", lambda st: True),            # no per-tile DP pass (the large-batch configuration)
     ("dp_tiles", "100000000", lambda st: True),    # ... and always
     ("prep_rounds", "0", lambda st: st["pending"] == st["linked"] > 0),   # every linked anchor walked by k_chain_dp
-    ("prep_rounds", "1", lambda st: 0 < st["pending"] < st["linked"]),
+    ("prep_rounds", "2", lambda st: 0 < st["pending"] < st["linked"]),
     ("prep_rounds", "5", lambda st: 0 < st["pending"] < st["linked"]),
     ("prep_bound", "0", lambda st: True),          # link test over the whole 5 000-position range
     ("pipeline", "on", lambda st: True),           # wave-pipelined ticks (one wave on this small input)
@@ -50,7 +50,7 @@ PATHS = [
     ("events_overlap", "0", lambda st: True),
     ("part", "small", lambda st: st["part_sort_steps"] > 0),
 ]
-RESET = {"pipeline": "auto", "prep_bound": "1", "prep_rounds": "2", "sort_queries_min": "200000", "dp_tiles": "8192", "sort": "part", "runs_cap": "0", "search": "lean", "front_cap": "384", "grab": "0", "dp": "dynamic",
+RESET = {"pipeline": "auto", "prep_bound": "1", "prep_rounds": "1", "sort_queries_min": "200000", "dp_tiles": "8192", "sort": "part", "runs_cap": "0", "search": "lean", "front_cap": "384", "grab": "0", "dp": "dynamic",
          "dp_passes": "1", "events": "auto", "events_overlap": "1", "part": "big"}
 
 
