@@ -477,49 +477,36 @@ __global__ void __launch_bounds__(THREADS, THREADS >= 1024 ? 1 : (THREADS >= 512
         __syncthreads();
       }
       const uint32_t tile_end = s_run_off[kRunsCap];
-      // the tile's anchors as one flat range: a warp takes four windows of 32 consecutive slots at
-      // a time; the run holding a window's first slot by binary search (uniform), a lane's own run
-      // a few steps further (runs are ~16 anchors: a query's hits of one part), so every lane has an
-      // anchor whatever the run lengths are and eight loads per lane are in flight
-      const uint32_t tile_total = tile_end - tile_base;
-      for (uint32_t w0 = (uint32_t)wid * 128u; w0 < tile_total; w0 += (THREADS / 32) * 128u) {
-        uint32_t hh[4], src[4];
+      // (a flat mapping -- 32 consecutive slots per warp, the run of each slot by binary search --
+      // keeps every lane busy but measured slower: 89 against 76 ms per pass of config 2)
+      for (uint32_t r0 = (uint32_t)wid * 4u; r0 < tn; r0 += (THREADS / 32) * 4u) {
+        uint32_t st[4], of[4], cn[4];
         uint64_t kq[4];
         float dq[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          const uint32_t f0 = w0 + 32u * (uint32_t)u;  // warp-uniform
-          hh[u] = 0xFFFFFFFFu;
-          src[u] = 0u;
-          if (f0 < tile_total) {
-            const uint32_t h0 = tile_base + f0;
-            uint32_t lo = 0u, hi = tn;
-            while (hi - lo > 1u) {
-              const uint32_t mid = (lo + hi) >> 1;
-              if (s_run_off[mid] <= h0) lo = mid;
-              else hi = mid;
-            }
-            const uint32_t h = h0 + (uint32_t)lane;
-            if (h < tile_end) {
-              uint32_t r = lo;
-              while (r + 1u < tn && s_run_off[r + 1u] <= h) ++r;
-              hh[u] = h;
-              src[u] = s_run_start[r] + (h - s_run_off[r]);
-            }
+          const uint32_t r = r0 + u;
+          st[u] = 0;
+          of[u] = 0;
+          cn[u] = 0;
+          if (r < tn) {
+            st[u] = s_run_start[r];
+            of[u] = s_run_off[r];
+            cn[u] = (r + 1 < tn ? s_run_off[r + 1] : tile_end) - of[u];
+          }
+          kq[u] = ~0ull;
+          dq[u] = 0.0f;
+          if ((uint32_t)lane < cn[u]) {
+            kq[u] = a.key_in[st[u] + lane];
+            dq[u] = a.dist_in[st[u] + lane];
           }
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          kq[u] = ~0ull;
-          dq[u] = 0.0f;
-          if (hh[u] != 0xFFFFFFFFu) {
-            kq[u] = a.key_in[src[u]];
-            dq[u] = a.dist_in[src[u]];
-          }
+          if ((uint32_t)lane < cn[u]) place(of[u] + lane, kq[u], dq[u]);
+          for (uint32_t i = 32u + lane; i < cn[u]; i += 32u)  // runs longer than a warp
+            place(of[u] + i, a.key_in[st[u] + i], a.dist_in[st[u] + i]);
         }
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-          if (hh[u] != 0xFFFFFFFFu) place(hh[u], kq[u], dq[u]);
       }
       __syncthreads();  // the tile's records are not needed any more
       if (tid == 0) s_misc[34] = tile_end;
