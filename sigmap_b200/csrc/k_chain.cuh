@@ -251,16 +251,36 @@ __global__ void __launch_bounds__(kPrepThreads, 8) k_chain_prep(ChainArgs a) {
   const uint32_t tile0 = blockIdx.x * kPrepTile;
   if (tile0 >= n) return;  // the grid is sized for the buffers, not for the count
   const KeyLayout kl = a.kl;
-  for (int x = threadIdx.x; x < kPrepHalo + kPrepTile; x += kPrepThreads) {
-    const long long g = (long long)tile0 - kPrepHalo + x;
-    int4 v = make_int4(-1, 0, 0, 0);
-    if (g >= 0 && g < (long long)n) {
-      const uint64_t k = a.key[g];
-      v.x = (int)(uint32_t)kl.seg(k);
-      v.y = (int32_t)kl.target(k);
-      v.z = (int32_t)kl.query(k);
+  {
+    // all of a thread's key loads first, then the unpacking: five loads in flight instead of one
+    // (the wait for a single load before its use was the kernel's largest stall)
+    constexpr int kStage = (kPrepHalo + kPrepTile + kPrepThreads - 1) / kPrepThreads;
+    uint64_t kreg[kStage];
+    unsigned have = 0u;
+#pragma unroll
+    for (int j = 0; j < kStage; ++j) {
+      const int x = threadIdx.x + j * kPrepThreads;
+      const long long g = (long long)tile0 - kPrepHalo + x;
+      kreg[j] = 0ull;
+      if (x < kPrepHalo + kPrepTile && g >= 0 && g < (long long)n) {
+        kreg[j] = a.key[g];
+        have |= 1u << j;
+      }
     }
-    s_a[x] = v;
+#pragma unroll
+    for (int j = 0; j < kStage; ++j) {
+      const int x = threadIdx.x + j * kPrepThreads;
+      if (x < kPrepHalo + kPrepTile) {
+        const uint64_t k = kreg[j];
+        int4 v = make_int4(-1, 0, 0, 0);
+        if ((have >> j) & 1u) {
+          v.x = (int)(uint32_t)kl.seg(k);
+          v.y = (int32_t)kl.target(k);
+          v.z = (int32_t)kl.query(k);
+        }
+        s_a[x] = v;
+      }
+    }
   }
   __syncthreads();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
