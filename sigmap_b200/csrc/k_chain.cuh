@@ -706,9 +706,10 @@ __device__ __forceinline__ void dp_segment(const ChainArgs &a, const uint32_t sl
 // after their pending bit was seen cleared; the writer orders score before bit with a fence.  On
 // large batches this loses to the in-segment pass (every cross-warp score is an L2 round trip in
 // the middle of a walk; measured 7 ms against 5.5 ms on 360 M anchors), so the host only launches
-// it below kDpPassMaxSlots segments.
+// it up to kDpPassMaxEntries chunks per step (the segments of one chunk are what a warp of the
+// in-segment kernel would walk alone, however many buckets the reference has).
 constexpr int kDpPassThreads = 256;
-constexpr uint32_t kDpPassMaxSlots = 8192;
+constexpr uint32_t kDpPassMaxEntries = 4096;
 constexpr int kDpIters = 3;      // tries per anchor inside its warp before it is left to the in-order kernel
 
 __global__ void __launch_bounds__(kDpPassThreads, 6) k_dp_pass(ChainArgs a) {
@@ -859,6 +860,7 @@ struct ChainTmp {
   CandRec c;
   uint32_t state;  // 0 candidate, 1 primary (order in `rank`), 2 rejected
   uint32_t rank;
+  uint32_t order;  // record r: index of the primary chain of rank r (k_sel_pick -> k_sel_commit)
 };
 
 struct SelectArgs {
@@ -892,6 +894,7 @@ __device__ __forceinline__ void add_candidate(const SelectArgs &a, const CandRec
     t.c = c;
     t.state = 0;
     t.rank = 0;
+    t.order = 0;
     a.scratch[(size_t)c.entry * a.max_chains + at] = t;
   } else {
     atomicOr(&a.c.ctr->error, 4u);
@@ -1031,40 +1034,81 @@ __global__ void __launch_bounds__(kFinalThreads) k_sel_pick(SelectArgs a, PickRe
     }
     return;
   }
-  if (lane != 0) return;
+  // The reference sorts the candidates in descending order and walks them (:222-253); here the
+  // maximum is extracted again and again by the whole warp: every lane scans its share of the
+  // candidates, a shuffle tournament under the reference's order (ties: the lower index, which is
+  // what a sequential first-maximum scan keeps) picks the next one, and the overlap test against the
+  // primaries found so far is shared the same way.  A weak first chain lets every candidate through
+  // the score test, so one lane alone paid candidates^2 dependent loads (1.4 ms of a read-until round
+  // on a 32-bucket reference).
+  const unsigned full = 0xffffffffu;
   ChainTmp *ch = a.scratch + (size_t)b * a.max_chains;
   const uint32_t nch = min(a.n_scratch[b], a.max_chains);
   uint32_t n_prim = 0, prim_first = 0, prim_second = 0, total_anchors = 0;
   float last_primary_score = 0.0f;
-  for (;;) {  // repeated extraction of the max = the reference's descending sort, lazily
+  for (;;) {
     int best = -1;
-    for (uint32_t c = 0; c < nch; ++c)
-      if (ch[c].state == 0 && (best < 0 || chain_greater(ch[c].c, ch[best].c))) best = (int)c;
+    CandRec bc{};
+    for (uint32_t c = lane; c < nch; c += 32) {
+      if (ch[c].state != 0) continue;
+      const CandRec cc = ch[c].c;
+      if (best < 0 || chain_greater(cc, bc)) {
+        best = (int)c;
+        bc = cc;
+      }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      CandRec oc = bc;
+      const int ob = __shfl_xor_sync(full, best, d);
+      oc.score = __shfl_xor_sync(full, bc.score, d);
+      oc.n = __shfl_xor_sync(full, bc.n, d);
+      oc.bucket = __shfl_xor_sync(full, bc.bucket, d);
+      oc.start = __shfl_xor_sync(full, bc.start, d);
+      oc.end = __shfl_xor_sync(full, bc.end, d);
+      if (ob >= 0 && (best < 0 || chain_greater(oc, bc) || (!chain_greater(bc, oc) && ob < best))) {
+        best = ob;
+        bc.score = oc.score;
+        bc.n = oc.n;
+        bc.bucket = oc.bucket;
+        bc.start = oc.start;
+        bc.end = oc.end;
+      }
+    }
     if (best < 0) break;
-    const CandRec cb = ch[best].c;
+    const CandRec cb = ch[best].c;  // the same record on every lane
     if (n_prim > 0 && cb.score < __fdiv_rn(last_primary_score, 3.0f)) break;
-    bool ok = true;
-    for (uint32_t c = 0; c < nch && ok; ++c) {
+    bool clash = false;
+    for (uint32_t c = lane; c < nch; c += 32) {
       if (ch[c].state != 1 || (ch[c].c.bucket >> 1) != (cb.bucket >> 1)) continue;
       const uint32_t mx = max(cb.start, ch[c].c.start), mn = min(cb.end, ch[c].c.end);
-      if (!(mx > mn)) ok = false;
+      if (!(mx > mn)) clash = true;
+    }
+    const bool ok = !__any_sync(full, clash);
+    if (lane == 0) {
+      if (ok) {
+        ch[best].state = 1;
+        ch[best].rank = n_prim;
+        ch[n_prim].order = (uint32_t)best;
+      } else {
+        ch[best].state = 2;
+      }
     }
     if (ok) {
-      ch[best].state = 1;
-      ch[best].rank = n_prim;
       if (n_prim == 0) prim_first = (uint32_t)best;
       if (n_prim == 1) prim_second = (uint32_t)best;
       last_primary_score = cb.score;
       if (cb.owner == a.rank) total_anchors += cb.n;
       ++n_prim;
-    } else {
-      ch[best].state = 2;
     }
+    __syncwarp(full);  // the new state is visible to every lane's next scan
   }
-  pick[b] = PickRec{n_prim, prim_first, prim_second, total_anchors};
-  if (n_prim) {
-    atomicAdd(&ctr->need_chain, (unsigned long long)n_prim);
-    atomicAdd(&ctr->need_anchor, (unsigned long long)total_anchors);
+  if (lane == 0) {
+    pick[b] = PickRec{n_prim, prim_first, prim_second, total_anchors};
+    if (n_prim) {
+      atomicAdd(&ctr->need_chain, (unsigned long long)n_prim);
+      atomicAdd(&ctr->need_anchor, (unsigned long long)total_anchors);
+    }
   }
 }
 
@@ -1140,8 +1184,7 @@ __global__ void __launch_bounds__(kFinalThreads) k_sel_commit(SelectArgs a, cons
   if (n_prim > 0) {
     uint32_t aoff = 0;
     for (uint32_t r = 0; r < n_prim; ++r) {  // ranks are 0..n_prim-1; emit in rank order
-      uint32_t c = 0;
-      while (!(ch[c].state == 1 && ch[c].rank == r)) ++c;
+      const uint32_t c = ch[r].order;
       const CandRec cc = ch[c].c;
       mean = __fadd_rn(mean, cc.score);
       const bool owned = cc.owner == a.rank;

@@ -254,7 +254,7 @@ struct smb_ctx {
   int dp_passes = kDpFreePasses;  // SMB_DP_PASSES=n
   bool prep_bound = true;         // SMB_PREP_BOUND=0: link test over the whole 5 000-position range
   int prep_rounds = kPrepRounds;  // SMB_PREP_ROUNDS=n: settle rounds inside k_chain_prep (0 = none)
-  uint32_t dp_pass_max_slots = kDpPassMaxSlots;  // SMB_DP_TILES=n: per-tile DP pass below n segments (0 = never)
+  uint32_t dp_pass_max_entries = kDpPassMaxEntries;  // SMB_DP_TILES=n: per-tile DP pass up to n chunks per step (0 = never)
   int pipeline_mode = 0;          // SMB_PIPELINE=auto|on|off: wave-pipelined ticks (see map_uploaded_impl)
   bool index_kd = true;           // SMB_INDEX=morton: points in Morton order instead of the aligned KD order
   uint32_t sort_queries_min = 200000;  // SMB_SORT_QUERIES_MIN=n: batches with fewer queries keep their natural order
@@ -1136,7 +1136,7 @@ static int run_step(smb_ctx *ctx, SlotSpace &sp, const StepEntries &en, StepSour
   ca.prep_rounds = ctx->prep_rounds;
   k_chain_prep<<<n_tiles, kPrepThreads, 0, s>>>(ca);
   LAUNCH_CHECK();
-  if (ca.n_slots <= ctx->dp_pass_max_slots) {  // small batch: per-tile parallel pass first (latency)
+  if (B <= ctx->dp_pass_max_entries) {  // small batch: per-tile parallel pass first (latency)
     k_dp_pass<<<ctx->n_sm * 6u, kDpPassThreads, 0, s>>>(ca);
     LAUNCH_CHECK();
   }
@@ -1513,7 +1513,7 @@ static bool apply_option(smb_ctx *ctx, const char *name_in, const char *value) {
   } else if (name == "INDEX") {  // kd (default) | morton; takes effect at the next index build
     ctx->index_kd = strcmp(value, "morton") != 0;
   } else if (name == "DP_TILES") {
-    ctx->dp_pass_max_slots = (uint32_t)std::max(atoi(value), 0);
+    ctx->dp_pass_max_entries = (uint32_t)std::max(atoi(value), 0);
   } else if (name == "SORT_QUERIES_MIN") {
     ctx->sort_queries_min = (uint32_t)std::max(atoi(value), 0);
   } else if (name == "PIPELINE") {

@@ -50,7 +50,7 @@ PATHS = [
     ("events_overlap", "0", lambda st: True),
     ("part", "small", lambda st: st["part_sort_steps"] > 0),
 ]
-RESET = {"pipeline": "auto", "prep_bound": "1", "prep_rounds": "1", "sort_queries_min": "200000", "dp_tiles": "8192", "sort": "part", "runs_cap": "0", "search": "lean", "front_cap": "384", "grab": "0", "dp": "dynamic",
+RESET = {"pipeline": "auto", "prep_bound": "1", "prep_rounds": "1", "sort_queries_min": "200000", "dp_tiles": "4096", "sort": "part", "runs_cap": "0", "search": "lean", "front_cap": "384", "grab": "0", "dp": "dynamic",
          "dp_passes": "1", "events": "auto", "events_overlap": "1", "part": "big"}
 
 
