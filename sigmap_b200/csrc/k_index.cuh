@@ -308,7 +308,10 @@ constexpr int kSearchGrab = 8;           // queries per grab of the dynamic work
 constexpr int kMaxParts = 32;            // parts per entry the flush can route to (k_part_sort)
 constexpr int kLeanWarps = 32;           // lean kernel: one 1024-thread CTA per SM
 constexpr int kFrontCap = 384;           // lean kernel: frontier slots (nodes of a level / leaves) per query
-constexpr int kLeanStage = 128;          // lean kernel: staged hits per warp
+constexpr int kLeanStage = 128;          // lean kernel: staged hits per warp, at least (SearchArgs::stage_cap: up to 256
+                                         // where the staged top levels leave room, so that a query of a dense
+                                         // index leaves one run per part instead of two or three short ones)
+constexpr int kLeanStageMax = 256;       // ranks inside a part are 8 bits
 constexpr int kLeanGrab = 4;             // lean kernel: sorted queries per grab
 constexpr int kQueryBits = 12;           // query payload = entry << kQueryBits | query number inside the entry
 
@@ -319,12 +322,22 @@ __host__ __device__ inline size_t search_smem_per_warp(int n_levels) {
          (size_t)n_levels * kLevelCap * 4;
 }
 // lean kernel, per warp: staged keys (8 B), distances and part|rank (2 B), two frontiers, per-part counts
+__host__ __device__ inline size_t lean_warp_smem(uint32_t stage_cap) {
+  return (size_t)stage_cap * 14 + 2 * (size_t)kFrontCap * 4 + kMaxParts * 4;
+}
 constexpr size_t kLeanWarpSmem = (size_t)kLeanStage * 14 + 2 * (size_t)kFrontCap * 4 + kMaxParts * 4;
+constexpr size_t kLeanSmemLimit = 232448 - 1024;  // 227 KB per SM less the kernel's static shared memory
 __host__ __device__ inline size_t lean_top_region(uint32_t smem_bytes) { return ((size_t)smem_bytes + 127) & ~(size_t)127; }
 static_assert((size_t)kFrontCap * kLeaf < SMB_MAX_HITS, "the lean kernel must never be able to reach the hit cap");
-static_assert(kLeanStage >= 64 && kLeanStage <= 256, "a leaf step stages up to 64 hits; ranks are 8 bits");
-__host__ __device__ inline size_t lean_smem(uint32_t smem_bytes) {
-  return lean_top_region(smem_bytes) + (size_t)kLeanWarps * kLeanWarpSmem;
+static_assert(kLeanStage >= 64 && kLeanStageMax <= 256, "a leaf step stages up to 64 hits; ranks are 8 bits");
+__host__ __device__ inline size_t lean_smem(uint32_t smem_bytes, uint32_t stage_cap) {
+  return lean_top_region(smem_bytes) + (size_t)kLeanWarps * lean_warp_smem(stage_cap);
+}
+// the largest staging size (a multiple of 32) that fits next to the staged top levels
+__host__ inline uint32_t lean_stage_cap(uint32_t smem_bytes) {
+  uint32_t s = (uint32_t)kLeanStageMax;
+  while (s > (uint32_t)kLeanStage && lean_smem(smem_bytes, s) > kLeanSmemLimit) s -= 32u;
+  return s;
 }
 
 struct SearchArgs {
@@ -364,6 +377,7 @@ struct SearchArgs {
                                // than that raise error bit 6 and the host redoes the step)
   const uint2 *entry_info;     // pipeline: {feature row, query offset (num_events)} per entry
   uint32_t front_cap;          // frontier slots a query may use (<= kFrontCap; tests lower it)
+  uint32_t stage_cap;          // lean kernel: staged hits per warp (kLeanStage .. kLeanStageMax, multiple of 32)
   uint32_t *ovf_list;          // payloads of the queries left to the general kernel
   // general kernel: qlist != nullptr -> work through qlist[0 .. *qlist_n) instead of all queries
   const uint32_t *qlist;
@@ -516,15 +530,11 @@ __device__ __noinline__ void flush_plain(const SearchArgs &a, const uint64_t *__
   unsigned long long base = 0;
   if (lane == 0) base = atomicAdd(&a.ctr->n_anchors, (unsigned long long)n);
   base = __shfl_sync(0xffffffffu, base, 0);
-#pragma unroll
-  for (int i0 = 0; i0 < CAP; i0 += 32) {
-    const int i = i0 + lane;
-    if (i < n) {
-      const unsigned long long o = base + i;
-      if (o < a.cap) {
-        a.out_key[o] = st_key[i];
-        a.out_dist[o] = st_dist[i];
-      }
+  for (int i = lane; i < n; i += 32) {  // n <= CAP
+    const unsigned long long o = base + i;
+    if (o < a.cap) {
+      a.out_key[o] = st_key[i];
+      a.out_dist[o] = st_dist[i];
     }
   }
   __syncwarp();
@@ -653,10 +663,11 @@ k_search_lean(const __grid_constant__ IndexView ix, const __grid_constant__ Sear
   const unsigned full = 0xffffffffu;
   const unsigned lt = (1u << lane) - 1u;
   const uint2 *s_top = reinterpret_cast<const uint2 *>(s_dyn);
-  unsigned char *mine = s_dyn + lean_top_region(ix.smem_bytes) + (size_t)wid * kLeanWarpSmem;
+  const int stage_cap = (int)a.stage_cap;
+  unsigned char *mine = s_dyn + lean_top_region(ix.smem_bytes) + (size_t)wid * lean_warp_smem(a.stage_cap);
   uint64_t *st_key = reinterpret_cast<uint64_t *>(mine);
-  float *st_dist = reinterpret_cast<float *>(mine + (size_t)kLeanStage * 8);
-  uint32_t *fa = reinterpret_cast<uint32_t *>(mine + (size_t)kLeanStage * 12);
+  float *st_dist = reinterpret_cast<float *>(mine + (size_t)stage_cap * 8);
+  uint32_t *fa = reinterpret_cast<uint32_t *>(mine + (size_t)stage_cap * 12);
   uint32_t *fb = fa + kFrontCap;
   uint32_t *pcnt = fb + kFrontCap;
   uint16_t *st_where = reinterpret_cast<uint16_t *>(pcnt + kMaxParts);
@@ -772,9 +783,9 @@ k_search_lean(const __grid_constant__ IndexView ix, const __grid_constant__ Sear
         const unsigned hitB = __ballot_sync(full, hasB && d2b < r2);
         if (hitA | hitB) {
           const int nA = __popc(hitA), nh = nA + __popc(hitB);
-          if (staged + nh > kLeanStage) {
+          if (staged + nh > stage_cap) {
             if (routed) flush_routed(a, st_key, st_dist, st_where, pcnt, s_bb, staged, staged_entry);
-            else flush_plain<kLeanStage>(a, st_key, st_dist, staged);
+            else flush_plain<kLeanStageMax>(a, st_key, st_dist, staged);
             staged = 0;
           }
           if ((hitA >> lane) & 1u) {
@@ -811,7 +822,7 @@ k_search_lean(const __grid_constant__ IndexView ix, const __grid_constant__ Sear
   }
   if (staged) {
     if (routed) flush_routed(a, st_key, st_dist, st_where, pcnt, s_bb, staged, staged_entry);
-    else flush_plain<kLeanStage>(a, st_key, st_dist, staged);
+    else flush_plain<kLeanStageMax>(a, st_key, st_dist, staged);
   }
   if (lane == 0 && my_hits) atomicAdd(&a.ctr->n_hits, my_hits);
 }

@@ -256,6 +256,7 @@ struct smb_ctx {
   int prep_rounds = kPrepRounds;  // SMB_PREP_ROUNDS=n: settle rounds inside k_chain_prep (0 = none)
   uint32_t dp_pass_max_entries = kDpPassMaxEntries;  // SMB_DP_TILES=n: per-tile DP pass up to n chunks per step (0 = never)
   int pipeline_mode = 0;          // SMB_PIPELINE=auto|on|off: wave-pipelined ticks (see map_uploaded_impl)
+  bool stage_big = true;          // SMB_STAGE=small: 128 staged hits per warp of the lean search kernel whatever the room
   bool index_kd = true;           // SMB_INDEX=morton: points in Morton order instead of the aligned KD order
   uint32_t sort_queries_min = 200000;  // SMB_SORT_QUERIES_MIN=n: batches with fewer queries keep their natural order
   bool dp_dynamic = true;         // SMB_DP=static: warp w of the DP grid handles segment w
@@ -392,13 +393,14 @@ static int launch_search(smb_ctx *ctx, SearchArgs sa, uint32_t nq_max, cudaStrea
       LAUNCH_CHECK();
     }
     sa.order = nullptr;
+    sa.stage_cap = ctx->stage_big ? lean_stage_cap(ctx->ix.smem_bytes) : (uint32_t)kLeanStage;
     sa.nq_cap = 0xFFFFFFFFu;
     sa.entry_info = w.entry_info.p;
     sa.front_cap = std::min<uint32_t>(std::max<uint32_t>(ctx->front_cap, 72u), (uint32_t)kFrontCap);
     sa.ovf_list = w.ovf_list.p;
     sa.work = &ctx->d_ctr->work;
     sa.grab = ctx->search_grab;
-    k_search_lean<STAGE><<<ctx->n_sm, kLeanWarps * 32, lean_smem(ctx->ix.smem_bytes), s>>>(ctx->ix, sa);
+    k_search_lean<STAGE><<<ctx->n_sm, kLeanWarps * 32, lean_smem(ctx->ix.smem_bytes, sa.stage_cap), s>>>(ctx->ix, sa);
     LAUNCH_CHECK();
     sa.qlist = w.ovf_list.p;
     sa.qlist_n = &ctx->d_ctr->n_overflow;
@@ -431,12 +433,13 @@ static int launch_search(smb_ctx *ctx, SearchArgs sa, uint32_t nq_max, cudaStrea
                                      0, 24, s));
   ctx->stats.launches += 5;
   sa.order = w.qpay_b.p;
+  sa.stage_cap = ctx->stage_big ? lean_stage_cap(ctx->ix.smem_bytes) : (uint32_t)kLeanStage;
   sa.entry_info = w.entry_info.p;
   sa.front_cap = std::min<uint32_t>(std::max<uint32_t>(ctx->front_cap, 72u), (uint32_t)kFrontCap);
   sa.ovf_list = w.ovf_list.p;
   sa.work = &ctx->d_ctr->work;
   sa.grab = ctx->search_grab;
-  k_search_lean<STAGE><<<ctx->n_sm, kLeanWarps * 32, lean_smem(ctx->ix.smem_bytes), s>>>(ctx->ix, sa);
+  k_search_lean<STAGE><<<ctx->n_sm, kLeanWarps * 32, lean_smem(ctx->ix.smem_bytes, sa.stage_cap), s>>>(ctx->ix, sa);
   LAUNCH_CHECK();
   // the queries whose frontier outgrew the lean kernel's slots (none, mostly: the launch then
   // finds an empty list and returns)
@@ -1516,6 +1519,8 @@ static bool apply_option(smb_ctx *ctx, const char *name_in, const char *value) {
     ctx->dp_pass_max_entries = (uint32_t)std::max(atoi(value), 0);
   } else if (name == "SORT_QUERIES_MIN") {
     ctx->sort_queries_min = (uint32_t)std::max(atoi(value), 0);
+  } else if (name == "STAGE") {
+    ctx->stage_big = strcmp(value, "small") != 0;
   } else if (name == "PIPELINE") {
     ctx->pipeline_mode = strcmp(value, "on") == 0 ? 1 : (strcmp(value, "off") == 0 ? 2 : 0);
   } else if (name == "PREP_BOUND") {
@@ -1607,7 +1612,7 @@ int smb_create(smb_ctx **out, int device) {
     if ((e = cudaFuncSetAttribute(k_radius_search<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, need)) != cudaSuccess ||
         (e = cudaFuncSetAttribute(k_radius_search<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, need)) != cudaSuccess)
       return bail("cudaFuncSetAttribute(k_radius_search)", e);
-    const int lean = (int)lean_smem(kTopSmemMax);
+    const int lean = (int)kLeanSmemLimit;  // the staging buffers take what the staged top levels leave
     static_assert(kTopSmemMax + kLeanWarps * kLeanWarpSmem + 1024 <= 232448, "lean search kernel: 227 KB of shared memory per SM");
     if ((e = cudaFuncSetAttribute(k_search_lean<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lean)) != cudaSuccess ||
         (e = cudaFuncSetAttribute(k_search_lean<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lean)) != cudaSuccess)
@@ -1622,7 +1627,7 @@ int smb_create(smb_ctx **out, int device) {
                                 (int)part_sort_smem_bytes(kPartSortCapSmall, 2304))) != cudaSuccess)
     return bail("cudaFuncSetAttribute(k_part_sort)", e);
   for (const char *name : {"SORT", "SEARCH", "FRONT_CAP", "RUNS_CAP", "GRAB", "PART_FILL", "PART", "DP", "DP_PASSES",
-                           "DP_TILES", "SORT_QUERIES_MIN", "INDEX", "PREP_ROUNDS", "PREP_BOUND", "PIPELINE", "EVENTS_OVERLAP", "EVENTS", "UPLOAD_SLICE_MB"})
+                           "DP_TILES", "SORT_QUERIES_MIN", "INDEX", "PREP_ROUNDS", "PREP_BOUND", "PIPELINE", "STAGE", "EVENTS_OVERLAP", "EVENTS", "UPLOAD_SLICE_MB"})
     if (const char *env = getenv((std::string("SMB_") + name).c_str())) apply_option(ctx, name, env);
   {
     int per_sm = 0, n_sm = 148;

@@ -41,6 +41,7 @@ PATHS = [
     ("prep_bound", "0", lambda st: True),          # link test over the whole 5 000-position range
     ("pipeline", "on", lambda st: True),           # wave-pipelined ticks (one wave on this small input)
     ("pipeline", "off", lambda st: True),
+    ("stage", "small", lambda st: True),           # 128 staged hits per warp whatever the room
     ("grab", "1", lambda st: True),
     ("dp", "static", lambda st: True),
     ("dp_passes", "0", lambda st: True),   # the cooperative in-order DP path settles everything
@@ -50,7 +51,7 @@ PATHS = [
     ("events_overlap", "0", lambda st: True),
     ("part", "small", lambda st: st["part_sort_steps"] > 0),
 ]
-RESET = {"pipeline": "auto", "prep_bound": "1", "prep_rounds": "1", "sort_queries_min": "200000", "dp_tiles": "4096", "sort": "part", "runs_cap": "0", "search": "lean", "front_cap": "384", "grab": "0", "dp": "dynamic",
+RESET = {"stage": "big", "pipeline": "auto", "prep_bound": "1", "prep_rounds": "1", "sort_queries_min": "200000", "dp_tiles": "4096", "sort": "part", "runs_cap": "0", "search": "lean", "front_cap": "384", "grab": "0", "dp": "dynamic",
          "dp_passes": "1", "events": "auto", "events_overlap": "1", "part": "big"}
 
 
