@@ -63,3 +63,23 @@ def test_cli_entry_points(tmp_path, capsys):
     assert "100.000 %" in capsys.readouterr().out
     assert E.main(["truth", str(p), str(t)]) == 0
     assert "Sigmap precision: 1.0" in capsys.readouterr().out
+
+
+def test_rows_sequence_over_a_ctypes_array():
+    """Mapping calls hand their rows back as a sequence over the ctypes array the library filled
+    (no per-row Python work inside the timed call): length, indexing, slices, iteration."""
+    import ctypes as C
+    from sigmap_b200 import _ffi as F
+    from sigmap_b200.mapper import Rows
+    arr = (F.Mapping * 5)()
+    for i in range(5):
+        arr[i].read_len = 100 + i
+    rows = Rows(arr, 4)  # the array may be longer than the read set (never shorter)
+    assert len(rows) == 4 and rows[0].read_len == 100 and rows[-1].read_len == 103
+    assert [m.read_len for m in rows] == [100, 101, 102, 103]
+    assert [m.read_len for m in rows[1:3]] == [101, 102]
+    import pytest
+    with pytest.raises(IndexError):
+        rows[4]
+    assert len(Rows((F.Mapping * 1)(), 0)) == 0 and list(Rows((F.Mapping * 1)(), 0)) == []
+    assert bytes(rows[2]) == bytes(arr[2]) and C.sizeof(rows[0]) == C.sizeof(F.Mapping)
