@@ -58,7 +58,7 @@ def parse_args():
     ap.add_argument("--cpu-sample-reads", type=int, default=0,
                     help="reads the CPU reference maps beside the GPU (0 = max(1500, 50 x host cores))")
     ap.add_argument("--ref-step-reads", type=int, default=0,
-                    help="--impl reference: reads per step (0 = max(1500, 50 x host cores))")
+                    help="--impl reference: reads per step (0 = max(50 x host cores, min(1500, 20000 / steps)))")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-config3", action="store_true", help="N=1: skip the config 3 leg")
     ap.add_argument("--c3-steps", type=int, default=2)
@@ -97,7 +97,9 @@ def resolve_workload(args, world):
     if args.cpu_sample_reads <= 0:
         args.cpu_sample_reads = max(1500, 50 * cores)
     if args.ref_step_reads <= 0:
-        args.ref_step_reads = max(1500, 50 * cores)
+        # the reference arm: every step a bounded sample, at least 50 reads per host thread (fewer
+        # starve the reference's taskloop) and sized so that --steps K ends within a few minutes
+        args.ref_step_reads = max(50 * cores, min(1500, 20000 // max(args.steps, 1)))
     return args
 
 
