@@ -2,20 +2,21 @@
 // KD-tree (nanoflann.hpp:858-1004 build, :1278-1410 radius search), and its build kernels.
 //
 // Layout (see IndexView in sb_device.cuh): the N-5 window points value[w..w+5]
-// (sigmap_adaptor.h:89-97) are sorted by a 60-bit Morton code (6 dims x 10 bits) and cut into
-// 8-point leaves; 8 consecutive leaves / nodes form the next level's node, pointer-free.  A
-// query is handled by ONE WARP that advances FOUR tree nodes (or four leaves) per step, one per
-// 8-lane group: every lane tests one child box (three 16-byte loads) or evaluates one point
-// (three 8-byte loads), so each step keeps four independent 128/64-byte-coalesced request
-// groups in flight and the whole warp stays busy at fan-out 8 -- where a 6-D hierarchy prunes
-// far better than at fan-out 32 (the ball of radius 0.28 meets ~30 8-point leaves but ~28
-// 32-point blocks: 4x fewer points to evaluate, 2.5x fewer boxes to test).
+// (sigmap_adaptor.h:89-97) are put into the aligned KD order (below; or sorted by a 60-bit Morton
+// code, 6 dims x 10 bits) and cut into 8-point leaves; 8 consecutive leaves / nodes form the next
+// level's node, pointer-free.  A query is handled by ONE WARP that advances EIGHT tree nodes (or
+// eight leaves) per step, two per 8-lane group: every lane tests two child boxes (three 8-byte
+// loads each) or evaluates two points, so each step keeps six independent loads per lane in
+// flight and the whole warp stays busy at fan-out 8 -- where a 6-D hierarchy prunes far better
+// than at fan-out 32 (the ball of radius 0.28 meets ~30 8-point leaves but ~28 32-point blocks:
+// 4x fewer points to evaluate, 2.5x fewer boxes to test).
 //
 // Exactness: the accept test is the reference's own fp32 expression
 //   d2 = ((e0+e1)+e2)+e3, then +e4, +e5, e_k = (q_k - v_k)^2, accept iff d2 < radius
 // (nanoflann.hpp:383-408, :249-251, :1362; the "radius" is already squared, Q4) without FMA.
-// Boxes only prune: half extents are rounded outwards when built and the test keeps a relative
-// slack of 1e-4 on the squared radius, so no point the exact test would accept is ever lost.
+// Boxes only prune: their binary16 corners are rounded outwards when built and the tests keep a
+// slack on the squared radius (box_d2_h; 1e-4 relative in the general kernel), so no point the
+// exact test would accept is ever lost.
 #ifndef SB_K_INDEX_CUH
 #define SB_K_INDEX_CUH
 
